@@ -1,0 +1,273 @@
+"""Host planner: notes + RNG draws -> flat event records bucketed by output tile.
+
+This is the integer / float32 bookkeeping of the reference's per-note loop
+(``modules/synthetiser.py:255-292``) separated from the audio arithmetic, so
+that the GPU only sees plain arrays:
+
+* RNG call order of the reference, reproduced draw for draw from the same
+  ``random`` stream - per *new* instrument ``choice(groups)``, ``choice(keys)``
+  for the main then the sub timbre (``:192-202, 274-281``); per note
+  ``uniform(0, mixup_range)`` (``:217``); one final ``random()`` for the FX
+  coin (``:154``).
+* index rules in the dtype the reference computes them in (float32 unless the
+  caller hands in float64 notes): ``note_start = int(onset * sr)`` (``:229``),
+  ``wave_length = int(max(max_offset + 0.1, input_sec) * sr)`` (``:262, 243``),
+  copy length ``min(max(len_a, len_b), wave_length - note_start)``
+  (``:230-237``).  These must be bit-exact; tests/test_planner.py checks them
+  against the running reference.
+* velocity -> volume curve (``:204-212``) and the per-instrument gain
+  (``:104-113, 152-153``) folded into one float32 gain per event.
+
+Events are emitted in *track order* - instruments by first appearance, notes in
+input order inside an instrument - which is the order the reference accumulates
+them in (per-instrument tracks ``:290``, then ``instrument_mixer`` ``:149-153``).
+The tile mixer adds them in exactly this order, so the output is deterministic.
+"""
+from __future__ import annotations
+
+import math
+import random as _random
+from dataclasses import dataclass, field
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+from .bank import OneShotBank
+from .config import SynthDrumConfig
+from .mapping import (ADTOF_INVERSE, PITCH_MAX, PITCH_MIN, SIMILARITY_GROUPS,
+                      instrument_gain)
+
+TILE = 2048  # output samples owned by one CTA of the tile mixer
+
+#: numpy view of ``adtfe_event`` in include/adtfe.h (32 bytes)
+EVENT_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("main_id", "<i4"), ("sub_id", "<i4"),
+                        ("ca", "<f4"), ("cb", "<f4"), ("gain", "<f4"), ("seg", "<i4")])
+#: numpy view of ``adtfe_segment`` (16 bytes)
+SEGMENT_DTYPE = np.dtype([("len", "<i4"), ("flags", "<i4"), ("max_volume", "<f4"), ("first_event", "<i4")])
+SEG_EMPTY = 0      # no notes: all-zero waveform of int(input_sec*sr) samples, no normalisation
+SEG_NORMALISE = 1  # wav / max|wav| * max_volume (NaN when the mix is all zero, like the reference)
+
+
+def similarity_groups(threshold: float) -> List[str]:
+    """Sub-groups admitted by a similarity threshold, best first
+    (reference ``synthetiser.py:168-190``; same float loop, so 0.8 -> 3 groups)."""
+    floor = math.floor(threshold * 10) / 10
+    level, groups = 1.0, []
+    while level >= floor:
+        groups.append(SIMILARITY_GROUPS[10 - int(round(round(level, 1) * 10))])
+        level -= 0.1
+    return groups
+
+
+def velocity_to_volume(velocity: np.ndarray) -> np.ndarray:
+    """``0.1 + 0.9 * (6**(clamp(v,0,127)/127) - 1) / 5`` in the dtype of ``velocity``;
+    exactly 0 for v == 0 (reference ``synthetiser.py:204-212``)."""
+    dt = velocity.dtype.type
+    x = np.clip(velocity, dt(0), dt(127)) / dt(127.0)
+    p = np.power(dt(6), x)
+    vol = dt(0.1) + (dt(0.9) * (p - dt(1))) / dt(5)
+    return np.where(velocity == 0, dt(0), vol).astype(velocity.dtype)
+
+
+def notes_to_array(notes) -> np.ndarray:
+    """(N, 4) array in the dtype ``torch.tensor(notes)`` would infer
+    (reference ``synthetiser.py:259``): python floats -> float32, numpy/torch keep theirs."""
+    if isinstance(notes, torch.Tensor):
+        t = notes.detach().cpu()
+    else:
+        t = torch.tensor(notes)
+    if not t.dtype.is_floating_point or t.dtype not in (torch.float32, torch.float64):
+        t = t.to(torch.float32)
+    a = t.numpy()
+    if a.ndim != 2 or a.shape[1] != 4:
+        raise ValueError(f"notes must have shape (N, 4), got {tuple(a.shape)}")
+    return a
+
+
+@dataclass
+class SegmentPlan:
+    wave_length: int
+    flags: int
+    max_volume: float
+    events: np.ndarray            # EVENT_DTYPE, track order, seg field = 0
+    mix_len: np.ndarray           # int32 per event: max(len_a, len_b) before truncation
+    group_ptr: np.ndarray         # int32 (n_groups+1,): events of one instrument are contiguous
+
+
+def plan_segment(notes, config: SynthDrumConfig, bank: OneShotBank, rng=_random) -> SegmentPlan:
+    """Plan one ``SynthDrum.__call__``.  ``rng`` is the ``random`` module (default, so a
+    seeded reference run and a seeded run here draw the same numbers) or a ``random.Random``."""
+    sr = config.sample_rate
+    if len(notes) == 0:  # synthetiser.py:257-258
+        return SegmentPlan(int(config.input_sec * sr), SEG_EMPTY, 0.0,
+                           np.zeros(0, EVENT_DTYPE), np.zeros(0, np.int32), np.zeros(1, np.int32))
+    a = notes_to_array(notes)
+    dt = a.dtype.type
+    n = a.shape[0]
+
+    # ---- segment length (synthetiser.py:262, 243)
+    end = dt(a[:, 1].max()) + dt(0.1)
+    if end < dt(config.input_sec):
+        wave_length = int(config.input_sec * sr)
+    else:
+        wave_length = int(end * dt(sr))
+
+    # ---- per-note draws, in the reference's order
+    groups = similarity_groups(config.similarity_threshold)
+    chosen, rank = {}, {}
+    main_id = np.empty(n, np.int32)
+    sub_id = np.empty(n, np.int32)
+    order_rank = np.empty(n, np.int32)
+    alpha = np.empty(n, np.float64)
+    gains = np.empty(n, np.float32)
+
+    def choose(pitch: int) -> int:  # synthetiser.py:192-202
+        if config.ADTOF_mapping:
+            pitch = rng.choice(ADTOF_INVERSE[pitch])
+        valid = [g for g in groups if bank.has_group(int(pitch), g)]
+        g = rng.choice(valid)
+        first, count = bank.group_range(int(pitch), g)
+        return first + rng.choice(range(count))
+
+    onset, offset, pitch = a[:, 0], a[:, 1], a[:, 2]
+    for i in range(n):
+        if not (PITCH_MIN <= pitch[i] <= PITCH_MAX and offset[i] >= onset[i]):
+            raise ValueError(f"Invalid note: {a[i]}")  # synthetiser.py:270-271
+        if onset[i] < 0:
+            raise ValueError(f"Invalid note: {a[i]} (negative onset)")
+        inst = int(pitch[i])
+        if inst != pitch[i]:
+            raise KeyError(inst)  # the reference's float-keyed track dict misses here too
+        if inst not in chosen:
+            chosen[inst] = (choose(inst), choose(inst))
+            rank[inst] = len(rank)
+        main_id[i], sub_id[i] = chosen[inst]
+        order_rank[i] = rank[inst]
+        alpha[i] = rng.uniform(0, config.mixup_range)  # synthetiser.py:217
+    for inst in rank:  # gain lookup happens in instrument_mixer, after the loop
+        g = instrument_gain(inst, config.ADTOF_mapping)
+        gains[pitch == inst] = g
+    if rng.random() < config.use_fx_prob:  # synthetiser.py:154
+        raise NotImplementedError(
+            "the pedalboard FX chain (synthetiser.py:121-137) is outside the GPU path; set use_fx_prob=0")
+
+    # ---- vectorised index rules
+    vel = a[:, 3]
+    vol = velocity_to_volume(vel)
+    max_volume = float(velocity_to_volume(np.array([max(dt(0), vel.max())], a.dtype))[0])
+    start = (onset * dt(sr)).astype(np.int64)              # float product in dt, C truncation
+    mix_len = np.maximum(bank.lengths[main_id], bank.lengths[sub_id]).astype(np.int64)
+    length = np.minimum(mix_len, wave_length - start)       # synthetiser.py:232-237
+    length = np.maximum(length, 0)
+
+    ev = np.zeros(n, EVENT_DTYPE)
+    ev["start"], ev["len"] = start, length
+    ev["main_id"], ev["sub_id"] = main_id, sub_id
+    ev["ca"] = (1.0 - alpha).astype(np.float32)             # python float (1 - mixup) -> f32 (synthetiser.py:223)
+    ev["cb"] = alpha.astype(np.float32)
+    ev["gain"] = vol.astype(np.float32) * gains
+    perm = np.argsort(order_rank, kind="stable")
+    ev, mix_len = ev[perm], mix_len[perm].astype(np.int32)
+    sorted_rank = order_rank[perm]
+    group_ptr = np.concatenate([[0], np.flatnonzero(np.diff(sorted_rank)) + 1, [n]]).astype(np.int32)
+    return SegmentPlan(wave_length, SEG_NORMALISE, max_volume, ev, mix_len, group_ptr)
+
+
+@dataclass
+class RenderPlan:
+    """A batch of segment plans flattened for the device (all little-endian, C layout)."""
+    n_seg: int
+    ld_wav: int                   # row pitch of the (n_seg, ld_wav) waveform matrix, multiple of 4
+    tiles_per_seg: int
+    segments: np.ndarray          # SEGMENT_DTYPE (n_seg,)
+    events: np.ndarray            # EVENT_DTYPE (n_events,)
+    mix_len: np.ndarray           # int32 (n_events,)
+    group_ptr: np.ndarray         # int32 (n_groups+1,)
+    tile_ptr: np.ndarray          # int32 (n_seg*tiles_per_seg+1,)
+    tile_events: np.ndarray       # int32 (n_refs,) event ids, ascending inside a tile
+    wave_lengths: np.ndarray = field(default=None)  # int64 (n_seg,)
+
+    @property
+    def n_events(self) -> int:
+        return int(self.events.shape[0])
+
+    @property
+    def n_groups(self) -> int:
+        return int(self.group_ptr.shape[0] - 1)
+
+    def bank_bytes(self, bank: OneShotBank) -> int:
+        """Sum over (segment, distinct one-shot) of 4*min(len_u, L_seg - first_start_u): the
+        bank bytes one segment cannot avoid reading."""
+        if self.n_events == 0:
+            return 0
+        ev = self.events
+        ids = np.concatenate([ev["main_id"], ev["sub_id"]]).astype(np.int64)
+        seg = np.concatenate([ev["seg"], ev["seg"]]).astype(np.int64)
+        start = np.concatenate([ev["start"], ev["start"]]).astype(np.int64)
+        key = seg * (len(bank) + 1) + ids
+        order = np.lexsort((start, key))               # by (segment, one-shot), earliest start first
+        k = key[order]
+        first = np.ones(len(order), bool)
+        first[1:] = k[1:] != k[:-1]
+        sel = order[first]
+        room = self.segments["len"][seg[sel]].astype(np.int64) - start[sel]
+        total = np.minimum(bank.lengths[ids[sel]].astype(np.int64), room).clip(0).sum()
+        return 4 * int(total)
+
+    def bytes_alg(self, bank: OneShotBank, n_frames: int, n_mels: int) -> int:
+        """Algorithmic bytes of render + log-mel for this batch:
+        wav write + mel write + distinct one-shot reads + 32 B per event."""
+        return (4 * int(self.segments["len"].sum()) + 4 * n_frames * n_mels * self.n_seg
+                + self.bank_bytes(bank) + EVENT_DTYPE.itemsize * self.n_events)
+
+
+def bucket_tiles(start: np.ndarray, length: np.ndarray, seg: np.ndarray, n_seg: int, tiles_per_seg: int):
+    """CSR ``tile -> event ids``.  An event lands in every tile its
+    ``[start, start+len)`` touches; ids ascend inside a tile (= track order)."""
+    n_tiles = n_seg * tiles_per_seg
+    live = length > 0
+    first = start // TILE
+    count = np.where(live, (start + length - 1) // TILE - first + 1, 0).astype(np.int64)
+    ev_id = np.repeat(np.arange(len(start), dtype=np.int64), count)
+    within = np.arange(int(count.sum()), dtype=np.int64) - np.repeat(np.cumsum(count) - count, count)
+    tile = seg.astype(np.int64)[ev_id] * tiles_per_seg + first.astype(np.int64)[ev_id] + within
+    order = np.argsort(tile, kind="stable")
+    tile_events = ev_id[order].astype(np.int32)
+    tile_ptr = np.zeros(n_tiles + 1, np.int64)
+    np.add.at(tile_ptr, tile + 1, 1)
+    return np.cumsum(tile_ptr).astype(np.int32), tile_events
+
+
+def assemble(plans: Sequence[SegmentPlan], ld_wav: int | None = None) -> RenderPlan:
+    n_seg = len(plans)
+    max_len = max((p.wave_length for p in plans), default=0)
+    if ld_wav is None:
+        ld_wav = -(-max_len // 4) * 4
+    if ld_wav < max_len or ld_wav % 4:
+        raise ValueError("ld_wav must be a multiple of 4 and cover the longest segment")
+    tiles_per_seg = -(-ld_wav // TILE) if ld_wav else 0
+    segments = np.zeros(n_seg, SEGMENT_DTYPE)
+    evs, mls, gps, base = [], [], [np.zeros(1, np.int32)], 0
+    for s, p in enumerate(plans):
+        segments[s] = (p.wave_length, p.flags, p.max_volume, base)
+        e = p.events.copy()
+        e["seg"] = s
+        evs.append(e)
+        mls.append(p.mix_len)
+        gps.append(p.group_ptr[1:] + base)
+        base += len(e)
+    events = np.concatenate(evs) if evs else np.zeros(0, EVENT_DTYPE)
+    mix_len = np.concatenate(mls).astype(np.int32) if mls else np.zeros(0, np.int32)
+    group_ptr = np.concatenate(gps).astype(np.int32)
+    tile_ptr, tile_events = bucket_tiles(events["start"].astype(np.int64), events["len"].astype(np.int64),
+                                         events["seg"], n_seg, tiles_per_seg)
+    return RenderPlan(n_seg, ld_wav, tiles_per_seg, segments, events, mix_len, group_ptr, tile_ptr,
+                      tile_events, np.array([p.wave_length for p in plans], np.int64))
+
+
+def plan_batch(batch_notes: Sequence, config: SynthDrumConfig, bank: OneShotBank, rng=_random,
+               ld_wav: int | None = None) -> RenderPlan:
+    """Plan ``len(batch_notes)`` independent ``SynthDrum.__call__``s, in order (the RNG
+    stream advances exactly as that many reference calls would advance it)."""
+    return assemble([plan_segment(n, config, bank, rng) for n in batch_notes], ld_wav)
