@@ -1,0 +1,77 @@
+"""ctypes binding of libadtfe.so (include/adtfe.h).  There is no fallback: if the
+library cannot be loaded, or the device is not sm_100, every entry raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadtfe.so")
+
+EXPORTS = [
+    "adtfe_version", "adtfe_last_error", "adtfe_device_ok",
+    "adtfe_bank_create", "adtfe_bank_destroy", "adtfe_bank_bytes",
+    "adtfe_render_workspace_bytes", "adtfe_render",
+    "adtfe_mel_create", "adtfe_mel_destroy", "adtfe_mel_frames", "adtfe_logmel",
+    "adtfe_render_logmel", "adtfe_frontend_host", "adtfe_plan_blob_layout",
+]
+
+
+class AdtfeError(RuntimeError):
+    pass
+
+
+class Plan(C.Structure):
+    """adtfe_plan"""
+    _fields_ = [("events_dev", C.c_void_p), ("mix_len_dev", C.c_void_p), ("group_ptr_dev", C.c_void_p),
+                ("segments_dev", C.c_void_p), ("tile_ptr_dev", C.c_void_p), ("tile_events_dev", C.c_void_p),
+                ("n_events", C.c_int32), ("n_groups", C.c_int32), ("n_seg", C.c_int32),
+                ("tiles_per_seg", C.c_int32), ("ld_wav", C.c_int64)]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def _declare(lib) -> None:
+    vp, i32, i64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+    lib.adtfe_version.restype = C.c_int
+    lib.adtfe_last_error.restype = C.c_char_p
+    lib.adtfe_device_ok.argtypes = [C.c_int]
+    lib.adtfe_bank_create.argtypes = [vp, i64, vp, vp, i32, C.c_int, C.POINTER(vp)]
+    lib.adtfe_bank_destroy.argtypes = [vp]
+    lib.adtfe_bank_bytes.argtypes = [vp]
+    lib.adtfe_bank_bytes.restype = i64
+    lib.adtfe_render_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.adtfe_render_workspace_bytes.restype = sz
+    lib.adtfe_render.argtypes = [vp, C.POINTER(Plan), vp, vp, sz, vp]
+    lib.adtfe_mel_create.argtypes = [i32, i32, i32, vp, vp, C.c_int, C.POINTER(vp)]
+    lib.adtfe_mel_destroy.argtypes = [vp]
+    lib.adtfe_mel_frames.argtypes = [vp, i64, C.POINTER(i32), C.POINTER(i32)]
+    lib.adtfe_logmel.argtypes = [vp, vp, i32, i64, i64, vp, vp]
+    lib.adtfe_render_logmel.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, vp, vp, sz, vp]
+    lib.adtfe_frontend_host.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp]
+    lib.adtfe_plan_blob_layout.argtypes = [C.POINTER(Plan), C.POINTER(sz * 6), C.POINTER(sz)]
+
+
+def load():
+    """The loaded library.  Raises AdtfeError when libadtfe.so is missing - build it with
+    ``python -m adt_str_b200.build`` (or ``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise AdtfeError(f"{LIB_PATH} not found: the CUDA library has not been built "
+                                     "(python -m adt_str_b200.build); there is no CPU fallback")
+                lib = C.CDLL(LIB_PATH)
+                _declare(lib)
+                _lib = lib
+    return _lib
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().adtfe_last_error().decode(errors="replace")
+        raise AdtfeError(f"{what or 'adtfe'} failed ({status}): {msg}")

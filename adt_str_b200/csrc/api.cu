@@ -1,0 +1,151 @@
+// libadtfe: error state, device checks, bank, fused and host-buffer entry points.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace adtfe {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int device_sm_count(int device) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
+    return n;
+}
+
+}  // namespace adtfe
+
+using namespace adtfe;
+
+extern "C" int adtfe_version(void) { return ADTFE_VERSION; }
+extern "C" const char* adtfe_last_error(void) { return g_error; }
+
+extern "C" int adtfe_device_ok(int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        set_error("no CUDA device %d (found %d)", device, count);
+        return ADTFE_ERR_NO_DEVICE;
+    }
+    int major = 0;
+    ADTFE_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    ADTFE_REQUIRE(major == 10, ADTFE_ERR_NO_DEVICE,
+                  "device %d is compute capability %d.x; this library is built for sm_100a only", device, major);
+    return ADTFE_OK;
+}
+
+extern "C" int adtfe_bank_destroy(adtfe_bank* bank) {
+    if (!bank) return ADTFE_OK;
+    cudaSetDevice(bank->device);
+    cudaFree(bank->pcm);
+    cudaFree(bank->offsets);
+    cudaFree(bank->lengths);
+    delete bank;
+    return ADTFE_OK;
+}
+
+extern "C" int64_t adtfe_bank_bytes(const adtfe_bank* bank) { return bank ? bank->total * 4 : 0; }
+
+extern "C" int adtfe_bank_create(const float* pcm_host, int64_t total_floats, const int64_t* offsets_host,
+                                 const int32_t* lengths_host, int32_t n_oneshots, int device, adtfe_bank** out) {
+    ADTFE_REQUIRE(out, ADTFE_ERR_BAD_ARG, "adtfe_bank_create: null out");
+    *out = nullptr;
+    ADTFE_REQUIRE(total_floats >= 0 && n_oneshots >= 0, ADTFE_ERR_BAD_ARG, "adtfe_bank_create: negative size");
+    ADTFE_REQUIRE(n_oneshots == 0 || (pcm_host && offsets_host && lengths_host), ADTFE_ERR_BAD_ARG,
+                  "adtfe_bank_create: null array");
+    for (int32_t i = 0; i < n_oneshots; ++i) {
+        const int64_t padded = ((int64_t)lengths_host[i] + 3) & ~(int64_t)3;
+        ADTFE_REQUIRE(offsets_host[i] >= 0 && offsets_host[i] % 4 == 0 && lengths_host[i] >= 0 &&
+                          offsets_host[i] + padded <= total_floats,
+                      ADTFE_ERR_BAD_ARG,
+                      "adtfe_bank_create: one-shot %d (offset %lld, length %d) is misaligned or outside the bank "
+                      "(starts must be multiples of 4 floats and storage padded to 4)",
+                      i, (long long)offsets_host[i], lengths_host[i]);
+    }
+    int rc = adtfe_device_ok(device);
+    if (rc != ADTFE_OK) return rc;
+    ADTFE_CUDA(cudaSetDevice(device));
+    adtfe_bank* b = new adtfe_bank();
+    b->device = device;
+    b->n = n_oneshots;
+    b->total = total_floats;
+    auto up = [&](void** dst, const void* src, size_t bytes) -> bool {
+        if (cudaMalloc(dst, bytes ? bytes : 16) != cudaSuccess) return false;
+        return bytes == 0 || cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    if (!up((void**)&b->pcm, pcm_host, (size_t)total_floats * 4) ||
+        !up((void**)&b->offsets, offsets_host, (size_t)n_oneshots * 8) ||
+        !up((void**)&b->lengths, lengths_host, (size_t)n_oneshots * 4)) {
+        set_error("adtfe_bank_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        adtfe_bank_destroy(b);
+        return ADTFE_ERR_CUDA;
+    }
+    *out = b;
+    return ADTFE_OK;
+}
+
+extern "C" int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel, const adtfe_plan* plan,
+                                   int64_t n_samples, float* wav_out_dev, float* mel_out_dev, void* workspace_dev,
+                                   size_t workspace_bytes, void* stream) {
+    ADTFE_REQUIRE(plan && n_samples <= plan->ld_wav, ADTFE_ERR_BAD_ARG,
+                  "adtfe_render_logmel: n_samples exceeds the row pitch");
+    int rc = adtfe_render(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream);
+    if (rc != ADTFE_OK) return rc;
+    return adtfe_logmel(mel, wav_out_dev, plan->n_seg, plan->ld_wav, n_samples, mel_out_dev, stream);
+}
+
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+extern "C" int adtfe_plan_blob_layout(const adtfe_plan* s, size_t offsets[6], size_t* blob_bytes) {
+    ADTFE_REQUIRE(s && offsets && blob_bytes, ADTFE_ERR_BAD_ARG, "adtfe_plan_blob_layout: null pointer");
+    ADTFE_REQUIRE(s->n_events >= 0 && s->n_groups >= 0 && s->n_seg >= 0 && s->tiles_per_seg >= 0,
+                  ADTFE_ERR_BAD_ARG, "adtfe_plan_blob_layout: negative count");
+    size_t o = 0;
+    offsets[0] = o; o = align16(o + (size_t)s->n_events * sizeof(adtfe_event));
+    offsets[1] = o; o = align16(o + (size_t)s->n_events * 4);
+    offsets[2] = o; o = align16(o + (size_t)(s->n_groups + 1) * 4);
+    offsets[3] = o; o = align16(o + (size_t)s->n_seg * sizeof(adtfe_segment));
+    offsets[4] = o; o = align16(o + ((size_t)s->n_seg * s->tiles_per_seg + 1) * 4);
+    offsets[5] = o;  // tile_events runs to the end of the blob; its length is tile_ptr's last entry
+    *blob_bytes = o;
+    return ADTFE_OK;
+}
+
+extern "C" int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel, const adtfe_plan* shape,
+                                   int64_t n_samples, const void* blob_host, size_t blob_bytes, void* blob_dev,
+                                   float* wav_dev, float* mel_dev, void* workspace_dev, size_t workspace_bytes,
+                                   float* mel_out_host, float* wav_out_host, void* stream) {
+    ADTFE_REQUIRE(bank && mel && shape && blob_host && blob_dev && mel_out_host, ADTFE_ERR_BAD_ARG,
+                  "adtfe_frontend_host: null pointer");
+    size_t off[6], fixed = 0;
+    int rc = adtfe_plan_blob_layout(shape, off, &fixed);
+    if (rc != ADTFE_OK) return rc;
+    ADTFE_REQUIRE(blob_bytes >= fixed, ADTFE_ERR_BAD_ARG, "adtfe_frontend_host: plan blob %zu B < %zu B", blob_bytes,
+                  fixed);
+    cudaStream_t st = (cudaStream_t)stream;
+    ADTFE_CUDA(cudaMemcpyAsync(blob_dev, blob_host, blob_bytes, cudaMemcpyHostToDevice, st));
+    adtfe_plan p = *shape;
+    const char* d = (const char*)blob_dev;
+    p.events_dev = (const adtfe_event*)(d + off[0]);
+    p.mix_len_dev = (const int32_t*)(d + off[1]);
+    p.group_ptr_dev = (const int32_t*)(d + off[2]);
+    p.segments_dev = (const adtfe_segment*)(d + off[3]);
+    p.tile_ptr_dev = (const int32_t*)(d + off[4]);
+    p.tile_events_dev = (const int32_t*)(d + off[5]);
+    rc = adtfe_render_logmel(bank, mel, &p, n_samples, wav_dev, mel_dev, workspace_dev, workspace_bytes, stream);
+    if (rc != ADTFE_OK) return rc;
+    int32_t first = 0, count = 0;
+    adtfe_mel_frames(mel, n_samples, &first, &count);
+    const size_t mel_bytes = (size_t)p.n_seg * count * mel->n_mels * 4;
+    if (mel_bytes) ADTFE_CUDA(cudaMemcpyAsync(mel_out_host, mel_dev, mel_bytes, cudaMemcpyDeviceToHost, st));
+    if (wav_out_host && p.n_seg)
+        ADTFE_CUDA(cudaMemcpyAsync(wav_out_host, wav_dev, (size_t)p.n_seg * p.ld_wav * 4, cudaMemcpyDeviceToHost, st));
+    return ADTFE_OK;
+}

@@ -1,0 +1,70 @@
+// Shared declarations for libadtfe (sm_100a).  See include/adtfe.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/adtfe.h"
+
+namespace adtfe {
+
+void set_error(const char* fmt, ...);
+
+#define ADTFE_CUDA(call)                                                                   \
+    do {                                                                                   \
+        cudaError_t err__ = (call);                                                        \
+        if (err__ != cudaSuccess) {                                                        \
+            adtfe::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(err__), __FILE__, __LINE__); \
+            return ADTFE_ERR_CUDA;                                                         \
+        }                                                                                  \
+    } while (0)
+
+#define ADTFE_REQUIRE(cond, status, ...)       \
+    do {                                       \
+        if (!(cond)) {                         \
+            adtfe::set_error(__VA_ARGS__);     \
+            return (status);                   \
+        }                                      \
+    } while (0)
+
+// Event with its bank lookups resolved by the peak pass, so the tile mixer does one
+// broadcast load per event instead of a three-deep dependent chain (48 bytes).
+struct ResolvedEvent {
+    int64_t a_off, b_off;  // float offsets of the main / sub one-shot in the bank
+    int32_t la, lb;        // their true lengths
+    int32_t start, len;
+    float ca, cb;
+    float scale;           // gain / max|ca*a + cb*b|
+    int32_t pad;
+};
+static_assert(sizeof(ResolvedEvent) == 48, "ResolvedEvent layout");
+static_assert(sizeof(adtfe_event) == 32, "adtfe_event layout");
+static_assert(sizeof(adtfe_segment) == 16, "adtfe_segment layout");
+
+int device_sm_count(int device);
+
+}  // namespace adtfe
+
+struct adtfe_bank {
+    int device = 0;
+    int32_t n = 0;
+    int64_t total = 0;
+    float* pcm = nullptr;
+    int64_t* offsets = nullptr;
+    int32_t* lengths = nullptr;
+};
+
+struct adtfe_mel {
+    int device = 0;
+    int sm_count = 148;
+    int32_t n_fft = 2048, hop = 240, n_mels = 128, wpi = 5;
+    int32_t nnz = 0;        // stored filter weights (first..last non-zero bin of every filter)
+    float* window = nullptr;   // n_fft
+    float2* twiddle = nullptr; // 32 x 32: W_2048^(k1*n2), k1 = 1..32, n2 = lane
+    float2* lane_tw = nullptr; // 3 x 32: per-lane twiddles of the cross-lane 32-point DFT
+    float* fb_w = nullptr;     // nnz
+    int32_t* fb_ptr = nullptr; // n_mels+1
+    int32_t* fb_lo = nullptr;  // n_mels: first bin of every filter
+    size_t smem_bytes = 0;
+};

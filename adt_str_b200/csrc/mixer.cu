@@ -1,0 +1,253 @@
+// Overlap-add tile mixer (sm_100a): peaks -> tiles -> normalise.
+//
+// Replaces the audio arithmetic of SynthDrum.__call__ (reference modules/synthetiser.py):
+//   drum_rendering 214-239:  o = (1-mixup)*a + mixup*b ; o /= max|o| ; o *= vol ;
+//                            track[start : start+len] += o[:len]
+//   instrument_mixer 149-156: wav = sum_i track_i * gain_i ; wav / max|wav| * max_volume
+// and the zero padding of collate_fn (data_modules/train_dataset.py:53).
+//
+// The two data-dependent maxima make it three short kernels:
+//   1. peak_kernel      one CTA per (segment, instrument): both one-shots are read once and
+//                       max|ca*a + cb*b| is taken for every note of that instrument at the
+//                       same time (each note has its own mixup); also resolves the bank
+//                       lookups into ResolvedEvent records.
+//   2. mix_kernel       one CTA per 2048-sample output tile; events come from the host-built
+//                       CSR (tile -> events) and are added in array order into registers,
+//                       so the result is deterministic and needs no atomics; emits the
+//                       tile's |max|.
+//   3. normalise_kernel per-segment max of the tile maxima, then wav / peak * max_volume
+//                       in place (an all-zero mix gives NaN, like the reference's 0/0).
+#include "common.cuh"
+
+namespace adtfe {
+
+constexpr int kPeakThreads = 256;
+constexpr int kPeakChunk = 8;   // notes of one instrument handled per sweep over the one-shots
+constexpr int kMixThreads = 256;
+constexpr int kPerThread = ADTFE_TILE / kMixThreads;  // 8 samples, stride kMixThreads
+constexpr int kStage = 64;      // resolved events staged in shared memory per round
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float nan_max(float a, float b) {  // torch.max propagates NaN
+    return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b);
+}
+
+__global__ void __launch_bounds__(kPeakThreads) peak_kernel(
+    const float* __restrict__ pcm, const int64_t* __restrict__ offsets, const int32_t* __restrict__ lengths,
+    const adtfe_event* __restrict__ events, const int32_t* __restrict__ mix_len,
+    const int32_t* __restrict__ group_ptr, ResolvedEvent* __restrict__ resolved) {
+    __shared__ float s_red[kPeakChunk][kPeakThreads / 32];
+    __shared__ float s_ca[kPeakChunk], s_cb[kPeakChunk];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const int e0 = group_ptr[g], e1 = group_ptr[g + 1];
+    if (e0 >= e1) return;
+    const adtfe_event head = events[e0];
+    const int64_t a_off = offsets[head.main_id], b_off = offsets[head.sub_id];
+    const int la = lengths[head.main_id], lb = lengths[head.sub_id];
+    const int n = mix_len[e0];
+    // every one-shot is padded to 4 floats, so whole float4s up to the padded length are readable
+    const int la4 = (la + 3) >> 2, lb4 = (lb + 3) >> 2, n4 = (n + 3) >> 2;
+    const float4* a4 = reinterpret_cast<const float4*>(pcm + a_off);
+    const float4* b4 = reinterpret_cast<const float4*>(pcm + b_off);
+
+    for (int c0 = e0; c0 < e1; c0 += kPeakChunk) {
+        const int nc = min(kPeakChunk, e1 - c0);
+        __syncthreads();
+        if (tid < kPeakChunk) {
+            const bool live = tid < nc;
+            s_ca[tid] = live ? events[c0 + tid].ca : 0.0f;
+            s_cb[tid] = live ? events[c0 + tid].cb : 0.0f;
+        }
+        __syncthreads();
+        float ca[kPeakChunk], cb[kPeakChunk], m[kPeakChunk];
+#pragma unroll
+        for (int i = 0; i < kPeakChunk; ++i) { ca[i] = s_ca[i]; cb[i] = s_cb[i]; m[i] = 0.0f; }
+        for (int i4 = tid; i4 < n4; i4 += kPeakThreads) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 va = i4 < la4 ? __ldg(a4 + i4) : z;
+            float4 vb = i4 < lb4 ? __ldg(b4 + i4) : z;
+            if (4 * i4 + 3 >= la) {  // last float4 of the one-shot: ignore whatever pads it
+                if (4 * i4 + 1 >= la) va.y = 0.f;
+                if (4 * i4 + 2 >= la) va.z = 0.f;
+                va.w = 0.f;
+            }
+            if (4 * i4 + 3 >= lb) {
+                if (4 * i4 + 1 >= lb) vb.y = 0.f;
+                if (4 * i4 + 2 >= lb) vb.z = 0.f;
+                vb.w = 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < kPeakChunk; ++i) {
+                // separate roundings, as torch's mul, mul, add (synthetiser.py:223)
+                m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va.x, ca[i]), __fmul_rn(cb[i], vb.x))));
+                m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va.y, ca[i]), __fmul_rn(cb[i], vb.y))));
+                m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va.z, ca[i]), __fmul_rn(cb[i], vb.z))));
+                m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va.w, ca[i]), __fmul_rn(cb[i], vb.w))));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < kPeakChunk; ++i) {
+            const float w = warp_max(m[i]);
+            if ((tid & 31) == 0) s_red[i][tid >> 5] = w;
+        }
+        __syncthreads();
+        if (tid < nc) {
+            float peak = 0.0f;
+#pragma unroll
+            for (int w = 0; w < kPeakThreads / 32; ++w) peak = fmaxf(peak, s_red[tid][w]);
+            const adtfe_event ev = events[c0 + tid];
+            ResolvedEvent r;
+            r.a_off = a_off; r.b_off = b_off; r.la = la; r.lb = lb;
+            r.start = ev.start; r.len = ev.len; r.ca = ev.ca; r.cb = ev.cb;
+            r.scale = ev.gain / peak;  // x/0 -> inf or NaN for an all-zero one-shot, as the reference
+            r.pad = 0;
+            resolved[c0 + tid] = r;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kMixThreads) mix_kernel(
+    const float* __restrict__ pcm, const ResolvedEvent* __restrict__ resolved,
+    const int32_t* __restrict__ tile_ptr, const int32_t* __restrict__ tile_events, int tiles_per_seg,
+    int64_t ld_wav, float* __restrict__ wav, float* __restrict__ tile_max) {
+    __shared__ __align__(16) ResolvedEvent s_ev[kStage];
+    __shared__ float s_red[kMixThreads / 32];
+    const int tile_id = blockIdx.x, tid = threadIdx.x;
+    const int seg = tile_id / tiles_per_seg, tile = tile_id - seg * tiles_per_seg;
+    const int lo = tile * ADTFE_TILE;
+    float acc[kPerThread];
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) acc[j] = 0.0f;
+
+    const int p0 = tile_ptr[tile_id], p1 = tile_ptr[tile_id + 1];
+    for (int base = p0; base < p1; base += kStage) {
+        const int nst = min(kStage, p1 - base);
+        __syncthreads();
+        // 48-byte records copied as 12 words each, coalesced over the CTA
+        for (int i = tid; i < nst * 12; i += kMixThreads) {
+            const int r = i / 12, w = i - r * 12;
+            reinterpret_cast<int32_t*>(s_ev)[i] =
+                __ldg(reinterpret_cast<const int32_t*>(resolved + tile_events[base + r]) + w);
+        }
+        __syncthreads();
+        for (int k = 0; k < nst; ++k) {
+            const ResolvedEvent ev = s_ev[k];
+            const float* a = pcm + ev.a_off;
+            const float* b = pcm + ev.b_off;
+            const int r0 = lo + tid - ev.start;
+            float va[kPerThread], vb[kPerThread];
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j) {
+                const int r = r0 + j * kMixThreads;
+                const bool in = r >= 0 && r < ev.len;
+                va[j] = (in && r < ev.la) ? __ldg(a + r) : 0.0f;
+                vb[j] = (in && r < ev.lb) ? __ldg(b + r) : 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j) {
+                const float mixed = __fadd_rn(__fmul_rn(va[j], ev.ca), __fmul_rn(ev.cb, vb[j]));
+                const int r = r0 + j * kMixThreads;
+                // samples outside the event must stay untouched even when scale is NaN/inf
+                if (r >= 0 && r < ev.len) acc[j] = fmaf(mixed, ev.scale, acc[j]);
+            }
+        }
+    }
+    float m = 0.0f;
+    float* row = wav + (int64_t)seg * ld_wav;
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+        const int n = lo + tid + j * kMixThreads;
+        if (n < ld_wav) row[n] = acc[j];
+        m = nan_max(m, fabsf(acc[j]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = nan_max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = m;
+    __syncthreads();
+    if (tid == 0) {
+        float r = s_red[0];
+        for (int i = 1; i < kMixThreads / 32; ++i) r = nan_max(r, s_red[i]);
+        tile_max[tile_id] = r;
+    }
+}
+
+__global__ void __launch_bounds__(kMixThreads) normalise_kernel(
+    const adtfe_segment* __restrict__ segments, const float* __restrict__ tile_max, int tiles_per_seg,
+    int64_t ld_wav, float* __restrict__ wav) {
+    __shared__ float s_peak;
+    const int tile_id = blockIdx.x, tid = threadIdx.x;
+    const int seg = tile_id / tiles_per_seg, tile = tile_id - seg * tiles_per_seg;
+    const adtfe_segment sg = segments[seg];
+    if (sg.flags == 0) return;  // empty note list: the mixer already wrote zeros
+    if (tid < 32) {
+        float m = 0.0f;
+        for (int t = tid; t < tiles_per_seg; t += 32) m = nan_max(m, tile_max[seg * tiles_per_seg + t]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = nan_max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (tid == 0) s_peak = m;
+    }
+    __syncthreads();
+    const float peak = s_peak, vol = sg.max_volume;
+    float* row = wav + (int64_t)seg * ld_wav;
+    const int lo = tile * ADTFE_TILE;
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) {
+        const int n = lo + tid + j * kMixThreads;
+        // the reference's row ends at len; beyond it collate_fn pads with exact zeros
+        if (n < sg.len) row[n] = __fmul_rn(__fdiv_rn(row[n], peak), vol);
+    }
+}
+
+}  // namespace adtfe
+
+using namespace adtfe;
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg) {
+    if (n_events < 0 || n_seg < 0 || tiles_per_seg < 0) return 0;
+    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_seg * tiles_per_seg * 4) + 256;
+}
+
+extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
+                            size_t workspace_bytes, void* stream) {
+    ADTFE_REQUIRE(bank && plan, ADTFE_ERR_BAD_ARG, "adtfe_render: null bank or plan");
+    ADTFE_REQUIRE(plan->n_seg >= 0 && plan->n_events >= 0 && plan->n_groups >= 0 && plan->tiles_per_seg >= 0,
+                  ADTFE_ERR_BAD_ARG, "adtfe_render: negative count");
+    if (plan->n_seg == 0 || plan->tiles_per_seg == 0) return ADTFE_OK;
+    ADTFE_REQUIRE(plan->ld_wav > 0 && plan->ld_wav % 4 == 0 &&
+                      plan->ld_wav <= (int64_t)plan->tiles_per_seg * ADTFE_TILE,
+                  ADTFE_ERR_BAD_ARG, "adtfe_render: ld_wav %lld must be a positive multiple of 4 within %d tiles",
+                  (long long)plan->ld_wav, plan->tiles_per_seg);
+    ADTFE_REQUIRE(wav_out_dev && plan->segments_dev && plan->tile_ptr_dev, ADTFE_ERR_BAD_ARG,
+                  "adtfe_render: null buffer");
+    ADTFE_REQUIRE(plan->n_events == 0 || (plan->events_dev && plan->mix_len_dev && plan->group_ptr_dev &&
+                                          plan->tile_events_dev && bank->pcm),
+                  ADTFE_ERR_BAD_ARG, "adtfe_render: null event buffers");
+    const size_t need = adtfe_render_workspace_bytes(plan->n_events, plan->n_seg, plan->tiles_per_seg);
+    ADTFE_REQUIRE(workspace_dev && workspace_bytes >= need, ADTFE_ERR_WORKSPACE,
+                  "adtfe_render: workspace %zu B < %zu B", workspace_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)(((uintptr_t)workspace_dev + 255) & ~(uintptr_t)255);
+    ResolvedEvent* resolved = (ResolvedEvent*)ws;
+    float* tile_max = (float*)(ws + align256((size_t)plan->n_events * sizeof(ResolvedEvent)));
+    const int n_tiles = plan->n_seg * plan->tiles_per_seg;
+    if (plan->n_groups > 0) {
+        peak_kernel<<<plan->n_groups, kPeakThreads, 0, st>>>(bank->pcm, bank->offsets, bank->lengths,
+                                                            plan->events_dev, plan->mix_len_dev,
+                                                            plan->group_ptr_dev, resolved);
+        ADTFE_CUDA(cudaGetLastError());
+    }
+    mix_kernel<<<n_tiles, kMixThreads, 0, st>>>(bank->pcm, resolved, plan->tile_ptr_dev, plan->tile_events_dev,
+                                               plan->tiles_per_seg, plan->ld_wav, wav_out_dev, tile_max);
+    ADTFE_CUDA(cudaGetLastError());
+    normalise_kernel<<<n_tiles, kMixThreads, 0, st>>>(plan->segments_dev, tile_max, plan->tiles_per_seg,
+                                                     plan->ld_wav, wav_out_dev);
+    ADTFE_CUDA(cudaGetLastError());
+    return ADTFE_OK;
+}

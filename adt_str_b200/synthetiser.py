@@ -1,0 +1,182 @@
+"""``SynthDrum`` - drop-in for reference ``modules/synthetiser.py:159-292``.
+
+``SynthDrum(config)(notes, eval_rendering=False) -> FloatTensor[L]`` keeps the
+reference's signature, RNG stream, error behaviour and CPU return value, but the
+audio is rendered on a B200: the host planner (``planner.py``) turns notes into
+event records and tile buckets, ``libadtfe``'s mixer kernels do the overlap-add
+against a one-shot bank that stays resident in HBM.  ``render_batch`` is the
+entry the training loop should call from the main process (one launch per batch,
+output left on the device for ``ComputeMelSpectrogram``); calling ``__call__``
+from forked DataLoader workers, as the reference does
+(``data_modules/train_dataset.py:228``), cannot work with CUDA.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import random as _random
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .bank import OneShotBank
+from .config import SynthDrumConfig
+from .planner import RenderPlan, plan_batch
+
+
+class DeviceBank:
+    """The packed bank uploaded once to one GPU (replaces h5py.File per note, synthetiser.py:273)."""
+
+    def __init__(self, bank: OneShotBank, device: torch.device):
+        lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(lib.adtfe_bank_create(bank.pcm.ctypes.data, bank.pcm.size, bank.offsets.ctypes.data,
+                                         bank.lengths.ctypes.data, len(bank), device.index, C.byref(h)),
+                   "adtfe_bank_create")
+        self.handle, self.lib, self.device = h, lib, device
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.adtfe_bank_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class PlanBuffers:
+    """Pinned host blob + device blob for one planned batch (grown on demand, reused)."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        self.host = torch.empty(0, dtype=torch.uint8).pin_memory()
+        self.dev = torch.empty(0, dtype=torch.uint8, device=device)
+        self.workspace = torch.empty(0, dtype=torch.uint8, device=device)
+        self.nbytes = 0
+
+    def pack(self, plan: RenderPlan) -> _lib.Plan:
+        lib = _lib.load()
+        shape = _lib.Plan(None, None, None, None, None, None, plan.n_events, plan.n_groups, plan.n_seg,
+                          plan.tiles_per_seg, plan.ld_wav)
+        off = (C.c_size_t * 6)()
+        fixed = C.c_size_t()
+        _lib.check(lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(fixed)), "adtfe_plan_blob_layout")
+        total = (fixed.value + 4 * len(plan.tile_events) + 15) & ~15
+        if self.host.numel() < total:
+            cap = max(total, 2 * self.host.numel(), 1 << 16)
+            self.host = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            self.dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        h = self.host.numpy()
+        for o, arr in zip(off, (plan.events, plan.mix_len, plan.group_ptr, plan.segments, plan.tile_ptr,
+                                plan.tile_events)):
+            raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+            h[o: o + raw.size] = raw
+        self.nbytes = total
+        need = lib.adtfe_render_workspace_bytes(plan.n_events, plan.n_seg, plan.tiles_per_seg)
+        if self.workspace.numel() < need:
+            self.workspace = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=self.device)
+        self.offsets = [int(o) for o in off]
+        return shape
+
+    def upload(self, shape: _lib.Plan) -> _lib.Plan:
+        """H2D of the packed blob on the current stream; returns the plan with device pointers."""
+        self.dev[: self.nbytes].copy_(self.host[: self.nbytes], non_blocking=True)
+        base = self.dev.data_ptr()
+        o = self.offsets
+        return _lib.Plan(base + o[0], base + o[1], base + o[2], base + o[3], base + o[4], base + o[5],
+                         shape.n_events, shape.n_groups, shape.n_seg, shape.tiles_per_seg, shape.ld_wav)
+
+
+class SynthDrum:
+    def __init__(self, config: SynthDrumConfig, bank: Optional[OneShotBank] = None,
+                 device: Optional[torch.device] = None):
+        self.config = config
+        self.sample_rate = config.sample_rate
+        self.oneshot_path = f"{config.oneshot_path}@{self.sample_rate}.hdf5"  # synthetiser.py:163
+        self.similarity_threshold = config.similarity_threshold
+        self.ADTOF_mapping = config.ADTOF_mapping
+        self._bank = bank
+        self._device = torch.device(device) if device is not None else None
+        self._device_bank: Optional[DeviceBank] = None
+        self._buffers: Optional[PlanBuffers] = None
+
+    # ------------------------------------------------------------------ bank
+    @property
+    def bank(self) -> OneShotBank:
+        """Packed bank: the one given, else ``<oneshot_path>@<sr>.npz``, else the reference's
+        ``.hdf5`` converted on the fly (needs h5py).  Opened lazily, like the reference."""
+        if self._bank is None:
+            packed = f"{self.config.oneshot_path}@{self.sample_rate}.npz"
+            if os.path.exists(packed):
+                self._bank = OneShotBank.load(packed)
+            elif os.path.exists(self.oneshot_path):
+                self._bank = OneShotBank.from_hdf5(self.oneshot_path)
+            else:
+                raise FileNotFoundError(f"no one-shot bank at {packed} or {self.oneshot_path}")
+        return self._bank
+
+    @property
+    def device(self) -> torch.device:
+        if self._device is None:
+            if not torch.cuda.is_available():
+                raise RuntimeError("SynthDrum needs a CUDA device (sm_100a); there is no CPU path")
+            self._device = torch.device("cuda", torch.cuda.current_device())
+        return self._device
+
+    def device_bank(self) -> DeviceBank:
+        if self._device_bank is None:
+            self._device_bank = DeviceBank(self.bank, self.device)
+        return self._device_bank
+
+    def buffers(self) -> PlanBuffers:
+        if self._buffers is None:
+            self._buffers = PlanBuffers(self.device)
+        return self._buffers
+
+    # ------------------------------------------------------------------ plan
+    def plan(self, batch_notes: Sequence, rng=_random, ld_wav: Optional[int] = None) -> RenderPlan:
+        return plan_batch(batch_notes, self.config, self.bank, rng, ld_wav)
+
+    # ---------------------------------------------------------------- render
+    def render_plan(self, plan: RenderPlan, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Enqueue one planned batch on the current stream -> (n_seg, ld_wav) float32 on the device."""
+        dev = self.device
+        bank = self.device_bank()
+        with torch.cuda.device(dev):
+            buf = self.buffers()
+            shape = buf.pack(plan)
+            if out is None:
+                out = torch.empty((plan.n_seg, plan.ld_wav), dtype=torch.float32, device=dev)
+            elif out.shape != (plan.n_seg, plan.ld_wav) or not out.is_contiguous() or out.dtype != torch.float32:
+                raise ValueError("out must be a contiguous float32 (n_seg, ld_wav) tensor")
+            if plan.n_seg and plan.ld_wav:
+                dplan = buf.upload(shape)
+                stream = torch.cuda.current_stream(dev).cuda_stream
+                _lib.check(bank.lib.adtfe_render(bank.handle, C.byref(dplan), out.data_ptr(),
+                                                 buf.workspace.data_ptr(), buf.workspace.numel(), stream),
+                           "adtfe_render")
+        return out
+
+    def render_batch(self, batch_notes: Sequence, rng=_random) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Render ``len(batch_notes)`` segments in one launch.  Returns the collated
+        ``(B, Lmax)`` waveform matrix on the device - what ``collate_fn``'s ``pad_sequence``
+        (train_dataset.py:53) would build - and the per-segment lengths."""
+        plan = self.plan(batch_notes, rng)
+        wav = self.render_plan(plan)
+        l_max = int(plan.wave_lengths.max()) if plan.n_seg else 0
+        return wav[:, :l_max], torch.from_numpy(plan.wave_lengths.copy())
+
+    def __call__(self, notes, eval_rendering=False):
+        if eval_rendering:
+            # the reference reads an attribute it never defines (synthetiser.py:287-288)
+            raise NotImplementedError("eval_rendering is not implemented (undefined in the reference as well)")
+        if len(notes) == 0:  # synthetiser.py:257-258, no device work needed
+            return torch.zeros(int(self.config.input_sec * self.config.sample_rate))
+        plan = self.plan([notes])
+        wav = self.render_plan(plan)
+        return wav[0, : int(plan.wave_lengths[0])].cpu()
+
+    def close(self) -> None:
+        self._device_bank = None
+        self._buffers = None

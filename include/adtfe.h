@@ -1,0 +1,146 @@
+/*
+ * adtfe - B200 (sm_100a) render + log-mel front end, C ABI.
+ *
+ * The reference (pier-maker92/ADT_STR) is pure Python, so there is no FFI in it to
+ * bind; this header is the boundary a maintainer would bind with ctypes (see
+ * INTEGRATION.md).  Every entry point names the reference code it replaces:
+ *
+ *   adtfe_bank_*          one-shot storage: the per-note h5py.File open + two gzip dataset
+ *                         reads of modules/synthetiser.py:273,283-284 (bank layout written by
+ *                         data_modules/convert_augmented_to_hdf5.py:70-138)
+ *   adtfe_render          SynthDrum.__call__ audio arithmetic: drum_rendering
+ *                         (modules/synthetiser.py:214-239), VolumeMixer.instrument_mixer and
+ *                         _normalize_audio (:142-156), and the zero padding of collate_fn
+ *                         (data_modules/train_dataset.py:53)
+ *   adtfe_mel_* / adtfe_logmel
+ *                         ComputeMelSpectrogram.__init__/forward (model.py:68-97) incl. the
+ *                         torchaudio MelSpectrogram it delegates to (model.py:71-78,89)
+ *   adtfe_render_logmel   both, back to back on one stream (train.py:52 H2D + model.py:248)
+ *   adtfe_frontend_host   the same with HOST buffers: plan blob in, log-mel (and optionally
+ *                         the waveform) out, copies included - the end-to-end entry
+ *
+ * Conventions: plain pointers and sizes; pointers named *_dev are device memory on the
+ * bank's / mel's device, *_host are host memory (pinned for asynchronous copies).  All
+ * work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default
+ * stream) and is asynchronous unless stated.  The library never allocates memory the
+ * caller sees; scratch comes from a caller workspace sized by adtfe_*_workspace_bytes.
+ * Every function returns ADTFE_OK (0) or a negative adtfe_status; adtfe_last_error()
+ * gives a thread-local message for the last failure.
+ */
+#ifndef ADTFE_H
+#define ADTFE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADTFE_VERSION 1
+#define ADTFE_TILE 2048 /* output samples owned by one mixer CTA */
+
+typedef enum adtfe_status {
+    ADTFE_OK = 0,
+    ADTFE_ERR_BAD_ARG = -1,     /* null pointer, negative size, misaligned pitch ... */
+    ADTFE_ERR_UNSUPPORTED = -2, /* n_fft != 2048, n_mels > 256, hop < 1 ... */
+    ADTFE_ERR_WORKSPACE = -3,   /* workspace too small */
+    ADTFE_ERR_CUDA = -4,        /* a CUDA call failed; message holds cudaGetErrorString */
+    ADTFE_ERR_NO_DEVICE = -5    /* no sm_100 device / wrong architecture */
+} adtfe_status;
+
+/* One rendered note (32 bytes).  Events of a batch are sorted by (seg, instrument
+ * first-appearance, note order); the mixer adds them in array order. */
+typedef struct adtfe_event {
+    int32_t start;   /* first output sample: (int)(onset * sr), float math as the reference */
+    int32_t len;     /* samples written: min(max(len_main, len_sub), seg_len - start), >= 0 */
+    int32_t main_id; /* one-shot ids in the bank */
+    int32_t sub_id;
+    float ca;        /* (float)(1 - mixup) */
+    float cb;        /* (float)mixup */
+    float gain;      /* vel_to_vol(velocity) * instrument gain */
+    int32_t seg;     /* segment (row of the waveform matrix) */
+} adtfe_event;
+
+/* One segment = one SynthDrum.__call__ (16 bytes). */
+typedef struct adtfe_segment {
+    int32_t len;         /* wave_length in samples; the row is zero beyond it */
+    int32_t flags;       /* 0: no notes, all-zero row; 1: wav / max|wav| * max_volume */
+    float max_volume;    /* vel_to_vol(max velocity) */
+    int32_t first_event; /* index of the segment's first event */
+} adtfe_segment;
+
+typedef struct adtfe_bank adtfe_bank; /* one-shot bank resident in HBM */
+typedef struct adtfe_mel adtfe_mel;   /* window, mel filterbank (CSR) and twiddles on device */
+
+/* A planned batch, all arrays in device memory. */
+typedef struct adtfe_plan {
+    const adtfe_event* events_dev;     /* n_events */
+    const int32_t* mix_len_dev;        /* n_events: max(len_main, len_sub), untruncated */
+    const int32_t* group_ptr_dev;      /* n_groups+1: events of one (segment, instrument) */
+    const adtfe_segment* segments_dev; /* n_seg */
+    const int32_t* tile_ptr_dev;       /* n_seg*tiles_per_seg+1: CSR tile -> tile_events */
+    const int32_t* tile_events_dev;    /* event ids, ascending inside a tile */
+    int32_t n_events, n_groups, n_seg, tiles_per_seg;
+    int64_t ld_wav; /* row pitch of the waveform matrix in floats, multiple of 4, <= tiles_per_seg*ADTFE_TILE */
+} adtfe_plan;
+
+int adtfe_version(void);
+const char* adtfe_last_error(void);
+/* 0 when device `device` exists and is compute capability 10.x */
+int adtfe_device_ok(int device);
+
+/* ---- bank -------------------------------------------------------------------------- */
+/* Copies `total_floats` floats of PCM (all one-shots, each start a multiple of 4 floats)
+ * and the per-one-shot offsets/lengths to `device`.  Synchronous. */
+int adtfe_bank_create(const float* pcm_host, int64_t total_floats, const int64_t* offsets_host,
+                      const int32_t* lengths_host, int32_t n_oneshots, int device, adtfe_bank** out);
+int adtfe_bank_destroy(adtfe_bank* bank);
+int64_t adtfe_bank_bytes(const adtfe_bank* bank);
+
+/* ---- render ------------------------------------------------------------------------ */
+size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg);
+/* Writes the (n_seg, ld_wav) float32 waveform matrix: every row normalised as the reference
+ * does and zero-padded to ld_wav.  Three kernels: per-event peak of the mixed one-shot,
+ * tile mixer (+ per-tile |max|), per-segment normalise. */
+int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
+                 size_t workspace_bytes, void* stream);
+
+/* ---- log-mel ----------------------------------------------------------------------- */
+/* window_host: n_fft floats; fb_host: (n_fft/2+1, n_mels) row-major float32 - the two
+ * buffers torchaudio's MelSpectrogram keeps in the state dict.  Synchronous. */
+int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, const float* window_host, const float* fb_host,
+                     int device, adtfe_mel** out);
+int adtfe_mel_destroy(adtfe_mel* mel);
+/* Frames the reference keeps for an n_samples-long input: t = *first .. *first+*count-1 of
+ * the centred STFT (model.py:79,95-97). */
+int adtfe_mel_frames(const adtfe_mel* mel, int64_t n_samples, int32_t* first, int32_t* count);
+/* wav_dev: (n_seg, ld_wav) rows of n_samples valid floats; out_dev: (n_seg, count, n_mels). */
+int adtfe_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav, int64_t n_samples,
+                 float* out_dev, void* stream);
+
+/* ---- fused call -------------------------------------------------------------------- */
+/* adtfe_render then adtfe_logmel over the first n_samples (<= plan->ld_wav) floats of every
+ * row: n_samples is the collated batch width (longest segment), which sets the frame count. */
+int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel, const adtfe_plan* plan, int64_t n_samples,
+                        float* wav_out_dev, float* mel_out_dev, void* workspace_dev, size_t workspace_bytes,
+                        void* stream);
+
+/* ---- host-buffer entry (end to end) ------------------------------------------------ */
+/* Plan blob layout (host, 16-byte aligned sections in this order):
+ *   events | mix_len | group_ptr | segments | tile_ptr | tile_events
+ * with the counts in `shape` (a plan whose pointers are ignored).  The blob is copied to
+ * `blob_dev` (>= blob_bytes), the batch rendered and featurised, then the log-mel matrix
+ * (and the waveform when wav_out_host != NULL) copied back.  Asynchronous on `stream`:
+ * the host buffers must be pinned and stay alive until the stream is synchronised. */
+int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel, const adtfe_plan* shape, int64_t n_samples,
+                        const void* blob_host, size_t blob_bytes, void* blob_dev, float* wav_dev, float* mel_dev,
+                        void* workspace_dev, size_t workspace_bytes, float* mel_out_host, float* wav_out_host,
+                        void* stream);
+/* Byte offsets of the six sections inside a plan blob (offsets[6], total in *blob_bytes). */
+int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[6], size_t* blob_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADTFE_H */

@@ -1,0 +1,116 @@
+#!/usr/bin/env python3
+"""Freeze outputs of the UNMODIFIED reference as fixtures under tests/golden/.
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container (needs /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+For every case it (1) generates a small synthetic bank and note lists, (2) runs the
+reference ``SynthDrum`` (h5py/pedalboard shimmed, FX off) and the reference
+``ComputeMelSpectrogram`` on the collated batch, (3) runs the NumPy oracle on the same
+seeds and REFUSES to write unless it agrees with the reference (lengths equal, waveform
+max-abs < 1e-6, float32 log-mel max-abs < 1e-6, float64 log-mel < 2e-5) and (4) stores inputs, reference outputs and the
+oracle's per-note trace (start / length / chosen one-shots / mixup - validated by the
+waveform agreement) in one .npz per case.
+"""
+from __future__ import annotations
+
+import os
+import random
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+warnings.filterwarnings("ignore")
+
+from adt_str_b200.config import SETTING_1  # noqa: E402  (plain dict of config values)
+from adt_str_b200.synthetic import make_bank, make_segments, make_dense_segment  # noqa: E402
+from oracle import mel_oracle, ref_harness, synth_oracle  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+CASES = {
+    # name: (config overrides, bank kwargs, n_segments, events seed, python-random seed)
+    "short_24k": (dict(input_sec=0.64), dict(n_oneshots=156, max_len=3000, min_len=200, seed=10), 8, 11, 1234),
+    "short_24k_tau04_adtof": (dict(input_sec=0.64, similarity_threshold=0.4, mixup_range=0.3, ADTOF_mapping=True),
+                              dict(n_oneshots=156, max_len=2500, min_len=200, seed=12,
+                                   groups=("gold", "90-80", "60-50", "50-40", "40-30")), 6, 13, 99),
+    "default_16k": (dict(sample_rate=16000), dict(n_oneshots=78, max_len=4000, min_len=300, seed=14, sample_rate=16000),
+                    2, 15, 5),
+    "setting1_24k": (dict(), dict(n_oneshots=78, max_len=6000, min_len=300, seed=16), 2, 17, 42),
+}
+
+
+def segments_for(cfg, n, seed):
+    segs = make_segments(n, seed=seed, input_sec=cfg["input_sec"], mean_events=10 if cfg["input_sec"] < 1 else 32,
+                         empty_fraction=0.0)
+    segs[1] = np.zeros((0, 4), np.float32)                       # an empty note list
+    if cfg["ADTOF_mapping"]:                                      # notes carry ADTOF class pitches then
+        for s in segs:                                            # (midi_tokenizer.py:37-40)
+            s[:, 2] = [synth_oracle._CLASS[int(p)] for p in s[:, 2]]
+    if n > 3:                                                     # a note whose offset pushes the end out
+        segs[2] = np.concatenate([segs[2], np.array([[cfg["input_sec"] - 0.04, cfg["input_sec"] + 0.06, 38, 0]],
+                                                    np.float32)])  # velocity 0: silent but extends the segment
+        segs[3][:, 3] = np.minimum(segs[3][:, 3], 50)             # low max velocity -> max_volume < 1
+    return segs
+
+
+def main():
+    if not ref_harness.available():
+        raise SystemExit("reference tree not available: fixtures can only be generated in the build container")
+    os.makedirs(OUT, exist_ok=True)
+    for name, (over, bank_kw, n, ev_seed, py_seed) in CASES.items():
+        cfg = dict(SETTING_1, **over)
+        cfg["oneshot_path"] = f"golden_{name}"
+        bank = make_bank(**{"sample_rate": cfg["sample_rate"], **bank_kw})
+        nested = bank.to_nested()
+        segs = segments_for(cfg, n, ev_seed)
+        ref = ref_harness.make_synth(cfg, nested)
+        random.seed(py_seed)
+        ref_wavs = [ref(s if len(s) else []).numpy() for s in segs]
+        random.seed(py_seed)
+        traces, ora_wavs = [], []
+        for s in segs:
+            t = []
+            ora_wavs.append(synth_oracle.render(s, cfg, nested, trace=t))
+            traces.append(t)
+        assert [len(w) for w in ref_wavs] == [len(w) for w in ora_wavs], name
+        wav_err = max(float(np.abs(a - b).max()) for a, b in zip(ref_wavs, ora_wavs))
+        assert wav_err < 1e-6, (name, wav_err)
+        batch = synth_oracle.collate(ref_wavs)
+        mel_mod = ref_harness.make_mel(cfg["sample_rate"], cfg["win_length"], cfg["time_res"], 128)
+        ref_mel = mel_mod(torch.from_numpy(batch)).numpy()
+        geo = (cfg["sample_rate"], cfg["win_length"], cfg["time_res"], 128)
+        ora_mel = mel_oracle.logmel_direct(batch, *geo, np.float32, fb=mel_mod.compute_spec.mel_scale.fb.numpy(),
+                                           window=mel_mod.compute_spec.spectrogram.window.numpy())
+        mel_err = float(np.abs(ref_mel - ora_mel).max())
+        assert mel_err < 1e-6, (name, mel_err)          # float32 restatement with the reference's own buffers
+        truth = mel_oracle.logmel_direct(batch, *geo, np.float64)
+        truth_err = float(np.abs(ref_mel - truth).max())
+        assert truth_err < 2e-5, (name, truth_err)      # float64 "truth": the reference's own rounding error
+        name_to_id = {nm: i for i, nm in enumerate(bank.names)}
+        flat = [(si, t["start"], t["len"], name_to_id[t["main"]], name_to_id[t["sub"]], t["pitch"])
+                for si, tr in enumerate(traces) for t in tr]
+        np.savez_compressed(
+            os.path.join(OUT, f"{name}.npz"),
+            cfg_keys=np.array(sorted(k for k in cfg if k != "oneshot_path")),
+            cfg_vals=np.array([repr(cfg[k]) for k in sorted(cfg) if k != "oneshot_path"]),
+            py_seed=py_seed,
+            bank_pcm=bank.pcm, bank_offsets=bank.offsets, bank_lengths=bank.lengths, bank_names=np.array(bank.names),
+            notes=np.concatenate([s.reshape(-1, 4) for s in segs]).astype(np.float32),
+            notes_count=np.array([len(s) for s in segs]),
+            ref_wav=np.concatenate(ref_wavs), ref_len=np.array([len(w) for w in ref_wavs]),
+            trace=np.array(flat, np.int64).reshape(-1, 6),
+            trace_mixup=np.array([t["mixup"] for tr in traces for t in tr], np.float64),
+            ref_mel=ref_mel,
+        )
+        print(f"{name}: {n} segments, lengths {[len(w) for w in ref_wavs]}, oracle-vs-reference wav {wav_err:.2e} "
+              f"mel {mel_err:.2e} (vs float64 {truth_err:.2e}), mel shape {ref_mel.shape}")
+
+
+if __name__ == "__main__":
+    main()
