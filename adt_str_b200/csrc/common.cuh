@@ -32,10 +32,10 @@ void set_error(const char* fmt, ...);
 // broadcast load per event instead of a three-deep dependent chain (48 bytes).
 struct ResolvedEvent {
     int64_t a_off, b_off;  // float offsets of the main / sub one-shot in the bank
-    int32_t la, lb;        // their true lengths
+    int32_t la, lb;        // their lengths, cut to the note's copy length
     int32_t start, len;
     float ca, cb;
-    float scale;           // gain / max|ca*a + cb*b|
+    float gain;            // vel_to_vol * instrument gain; divided by the peak in the mixer
     int32_t pad;
 };
 static_assert(sizeof(ResolvedEvent) == 48, "ResolvedEvent layout");
@@ -45,6 +45,8 @@ static_assert(sizeof(adtfe_segment) == 16, "adtfe_segment layout");
 int device_sm_count(int device);
 
 }  // namespace adtfe
+
+struct adtfe_mel_tables;
 
 struct adtfe_bank {
     int device = 0;
@@ -63,8 +65,6 @@ struct adtfe_mel {
     float* window = nullptr;   // n_fft
     float2* twiddle = nullptr; // 32 x 32: W_2048^(k1*n2), k1 = 1..32, n2 = lane
     float2* lane_tw = nullptr; // 3 x 32: per-lane twiddles of the cross-lane 32-point DFT
-    float* fb_w = nullptr;     // nnz
-    int32_t* fb_ptr = nullptr; // n_mels+1
-    int32_t* fb_lo = nullptr;  // n_mels: first bin of every filter
+    struct adtfe_mel_tables* tables = nullptr;  // filterbank CSR + warp schedule, passed as a kernel parameter
     size_t smem_bytes = 0;
 };

@@ -6,26 +6,50 @@
 // clamp[-23, 12], (x + 23) / 35, keep frames wpi .. T-wpi-2.  Only kept frames are
 // computed; their support never reaches the reflect padding.
 //
-// One warp owns one frame end to end; nothing but the (n_mels) result row goes to HBM.
+// A CTA (16 warps) works in rounds of 32 frames; nothing but the (32 x n_mels) result tile
+// goes to HBM.
+//  FFT phase - one warp owns one frame at a time (two per round):
 //   pass 1  lane n2 holds x[32*n1 + n2] * hann, n1 = 0..63, and runs a 64-point real DFT
 //           over n1 in registers (generated straight-line code, tools/gen_fft.py)
 //   twiddle Y[k1][n2] *= W_2048^(k1*n2)
-//   exchange through the warp's private shared-memory tile (row pitch 34 complex: the
-//           STS.64 rows and the LDS.128 columns are both conflict-free)
+//   exchange through the warp's private shared tile, real parts then imaginary parts
+//           (row pitch 36 floats: STS.32 rows and LDS.128 columns are both conflict-free)
 //   pass 2  lane k1 (0..31) runs a 32-point complex DFT over n2 -> X[k1 + 64*k2];
 //           bins above 1024 are the mirror images of bins 64-k1 + 64*(31-k2)
 //   column k1 = 32 (bins 32 + 64*k2) is a 32-point DFT across lanes with shuffles
-//   |X|^2 goes back to the same shared tile in natural bin order, then every lane
-//   accumulates filters lane, lane+32, ... from the CSR filterbank and writes log-mel.
+//   |X|^2 goes to the CTA's power matrix P[bin][frame] (pitch 33: consecutive bins of one
+//           frame land in distinct banks; only the 16 column-32 bins collide, once per frame)
+//  mel phase - lanes are the 32 frames, each warp takes the filters the host scheduled for it
+//   (longest-processing-time balance): acc += w * P[bin][lane] is conflict-free and the
+//   weight is warp-uniform, read from the kernel-parameter constant bank; then
+//   log / clamp / affine into a staging tile, and a coalesced copy-out.
 #include "common.cuh"
 #include "fft_gen.cuh"
 
 namespace adtfe {
 
-constexpr int kWarps = 16;                 // frames in flight per CTA
+constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
-constexpr int kRow = 34;                   // complex per exchange row (32 + 2 pad)
-constexpr int kWarpFloats = 32 * kRow * 2; // 2176 floats = 8704 B, also holds 1025 powers
+constexpr int kRound = 32;                  // frames per CTA round (lanes of the mel phase)
+constexpr int kXPitch = 36;                 // floats per exchange row
+constexpr int kXFloats = 32 * kXPitch;      // 1152 floats per warp
+constexpr int kPPitch = 33;
+constexpr int kPFloats = 1025 * kPPitch;
+constexpr int kOPitch = 129;                // staging tile pitch (aliases the exchange tiles)
+constexpr int kMaxNnz = 4096;
+constexpr int kMaxMels = 128;
+
+__device__ __forceinline__ int p_index(int bin) { return bin * kPPitch; }
+
+// Filterbank and its per-warp schedule, passed by value: lives in the kernel-parameter
+// constant bank, so the mel phase reads weights with uniform constant loads.
+struct MelTables {
+    float w[kMaxNnz];
+    int16_t ptr[kMaxMels + 1];   // weights of filter m: w[ptr[m] .. ptr[m+1])
+    int16_t lo[kMaxMels];        // first bin of filter m
+    int16_t sched_ptr[kWarps + 1];
+    uint8_t sched[kMaxMels];     // filters of warp w: sched[sched_ptr[w] .. sched_ptr[w+1])
+};
 
 struct LogmelArgs {
     const float* wav;
@@ -33,126 +57,157 @@ struct LogmelArgs {
     const float* window;
     const float2* twiddle;
     const float2* lane_tw;
-    const float* fb_w;
-    const int32_t* fb_ptr;
-    const int32_t* fb_lo;
     int64_t ld_wav;
-    int32_t n_seg, first, count, hop, n_mels, nnz;
+    int32_t n_seg, first, count, hop, n_mels;
 };
 
-__global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p) {
+__global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p, const __grid_constant__ MelTables tab) {
     extern __shared__ __align__(16) float smem[];
     float* s_win = smem;                                           // 2048
     float2* s_tw = reinterpret_cast<float2*>(s_win + 2048);        // 32*32
     float2* s_ltw = s_tw + 32 * 32;                                // 3*32
-    float* s_y = reinterpret_cast<float*>(s_ltw + 3 * 32);         // kWarps * kWarpFloats
-    float* s_fbw = s_y + kWarps * kWarpFloats;                     // nnz (padded to 4)
-    int32_t* s_ptr = reinterpret_cast<int32_t*>(s_fbw + ((p.nnz + 3) & ~3));  // n_mels+1
-    int32_t* s_lo = s_ptr + p.n_mels + 1;                          // n_mels
+    float* s_x = reinterpret_cast<float*>(s_ltw + 3 * 32);         // kWarps * kXFloats (also the staging tile)
+    float* s_p = s_x + kWarps * kXFloats;                          // kPFloats
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 2048; i += kThreads) s_win[i] = p.window[i];
     for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = p.twiddle[i];
     for (int i = tid; i < 3 * 32; i += kThreads) s_ltw[i] = p.lane_tw[i];
-    for (int i = tid; i < p.nnz; i += kThreads) s_fbw[i] = p.fb_w[i];
-    for (int i = tid; i <= p.n_mels; i += kThreads) s_ptr[i] = p.fb_ptr[i];
-    for (int i = tid; i < p.n_mels; i += kThreads) s_lo[i] = p.fb_lo[i];
     __syncthreads();
 
-    float2* y = reinterpret_cast<float2*>(s_y + warp * kWarpFloats);
-    float* pw = reinterpret_cast<float*>(y);
+    float* xw = s_x + warp * kXFloats;
     const int col32_bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);
 
     const long long total = (long long)p.n_seg * p.count;
-    const long long n_blocks = (total + kWarps - 1) / kWarps;
-    for (long long blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-        const long long g = blk * kWarps + warp;
-        if (g >= total) continue;  // warp-uniform
-        const int seg = (int)(g / p.count);
-        const int j = (int)(g - (long long)seg * p.count);
-        const float* x = p.wav + (long long)seg * p.ld_wav + (long long)(p.first + j) * p.hop - 1024 + lane;
+    const long long n_rounds = (total + kRound - 1) / kRound;
+    for (long long round = blockIdx.x; round < n_rounds; round += gridDim.x) {
+        const long long g0 = round * kRound;
+        // ================= FFT phase: frames g0 + warp and g0 + warp + 16 =================
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int f = warp + half * kWarps;
+            const long long g = g0 + f;
+            if (g >= total) break;  // warp-uniform
+            const int seg = (int)(g / p.count);
+            const int j = (int)(g - (long long)seg * p.count);
+            const float* x = p.wav + (long long)seg * p.ld_wav + (long long)(p.first + j) * p.hop - 1024 + lane;
 
-        // ---- pass 1: window + 64-point real DFT over n1 (stride-32 samples)
-        float yr[33], yi[33];
-        {
-            float v[64];
+            // ---- pass 1: window + 64-point real DFT over n1 (stride-32 samples)
+            float yr[33], yi[33];
+            {
+                float v[64];
 #pragma unroll
-            for (int n1 = 0; n1 < 64; ++n1) v[n1] = __ldg(x + 32 * n1) * s_win[32 * n1 + lane];
-            rdft64(v, yr, yi);
-        }
-        // ---- twiddle and hand rows 0..31 to the lanes that own them
-        y[lane] = make_float2(yr[0], 0.0f);
+                for (int n1 = 0; n1 < 64; ++n1) v[n1] = __ldg(x + 32 * n1) * s_win[32 * n1 + lane];
+                rdft64(v, yr, yi);
+            }
+            // ---- twiddle in place (rows 1..31), column 32 is real before its twiddle
 #pragma unroll
-        for (int k1 = 1; k1 < 32; ++k1) {
-            const float2 w = s_tw[(k1 - 1) * 32 + lane];
-            y[k1 * kRow + lane] = make_float2(yr[k1] * w.x - yi[k1] * w.y, yr[k1] * w.y + yi[k1] * w.x);
-        }
-        // column k1 = 32 is real before the twiddle
-        float cr, ci;
-        {
-            const float2 w = s_tw[31 * 32 + lane];
-            cr = yr[32] * w.x;
-            ci = yr[32] * w.y;
-        }
-        __syncwarp();
+            for (int k1 = 1; k1 < 32; ++k1) {
+                const float2 w = s_tw[(k1 - 1) * 32 + lane];
+                const float a = yr[k1] * w.x - yi[k1] * w.y;
+                yi[k1] = yr[k1] * w.y + yi[k1] * w.x;
+                yr[k1] = a;
+            }
+            float cr, ci;
+            {
+                const float2 w = s_tw[31 * 32 + lane];
+                cr = yr[32] * w.x;
+                ci = yr[32] * w.y;
+            }
+            // ---- exchange, real parts
+            float zr[32], zi[32];
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) xw[k1 * kXPitch + lane] = yr[k1];
+            __syncwarp();
+            {
+                const float4* row = reinterpret_cast<const float4*>(xw + lane * kXPitch);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 t = row[q];
+                    zr[4 * q] = t.x; zr[4 * q + 1] = t.y; zr[4 * q + 2] = t.z; zr[4 * q + 3] = t.w;
+                }
+            }
+            __syncwarp();
+            // ---- exchange, imaginary parts (row 0 is purely real)
+            xw[lane] = 0.0f;
+#pragma unroll
+            for (int k1 = 1; k1 < 32; ++k1) xw[k1 * kXPitch + lane] = yi[k1];
+            __syncwarp();
+            {
+                const float4* row = reinterpret_cast<const float4*>(xw + lane * kXPitch);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 t = row[q];
+                    zi[4 * q] = t.x; zi[4 * q + 1] = t.y; zi[4 * q + 2] = t.z; zi[4 * q + 3] = t.w;
+                }
+            }
+            __syncwarp();
 
-        // ---- 32-point DFT across lanes (decimation in frequency, result bit-reversed)
+            // ---- 32-point DFT across lanes for column 32 (decimation in frequency, bit-reversed)
 #pragma unroll
-        for (int s = 0; s < 5; ++s) {
-            const int half = 16 >> s;
-            const float orr = __shfl_xor_sync(0xffffffffu, cr, half);
-            const float oi = __shfl_xor_sync(0xffffffffu, ci, half);
-            const bool upper = (lane & half) != 0;
-            const float dr = upper ? orr - cr : cr + orr;
-            const float di = upper ? oi - ci : ci + oi;
-            if (s < 3) {            // W_{2*half}^(lane mod half) on the upper half, 1 on the lower
-                const float2 w = s_ltw[s * 32 + lane];
-                cr = dr * w.x - di * w.y;
-                ci = dr * w.y + di * w.x;
-            } else if (s == 3) {    // half = 2: twiddle is 1 or -i
-                const bool rot = upper && (lane & 1);
-                cr = rot ? di : dr;
-                ci = rot ? -dr : di;
-            } else {
-                cr = dr;
-                ci = di;
+            for (int s = 0; s < 5; ++s) {
+                const int hb = 16 >> s;
+                const float orr = __shfl_xor_sync(0xffffffffu, cr, hb);
+                const float oi = __shfl_xor_sync(0xffffffffu, ci, hb);
+                const bool upper = (lane & hb) != 0;
+                const float dr = upper ? orr - cr : cr + orr;
+                const float di = upper ? oi - ci : ci + oi;
+                if (s < 3) {            // W_{2*hb}^(lane mod hb) on the upper half, 1 on the lower
+                    const float2 w = s_ltw[s * 32 + lane];
+                    cr = dr * w.x - di * w.y;
+                    ci = dr * w.y + di * w.x;
+                } else if (s == 3) {    // hb = 2: twiddle is 1 or -i
+                    const bool rot = upper && (lane & 1);
+                    cr = rot ? di : dr;
+                    ci = rot ? -dr : di;
+                } else {
+                    cr = dr;
+                    ci = di;
+                }
+            }
+
+            // ---- pass 2: 32-point complex DFT over n2 for k1 = lane
+            cdft32(zr, zi);
+
+            // ---- power spectrum into P[bin][f]
+            float* pf = s_p + f;
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) pf[p_index(lane + 64 * k2)] = zr[k2] * zr[k2] + zi[k2] * zi[k2];
+#pragma unroll
+            for (int k2 = 16; k2 < 32; ++k2)
+                pf[p_index(64 - lane + 64 * (31 - k2))] = zr[k2] * zr[k2] + zi[k2] * zi[k2];
+            if ((lane & 1) == 0) pf[p_index(col32_bin)] = cr * cr + ci * ci;
+        }
+        __syncthreads();
+
+        // ================= mel phase: lane = frame, filters from the warp's schedule =================
+        {
+            const float* pl = s_p + lane;
+            float* stage = s_x + lane * kOPitch;
+            const int s0 = tab.sched_ptr[warp], s1 = tab.sched_ptr[warp + 1];
+            for (int si = s0; si < s1; ++si) {
+                const int m = tab.sched[si];
+                const int b = tab.ptr[m], e = tab.ptr[m + 1];
+                const float* pp = pl + p_index(tab.lo[m]);
+                float acc = 0.0f;
+                for (int i = b; i < e; ++i, pp += kPPitch) acc = fmaf(tab.w[i], *pp, acc);
+                float v = logf(acc + 1e-10f);
+                v = v != v ? v : fminf(fmaxf(v, -23.0f), 12.0f);  // torch.clamp keeps NaN
+                stage[m] = (v + 23.0f) / 35.0f;
             }
         }
+        __syncthreads();
 
-        // ---- pass 2: 32-point complex DFT over n2 for k1 = lane
-        float zr[32], zi[32];
-        {
-            const float4* row = reinterpret_cast<const float4*>(y + lane * kRow);
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const float4 t = row[q];
-                zr[2 * q] = t.x; zi[2 * q] = t.y; zr[2 * q + 1] = t.z; zi[2 * q + 1] = t.w;
-            }
+        // ================= copy-out: one warp per frame row, coalesced =================
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const int f = warp + half * kWarps;
+            const long long g = g0 + f;
+            if (g >= total) break;
+            float* out = p.out + g * p.n_mels;
+            for (int m = lane; m < p.n_mels; m += 32) out[m] = s_x[f * kOPitch + m];
         }
-        cdft32(zr, zi);
-        __syncwarp();  // every lane has read its row: the tile can take the powers
-
-        // ---- power spectrum in natural bin order
-#pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) pw[lane + 64 * k2] = zr[k2] * zr[k2] + zi[k2] * zi[k2];
-#pragma unroll
-        for (int k2 = 16; k2 < 32; ++k2)
-            pw[64 - lane + 64 * (31 - k2)] = zr[k2] * zr[k2] + zi[k2] * zi[k2];
-        if ((lane & 1) == 0) pw[col32_bin] = cr * cr + ci * ci;
-        __syncwarp();
-
-        // ---- mel filterbank (CSR by filter) + log / clamp / affine
-        float* out = p.out + g * p.n_mels;
-        for (int m = lane; m < p.n_mels; m += 32) {
-            const int b = s_ptr[m], e = s_ptr[m + 1];
-            const float* pp = pw + s_lo[m] - b;
-            float acc = 0.0f;
-            for (int i = b; i < e; ++i) acc = fmaf(s_fbw[i], pp[i], acc);
-            float v = logf(acc + 1e-10f);
-            v = fminf(fmaxf(v, -23.0f), 12.0f);
-            out[m] = (v + 23.0f) / 35.0f;
-        }
-        __syncwarp();  // powers consumed before the next frame reuses the tile
+        __syncthreads();  // staging tile and P are reused by the next round
     }
 }
 
@@ -160,10 +215,14 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p)
 
 using namespace adtfe;
 
-static size_t logmel_smem_bytes(int nnz, int n_mels) {
-    size_t floats = 2048 + 2 * 32 * 32 + 2 * 3 * 32 + (size_t)kWarps * kWarpFloats + ((nnz + 3) & ~3);
-    return floats * 4 + (size_t)(2 * n_mels + 1) * 4;
+static size_t logmel_smem_bytes() {
+    return ((size_t)2048 + 2 * 32 * 32 + 2 * 3 * 32 + (size_t)kWarps * kXFloats + kPFloats) * 4;
 }
+static_assert(kWarps * kXFloats >= kRound * kOPitch, "staging tile must fit in the exchange tiles");
+
+struct adtfe_mel_tables {
+    MelTables t;
+};
 
 extern "C" int adtfe_mel_frames(const adtfe_mel* mel, int64_t n_samples, int32_t* first, int32_t* count) {
     ADTFE_REQUIRE(mel && first && count && n_samples >= 0, ADTFE_ERR_BAD_ARG, "adtfe_mel_frames: bad argument");
@@ -189,12 +248,11 @@ extern "C" int adtfe_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t 
                   ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: frame support leaves the signal");
     LogmelArgs a;
     a.wav = wav_dev; a.out = out_dev; a.window = mel->window; a.twiddle = mel->twiddle; a.lane_tw = mel->lane_tw;
-    a.fb_w = mel->fb_w; a.fb_ptr = mel->fb_ptr; a.fb_lo = mel->fb_lo; a.ld_wav = ld_wav; a.n_seg = n_seg;
-    a.first = first; a.count = count; a.hop = mel->hop; a.n_mels = mel->n_mels; a.nnz = mel->nnz;
+    a.ld_wav = ld_wav; a.n_seg = n_seg; a.first = first; a.count = count; a.hop = mel->hop; a.n_mels = mel->n_mels;
     const long long total = (long long)n_seg * count;
-    const long long n_blocks = (total + kWarps - 1) / kWarps;
-    const int grid = (int)(n_blocks < mel->sm_count ? n_blocks : mel->sm_count);
-    logmel_kernel<<<grid, kThreads, mel->smem_bytes, (cudaStream_t)stream>>>(a);
+    const long long n_rounds = (total + kRound - 1) / kRound;
+    const int grid = (int)(n_rounds < mel->sm_count ? n_rounds : mel->sm_count);
+    logmel_kernel<<<grid, kThreads, mel->smem_bytes, (cudaStream_t)stream>>>(a, mel->tables->t);
     ADTFE_CUDA(cudaGetLastError());
     return ADTFE_OK;
 }
@@ -203,12 +261,14 @@ extern "C" int adtfe_mel_destroy(adtfe_mel* mel) {
     if (!mel) return ADTFE_OK;
     cudaSetDevice(mel->device);
     cudaFree(mel->window); cudaFree(mel->twiddle); cudaFree(mel->lane_tw);
-    cudaFree(mel->fb_w); cudaFree(mel->fb_ptr); cudaFree(mel->fb_lo);
+    delete mel->tables;
     delete mel;
     return ADTFE_OK;
 }
 
+#include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, const float* window_host,
@@ -217,7 +277,8 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
     *out = nullptr;
     ADTFE_REQUIRE(n_fft == 2048, ADTFE_ERR_UNSUPPORTED, "adtfe_mel_create: n_fft %d unsupported (only 2048)", n_fft);
     ADTFE_REQUIRE(hop >= 1 && hop <= 2048, ADTFE_ERR_UNSUPPORTED, "adtfe_mel_create: hop %d out of range", hop);
-    ADTFE_REQUIRE(n_mels >= 1 && n_mels <= 256, ADTFE_ERR_UNSUPPORTED, "adtfe_mel_create: n_mels %d out of range", n_mels);
+    ADTFE_REQUIRE(n_mels >= 1 && n_mels <= kMaxMels, ADTFE_ERR_UNSUPPORTED,
+                  "adtfe_mel_create: n_mels %d out of range (1..%d)", n_mels, kMaxMels);
     int rc = adtfe_device_ok(device);
     if (rc != ADTFE_OK) return rc;
     ADTFE_CUDA(cudaSetDevice(device));
@@ -255,17 +316,44 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
         }
     }
 
+    ADTFE_REQUIRE((int)w.size() <= kMaxNnz, ADTFE_ERR_UNSUPPORTED,
+                  "adtfe_mel_create: filterbank has %zu weights between first and last non-zero bins (max %d)",
+                  w.size(), kMaxNnz);
     adtfe_mel* mel = new adtfe_mel();
     mel->device = device; mel->n_fft = n_fft; mel->hop = hop; mel->n_mels = n_mels;
     mel->wpi = (n_fft / 2) / hop + 1;  // int((win/2)//hop + 1), model.py:79
     mel->nnz = (int32_t)w.size();
     mel->sm_count = device_sm_count(device);
-    mel->smem_bytes = logmel_smem_bytes(mel->nnz, n_mels);
-    auto fail = [&](int status) { adtfe_mel_destroy(mel); return status; };
-    if (mel->smem_bytes > 227 * 1024) {
-        set_error("adtfe_mel_create: filterbank needs %zu B of shared memory", mel->smem_bytes);
-        return fail(ADTFE_ERR_UNSUPPORTED);
+    mel->smem_bytes = logmel_smem_bytes();
+    mel->tables = new adtfe_mel_tables();
+    {
+        MelTables& t = mel->tables->t;
+        memset(&t, 0, sizeof(t));
+        for (size_t i = 0; i < w.size(); ++i) t.w[i] = w[i];
+        for (int m = 0; m <= n_mels; ++m) t.ptr[m] = (int16_t)ptr[m];
+        for (int m = 0; m < n_mels; ++m) t.lo[m] = (int16_t)lo[m];
+        // longest-processing-time schedule of filters onto the 16 warps of the mel phase
+        std::vector<int> order(n_mels);
+        for (int m = 0; m < n_mels; ++m) order[m] = m;
+        std::stable_sort(order.begin(), order.end(),
+                         [&](int a, int b) { return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b]; });
+        std::vector<std::vector<int>> bins(kWarps);
+        std::vector<long> load(kWarps, 0);
+        for (int m : order) {
+            int best = 0;
+            for (int wv = 1; wv < kWarps; ++wv)
+                if (load[wv] < load[best]) best = wv;
+            bins[best].push_back(m);
+            load[best] += (ptr[m + 1] - ptr[m]) + 12;  // + the log / store epilogue
+        }
+        int pos = 0;
+        for (int wv = 0; wv < kWarps; ++wv) {
+            t.sched_ptr[wv] = (int16_t)pos;
+            for (int m : bins[wv]) t.sched[pos++] = (uint8_t)m;
+        }
+        t.sched_ptr[kWarps] = (int16_t)pos;
     }
+    auto fail = [&](int status) { adtfe_mel_destroy(mel); return status; };
 #define MEL_UPLOAD(dst, src, bytes)                                                                  \
     if (cudaMalloc((void**)&(dst), (bytes) ? (bytes) : 4) != cudaSuccess ||                          \
         cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice) != cudaSuccess) {                  \
@@ -275,9 +363,6 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
     MEL_UPLOAD(mel->window, window_host, (size_t)n_fft * 4);
     MEL_UPLOAD(mel->twiddle, tw.data(), tw.size() * sizeof(float2));
     MEL_UPLOAD(mel->lane_tw, ltw.data(), ltw.size() * sizeof(float2));
-    MEL_UPLOAD(mel->fb_w, w.data(), w.size() * 4);
-    MEL_UPLOAD(mel->fb_ptr, ptr.data(), ptr.size() * 4);
-    MEL_UPLOAD(mel->fb_lo, lo.data(), lo.size() * 4);
 #undef MEL_UPLOAD
     if (cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel->smem_bytes) !=
         cudaSuccess) {

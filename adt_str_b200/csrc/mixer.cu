@@ -7,10 +7,11 @@
 // and the zero padding of collate_fn (data_modules/train_dataset.py:53).
 //
 // The two data-dependent maxima make it three short kernels:
-//   1. peak_kernel      one CTA per (segment, instrument): both one-shots are read once and
-//                       max|ca*a + cb*b| is taken for every note of that instrument at the
-//                       same time (each note has its own mixup); also resolves the bank
-//                       lookups into ResolvedEvent records.
+//   1. peak_kernel      one CTA per (segment, instrument, 4096-sample chunk): both one-shots are
+//                       read once and max|ca*a + cb*b| is taken for every note of that
+//                       instrument at the same time (each note has its own mixup); chunks meet
+//                       in an atomicMax on the float bits (order-independent); chunk 0 also
+//                       resolves the bank lookups into ResolvedEvent records.
 //   2. mix_kernel       one CTA per 2048-sample output tile; events come from the host-built
 //                       CSR (tile -> events) and are added in array order into registers,
 //                       so the result is deterministic and needs no atomics; emits the
@@ -23,6 +24,7 @@ namespace adtfe {
 
 constexpr int kPeakThreads = 256;
 constexpr int kPeakChunk = 8;   // notes of one instrument handled per sweep over the one-shots
+constexpr int kPeakSpan = ADTFE_PEAK_SPAN;  // samples of the mixed one-shot per peak work item
 constexpr int kMixThreads = 256;
 constexpr int kPerThread = ADTFE_TILE / kMixThreads;  // 8 samples, stride kMixThreads
 constexpr int kStage = 64;      // resolved events staged in shared memory per round
@@ -37,13 +39,19 @@ __device__ __forceinline__ float nan_max(float a, float b) {  // torch.max propa
     return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b);
 }
 
+// One CTA per (group, chunk) work item: a group is the notes of one instrument in one segment
+// (same two one-shots, one mixup each); a chunk is kPeakSpan samples of the mixed one-shot.
+// Peaks are combined with atomicMax on the float bits (non-negative floats order like ints,
+// and max is order-independent, so the result is deterministic).
 __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
     const float* __restrict__ pcm, const int64_t* __restrict__ offsets, const int32_t* __restrict__ lengths,
     const adtfe_event* __restrict__ events, const int32_t* __restrict__ mix_len,
-    const int32_t* __restrict__ group_ptr, ResolvedEvent* __restrict__ resolved) {
+    const int32_t* __restrict__ group_ptr, const int2* __restrict__ work, ResolvedEvent* __restrict__ resolved,
+    int* __restrict__ peak_bits) {
     __shared__ float s_red[kPeakChunk][kPeakThreads / 32];
     __shared__ float s_ca[kPeakChunk], s_cb[kPeakChunk];
-    const int g = blockIdx.x, tid = threadIdx.x;
+    const int2 item = work[blockIdx.x];
+    const int g = item.x, chunk = item.y, tid = threadIdx.x;
     const int e0 = group_ptr[g], e1 = group_ptr[g + 1];
     if (e0 >= e1) return;
     const adtfe_event head = events[e0];
@@ -51,10 +59,21 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
     const int la = lengths[head.main_id], lb = lengths[head.sub_id];
     const int n = mix_len[e0];
     // every one-shot is padded to 4 floats, so whole float4s up to the padded length are readable
-    const int la4 = (la + 3) >> 2, lb4 = (lb + 3) >> 2, n4 = (n + 3) >> 2;
+    const int la4 = (la + 3) >> 2, lb4 = (lb + 3) >> 2;
+    const int lo4 = chunk * (kPeakSpan / 4), hi4 = min((n + 3) >> 2, lo4 + kPeakSpan / 4);
     const float4* a4 = reinterpret_cast<const float4*>(pcm + a_off);
     const float4* b4 = reinterpret_cast<const float4*>(pcm + b_off);
 
+    if (chunk == 0) {  // resolve the bank lookups once per note for the tile mixer
+        for (int e = e0 + tid; e < e1; e += kPeakThreads) {
+            const adtfe_event ev = events[e];
+            ResolvedEvent r;
+            r.a_off = a_off; r.b_off = b_off;
+            r.la = min(la, ev.len); r.lb = min(lb, ev.len);
+            r.start = ev.start; r.len = ev.len; r.ca = ev.ca; r.cb = ev.cb; r.gain = ev.gain; r.pad = 0;
+            resolved[e] = r;
+        }
+    }
     for (int c0 = e0; c0 < e1; c0 += kPeakChunk) {
         const int nc = min(kPeakChunk, e1 - c0);
         __syncthreads();
@@ -67,7 +86,7 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
         float ca[kPeakChunk], cb[kPeakChunk], m[kPeakChunk];
 #pragma unroll
         for (int i = 0; i < kPeakChunk; ++i) { ca[i] = s_ca[i]; cb[i] = s_cb[i]; m[i] = 0.0f; }
-        for (int i4 = tid; i4 < n4; i4 += kPeakThreads) {
+        for (int i4 = lo4 + tid; i4 < hi4; i4 += kPeakThreads) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             float4 va = i4 < la4 ? __ldg(a4 + i4) : z;
             float4 vb = i4 < lb4 ? __ldg(b4 + i4) : z;
@@ -100,22 +119,24 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
             float peak = 0.0f;
 #pragma unroll
             for (int w = 0; w < kPeakThreads / 32; ++w) peak = fmaxf(peak, s_red[tid][w]);
-            const adtfe_event ev = events[c0 + tid];
-            ResolvedEvent r;
-            r.a_off = a_off; r.b_off = b_off; r.la = la; r.lb = lb;
-            r.start = ev.start; r.len = ev.len; r.ca = ev.ca; r.cb = ev.cb;
-            r.scale = ev.gain / peak;  // x/0 -> inf or NaN for an all-zero one-shot, as the reference
-            r.pad = 0;
-            resolved[c0 + tid] = r;
+            if (peak > 0.0f) atomicMax(peak_bits + c0 + tid, __float_as_int(peak));
         }
     }
 }
 
+// One source of one note inside one tile: acc[n] += coef * src[n - start] for start <= n < start+len.
+struct SubEvent {
+    const float* src;
+    int32_t start, len;
+    float coef;
+    int32_t pad;
+};
+
 __global__ void __launch_bounds__(kMixThreads) mix_kernel(
-    const float* __restrict__ pcm, const ResolvedEvent* __restrict__ resolved,
+    const float* __restrict__ pcm, const ResolvedEvent* __restrict__ resolved, const int* __restrict__ peak_bits,
     const int32_t* __restrict__ tile_ptr, const int32_t* __restrict__ tile_events, int tiles_per_seg,
     int64_t ld_wav, float* __restrict__ wav, float* __restrict__ tile_max) {
-    __shared__ __align__(16) ResolvedEvent s_ev[kStage];
+    __shared__ __align__(16) SubEvent s_sub[2 * kStage];
     __shared__ float s_red[kMixThreads / 32];
     const int tile_id = blockIdx.x, tid = threadIdx.x;
     const int seg = tile_id / tiles_per_seg, tile = tile_id - seg * tiles_per_seg;
@@ -128,33 +149,32 @@ __global__ void __launch_bounds__(kMixThreads) mix_kernel(
     for (int base = p0; base < p1; base += kStage) {
         const int nst = min(kStage, p1 - base);
         __syncthreads();
-        // 48-byte records copied as 12 words each, coalesced over the CTA
-        for (int i = tid; i < nst * 12; i += kMixThreads) {
-            const int r = i / 12, w = i - r * 12;
-            reinterpret_cast<int32_t*>(s_ev)[i] =
-                __ldg(reinterpret_cast<const int32_t*>(resolved + tile_events[base + r]) + w);
+        // (1 - mixup) * a and mixup * b become two independent sources, each scaled by
+        // gain / peak: o = (ca*a + cb*b) / peak * vol * gain up to float rounding (1e-7 relative)
+        if (tid < nst) {
+            const int e = tile_events[base + tid];
+            const ResolvedEvent ev = resolved[e];
+            // an all-zero one-shot has peak 0: gain/0 = inf (or NaN), and 0 * inf = NaN over the whole
+            // note - the reference's o / 0 (synthetiser.py:225)
+            const float scale = ev.gain / __int_as_float(peak_bits[e]);
+            SubEvent a, b;
+            a.src = pcm + ev.a_off; a.start = ev.start; a.len = ev.la; a.coef = ev.ca * scale; a.pad = 0;
+            b.src = pcm + ev.b_off; b.start = ev.start; b.len = ev.lb; b.coef = ev.cb * scale; b.pad = 0;
+            s_sub[2 * tid] = a;
+            s_sub[2 * tid + 1] = b;
         }
         __syncthreads();
-        for (int k = 0; k < nst; ++k) {
-            const ResolvedEvent ev = s_ev[k];
-            const float* a = pcm + ev.a_off;
-            const float* b = pcm + ev.b_off;
+        for (int k = 0; k < 2 * nst; ++k) {
+            const SubEvent ev = s_sub[k];
             const int r0 = lo + tid - ev.start;
-            float va[kPerThread], vb[kPerThread];
+            const float* src = ev.src + r0;
+            float v[kPerThread];
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j) {
-                const int r = r0 + j * kMixThreads;
-                const bool in = r >= 0 && r < ev.len;
-                va[j] = (in && r < ev.la) ? __ldg(a + r) : 0.0f;
-                vb[j] = (in && r < ev.lb) ? __ldg(b + r) : 0.0f;
-            }
+            for (int j = 0; j < kPerThread; ++j)
+                v[j] = (unsigned)(r0 + j * kMixThreads) < (unsigned)ev.len ? __ldg(src + j * kMixThreads) : 0.0f;
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j) {
-                const float mixed = __fadd_rn(__fmul_rn(va[j], ev.ca), __fmul_rn(ev.cb, vb[j]));
-                const int r = r0 + j * kMixThreads;
-                // samples outside the event must stay untouched even when scale is NaN/inf
-                if (r >= 0 && r < ev.len) acc[j] = fmaf(mixed, ev.scale, acc[j]);
-            }
+            for (int j = 0; j < kPerThread; ++j)
+                if ((unsigned)(r0 + j * kMixThreads) < (unsigned)ev.len) acc[j] = fmaf(v[j], ev.coef, acc[j]);
         }
     }
     float m = 0.0f;
@@ -211,7 +231,8 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg) {
     if (n_events < 0 || n_seg < 0 || tiles_per_seg < 0) return 0;
-    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_seg * tiles_per_seg * 4) + 256;
+    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_events * 4) +
+           align256((size_t)n_seg * tiles_per_seg * 4) + 256;
 }
 
 extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
@@ -227,7 +248,8 @@ extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, floa
     ADTFE_REQUIRE(wav_out_dev && plan->segments_dev && plan->tile_ptr_dev, ADTFE_ERR_BAD_ARG,
                   "adtfe_render: null buffer");
     ADTFE_REQUIRE(plan->n_events == 0 || (plan->events_dev && plan->mix_len_dev && plan->group_ptr_dev &&
-                                          plan->tile_events_dev && bank->pcm),
+                                          plan->tile_events_dev && plan->peak_work_dev && bank->pcm &&
+                                          plan->n_peak_work > 0),
                   ADTFE_ERR_BAD_ARG, "adtfe_render: null event buffers");
     const size_t need = adtfe_render_workspace_bytes(plan->n_events, plan->n_seg, plan->tiles_per_seg);
     ADTFE_REQUIRE(workspace_dev && workspace_bytes >= need, ADTFE_ERR_WORKSPACE,
@@ -235,16 +257,19 @@ extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, floa
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = (char*)(((uintptr_t)workspace_dev + 255) & ~(uintptr_t)255);
     ResolvedEvent* resolved = (ResolvedEvent*)ws;
-    float* tile_max = (float*)(ws + align256((size_t)plan->n_events * sizeof(ResolvedEvent)));
+    int* peak_bits = (int*)(ws + align256((size_t)plan->n_events * sizeof(ResolvedEvent)));
+    float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4));
     const int n_tiles = plan->n_seg * plan->tiles_per_seg;
-    if (plan->n_groups > 0) {
-        peak_kernel<<<plan->n_groups, kPeakThreads, 0, st>>>(bank->pcm, bank->offsets, bank->lengths,
-                                                            plan->events_dev, plan->mix_len_dev,
-                                                            plan->group_ptr_dev, resolved);
+    if (plan->n_events > 0) {
+        ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, (size_t)plan->n_events * 4, st));
+        peak_kernel<<<plan->n_peak_work, kPeakThreads, 0, st>>>(
+            bank->pcm, bank->offsets, bank->lengths, plan->events_dev, plan->mix_len_dev, plan->group_ptr_dev,
+            reinterpret_cast<const int2*>(plan->peak_work_dev), resolved, peak_bits);
         ADTFE_CUDA(cudaGetLastError());
     }
-    mix_kernel<<<n_tiles, kMixThreads, 0, st>>>(bank->pcm, resolved, plan->tile_ptr_dev, plan->tile_events_dev,
-                                               plan->tiles_per_seg, plan->ld_wav, wav_out_dev, tile_max);
+    mix_kernel<<<n_tiles, kMixThreads, 0, st>>>(bank->pcm, resolved, peak_bits, plan->tile_ptr_dev,
+                                               plan->tile_events_dev, plan->tiles_per_seg, plan->ld_wav, wav_out_dev,
+                                               tile_max);
     ADTFE_CUDA(cudaGetLastError());
     normalise_kernel<<<n_tiles, kMixThreads, 0, st>>>(plan->segments_dev, tile_max, plan->tiles_per_seg,
                                                      plan->ld_wav, wav_out_dev);

@@ -38,7 +38,8 @@ from .config import SynthDrumConfig
 from .mapping import (ADTOF_INVERSE, PITCH_MAX, PITCH_MIN, SIMILARITY_GROUPS,
                       instrument_gain)
 
-TILE = 2048  # output samples owned by one CTA of the tile mixer
+TILE = 2048       # output samples owned by one CTA of the tile mixer (ADTFE_TILE)
+PEAK_SPAN = 4096  # samples of a mixed one-shot scanned by one peak work item (ADTFE_PEAK_SPAN)
 
 #: numpy view of ``adtfe_event`` in include/adtfe.h (32 bytes)
 EVENT_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("main_id", "<i4"), ("sub_id", "<i4"),
@@ -186,6 +187,7 @@ class RenderPlan:
     group_ptr: np.ndarray         # int32 (n_groups+1,)
     tile_ptr: np.ndarray          # int32 (n_seg*tiles_per_seg+1,)
     tile_events: np.ndarray       # int32 (n_refs,) event ids, ascending inside a tile
+    peak_work: np.ndarray         # int32 (n_peak_work, 2): (group, chunk) items of the peak pass
     wave_lengths: np.ndarray = field(default=None)  # int64 (n_seg,)
 
     @property
@@ -263,7 +265,19 @@ def assemble(plans: Sequence[SegmentPlan], ld_wav: int | None = None) -> RenderP
     tile_ptr, tile_events = bucket_tiles(events["start"].astype(np.int64), events["len"].astype(np.int64),
                                          events["seg"], n_seg, tiles_per_seg)
     return RenderPlan(n_seg, ld_wav, tiles_per_seg, segments, events, mix_len, group_ptr, tile_ptr,
-                      tile_events, np.array([p.wave_length for p in plans], np.int64))
+                      tile_events, peak_work_items(mix_len, group_ptr),
+                      np.array([p.wave_length for p in plans], np.int64))
+
+
+def peak_work_items(mix_len: np.ndarray, group_ptr: np.ndarray) -> np.ndarray:
+    """(group, chunk) for every PEAK_SPAN-sample chunk of every group's mixed one-shot."""
+    n_groups = len(group_ptr) - 1
+    if n_groups <= 0:
+        return np.zeros((0, 2), np.int32)
+    chunks = np.maximum(1, -(-mix_len[group_ptr[:-1]].astype(np.int64) // PEAK_SPAN))
+    group = np.repeat(np.arange(n_groups, dtype=np.int64), chunks)
+    chunk = np.arange(int(chunks.sum()), dtype=np.int64) - np.repeat(np.cumsum(chunks) - chunks, chunks)
+    return np.stack([group, chunk], axis=1).astype(np.int32)
 
 
 def plan_batch(batch_notes: Sequence, config: SynthDrumConfig, bank: OneShotBank, rng=_random,

@@ -1,0 +1,41 @@
+"""Batch partitioning across the GPUs of one box.
+
+Segments are independent (every ``SynthDrum.__call__`` has its own draws, mix and
+normalisation; every log-mel row depends on one segment), so the path shards with
+**no data-path collective**: each rank plans, renders and featurises a contiguous
+slice of the batch against its own replica of the one-shot bank - what
+``DistributedSampler`` under HF Trainer / accelerate already does for the model
+(reference ``README.md:45,53-57``, ``train.py:307``).  The only cross-rank traffic is
+the host-side reduction of benchmark statistics below.
+"""
+from __future__ import annotations
+
+import random
+from typing import Tuple
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced ``[lo, hi)`` slice of ``n_items`` for ``rank``."""
+    base, extra = divmod(n_items, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def rank_rng(seed: int, rank: int) -> random.Random:
+    """Per-rank ``random.Random`` (timbre / mixup draws) - distinct streams, reproducible."""
+    return random.Random(seed * 1_000_003 + rank)
+
+
+def reduce_stats(units: float, elapsed_ms: float) -> Tuple[float, float]:
+    """(sum of units over ranks, max of elapsed over ranks) via torch.distributed when
+    initialised; identity for a single process."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return units, elapsed_ms
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    u = torch.tensor([units], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(u, op=dist.ReduceOp.SUM)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(u.item()), float(t.item())

@@ -1,0 +1,397 @@
+#!/usr/bin/env python3
+"""Benchmark of the render + log-mel front end (BASELINE.json metric).
+
+    python bench.py [--gpus N --steps K --warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [...]                      # the reference's CPU path (oracle port)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "training-shape batch"): setting-1 shapes - 64 segments
+x 2.56 s @ 24 kHz per batch (configs/train/setting-1.yaml:6-11,29-33), random MIDI event
+streams and a synthetic 10 000 one-shot bank.  One batch is only ~100 us of GPU
+work, so a *step* is ``--batches-per-step`` (256) distinct batches run back to back, each
+through its own ``adtfe_render_logmel`` call (SURVEY §8d "config 2").  Per rank the work is
+fixed (weak scaling); ranks share nothing but the final statistics.
+
+value  : audio-seconds rendered+featurised per second, plans already resident in HBM.
+e2e    : the same through the public API (FrontEnd.__call__ semantics): host planning of the
+         note lists, pinned-host plan blob -> H2D, kernels, log-mel -> pinned host (D2H),
+         all inside the timed region.
+roofline: dominant kernel (fused log-mel) - algorithmic bytes (4*L read + 4*T*n_mels write per
+         segment) / its CUDA-event time, against MEASURED_PEAKS.json hbm_gbs; the
+         whole path's figure (bytes_alg of SURVEY §8d / step time) is reported beside it.
+cpu_baseline: the CPU oracle port (oracle/, same arithmetic and library calls as the reference)
+         on the box's host cores over a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "render+log-mel audio-seconds/sec"
+UNIT = "audio-s/s"
+SR, INPUT_SEC, BATCH = 24000, 2.56, 64
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--batches-per-step", type=int, default=256)
+    p.add_argument("--bank-size", type=int, default=10_000)
+    p.add_argument("--e2e-steps", type=int, default=2)
+    p.add_argument("--cpu-segments", type=int, default=0, help="cpu_baseline sample size (0 = auto)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--streams", type=int, default=int(os.environ.get("ADTFE_BENCH_STREAMS", "1")))
+    return p.parse_args()
+
+
+def workload_name(args):
+    return (f"setting-1 training-shape batches: {BATCH} segments x {INPUT_SEC} s @ {SR} Hz, "
+            f"{args.batches_per_step} batches per step, {args.bank_size} one-shot synthetic bank")
+
+
+# --------------------------------------------------------------------------- CPU arm (oracle port)
+_CPU_STATE = {}
+
+
+def _cpu_task(task):
+    """One worker task: render `segs` with the oracle, collate, log-mel through torchaudio."""
+    import torch
+    from oracle import mel_oracle, synth_oracle
+    torch.set_num_threads(1)
+    seed, lo, hi = task
+    st = _CPU_STATE
+    rng = random.Random(seed)
+    wavs = [synth_oracle.render(s, st["cfg"], st["nested"], rng=rng) for s in st["segs"][lo:hi]]
+    batch = synth_oracle.collate(wavs)
+    mel = mel_oracle.logmel_torchaudio(batch, SR, 2048, 0.01, 128)
+    return float(sum(len(w) for w in wavs)) / SR, float(mel.sum())
+
+
+def cpu_pool(bank, segs, cfg):
+    """Fork a pool of one-thread workers (mirrors DataLoader workers, train.py:235-237).
+    Must be called before CUDA is initialised in this process."""
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = max(1, min(cores, 64))
+    _CPU_STATE.update(cfg=cfg, nested=bank.to_nested(), segs=segs)
+    ctx = mp.get_context("fork")
+    return ctx.Pool(cores), cores
+
+
+def cpu_run(pool, cores, n_segments, chunk=8, seed=0):
+    tasks = [(seed + i, lo, min(lo + chunk, n_segments)) for i, lo in enumerate(range(0, n_segments, chunk))]
+    t0 = time.perf_counter()
+    res = pool.map(_cpu_task, tasks, chunksize=max(1, len(tasks) // (cores * 4)))
+    dt = time.perf_counter() - t0
+    return sum(r[0] for r in res), dt
+
+
+# --------------------------------------------------------------------------- helpers
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(prefix="adtfe_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(gpu_index)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    from adt_str_b200.config import SETTING_1
+    from adt_str_b200.synthetic import make_bank, make_segments
+    bank = make_bank(args.bank_size, SR, seed=0)
+    segs = make_segments(4096, seed=1)
+    pool, cores = cpu_pool(bank, segs, dict(SETTING_1))
+    per_step = args.cpu_segments or min(len(segs), cores * 32)
+    try:
+        for w in range(args.warmup):
+            cpu_run(pool, cores, per_step, seed=1000 * w)
+        total_s, total_t = 0.0, 0.0
+        for k in range(args.steps):
+            s, t = cpu_run(pool, cores, per_step, seed=7 + 1000 * k)
+            total_s += s; total_t += t
+    finally:
+        pool.terminate()
+    value = total_s / total_t
+    sample = f"{per_step} segments per step ({per_step * INPUT_SEC:.0f} audio-s) of the same workload, {cores} one-thread worker processes"
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total_t / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": workload_name(args), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    rank, world, local = dist_env()
+    from adt_str_b200.config import SETTING_1, setting_1
+    from adt_str_b200.synthetic import make_bank, make_segments
+
+    n_batches = args.batches_per_step
+    bank = make_bank(args.bank_size, SR, seed=0)                      # replicated: same seed on every rank
+    segs = make_segments(n_batches * BATCH, seed=1 + rank)            # each rank its own event streams
+
+    # ---- CPU baseline first: forks must happen before CUDA exists in this process
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        pool, cores = cpu_pool(bank, segs, dict(SETTING_1))
+        try:
+            n = args.cpu_segments or min(len(segs), cores * 256)
+            cpu_run(pool, cores, min(n, cores * 8), seed=1)          # warm the workers
+            s, t = cpu_run(pool, cores, n, seed=2)
+        finally:
+            pool.terminate()
+        cpu = {"value": s / t, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {n} segments ({s:.0f} audio-s) of the step's workload, {cores} one-thread worker "
+                         f"processes, {t:.1f} s wall"}
+
+    import torch
+    import torch.distributed as dist
+    from adt_str_b200 import ComputeMelSpectrogram, FrontEnd, SynthDrum, _lib
+    from adt_str_b200.synthetiser import PlanBuffers
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    synth = SynthDrum(setting_1(), bank=bank, device=dev)
+    mel = ComputeMelSpectrogram(SR, 2048, 0.01, 128)
+    fe = FrontEnd(synth, mel)
+
+    # ---- plan every batch once and make the plans resident (not timed for `value`)
+    rng = random.Random(1234 + rank)
+    batches = [segs[b * BATCH:(b + 1) * BATCH] for b in range(n_batches)]
+    t0 = time.perf_counter()
+    plans = [synth.plan(b, rng) for b in batches]
+    plan_s = time.perf_counter() - t0
+    bufs = [PlanBuffers(dev) for _ in plans]
+    outs = []
+    for p, buf in zip(plans, bufs):
+        buf._dplan = buf.upload(buf.pack(p))
+        buf._resident = p
+        n_samples = int(p.wave_lengths.max())
+        outs.append((torch.empty((p.n_seg, p.ld_wav), dtype=torch.float32, device=dev),
+                     torch.empty((p.n_seg, mel.n_frames(n_samples), 128), dtype=torch.float32, device=dev)))
+    torch.cuda.synchronize(dev)
+
+    audio_s_step = float(sum(int(p.wave_lengths.sum()) for p in plans)) / SR
+    bytes_alg_step = sum(p.bytes_alg(bank, o[1].shape[1], 128) for p, o in zip(plans, outs))
+    launches_per_step = sum(3 + (1 if p.n_groups else 0) for p in plans)
+
+    streams = [torch.cuda.Stream(dev) for _ in range(max(1, args.streams))] if args.streams > 1 else [torch.cuda.current_stream(dev)]
+
+    def step():
+        if len(streams) == 1:
+            for p, buf, (w, f) in zip(plans, bufs, outs):
+                fe.run_plan(p, buffers=buf, wav=w, feat=f, upload=False)
+        else:
+            main = torch.cuda.current_stream(dev)
+            for s in streams:
+                s.wait_stream(main)
+            for i, (p, buf, (w, f)) in enumerate(zip(plans, bufs, outs)):
+                with torch.cuda.stream(streams[i % len(streams)]):
+                    fe.run_plan(p, buffers=buf, wav=w, feat=f, upload=False)
+            for s in streams:
+                main.wait_stream(s)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    elapsed_ms = e0.elapsed_time(e1)
+
+    # ---- per-kernel share: the two halves alone, CUDA events on the launching stream
+    lib, bh, mh = _lib.load(), synth.device_bank().handle, mel._handle(dev).handle
+    import ctypes as C
+    st = torch.cuda.current_stream(dev).cuda_stream
+
+    def time_loop(fn, reps=3):
+        fn(); torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record(); torch.cuda.synchronize(dev)
+        return a.elapsed_time(b) / reps
+
+    def render_all():
+        for p, buf, (w, _f) in zip(plans, bufs, outs):
+            _lib.check(lib.adtfe_render(bh, C.byref(buf._dplan), w.data_ptr(), buf.workspace.data_ptr(),
+                                        buf.workspace.numel(), st))
+
+    def logmel_all():
+        for p, (w, f) in zip(plans, outs):
+            _lib.check(lib.adtfe_logmel(mh, w.data_ptr(), p.n_seg, p.ld_wav, int(p.wave_lengths.max()), f.data_ptr(), st))
+
+    render_ms, logmel_ms = time_loop(render_all), time_loop(logmel_all)
+    one = time_loop(lambda: fe.run_plan(plans[0], buffers=bufs[0], wav=outs[0][0], feat=outs[0][1], upload=False), reps=20)
+
+    # ---- end to end: host notes -> plan -> pinned blob -> H2D -> kernels -> D2H log-mel (pinned)
+    mel_host = [torch.empty(o[1].shape, dtype=torch.float32).pin_memory() for o in outs[:4]]
+    e2e_rng = random.Random(99 + rank)
+    h2d = d2h = 0
+
+    def e2e_step():
+        nonlocal h2d, d2h
+        h2d = d2h = 0
+        for i, (b, buf, (w, f)) in enumerate(zip(batches, bufs, outs)):
+            p = synth.plan(b, e2e_rng)
+            if (p.n_seg, p.ld_wav) != tuple(w.shape) or mel.n_frames(int(p.wave_lengths.max())) != f.shape[1]:
+                w = torch.empty((p.n_seg, p.ld_wav), dtype=torch.float32, device=dev)
+                f = torch.empty((p.n_seg, mel.n_frames(int(p.wave_lengths.max())), 128), dtype=torch.float32, device=dev)
+            host = mel_host[i % len(mel_host)]
+            if host.numel() < f.numel():
+                host = mel_host[i % len(mel_host)] = torch.empty(f.shape, dtype=torch.float32).pin_memory()
+            fe.run_plan_host(p, host, None, buffers=buf, wav=w, feat=f)
+            h2d += buf.nbytes
+            d2h += f.numel() * 4
+        torch.cuda.synchronize(dev)
+
+    e2e_step()  # warm-up (allocations, pinned buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.e2e_steps)):
+        e2e_step()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / max(1, args.e2e_steps)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- reduce over ranks: units add, time is the max
+    from adt_str_b200.sharding import reduce_stats
+    total_audio, max_ms = reduce_stats(audio_s_step * args.steps, elapsed_ms)
+    total_audio_e2e, max_e2e_ms = reduce_stats(audio_s_step, e2e_ms)
+    total_bytes, _ = reduce_stats(float(bytes_alg_step), 0.0)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peak()
+    n_seg_step = n_batches * BATCH
+    logmel_bytes = sum(4 * p.n_seg * int(p.wave_lengths.max()) + 4 * o[1].numel() for p, o in zip(plans, outs))
+    logmel_gbs = logmel_bytes / (logmel_ms * 1e-3) / 1e9
+    path_gbs = (total_bytes / world) / (max_ms / args.steps * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": total_audio / (max_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": max_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "segments_per_step_per_gpu": n_seg_step,
+                   "audio_s_per_step_per_gpu": audio_s_step, "streams": len(streams),
+                   "l2": "no flush needed: per step 0.5 GB bank + ~6 GB of distinct outputs >> 126 MB L2",
+                   "single_batch_latency_ms": one, "plan_ms_per_batch_host": 1e3 * plan_s / n_batches},
+        "clocks": clocks,
+        "e2e": {"value": total_audio_e2e / (max_e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": max(1, args.e2e_steps),
+                "includes": "host planning of note lists, plan blob H2D, 4 kernels per batch, log-mel D2H"},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": {"bound": "hbm", "kernel": "logmel_kernel", "achieved": logmel_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": logmel_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": logmel_bytes / n_batches, "avg_launch_ms": logmel_ms / n_batches,
+                     "share_of_step": logmel_ms / (max_ms / args.steps),
+                     "render_ms_per_step": render_ms, "logmel_ms_per_step": logmel_ms,
+                     "path": {"bytes_alg_per_step": total_bytes / world, "achieved": path_gbs, "frac": path_gbs / peak,
+                              "frac_of_nominal_8TBs": path_gbs / 8000.0}},
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -38,7 +38,8 @@ extern "C" {
 #endif
 
 #define ADTFE_VERSION 1
-#define ADTFE_TILE 2048 /* output samples owned by one mixer CTA */
+#define ADTFE_TILE 2048      /* output samples owned by one mixer CTA */
+#define ADTFE_PEAK_SPAN 4096 /* samples of a mixed one-shot scanned by one peak work item */
 
 typedef enum adtfe_status {
     ADTFE_OK = 0,
@@ -81,7 +82,10 @@ typedef struct adtfe_plan {
     const adtfe_segment* segments_dev; /* n_seg */
     const int32_t* tile_ptr_dev;       /* n_seg*tiles_per_seg+1: CSR tile -> tile_events */
     const int32_t* tile_events_dev;    /* event ids, ascending inside a tile */
-    int32_t n_events, n_groups, n_seg, tiles_per_seg;
+    const int32_t* peak_work_dev;      /* n_peak_work pairs (group, chunk): chunk c of group g covers samples
+                                          [c*ADTFE_PEAK_SPAN, (c+1)*ADTFE_PEAK_SPAN) of its mixed one-shot;
+                                          every group needs chunks 0 .. ceil(mix_len/ADTFE_PEAK_SPAN)-1 */
+    int32_t n_events, n_groups, n_seg, tiles_per_seg, n_peak_work, reserved;
     int64_t ld_wav; /* row pitch of the waveform matrix in floats, multiple of 4, <= tiles_per_seg*ADTFE_TILE */
 } adtfe_plan;
 
@@ -128,7 +132,7 @@ int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel, const adtf
 
 /* ---- host-buffer entry (end to end) ------------------------------------------------ */
 /* Plan blob layout (host, 16-byte aligned sections in this order):
- *   events | mix_len | group_ptr | segments | tile_ptr | tile_events
+ *   events | mix_len | group_ptr | segments | tile_ptr | peak_work | tile_events
  * with the counts in `shape` (a plan whose pointers are ignored).  The blob is copied to
  * `blob_dev` (>= blob_bytes), the batch rendered and featurised, then the log-mel matrix
  * (and the waveform when wav_out_host != NULL) copied back.  Asynchronous on `stream`:
@@ -137,8 +141,9 @@ int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel, const adtf
                         const void* blob_host, size_t blob_bytes, void* blob_dev, float* wav_dev, float* mel_dev,
                         void* workspace_dev, size_t workspace_bytes, float* mel_out_host, float* wav_out_host,
                         void* stream);
-/* Byte offsets of the six sections inside a plan blob (offsets[6], total in *blob_bytes). */
-int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[6], size_t* blob_bytes);
+/* Byte offsets of the seven sections inside a plan blob (offsets[7]; *blob_bytes = offsets[6], where
+ * tile_events starts - it runs to the end of the blob). */
+int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[7], size_t* blob_bytes);
 
 #ifdef __cplusplus
 }

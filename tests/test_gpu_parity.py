@@ -1,0 +1,212 @@
+"""Parity of the CUDA path (through the C ABI) against the reference fixtures and the CPU oracle."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_logmel_close
+from oracle import mel_oracle, synth_oracle
+
+pytestmark = pytest.mark.gpu
+
+WAV_TOL = 1e-5      # north_star: rendered waveform within 1e-5 max abs of the reference CPU synthetiser
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _needs_b200():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from adt_str_b200 import _lib
+    _lib.check(_lib.load().adtfe_device_ok(0), "adtfe_device_ok")   # fails loudly off sm_100
+
+
+def _objects(cfg, bank):
+    from adt_str_b200 import ComputeMelSpectrogram, FrontEnd, SynthDrum
+    synth = SynthDrum(cfg, bank=bank)
+    mel = ComputeMelSpectrogram(cfg.sample_rate, cfg.win_length, cfg.time_res, 128)
+    return synth, mel, FrontEnd(synth, mel)
+
+
+def _truth(batch, c):
+    return mel_oracle.logmel_direct(batch, c["sample_rate"], c["win_length"], c["time_res"], 128, np.float64)
+
+
+# ------------------------------------------------------------------ fixtures from the reference
+def test_render_batch_matches_reference(golden):
+    synth, _, _ = _objects(golden.config(), golden.bank)
+    random.seed(golden.py_seed)
+    wav, lengths = synth.render_batch(golden.segments)
+    assert lengths.tolist() == golden.ref_len.tolist()
+    got = wav.cpu().numpy()
+    assert got.shape == golden.batch.shape
+    assert np.abs(got - golden.batch).max() <= WAV_TOL
+    for i, n in enumerate(golden.ref_len):                  # collate_fn padding is exact zeros
+        assert not got[i, n:].any()
+
+
+def test_single_calls_match_reference_and_rng_stream(golden):
+    synth, _, _ = _objects(golden.config(), golden.bank)
+    random.seed(golden.py_seed)
+    for notes, ref in zip(golden.segments, golden.ref_wavs):
+        got = synth(notes)
+        assert got.device.type == "cpu" and got.dtype == torch.float32 and got.shape == (len(ref),)
+        assert np.abs(got.numpy() - ref).max() <= WAV_TOL
+
+
+def test_logmel_matches_reference(golden):
+    _, mel, _ = _objects(golden.config(), golden.bank)
+    got = mel(torch.from_numpy(golden.batch).cuda())
+    assert got.is_cuda and got.dtype == torch.float32 and tuple(got.shape) == golden.ref_mel.shape
+    assert_logmel_close(got.cpu().numpy(), golden.ref_mel, truth=_truth(golden.batch, golden.cfg))
+    assert got.min() >= 0 and got.max() <= 1
+
+
+def test_fused_front_end_matches_reference(golden):
+    _, _, fe = _objects(golden.config(), golden.bank)
+    random.seed(golden.py_seed)
+    wav, feat = fe(golden.segments)
+    assert np.abs(wav.cpu().numpy() - golden.batch).max() <= WAV_TOL
+    assert_logmel_close(feat.cpu().numpy(), golden.ref_mel, truth=_truth(golden.batch, golden.cfg))
+    empty = [i for i, s in enumerate(golden.segments) if len(s) == 0]
+    assert empty and not feat[empty].any()                  # silence -> exactly 0.0 (log(1e-10) clamps to -23)
+
+
+def test_host_buffer_entry_equals_device_path(golden):
+    synth, mel, fe = _objects(golden.config(), golden.bank)
+    random.seed(golden.py_seed)
+    plan = synth.plan(golden.segments)
+    wav, feat = fe.run_plan(plan)
+    mel_host = torch.empty(feat.shape, dtype=torch.float32).pin_memory()
+    wav_host = torch.empty((plan.n_seg, plan.ld_wav), dtype=torch.float32).pin_memory()
+    fe.run_plan_host(plan, mel_host, wav_host)
+    torch.cuda.synchronize()
+    assert torch.equal(mel_host, feat.cpu())
+    assert torch.equal(wav_host[:, : wav.shape[1]], wav.cpu())
+
+
+# ------------------------------------------------------------------ oracle on seeded synthetic inputs
+@pytest.mark.parametrize("sr,n_seg", [(24000, 64), (16000, 16)])
+def test_training_shape_batch_vs_oracle(sr, n_seg):
+    from adt_str_b200.config import SETTING_1, SynthDrumConfig
+    from adt_str_b200.synthetic import make_bank, make_segments
+    cfg = dict(SETTING_1, sample_rate=sr)
+    bank = make_bank(312, sample_rate=sr, max_len=sr, seed=21)
+    segs = make_segments(n_seg, seed=22, empty_fraction=0.1)
+    nested = bank.to_nested()
+    random.seed(4321)
+    ref = synth_oracle.collate([synth_oracle.render(s, cfg, nested) for s in segs])
+    _, _, fe = _objects(SynthDrumConfig(**cfg), bank)
+    random.seed(4321)
+    wav, feat = fe(segs)
+    assert wav.shape == ref.shape and np.abs(wav.cpu().numpy() - ref).max() <= WAV_TOL
+    want = mel_oracle.logmel_torchaudio(ref, sr, 2048, 0.01, 128).numpy()
+    assert_logmel_close(feat.cpu().numpy(), want, truth=_truth(ref, cfg))
+
+
+def test_dense_polyphony_deterministic_and_correct():
+    from adt_str_b200.config import SETTING_1, setting_1
+    from adt_str_b200.planner import TILE
+    from adt_str_b200.synthetic import make_bank, make_dense_segment
+    bank = make_bank(156, min_len=24000, max_len=48000, seed=31)          # every one-shot >= 1 s
+    notes = make_dense_segment()
+    synth, _, fe = _objects(setting_1(), bank)
+    random.seed(8)
+    plan = synth.plan([notes] * 4)
+    per_tile = np.diff(plan.tile_ptr)
+    interior = per_tile.reshape(4, -1)[:, 12:-2]
+    assert interior.min() >= 20, "stress case must put >= 20 overlapping one-shots on a tile"
+    a_w, a_m = fe.run_plan(plan)
+    a_w, a_m = a_w.clone(), a_m.clone()
+    b_w, b_m = fe.run_plan(plan)
+    assert torch.equal(a_w, b_w) and torch.equal(a_m, b_m)                # fixed accumulation order, no atomics
+    nested = bank.to_nested()
+    random.seed(8)
+    ref = synth_oracle.collate([synth_oracle.render(notes, dict(SETTING_1), nested) for _ in range(4)])
+    assert np.abs(a_w.cpu().numpy() - ref).max() <= WAV_TOL
+    assert_logmel_close(a_m.cpu().numpy(), mel_oracle.logmel_torchaudio(ref, 24000, 2048, 0.01, 128).numpy(),
+                        truth=_truth(ref, SETTING_1))
+
+
+def test_long_form_render_chunk_and_featurise():
+    from adt_str_b200.config import SETTING_1, setting_1
+    from adt_str_b200.synthetic import make_bank, make_long_form
+    bank = make_bank(156, max_len=24000, seed=41)
+    notes = make_long_form(60.0, seed=5)                                  # oracle-sized slice of config 5
+    synth, mel, _ = _objects(setting_1(), bank)
+    random.seed(6)
+    wav = synth(notes)
+    random.seed(6)
+    ref = synth_oracle.render(notes, dict(SETTING_1), bank.to_nested())
+    assert wav.shape == ref.shape and np.abs(wav.numpy() - ref).max() <= WAV_TOL
+    chunks = synth_oracle.chunk_audio(ref, 61440)                         # inference.py:35-48
+    got = mel(torch.from_numpy(chunks).cuda()).cpu().numpy()
+    assert got.shape == (len(chunks), 246, 128)
+    assert_logmel_close(got, mel_oracle.logmel_torchaudio(chunks, 24000, 2048, 0.01, 128).numpy(),
+                        truth=_truth(chunks, SETTING_1))
+
+
+# ------------------------------------------------------------------ edge cases
+def test_silent_mix_is_nan_like_the_reference_and_neighbours_are_untouched():
+    from adt_str_b200.config import SETTING_1, setting_1
+    from adt_str_b200.synthetic import make_bank
+    bank = make_bank(78, min_len=200, max_len=2000, seed=51)
+    synth, _, fe = _objects(setting_1(), bank)
+    batch = [[[0.1, 0.2, 36, 0]], [[0.1, 0.2, 36, 100]], []]              # velocity 0 -> 0/0
+    random.seed(3)
+    wav, feat = fe(batch)
+    random.seed(3)
+    nested = bank.to_nested()
+    ref = [synth_oracle.render(b, dict(SETTING_1), nested) for b in batch]
+    assert np.isnan(ref[0]).all() and torch.isnan(wav[0, : len(ref[0])]).all()
+    assert np.abs(wav[1].cpu().numpy()[: len(ref[1])] - ref[1]).max() <= WAV_TOL
+    assert not wav[2].any() and torch.isnan(feat[0]).all() and not torch.isnan(feat[1:]).any()
+
+
+def test_mel_input_variants_and_state_dict():
+    from adt_str_b200 import ComputeMelSpectrogram
+    mel = ComputeMelSpectrogram(24000, 2048, 0.01, 128)
+    x = torch.randn(3, 61440, generator=torch.Generator().manual_seed(0))
+    base = mel(x.cuda())
+    assert torch.equal(mel(x).cuda(), base) and mel(x).device.type == "cpu"      # CPU in -> CPU out, GPU compute
+    wide = torch.zeros(3, 70000).cuda()
+    wide[:, :61440] = x.cuda()
+    assert torch.equal(mel(wide[:, :61440]), base)                                # strided rows
+    assert torch.equal(mel(x.cuda().double()), base)                              # wave.float()
+    bf = mel(x.cuda().bfloat16())
+    assert bf.dtype == torch.float32 and torch.equal(bf, mel(x.cuda().bfloat16().float()))
+    assert mel(torch.zeros(2, 1000).cuda()).shape == (2, 0, 128)                  # shorter than the window
+    assert mel(torch.zeros(0, 61440).cuda()).shape == (0, 246, 128)
+    for i in range(3):                                                            # rows are independent
+        assert torch.equal(mel(x[i: i + 1].cuda())[0], base[i])
+    sd = {k: v.clone() for k, v in mel.state_dict().items()}
+    sd["compute_spec.mel_scale.fb"] *= 2.0
+    mel.load_state_dict(sd, strict=True)                                          # buffers are what the kernel uses
+    doubled = mel(x.cuda())
+    live = (base > 0.05) & (base < 0.95)
+    assert torch.allclose(doubled[live], base[live] + np.log(2.0) / 35.0, atol=2e-6)
+    with pytest.raises(ValueError):
+        mel(torch.zeros(61440).cuda())
+
+
+def test_abi_status_codes_on_device():
+    from adt_str_b200 import _lib
+    from adt_str_b200.config import setting_1
+    from adt_str_b200.synthetic import make_bank, make_segments
+    bank = make_bank(78, min_len=200, max_len=2000, seed=61)
+    synth, _, _ = _objects(setting_1(), bank)
+    random.seed(1)
+    plan = synth.plan(make_segments(2, empty_fraction=0.0))
+    buf = synth.buffers()
+    dplan = buf.upload(buf.pack(plan))
+    lib, h = _lib.load(), synth.device_bank().handle
+    out = torch.empty((plan.n_seg, plan.ld_wav), device="cuda")
+    assert lib.adtfe_render(h, C.byref(dplan), out.data_ptr(), buf.workspace.data_ptr(), 16, None) == -3
+    assert b"workspace" in lib.adtfe_last_error()
+    bad = _lib.Plan(*[getattr(dplan, f) for f, _ in _lib.Plan._fields_])
+    bad.ld_wav = plan.ld_wav + 1
+    assert lib.adtfe_render(h, C.byref(bad), out.data_ptr(), buf.workspace.data_ptr(), buf.workspace.numel(), None) == -1
+    w = torch.hann_window(1024)
+    hm = C.c_void_p()
+    assert lib.adtfe_mel_create(1024, 240, 128, w.data_ptr(), w.data_ptr(), 0, C.byref(hm)) == -2   # n_fft != 2048
+    torch.cuda.synchronize()

@@ -1,0 +1,176 @@
+"""Host logic: planner indices bit-exact against the fixtures, bucketing, errors, bank, config."""
+import random
+
+import numpy as np
+import pytest
+
+from adt_str_b200 import planner
+from adt_str_b200.bank import OneShotBank
+from adt_str_b200.config import SETTING_1, SynthDrumConfig, deep_merge, setting_1, synth_config_from_sections
+from adt_str_b200.mapping import instrument_gain
+from adt_str_b200.synthetic import make_bank, make_dense_segment, make_long_form, make_segments
+from oracle import synth_oracle
+
+
+def _track_order(rows):
+    """note-order trace rows of one segment -> the planner's track order."""
+    rank = {}
+    for r in rows:
+        rank.setdefault(int(r[5]), len(rank))
+    return sorted(range(len(rows)), key=lambda i: (rank[int(rows[i][5])], i))
+
+
+def test_planner_indices_bit_exact_vs_reference_trace(golden):
+    cfg = golden.config()
+    random.seed(golden.py_seed)
+    plan = planner.plan_batch(golden.segments, cfg, golden.bank)
+    assert plan.wave_lengths.tolist() == golden.ref_len.tolist()
+    assert plan.segments["len"].tolist() == golden.ref_len.tolist()
+    assert plan.ld_wav % 4 == 0 and plan.ld_wav >= golden.ref_len.max()
+    for s in range(plan.n_seg):
+        sel = golden.trace[:, 0] == s
+        rows, mix = golden.trace[sel], golden.trace_mixup[sel]
+        ev = plan.events[plan.events["seg"] == s]
+        order = _track_order(rows)
+        assert len(ev) == len(rows)
+        for e, i in zip(ev, order):
+            assert (e["start"], e["len"], e["main_id"], e["sub_id"]) == tuple(rows[i][1:5])
+            assert e["cb"] == np.float32(mix[i]) and e["ca"] == np.float32(1.0 - mix[i])
+        assert (plan.segments["flags"][s] == planner.SEG_EMPTY) == (len(rows) == 0)
+
+
+def test_tile_buckets_equal_plain_loop(golden):
+    random.seed(golden.py_seed)
+    plan = planner.plan_batch(golden.segments, golden.config(), golden.bank)
+    ev = plan.events
+    n_tiles = plan.n_seg * plan.tiles_per_seg
+    start = ev["seg"].astype(np.int64) * plan.tiles_per_seg * planner.TILE + ev["start"]
+    want = synth_oracle.bucket_tiles(start.tolist(), ev["len"].tolist(), planner.TILE, n_tiles)
+    assert plan.tile_ptr[0] == 0 and plan.tile_ptr[-1] == len(plan.tile_events)
+    for t in range(n_tiles):
+        assert plan.tile_events[plan.tile_ptr[t]: plan.tile_ptr[t + 1]].tolist() == want[t]
+
+
+def test_groups_cover_events_and_share_oneshots():
+    bank = make_bank(156, max_len=3000)
+    random.seed(3)
+    plan = planner.plan_batch(make_segments(12) + [make_dense_segment()], setting_1(), bank)
+    gp = plan.group_ptr
+    assert gp[0] == 0 and gp[-1] == plan.n_events and (np.diff(gp) > 0).all()
+    for a, b in zip(gp[:-1], gp[1:]):
+        e = plan.events[a:b]
+        assert len({(x["seg"], x["main_id"], x["sub_id"]) for x in e}) == 1
+        assert (plan.mix_len[a:b] == max(bank.lengths[e["main_id"][0]], bank.lengths[e["sub_id"][0]])).all()
+    assert (plan.events["len"] <= plan.mix_len).all() and (plan.events["len"] >= 0).all()
+    ends = plan.events["start"] + plan.events["len"]
+    assert (ends <= plan.segments["len"][plan.events["seg"]]).all()
+
+
+def test_rng_stream_advances_like_the_reference_call_order():
+    bank = make_bank(156, max_len=2000)
+    notes = [[0.1, 0.2, 36, 100], [0.2, 0.3, 38, 90], [0.3, 0.4, 36, 80]]
+    random.seed(5)
+    planner.plan_segment(notes, setting_1(), bank)
+    got = random.random()
+    random.seed(5)
+    for _pitch in (36, 38):          # kick: group, key, group, key, then its mixup ... (synthetiser.py:274-281, 217)
+        pass
+    draws = []
+    random.seed(5)
+    g = planner.similarity_groups(0.8)
+    for new_instrument in (True, True, False):
+        if new_instrument:
+            for _ in range(2):
+                grp = random.choice(g)
+                random.choice(range(2))      # 156 one-shots / 78 cells = 2 per (pitch, group)
+        draws.append(random.uniform(0, 0.8))
+    random.random()                          # FX coin
+    assert got == random.random()
+
+
+def test_invalid_notes_raise_like_the_reference():
+    bank = make_bank(78, min_len=100, max_len=1000)
+    with pytest.raises(ValueError, match="Invalid note"):
+        planner.plan_segment([[0.1, 0.2, 62, 100]], setting_1(), bank)      # pitch > 61
+    with pytest.raises(ValueError, match="Invalid note"):
+        planner.plan_segment([[0.3, 0.2, 36, 100]], setting_1(), bank)      # offset < onset
+    with pytest.raises(IndexError):                                         # pitch 61 has no one-shots: choice([])
+        planner.plan_segment([[0.1, 0.2, 61, 100]], setting_1(), bank)
+    with pytest.raises(NotImplementedError):
+        planner.plan_segment([[0.1, 0.2, 36, 100]], setting_1(use_fx_prob=1.0), bank)
+    with pytest.raises(KeyError):                                           # ADTOF mode expects class pitches
+        planner.plan_segment([[0.1, 0.2, 36, 100]], setting_1(ADTOF_mapping=True), bank)
+
+
+def test_empty_and_silent_segments():
+    bank = make_bank(78, min_len=100, max_len=1000)
+    p = planner.plan_segment([], setting_1(), bank)
+    assert (p.wave_length, p.flags, len(p.events)) == (61440, planner.SEG_EMPTY, 0)
+    p = planner.plan_segment(np.zeros((0, 4), np.float32), config_16k(), bank)
+    assert p.wave_length == 40960
+    p = planner.plan_segment([[0.1, 0.2, 36, 0]], setting_1(), bank)         # velocity 0 -> volume 0 -> NaN mix
+    assert p.flags == planner.SEG_NORMALISE and p.max_volume == 0.0 and p.events["gain"][0] == 0.0
+
+
+def config_16k():
+    return SynthDrumConfig(**dict(SETTING_1, sample_rate=16000))
+
+
+def test_velocity_curve_and_gains():
+    v = planner.velocity_to_volume(np.array([0, 1, 64, 127, 200], np.float32))
+    assert v[0] == 0 and abs(v[3] - 1.0) < 1e-6 and v[4] == v[3] and 0.1 < v[1] < v[2] < 1
+    assert instrument_gain(36, False) == 1.0 and instrument_gain(42, False) == 0.7 and instrument_gain(46, False) == 0.7
+    assert instrument_gain(48, True) == 0.7
+    assert planner.similarity_groups(0.8) == ["gold", "100-90", "90-80"]
+    assert len(planner.similarity_groups(0.4)) == 7 and planner.similarity_groups(1.1) == []
+
+
+def test_bank_roundtrip_and_name_order(tmp_path):
+    nested = {"36": {"gold": {"b": np.ones(5, np.float32), "a": np.arange(7, dtype=np.float32)}},
+              "38": {"90-80": {"z": np.zeros(3, np.float32)}}}
+    bank = OneShotBank.from_nested(nested)
+    assert bank.names == ["36/gold/a", "36/gold/b", "38/90-80/z"]           # sorted like h5py keys()
+    assert bank.group_range(36, "gold") == (0, 2) and not bank.has_group(36, "90-80")
+    assert (bank.offsets % 32 == 0).all() and bank.oneshot(0).tolist() == list(range(7))
+    path = str(tmp_path / "bank.npz")
+    bank.save(path)
+    back = OneShotBank.load(path)
+    assert back.names == bank.names and np.array_equal(back.pcm, bank.pcm) and back.index == bank.index
+    assert set(back.to_nested()["36"]["gold"]) == {"a", "b"}
+
+
+def test_config_sections_and_merge():
+    cfg = {"shared": dict(input_sec=2.56, time_res=0.01, win_length=2048, sample_rate=24000),
+           "synthetiser": {k: SETTING_1[k] for k in ("oneshot_path", "similarity_threshold", "max_hat_std_velocity",
+                                                     "max_hat_mean_velocity", "max_cymbals_std_velocity",
+                                                     "max_cymbals_mean_velocity", "mixup_range", "use_fx_prob",
+                                                     "use_reverb_prob", "use_limiter_prob", "use_compression_prob")},
+           "tokenizer": {"ADTOF_mapping": False}}
+    c = synth_config_from_sections(cfg)
+    assert c == setting_1()
+    assert deep_merge({"a": {"b": 1, "c": 2}}, {"a": {"b": 3}}) == {"a": {"b": 3, "c": 2}}
+
+
+def test_bytes_alg_counts_every_term():
+    bank = make_bank(156, max_len=3000)
+    random.seed(9)
+    plan = planner.plan_batch(make_segments(4, empty_fraction=0.0), setting_1(), bank)
+    ev = plan.events
+    want = 0
+    for s in range(plan.n_seg):
+        e = ev[ev["seg"] == s]
+        firsts = {}
+        for x in e:
+            for u in (int(x["main_id"]), int(x["sub_id"])):
+                firsts[u] = min(firsts.get(u, 1 << 60), int(x["start"]))
+        want += sum(4 * max(0, min(int(bank.lengths[u]), int(plan.segments["len"][s]) - st)) for u, st in firsts.items())
+    assert plan.bank_bytes(bank) == want
+    assert plan.bytes_alg(bank, 246, 128) == want + 4 * int(plan.segments["len"].sum()) + 4 * 246 * 128 * 4 + 32 * len(ev)
+
+
+def test_long_form_plan_is_one_segment():
+    bank = make_bank(156, max_len=3000)
+    random.seed(2)
+    notes = make_long_form(30.0)
+    plan = planner.plan_batch([notes], setting_1(), bank)
+    assert plan.n_seg == 1 and plan.wave_lengths[0] >= 29 * 24000 and plan.tiles_per_seg == -(-plan.ld_wav // 2048)
