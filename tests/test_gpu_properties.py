@@ -68,8 +68,8 @@ def test_full_size_logmel_gain_shift_and_row_independence(full):
     wav, base = fe.run_plan(plan)
     wav = wav.contiguous()
     louder = mel(wav * 2.0)
-    mid = (base > 0.05) & (base < 0.9) & ~torch.isnan(base)
-    assert mid.float().mean() > 0.5
+    mid = (base > 0.3) & (base < 0.9) & ~torch.isnan(base)   # mel power >> 1e-10
+    assert mid.float().mean() > 0.4
     # power x4 -> log-mel + ln(4)/35 wherever neither clamp is active (the +1e-10 is negligible there)
     assert (louder[mid] - base[mid] - np.log(4.0) / 35.0).abs().max() < 2e-6
     for i in (0, 100, 255):
