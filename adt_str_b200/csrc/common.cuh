@@ -65,6 +65,7 @@ struct adtfe_mel {
     float* window = nullptr;   // n_fft
     float2* twiddle = nullptr; // 32 x 32: W_2048^(k1*n2), k1 = 1..32, n2 = lane
     float2* lane_tw = nullptr; // 3 x 32: per-lane twiddles of the cross-lane 32-point DFT
+    float* sched_w = nullptr;  // filter weights packed in mel-phase schedule order (per warp)
     struct adtfe_mel_tables* tables = nullptr;  // filterbank CSR + warp schedule, passed as a kernel parameter
     size_t smem_bytes = 0;
 };

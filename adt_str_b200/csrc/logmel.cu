@@ -19,10 +19,18 @@
 //   column k1 = 32 (bins 32 + 64*k2) is a 32-point DFT across lanes with shuffles
 //   |X|^2 goes to the CTA's power matrix P[bin][frame] (pitch 33: consecutive bins of one
 //           frame land in distinct banks; only the 16 column-32 bins collide, once per frame)
-//  mel phase - lanes are the 32 frames, each warp takes the filters the host scheduled for it
-//   (longest-processing-time balance): acc += w * P[bin][lane] is conflict-free and the
-//   weight is warp-uniform, read from the kernel-parameter constant bank; then
-//   log / clamp / affine into a staging tile, and a coalesced copy-out.
+//  mel phase - lanes are the 32 frames, each warp owns a contiguous, cost-balanced range of
+//   filters: acc += w * P[bin][lane] is conflict-free, weights are broadcast reads (4 per
+//   LDS.128) from the warp's (now idle) exchange tile; then log / clamp / affine, staged in
+//   the same tile and written out in runs of consecutive filters.
+//  The samples of a warp's next frame are requested before the mel phase, so their latency
+//  hides behind it.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
 #include "common.cuh"
 #include "fft_gen.cuh"
 
@@ -34,21 +42,25 @@ constexpr int kRound = 32;                  // frames per CTA round (lanes of th
 constexpr int kXPitch = 36;                 // floats per exchange row
 constexpr int kXFloats = 32 * kXPitch;      // 1152 floats per warp
 constexpr int kPPitch = 33;
-constexpr int kPFloats = 1025 * kPPitch;
-constexpr int kOPitch = 129;                // staging tile pitch (aliases the exchange tiles)
-constexpr int kMaxNnz = 4096;
+constexpr int kPRows = 1025 + 3;               // 3 zero rows: filter weights are padded to groups of 4
+constexpr int kPFloats = kPRows * kPPitch;
+constexpr int kWtsMax = 384;                // packed filter weights one warp parks in its tile ...
+constexpr int kStagePitchMax = 23;          // ... followed by its (32 frames x n filters) result tile
+static_assert(kWtsMax + 32 * kStagePitchMax <= kXFloats, "weights + staging must fit in one exchange tile");
 constexpr int kMaxMels = 128;
 
 __device__ __forceinline__ int p_index(int bin) { return bin * kPPitch; }
 
-// Filterbank and its per-warp schedule, passed by value: lives in the kernel-parameter
-// constant bank, so the mel phase reads weights with uniform constant loads.
+// Per-warp schedule of the mel phase, passed by value (kernel-parameter constant bank).  The
+// weights themselves are packed per warp in global memory (adtfe_mel::sched_w) and copied into
+// the warp's idle exchange tile every round, where they are read with broadcast LDS.
+struct MelEntry {
+    int16_t lo, cnt4, woff, pad;  // first bin, weights padded to a multiple of 4, offset in the warp's pack
+};
 struct MelTables {
-    float w[kMaxNnz];
-    int16_t ptr[kMaxMels + 1];   // weights of filter m: w[ptr[m] .. ptr[m+1])
-    int16_t lo[kMaxMels];        // first bin of filter m
-    int16_t sched_ptr[kWarps + 1];
-    uint8_t sched[kMaxMels];     // filters of warp w: sched[sched_ptr[w] .. sched_ptr[w+1])
+    MelEntry entry[kMaxMels];
+    int16_t first[kWarps + 1];   // warp w owns the contiguous filters first[w] .. first[w+1]-1
+    int16_t wbase[kWarps + 1];   // its packed weights: sched_w[wbase[w] .. wbase[w+1])
 };
 
 struct LogmelArgs {
@@ -57,9 +69,45 @@ struct LogmelArgs {
     const float* window;
     const float2* twiddle;
     const float2* lane_tw;
+    const float* sched_w;
+    long long* trace;  // ADTFE_TRACE builds only: per-warp clock64 stamps
     int64_t ld_wav;
     int32_t n_seg, first, count, hop, n_mels;
 };
+
+// Mel phase of one warp: lane = frame, the warp owns a contiguous range of filters.
+// acc += w * P[bin][lane]: the P read is conflict-free (pitch 33), four weights come from one
+// broadcast LDS.128 out of the warp's own tile.  Results are staged in the same tile and
+// copied out in runs of n consecutive filters per frame.
+__device__ __forceinline__ void mel_phase(const MelTables& tab, int warp, int lane, const float* __restrict__ pl,
+                                          float* __restrict__ tile, float* __restrict__ out, long long g0,
+                                          long long total, int n_mels) {
+    const int f0 = tab.first[warp], n = tab.first[warp + 1] - f0;
+    const int pitch = n | 1;
+    float* stage = tile + kWtsMax;
+    for (int i = 0; i < n; ++i) {
+        const MelEntry en = tab.entry[f0 + i];
+        const float* pp = pl + p_index(en.lo);
+        const float4* ww = reinterpret_cast<const float4*>(tile + en.woff);
+        float acc0 = 0.0f, acc1 = 0.0f;
+        for (int k = 0; k < en.cnt4; k += 4, pp += 4 * kPPitch) {
+            const float4 w = ww[k >> 2];
+            acc0 = fmaf(w.x, pp[0], acc0);
+            acc1 = fmaf(w.y, pp[kPPitch], acc1);
+            acc0 = fmaf(w.z, pp[2 * kPPitch], acc0);
+            acc1 = fmaf(w.w, pp[3 * kPPitch], acc1);
+        }
+        float v = __logf((acc0 + acc1) + 1e-10f);           // |err| ~1e-7 in ln, 35x below the tolerance
+        v = v != v ? v : fminf(fmaxf(v, -23.0f), 12.0f);    // torch.clamp keeps NaN
+        stage[lane * pitch + i] = (v + 23.0f) * (1.0f / 35.0f);
+    }
+    __syncwarp();
+    for (int idx = lane; idx < 32 * n; idx += 32) {
+        const int f = idx / n, i = idx - f * n;
+        const long long g = g0 + f;
+        if (g < total) out[g * n_mels + f0 + i] = stage[f * pitch + i];
+    }
+}
 
 __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p, const __grid_constant__ MelTables tab) {
     extern __shared__ __align__(16) float smem[];
@@ -69,37 +117,67 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
     float* s_x = reinterpret_cast<float*>(s_ltw + 3 * 32);         // kWarps * kXFloats (also the staging tile)
     float* s_p = s_x + kWarps * kXFloats;                          // kPFloats
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // broadcast from lane 0 so the compiler knows the warp index (and everything the mel phase
+    // derives from it: schedule, filter bounds, weight index) is warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     for (int i = tid; i < 2048; i += kThreads) s_win[i] = p.window[i];
     for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = p.twiddle[i];
     for (int i = tid; i < 3 * 32; i += kThreads) s_ltw[i] = p.lane_tw[i];
     __syncthreads();
 
+#ifdef ADTFE_TRACE
+#define TRACE(slot) do { if (lane == 0 && p.trace && tr_round < 3) p.trace[((blockIdx.x * kWarps + warp) * 3 + tr_round) * 16 + (slot)] = clock64(); } while (0)
+    int tr_round = 0;
+#else
+#define TRACE(slot) do {} while (0)
+#endif
     float* xw = s_x + warp * kXFloats;
     const int col32_bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);
+    const int wb = tab.wbase[warp], wn = tab.wbase[warp + 1] - wb;
+    for (int i = tid; i < 3 * kPPitch; i += kThreads) s_p[1025 * kPPitch + i] = 0.0f;  // padding rows
 
     const long long total = (long long)p.n_seg * p.count;
     const long long n_rounds = (total + kRound - 1) / kRound;
+
+    auto frame_ptr = [&](long long g) -> const float* {
+        const int seg = (int)(g / p.count);
+        const int j = (int)(g - (long long)seg * p.count);
+        return p.wav + (long long)seg * p.ld_wav + (long long)(p.first + j) * p.hop - 1024 + lane;
+    };
+
+    // samples of the warp's first frame of the coming round, fetched one round ahead
+    float v[64];
+    {
+        const long long g = (long long)blockIdx.x * kRound + warp;
+        if (g < total) {
+            const float* x = frame_ptr(g);
+#pragma unroll
+            for (int n1 = 0; n1 < 64; ++n1) v[n1] = __ldg(x + 32 * n1);
+        }
+    }
+
     for (long long round = blockIdx.x; round < n_rounds; round += gridDim.x) {
         const long long g0 = round * kRound;
+        TRACE(0);
         // ================= FFT phase: frames g0 + warp and g0 + warp + 16 =================
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             const int f = warp + half * kWarps;
             const long long g = g0 + f;
             if (g >= total) break;  // warp-uniform
-            const int seg = (int)(g / p.count);
-            const int j = (int)(g - (long long)seg * p.count);
-            const float* x = p.wav + (long long)seg * p.ld_wav + (long long)(p.first + j) * p.hop - 1024 + lane;
-
+            if (half == 1) {
+                const float* x = frame_ptr(g);
+#pragma unroll
+                for (int n1 = 0; n1 < 64; ++n1) v[n1] = __ldg(x + 32 * n1);
+            }
             // ---- pass 1: window + 64-point real DFT over n1 (stride-32 samples)
             float yr[33], yi[33];
-            {
-                float v[64];
 #pragma unroll
-                for (int n1 = 0; n1 < 64; ++n1) v[n1] = __ldg(x + 32 * n1) * s_win[32 * n1 + lane];
-                rdft64(v, yr, yi);
-            }
+            for (int n1 = 0; n1 < 64; ++n1) v[n1] *= s_win[32 * n1 + lane];
+            TRACE(1 + half * 5);
+            rdft64(v, yr, yi);
+            TRACE(2 + half * 5);
             // ---- twiddle in place (rows 1..31), column 32 is real before its twiddle
 #pragma unroll
             for (int k1 = 1; k1 < 32; ++k1) {
@@ -167,7 +245,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
             }
 
             // ---- pass 2: 32-point complex DFT over n2 for k1 = lane
+            TRACE(3 + half * 5);
             cdft32(zr, zi);
+            TRACE(4 + half * 5);
 
             // ---- power spectrum into P[bin][f]
             float* pf = s_p + f;
@@ -177,37 +257,31 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
             for (int k2 = 16; k2 < 32; ++k2)
                 pf[p_index(64 - lane + 64 * (31 - k2))] = zr[k2] * zr[k2] + zi[k2] * zi[k2];
             if ((lane & 1) == 0) pf[p_index(col32_bin)] = cr * cr + ci * ci;
+            TRACE(5 + half * 5);
         }
-        __syncthreads();
-
-        // ================= mel phase: lane = frame, filters from the warp's schedule =================
+        // the exchange tile is idle until the next round: park this warp's filter weights in it
+        for (int i = lane; i < wn; i += 32) xw[i] = __ldg(p.sched_w + wb + i);
+        // and start fetching the first frame of the next round; it lands during the mel phase
         {
-            const float* pl = s_p + lane;
-            float* stage = s_x + lane * kOPitch;
-            const int s0 = tab.sched_ptr[warp], s1 = tab.sched_ptr[warp + 1];
-            for (int si = s0; si < s1; ++si) {
-                const int m = tab.sched[si];
-                const int b = tab.ptr[m], e = tab.ptr[m + 1];
-                const float* pp = pl + p_index(tab.lo[m]);
-                float acc = 0.0f;
-                for (int i = b; i < e; ++i, pp += kPPitch) acc = fmaf(tab.w[i], *pp, acc);
-                float v = logf(acc + 1e-10f);
-                v = v != v ? v : fminf(fmaxf(v, -23.0f), 12.0f);  // torch.clamp keeps NaN
-                stage[m] = (v + 23.0f) / 35.0f;
+            const long long g = (round + gridDim.x) * kRound + warp;
+            if (g < total) {
+                const float* x = frame_ptr(g);
+#pragma unroll
+                for (int n1 = 0; n1 < 64; ++n1) v[n1] = __ldg(x + 32 * n1);
             }
         }
+        TRACE(11);
         __syncthreads();
+        TRACE(12);
 
-        // ================= copy-out: one warp per frame row, coalesced =================
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const int f = warp + half * kWarps;
-            const long long g = g0 + f;
-            if (g >= total) break;
-            float* out = p.out + g * p.n_mels;
-            for (int m = lane; m < p.n_mels; m += 32) out[m] = s_x[f * kOPitch + m];
-        }
-        __syncthreads();  // staging tile and P are reused by the next round
+        // ================= mel phase: lane = frame, the warp's own filter range =================
+        mel_phase(tab, warp, lane, s_p + lane, xw, p.out, g0, total, p.n_mels);
+        TRACE(13);
+        __syncthreads();  // P and the exchange tiles are reused by the next round
+        TRACE(14);
+#ifdef ADTFE_TRACE
+        ++tr_round;
+#endif
     }
 }
 
@@ -215,10 +289,19 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
 
 using namespace adtfe;
 
+// ADTFE_TRACE builds: a device buffer address handed over in the environment by tools/trace_logmel.py
+static void* getenv_trace() {
+#ifdef ADTFE_TRACE
+    const char* e = getenv("ADTFE_TRACE_PTR");
+    return e ? (void*)strtoull(e, nullptr, 0) : nullptr;
+#else
+    return nullptr;
+#endif
+}
+
 static size_t logmel_smem_bytes() {
     return ((size_t)2048 + 2 * 32 * 32 + 2 * 3 * 32 + (size_t)kWarps * kXFloats + kPFloats) * 4;
 }
-static_assert(kWarps * kXFloats >= kRound * kOPitch, "staging tile must fit in the exchange tiles");
 
 struct adtfe_mel_tables {
     MelTables t;
@@ -248,7 +331,7 @@ extern "C" int adtfe_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t 
                   ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: frame support leaves the signal");
     LogmelArgs a;
     a.wav = wav_dev; a.out = out_dev; a.window = mel->window; a.twiddle = mel->twiddle; a.lane_tw = mel->lane_tw;
-    a.ld_wav = ld_wav; a.n_seg = n_seg; a.first = first; a.count = count; a.hop = mel->hop; a.n_mels = mel->n_mels;
+    a.sched_w = mel->sched_w; a.trace = (long long*)getenv_trace(); a.ld_wav = ld_wav; a.n_seg = n_seg; a.first = first; a.count = count; a.hop = mel->hop; a.n_mels = mel->n_mels;
     const long long total = (long long)n_seg * count;
     const long long n_rounds = (total + kRound - 1) / kRound;
     const int grid = (int)(n_rounds < mel->sm_count ? n_rounds : mel->sm_count);
@@ -260,16 +343,12 @@ extern "C" int adtfe_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t 
 extern "C" int adtfe_mel_destroy(adtfe_mel* mel) {
     if (!mel) return ADTFE_OK;
     cudaSetDevice(mel->device);
-    cudaFree(mel->window); cudaFree(mel->twiddle); cudaFree(mel->lane_tw);
+    cudaFree(mel->window); cudaFree(mel->twiddle); cudaFree(mel->lane_tw); cudaFree(mel->sched_w);
     delete mel->tables;
     delete mel;
     return ADTFE_OK;
 }
 
-#include <algorithm>
-#include <cmath>
-#include <cstring>
-#include <vector>
 
 extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, const float* window_host,
                                 const float* fb_host, int device, adtfe_mel** out) {
@@ -316,9 +395,6 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
         }
     }
 
-    ADTFE_REQUIRE((int)w.size() <= kMaxNnz, ADTFE_ERR_UNSUPPORTED,
-                  "adtfe_mel_create: filterbank has %zu weights between first and last non-zero bins (max %d)",
-                  w.size(), kMaxNnz);
     adtfe_mel* mel = new adtfe_mel();
     mel->device = device; mel->n_fft = n_fft; mel->hop = hop; mel->n_mels = n_mels;
     mel->wpi = (n_fft / 2) / hop + 1;  // int((win/2)//hop + 1), model.py:79
@@ -326,32 +402,46 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
     mel->sm_count = device_sm_count(device);
     mel->smem_bytes = logmel_smem_bytes();
     mel->tables = new adtfe_mel_tables();
+    std::vector<float> packed;
     {
         MelTables& t = mel->tables->t;
         memset(&t, 0, sizeof(t));
-        for (size_t i = 0; i < w.size(); ++i) t.w[i] = w[i];
-        for (int m = 0; m <= n_mels; ++m) t.ptr[m] = (int16_t)ptr[m];
-        for (int m = 0; m < n_mels; ++m) t.lo[m] = (int16_t)lo[m];
-        // longest-processing-time schedule of filters onto the 16 warps of the mel phase
-        std::vector<int> order(n_mels);
-        for (int m = 0; m < n_mels; ++m) order[m] = m;
-        std::stable_sort(order.begin(), order.end(),
-                         [&](int a, int b) { return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b]; });
-        std::vector<std::vector<int>> bins(kWarps);
-        std::vector<long> load(kWarps, 0);
-        for (int m : order) {
-            int best = 0;
-            for (int wv = 1; wv < kWarps; ++wv)
-                if (load[wv] < load[best]) best = wv;
-            bins[best].push_back(m);
-            load[best] += (ptr[m + 1] - ptr[m]) + 12;  // + the log / store epilogue
-        }
-        int pos = 0;
+        // contiguous filter ranges for the 16 warps of the mel phase, balanced by estimated cost
+        auto cost = [&](int m) { return 1.5 * (ptr[m + 1] - ptr[m]) + 14.0; };
+        double total_cost = 0;
+        for (int m = 0; m < n_mels; ++m) total_cost += cost(m);
+        int m = 0;
+        bool fits = true;
+        double spent = 0;
         for (int wv = 0; wv < kWarps; ++wv) {
-            t.sched_ptr[wv] = (int16_t)pos;
-            for (int m : bins[wv]) t.sched[pos++] = (uint8_t)m;
+            t.first[wv] = (int16_t)m;
+            t.wbase[wv] = (int16_t)packed.size();
+            const size_t base = packed.size();
+            const double target = total_cost * (wv + 1) / kWarps;
+            int taken = 0;
+            while (m < n_mels && taken < kStagePitchMax &&
+                   (wv == kWarps - 1 || taken == 0 || spent + 0.5 * cost(m) <= target)) {
+                MelEntry en;
+                const int cnt = ptr[m + 1] - ptr[m];
+                en.lo = (int16_t)lo[m]; en.cnt4 = (int16_t)((cnt + 3) & ~3);
+                en.woff = (int16_t)(packed.size() - base); en.pad = 0;
+                t.entry[m] = en;
+                packed.insert(packed.end(), w.begin() + ptr[m], w.begin() + ptr[m + 1]);
+                packed.resize(base + en.woff + en.cnt4, 0.0f);
+                fits = fits && lo[m] + en.cnt4 <= kPRows;
+                spent += cost(m);
+                ++m; ++taken;
+            }
+            fits = fits && packed.size() - base <= (size_t)kWtsMax;
         }
-        t.sched_ptr[kWarps] = (int16_t)pos;
+        t.first[kWarps] = (int16_t)m;
+        t.wbase[kWarps] = (int16_t)packed.size();
+        if (!fits || m != n_mels || packed.size() > 32000) {
+            set_error("adtfe_mel_create: filterbank does not fit the mel-phase tiles (%zu stored weights, %d of %d "
+                      "filters placed)", packed.size(), m, n_mels);
+            adtfe_mel_destroy(mel);
+            return ADTFE_ERR_UNSUPPORTED;
+        }
     }
     auto fail = [&](int status) { adtfe_mel_destroy(mel); return status; };
 #define MEL_UPLOAD(dst, src, bytes)                                                                  \
@@ -363,6 +453,7 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
     MEL_UPLOAD(mel->window, window_host, (size_t)n_fft * 4);
     MEL_UPLOAD(mel->twiddle, tw.data(), tw.size() * sizeof(float2));
     MEL_UPLOAD(mel->lane_tw, ltw.data(), ltw.size() * sizeof(float2));
+    MEL_UPLOAD(mel->sched_w, packed.data(), packed.size() * 4);
 #undef MEL_UPLOAD
     if (cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel->smem_bytes) !=
         cudaSuccess) {
