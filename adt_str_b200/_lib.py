@@ -15,6 +15,7 @@ EXPORTS = [
     "adtfe_render_workspace_bytes", "adtfe_render",
     "adtfe_mel_create", "adtfe_mel_destroy", "adtfe_mel_frames", "adtfe_logmel",
     "adtfe_render_logmel", "adtfe_frontend_host", "adtfe_plan_blob_layout",
+    "adtfe_planner_create", "adtfe_planner_destroy", "adtfe_planner_plan", "adtfe_planner_export",
 ]
 
 
@@ -55,6 +56,11 @@ def _declare(lib) -> None:
     lib.adtfe_render_logmel.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, vp, vp, sz, vp]
     lib.adtfe_frontend_host.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp]
     lib.adtfe_plan_blob_layout.argtypes = [C.POINTER(Plan), C.POINTER(sz * 7), C.POINTER(sz)]
+    lib.adtfe_planner_create.argtypes = [i32, C.c_double, C.c_double, C.c_double, i32, vp, i32, vp, vp, vp, vp, vp, vp,
+                                         C.POINTER(vp)]
+    lib.adtfe_planner_destroy.argtypes = [vp]
+    lib.adtfe_planner_plan.argtypes = [vp, vp, vp, i32, vp, i64, vp, vp]
+    lib.adtfe_planner_export.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
 
 
 def load():

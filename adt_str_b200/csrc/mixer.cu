@@ -25,6 +25,8 @@ namespace adtfe {
 constexpr int kPeakThreads = 256;
 constexpr int kPeakChunk = 8;   // notes of one instrument handled per sweep over the one-shots
 constexpr int kPeakSpan = ADTFE_PEAK_SPAN;  // samples of the mixed one-shot per peak work item
+constexpr int kPeakIters = kPeakSpan / 4 / kPeakThreads;  // float4 per thread per one-shot
+static_assert(kPeakIters * kPeakThreads * 4 == kPeakSpan, "peak span must be a multiple of 4 * threads");
 constexpr int kMixThreads = 256;
 constexpr int kPerThread = ADTFE_TILE / kMixThreads;  // 8 samples, stride kMixThreads
 constexpr int kStage = 64;      // resolved events staged in shared memory per round
@@ -39,8 +41,35 @@ __device__ __forceinline__ float nan_max(float a, float b) {  // torch.max propa
     return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b);
 }
 
+// max|ca*a + cb*b| over the float4s held in registers, for NC notes at once
+template <int NC>
+__device__ __forceinline__ void peak_chunk(const float4 (&va)[kPeakIters], const float4 (&vb)[kPeakIters],
+                                           const float* __restrict__ s_ca, const float* __restrict__ s_cb,
+                                           float (*s_red)[kPeakThreads / 32], int tid) {
+    float ca[NC], cb[NC], m[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) { ca[i] = s_ca[i]; cb[i] = s_cb[i]; m[i] = 0.0f; }
+#pragma unroll
+    for (int it = 0; it < kPeakIters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+            // separate roundings, as torch's mul, mul, add (synthetiser.py:223)
+            m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va[it].x, ca[i]), __fmul_rn(cb[i], vb[it].x))));
+            m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va[it].y, ca[i]), __fmul_rn(cb[i], vb[it].y))));
+            m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va[it].z, ca[i]), __fmul_rn(cb[i], vb[it].z))));
+            m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va[it].w, ca[i]), __fmul_rn(cb[i], vb[it].w))));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        const float w = warp_max(m[i]);
+        if ((tid & 31) == 0) s_red[i][tid >> 5] = w;
+    }
+}
+
 // One CTA per (group, chunk) work item: a group is the notes of one instrument in one segment
-// (same two one-shots, one mixup each); a chunk is kPeakSpan samples of the mixed one-shot.
+// (same two one-shots, one mixup each); a chunk is kPeakSpan samples of the mixed one-shot, read
+// once into registers (all loads in flight together) and reused for every note of the group.
 // Peaks are combined with atomicMax on the float bits (non-negative floats order like ints,
 // and max is order-independent, so the result is deterministic).
 __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
@@ -64,6 +93,14 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
     const float4* a4 = reinterpret_cast<const float4*>(pcm + a_off);
     const float4* b4 = reinterpret_cast<const float4*>(pcm + b_off);
 
+    float4 va[kPeakIters], vb[kPeakIters];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int it = 0; it < kPeakIters; ++it) {
+        const int i4 = lo4 + tid + it * kPeakThreads;
+        va[it] = (i4 < hi4 && i4 < la4) ? __ldg(a4 + i4) : z;
+        vb[it] = (i4 < hi4 && i4 < lb4) ? __ldg(b4 + i4) : z;
+    }
     if (chunk == 0) {  // resolve the bank lookups once per note for the tile mixer
         for (int e = e0 + tid; e < e1; e += kPeakThreads) {
             const adtfe_event ev = events[e];
@@ -72,6 +109,20 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
             r.la = min(la, ev.len); r.lb = min(lb, ev.len);
             r.start = ev.start; r.len = ev.len; r.ca = ev.ca; r.cb = ev.cb; r.gain = ev.gain; r.pad = 0;
             resolved[e] = r;
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < kPeakIters; ++it) {  // last float4 of a one-shot: ignore whatever pads it
+        const int i4 = lo4 + tid + it * kPeakThreads;
+        if (4 * i4 + 3 >= la) {
+            if (4 * i4 + 1 >= la) va[it].y = 0.f;
+            if (4 * i4 + 2 >= la) va[it].z = 0.f;
+            va[it].w = 0.f;
+        }
+        if (4 * i4 + 3 >= lb) {
+            if (4 * i4 + 1 >= lb) vb[it].y = 0.f;
+            if (4 * i4 + 2 >= lb) vb[it].z = 0.f;
+            vb[it].w = 0.f;
         }
     }
     for (int c0 = e0; c0 < e1; c0 += kPeakChunk) {
@@ -83,37 +134,10 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
             s_cb[tid] = live ? events[c0 + tid].cb : 0.0f;
         }
         __syncthreads();
-        float ca[kPeakChunk], cb[kPeakChunk], m[kPeakChunk];
-#pragma unroll
-        for (int i = 0; i < kPeakChunk; ++i) { ca[i] = s_ca[i]; cb[i] = s_cb[i]; m[i] = 0.0f; }
-        for (int i4 = lo4 + tid; i4 < hi4; i4 += kPeakThreads) {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 va = i4 < la4 ? __ldg(a4 + i4) : z;
-            float4 vb = i4 < lb4 ? __ldg(b4 + i4) : z;
-            if (4 * i4 + 3 >= la) {  // last float4 of the one-shot: ignore whatever pads it
-                if (4 * i4 + 1 >= la) va.y = 0.f;
-                if (4 * i4 + 2 >= la) va.z = 0.f;
-                va.w = 0.f;
-            }
-            if (4 * i4 + 3 >= lb) {
-                if (4 * i4 + 1 >= lb) vb.y = 0.f;
-                if (4 * i4 + 2 >= lb) vb.z = 0.f;
-                vb.w = 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < kPeakChunk; ++i) {
-                // separate roundings, as torch's mul, mul, add (synthetiser.py:223)
-                m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va.x, ca[i]), __fmul_rn(cb[i], vb.x))));
-                m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va.y, ca[i]), __fmul_rn(cb[i], vb.y))));
-                m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va.z, ca[i]), __fmul_rn(cb[i], vb.z))));
-                m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va.w, ca[i]), __fmul_rn(cb[i], vb.w))));
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < kPeakChunk; ++i) {
-            const float w = warp_max(m[i]);
-            if ((tid & 31) == 0) s_red[i][tid >> 5] = w;
-        }
+        if (nc <= 1) peak_chunk<1>(va, vb, s_ca, s_cb, s_red, tid);
+        else if (nc <= 2) peak_chunk<2>(va, vb, s_ca, s_cb, s_red, tid);
+        else if (nc <= 4) peak_chunk<4>(va, vb, s_ca, s_cb, s_red, tid);
+        else peak_chunk<8>(va, vb, s_ca, s_cb, s_red, tid);
         __syncthreads();
         if (tid < nc) {
             float peak = 0.0f;
@@ -164,17 +188,26 @@ __global__ void __launch_bounds__(kMixThreads) mix_kernel(
             s_sub[2 * tid + 1] = b;
         }
         __syncthreads();
-        for (int k = 0; k < 2 * nst; ++k) {
-            const SubEvent ev = s_sub[k];
-            const int r0 = lo + tid - ev.start;
-            const float* src = ev.src + r0;
-            float v[kPerThread];
+        // the two sources of one note are processed together: 16 loads in flight per thread
+        for (int k = 0; k < 2 * nst; k += 2) {
+            const SubEvent ea = s_sub[k], eb = s_sub[k + 1];
+            const int r0 = lo + tid - ea.start;  // same start for both
+            const float* sa = ea.src + r0;
+            const float* sb = eb.src + r0;
+            float va[kPerThread], vb[kPerThread];
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j)
-                v[j] = (unsigned)(r0 + j * kMixThreads) < (unsigned)ev.len ? __ldg(src + j * kMixThreads) : 0.0f;
+            for (int j = 0; j < kPerThread; ++j) {
+                const unsigned r = (unsigned)(r0 + j * kMixThreads);
+                va[j] = r < (unsigned)ea.len ? __ldg(sa + j * kMixThreads) : 0.0f;
+                vb[j] = r < (unsigned)eb.len ? __ldg(sb + j * kMixThreads) : 0.0f;
+            }
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j)
-                if ((unsigned)(r0 + j * kMixThreads) < (unsigned)ev.len) acc[j] = fmaf(v[j], ev.coef, acc[j]);
+            for (int j = 0; j < kPerThread; ++j) {
+                const unsigned r = (unsigned)(r0 + j * kMixThreads);
+                // samples outside the note stay untouched even when coef is inf / NaN
+                if (r < (unsigned)ea.len) acc[j] = fmaf(va[j], ea.coef, acc[j]);
+                if (r < (unsigned)eb.len) acc[j] = fmaf(vb[j], eb.coef, acc[j]);
+            }
         }
     }
     float m = 0.0f;

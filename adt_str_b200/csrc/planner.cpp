@@ -1,0 +1,291 @@
+// Host planner in C++: notes + Python's random stream -> event records, tile buckets, peak work.
+//
+// Same semantics as adt_str_b200/planner.py (which stays the readable restatement and the
+// fallback for float64 note arrays); this one exists because at >1e6 audio-s/s the Python
+// per-note loop is the bottleneck (SURVEY §7 "host planner throughput").
+//
+// The reference draws from Python's `random` module (modules/synthetiser.py:194-199, 217, 154).
+// To stay on the *same stream* the caller hands over `random.getstate()` (624 MT19937 words +
+// index) and gets the advanced state back for `random.setstate()`.  The generator, the 53-bit
+// `random()`, `getrandbits(k)`, `_randbelow` (rejection on k = bit_length(n) bits), `choice` and
+// `uniform` below follow CPython 3.12 (Modules/_randommodule.c, Lib/random.py).
+//
+// Index rules are float32 like `torch.tensor(notes)` arithmetic (synthetiser.py:229, 262, 243).
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/adtfe.h"
+
+namespace adtfe {
+void set_error(const char* fmt, ...);
+}
+
+namespace {
+
+struct MT {
+    uint32_t s[624];
+    int pos;
+    uint32_t next() {
+        if (pos >= 624) {
+            static const uint32_t mag01[2] = {0u, 0x9908b0dfu};
+            int kk;
+            uint32_t y;
+            for (kk = 0; kk < 624 - 397; kk++) {
+                y = (s[kk] & 0x80000000u) | (s[kk + 1] & 0x7fffffffu);
+                s[kk] = s[kk + 397] ^ (y >> 1) ^ mag01[y & 1u];
+            }
+            for (; kk < 623; kk++) {
+                y = (s[kk] & 0x80000000u) | (s[kk + 1] & 0x7fffffffu);
+                s[kk] = s[kk + (397 - 624)] ^ (y >> 1) ^ mag01[y & 1u];
+            }
+            y = (s[623] & 0x80000000u) | (s[0] & 0x7fffffffu);
+            s[623] = s[396] ^ (y >> 1) ^ mag01[y & 1u];
+            pos = 0;
+        }
+        uint32_t y = s[pos++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+    double random() {  // genrand_res53
+        const uint32_t a = next() >> 5, b = next() >> 6;
+        return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+    }
+    uint32_t below(uint32_t n) {  // Random._randbelow_with_getrandbits, n >= 1
+        int k = 0;
+        for (uint32_t t = n; t; t >>= 1) ++k;  // n.bit_length()
+        uint32_t r = next() >> (32 - k);
+        while (r >= n) r = next() >> (32 - k);
+        return r;
+    }
+};
+
+struct GroupRange {
+    int32_t first, count;
+};
+
+}  // namespace
+
+struct adtfe_planner {
+    int32_t sample_rate = 24000;
+    double input_sec = 2.56, mixup_range = 0.8, use_fx_prob = 0.0;
+    int adtof = 0;
+    std::vector<int32_t> lengths;                 // one-shot lengths
+    std::vector<GroupRange> groups[27];           // pitch 35..61 -> admitted (first id, count), best group first
+    float gain[27];                               // per-pitch mixing gain, < 0 = KeyError in the reference
+    std::vector<int32_t> inverse[27];             // ADTOF class -> member pitches (empty = KeyError)
+    // last plan
+    std::vector<adtfe_event> events;
+    std::vector<int32_t> mix_len, group_ptr, tile_ptr, tile_events, peak_work;
+    std::vector<adtfe_segment> segments;
+    int64_t ld_wav = 0;
+    int32_t tiles_per_seg = 0;
+};
+
+extern "C" int adtfe_planner_create(int32_t sample_rate, double input_sec, double mixup_range, double use_fx_prob,
+                                    int32_t adtof_mapping, const int32_t* lengths, int32_t n_oneshots,
+                                    const int32_t* group_ptr /*28*/, const int32_t* group_first,
+                                    const int32_t* group_count, const float* gain /*27*/,
+                                    const int32_t* inverse_ptr /*28*/, const int32_t* inverse_pitch,
+                                    adtfe_planner** out) {
+    if (!out || !lengths || !group_ptr || !gain || !inverse_ptr || n_oneshots < 0) {
+        adtfe::set_error("adtfe_planner_create: bad argument");
+        return ADTFE_ERR_BAD_ARG;
+    }
+    adtfe_planner* p = new adtfe_planner();
+    p->sample_rate = sample_rate; p->input_sec = input_sec; p->mixup_range = mixup_range;
+    p->use_fx_prob = use_fx_prob; p->adtof = adtof_mapping;
+    p->lengths.assign(lengths, lengths + n_oneshots);
+    for (int i = 0; i < 27; ++i) {
+        for (int j = group_ptr[i]; j < group_ptr[i + 1]; ++j) p->groups[i].push_back({group_first[j], group_count[j]});
+        p->gain[i] = gain[i];
+        for (int j = inverse_ptr[i]; j < inverse_ptr[i + 1]; ++j) p->inverse[i].push_back(inverse_pitch[j]);
+    }
+    *out = p;
+    return ADTFE_OK;
+}
+
+extern "C" int adtfe_planner_destroy(adtfe_planner* p) {
+    delete p;
+    return ADTFE_OK;
+}
+
+static float vel_to_vol(float v) {  // synthetiser.py:204-212, float32 throughout
+    if (v == 0.0f) return 0.0f;
+    const float c = v < 0.0f ? 0.0f : (v > 127.0f ? 127.0f : v);
+    const float x = c / 127.0f;
+    const float pw = powf(6.0f, x);
+    const float t = 0.9f * (pw - 1.0f);
+    return 0.1f + t / 5.0f;
+}
+
+// status: 0 ok; 1 ValueError (invalid note); 2 IndexError (no admitted group); 3 KeyError; 4 FX hit;
+// info[0] = segment, info[1] = note index of the failure.
+extern "C" int adtfe_planner_plan(adtfe_planner* P, const float* notes, const int32_t* counts, int32_t n_seg,
+                                  uint32_t* mt_state /*625, updated*/, int64_t ld_wav_in, int64_t* out_counts /*8*/,
+                                  int32_t* info /*2*/) {
+    if (!P || !counts || !mt_state || !out_counts || !info || n_seg < 0) {
+        adtfe::set_error("adtfe_planner_plan: bad argument");
+        return ADTFE_ERR_BAD_ARG;
+    }
+    MT rng;
+    memcpy(rng.s, mt_state, 624 * 4);
+    rng.pos = (int)mt_state[624];
+    const float sr_f = (float)P->sample_rate;
+    P->events.clear(); P->mix_len.clear(); P->segments.clear();
+    P->group_ptr.assign(1, 0);
+    int status = 0;
+    info[0] = info[1] = -1;
+
+    std::vector<adtfe_event> ev;
+    std::vector<int32_t> ml, rank_of;
+    std::vector<int> order;
+    const float* row = notes;
+    int64_t max_len = 0;
+    for (int32_t s = 0; s < n_seg && status == 0; ++s) {
+        const int32_t n = counts[s];
+        adtfe_segment seg;
+        seg.first_event = (int32_t)P->events.size();
+        if (n == 0) {  // synthetiser.py:257-258
+            seg.len = (int32_t)(P->input_sec * P->sample_rate);
+            seg.flags = 0; seg.max_volume = 0.0f;
+            P->segments.push_back(seg);
+            max_len = std::max<int64_t>(max_len, seg.len);
+            continue;
+        }
+        float max_off = row[1], max_vel = 0.0f;
+        for (int32_t i = 0; i < n; ++i) {
+            max_off = std::max(max_off, row[4 * i + 1]);
+            max_vel = std::max(max_vel, row[4 * i + 3]);
+        }
+        const float end = max_off + 0.1f;  // synthetiser.py:262
+        const int32_t wave_length = end < (float)P->input_sec ? (int32_t)(P->input_sec * P->sample_rate)
+                                                               : (int32_t)(end * sr_f);
+        int32_t main_of[27], sub_of[27], rank[27], n_rank = 0;
+        for (int i = 0; i < 27; ++i) rank[i] = -1;
+        ev.assign(n, adtfe_event());
+        ml.assign(n, 0);
+        rank_of.assign(n, 0);
+        for (int32_t i = 0; i < n && status == 0; ++i) {
+            const float on = row[4 * i], off = row[4 * i + 1], pitch = row[4 * i + 2], vel = row[4 * i + 3];
+            if (!(pitch >= 35.0f && pitch <= 61.0f && off >= on) || on < 0.0f) { status = 1; info[0] = s; info[1] = i; break; }
+            const int inst = (int)pitch;
+            if ((float)inst != pitch) { status = 3; info[0] = s; info[1] = i; break; }
+            const int pi = inst - 35;
+            if (rank[pi] < 0) {
+                int32_t chosen[2];
+                for (int c = 0; c < 2 && status == 0; ++c) {  // synthetiser.py:192-202, main then sub
+                    int gp = pi;
+                    if (P->adtof) {
+                        if (P->inverse[pi].empty()) { status = 3; break; }
+                        gp = P->inverse[pi][rng.below((uint32_t)P->inverse[pi].size())] - 35;
+                    }
+                    const std::vector<GroupRange>& g = P->groups[gp];
+                    if (g.empty()) { status = 2; break; }
+                    const GroupRange& r = g[rng.below((uint32_t)g.size())];
+                    chosen[c] = r.first + (int32_t)rng.below((uint32_t)r.count);
+                }
+                if (status) { info[0] = s; info[1] = i; break; }
+                main_of[pi] = chosen[0]; sub_of[pi] = chosen[1];
+                rank[pi] = n_rank++;
+            }
+            const double alpha = 0.0 + (P->mixup_range - 0.0) * rng.random();  // random.uniform(0, mixup_range)
+            adtfe_event& e = ev[i];
+            e.main_id = main_of[pi]; e.sub_id = sub_of[pi];
+            e.ca = (float)(1.0 - alpha); e.cb = (float)alpha;
+            e.start = (int32_t)(on * sr_f);
+            const int32_t mix = std::max(P->lengths[e.main_id], P->lengths[e.sub_id]);
+            e.len = std::max(0, std::min(mix, wave_length - e.start));
+            e.gain = vel_to_vol(vel);
+            e.seg = s;
+            ml[i] = mix;
+            rank_of[i] = rank[pi];
+        }
+        if (status) break;
+        for (int pi = 0; pi < 27; ++pi)  // gain lookup happens in instrument_mixer, after the loop
+            if (rank[pi] >= 0 && P->gain[pi] < 0.0f) { status = 3; info[0] = s; info[1] = -1; }
+        if (status) break;
+        if (rng.random() < P->use_fx_prob) { status = 4; info[0] = s; break; }  // synthetiser.py:154
+        for (int32_t i = 0; i < n; ++i) ev[i].gain *= P->gain[(int)row[4 * i + 2] - 35];
+        // track order: instrument by first appearance, then note order
+        order.resize(n);
+        for (int i = 0; i < n; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rank_of[a] < rank_of[b]; });
+        for (int k = 0; k < n; ++k) {
+            const int i = order[k];
+            if (k > 0 && rank_of[i] != rank_of[order[k - 1]]) P->group_ptr.push_back((int32_t)P->events.size());
+            P->events.push_back(ev[i]);
+            P->mix_len.push_back(ml[i]);
+        }
+        P->group_ptr.push_back((int32_t)P->events.size());
+        seg.len = wave_length; seg.flags = 1; seg.max_volume = vel_to_vol(std::max(0.0f, max_vel));
+        P->segments.push_back(seg);
+        max_len = std::max<int64_t>(max_len, wave_length);
+        row += 4 * (int64_t)n;
+    }
+    memcpy(mt_state, rng.s, 624 * 4);
+    mt_state[624] = (uint32_t)rng.pos;
+    if (status) return status;
+
+    // ---- geometry, tile CSR, peak work list
+    int64_t ld = ld_wav_in > 0 ? ld_wav_in : ((max_len + 3) / 4) * 4;
+    if (ld < max_len || ld % 4) {
+        adtfe::set_error("adtfe_planner_plan: ld_wav must be a multiple of 4 and cover the longest segment");
+        return ADTFE_ERR_BAD_ARG;
+    }
+    P->ld_wav = ld;
+    P->tiles_per_seg = (int32_t)((ld + ADTFE_TILE - 1) / ADTFE_TILE);
+    const int64_t n_tiles = (int64_t)n_seg * P->tiles_per_seg;
+    P->tile_ptr.assign(n_tiles + 1, 0);
+    for (const adtfe_event& e : P->events)
+        if (e.len > 0)
+            for (int t = e.start / ADTFE_TILE; t <= (e.start + e.len - 1) / ADTFE_TILE; ++t)
+                ++P->tile_ptr[(int64_t)e.seg * P->tiles_per_seg + t + 1];
+    for (int64_t t = 0; t < n_tiles; ++t) P->tile_ptr[t + 1] += P->tile_ptr[t];
+    P->tile_events.assign(P->tile_ptr[n_tiles], 0);
+    {
+        std::vector<int32_t> cursor(P->tile_ptr.begin(), P->tile_ptr.end() - 1);
+        for (int32_t i = 0; i < (int32_t)P->events.size(); ++i) {
+            const adtfe_event& e = P->events[i];
+            if (e.len > 0)
+                for (int t = e.start / ADTFE_TILE; t <= (e.start + e.len - 1) / ADTFE_TILE; ++t)
+                    P->tile_events[cursor[(int64_t)e.seg * P->tiles_per_seg + t]++] = i;  // ascending event id
+        }
+    }
+    P->peak_work.clear();
+    for (int32_t g = 0; g + 1 < (int32_t)P->group_ptr.size(); ++g) {
+        const int32_t mix = P->mix_len[P->group_ptr[g]];
+        const int32_t chunks = std::max(1, (mix + ADTFE_PEAK_SPAN - 1) / ADTFE_PEAK_SPAN);
+        for (int32_t c = 0; c < chunks; ++c) { P->peak_work.push_back(g); P->peak_work.push_back(c); }
+    }
+    out_counts[0] = (int64_t)P->events.size();
+    out_counts[1] = (int64_t)P->group_ptr.size() - 1;
+    out_counts[2] = n_seg;
+    out_counts[3] = P->tiles_per_seg;
+    out_counts[4] = (int64_t)P->peak_work.size() / 2;
+    out_counts[5] = (int64_t)P->tile_events.size();
+    out_counts[6] = ld;
+    out_counts[7] = max_len;
+    return ADTFE_OK;
+}
+
+// Copies the last plan into caller arrays (any may be NULL to skip).
+extern "C" int adtfe_planner_export(const adtfe_planner* P, adtfe_event* events, int32_t* mix_len, int32_t* group_ptr,
+                                    adtfe_segment* segments, int32_t* tile_ptr, int32_t* peak_work,
+                                    int32_t* tile_events) {
+    if (!P) return ADTFE_ERR_BAD_ARG;
+    if (events && !P->events.empty()) memcpy(events, P->events.data(), P->events.size() * sizeof(adtfe_event));
+    if (mix_len && !P->mix_len.empty()) memcpy(mix_len, P->mix_len.data(), P->mix_len.size() * 4);
+    if (group_ptr) memcpy(group_ptr, P->group_ptr.data(), P->group_ptr.size() * 4);
+    if (segments && !P->segments.empty()) memcpy(segments, P->segments.data(), P->segments.size() * sizeof(adtfe_segment));
+    if (tile_ptr) memcpy(tile_ptr, P->tile_ptr.data(), P->tile_ptr.size() * 4);
+    if (peak_work && !P->peak_work.empty()) memcpy(peak_work, P->peak_work.data(), P->peak_work.size() * 4);
+    if (tile_events && !P->tile_events.empty()) memcpy(tile_events, P->tile_events.data(), P->tile_events.size() * 4);
+    return ADTFE_OK;
+}

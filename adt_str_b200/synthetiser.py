@@ -101,6 +101,7 @@ class SynthDrum:
         self._device = torch.device(device) if device is not None else None
         self._device_bank: Optional[DeviceBank] = None
         self._buffers: Optional[PlanBuffers] = None
+        self._native_planner = None
 
     # ------------------------------------------------------------------ bank
     @property
@@ -136,8 +137,15 @@ class SynthDrum:
         return self._buffers
 
     # ------------------------------------------------------------------ plan
-    def plan(self, batch_notes: Sequence, rng=_random, ld_wav: Optional[int] = None) -> RenderPlan:
-        return plan_batch(batch_notes, self.config, self.bank, rng, ld_wav)
+    def plan(self, batch_notes: Sequence, rng=_random, ld_wav: Optional[int] = None, native: bool = True) -> RenderPlan:
+        """Plan a batch on the host.  ``native`` uses the C++ planner (same RNG stream, same
+        indices); it falls back to ``planner.plan_batch`` by itself for float64 note arrays."""
+        if not native:
+            return plan_batch(batch_notes, self.config, self.bank, rng, ld_wav)
+        if self._native_planner is None:
+            from .native_planner import NativePlanner
+            self._native_planner = NativePlanner(self.config, self.bank)
+        return self._native_planner.plan_batch(batch_notes, rng, ld_wav)
 
     # ---------------------------------------------------------------- render
     def render_plan(self, plan: RenderPlan, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -145,6 +145,29 @@ int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel, const adtf
  * tile_events starts - it runs to the end of the blob). */
 int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[7], size_t* blob_bytes);
 
+/* ---- host planner (no GPU work) ------------------------------------------------------ */
+/* C++ restatement of the per-note bookkeeping of SynthDrum.__call__ (modules/synthetiser.py:255-292:
+ * RNG draws in the reference's order from Python's MT19937 stream, float32 index rules, velocity
+ * curve, track order) plus the tile bucketing - what adt_str_b200/planner.py does in Python.
+ * group_ptr[28]: for pitch 35+i the admitted similarity groups are entries group_ptr[i]..group_ptr[i+1]
+ * of (group_first, group_count) = contiguous one-shot id ranges, best group first; gain[27] = mixing gain
+ * per pitch (< 0: the reference raises KeyError); inverse_ptr/inverse_pitch: ADTOF class -> member pitches. */
+typedef struct adtfe_planner adtfe_planner;
+int adtfe_planner_create(int32_t sample_rate, double input_sec, double mixup_range, double use_fx_prob,
+                         int32_t adtof_mapping, const int32_t* lengths, int32_t n_oneshots, const int32_t* group_ptr,
+                         const int32_t* group_first, const int32_t* group_count, const float* gain,
+                         const int32_t* inverse_ptr, const int32_t* inverse_pitch, adtfe_planner** out);
+int adtfe_planner_destroy(adtfe_planner* planner);
+/* notes: float32 rows [onset, offset, pitch, velocity] of all segments back to back, counts[n_seg] rows
+ * each.  mt_state[625]: random.getstate()[1], advanced in place.  ld_wav_in: 0 = derive.  Returns 0, a
+ * negative adtfe_status, or 1 invalid note (ValueError) / 2 no admitted group (IndexError) / 3 KeyError /
+ * 4 FX coin hit (NotImplementedError) with info = {segment, note}.
+ * out_counts = {n_events, n_groups, n_seg, tiles_per_seg, n_peak_work, n_tile_events, ld_wav, max_len}. */
+int adtfe_planner_plan(adtfe_planner* planner, const float* notes, const int32_t* counts, int32_t n_seg,
+                       uint32_t* mt_state, int64_t ld_wav_in, int64_t* out_counts, int32_t* info);
+int adtfe_planner_export(const adtfe_planner* planner, adtfe_event* events, int32_t* mix_len, int32_t* group_ptr,
+                         adtfe_segment* segments, int32_t* tile_ptr, int32_t* peak_work, int32_t* tile_events);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,3 +174,65 @@ def test_long_form_plan_is_one_segment():
     notes = make_long_form(30.0)
     plan = planner.plan_batch([notes], setting_1(), bank)
     assert plan.n_seg == 1 and plan.wave_lengths[0] >= 29 * 24000 and plan.tiles_per_seg == -(-plan.ld_wav // 2048)
+
+
+# ------------------------------------------------------------------ C++ planner (csrc/planner.cpp)
+def _plans_equal(a, b):
+    for f in ("start", "len", "main_id", "sub_id", "ca", "cb", "seg"):
+        assert np.array_equal(a.events[f], b.events[f]), f
+    assert np.allclose(a.events["gain"], b.events["gain"], rtol=3e-7, atol=0)        # powf vs numpy: 1 ulp
+    for f in ("mix_len", "group_ptr", "tile_ptr", "tile_events", "peak_work", "wave_lengths"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    for f in ("len", "flags", "first_event"):
+        assert np.array_equal(a.segments[f], b.segments[f]), f
+    assert np.allclose(a.segments["max_volume"], b.segments["max_volume"], rtol=3e-7)
+    assert (a.n_seg, a.ld_wav, a.tiles_per_seg) == (b.n_seg, b.ld_wav, b.tiles_per_seg)
+
+
+def test_native_planner_equals_python_planner_and_rng_stream(golden):
+    from adt_str_b200.native_planner import NativePlanner
+    cfg = golden.config()
+    random.seed(golden.py_seed)
+    want = planner.plan_batch(golden.segments, cfg, golden.bank)
+    state = random.getstate()
+    random.seed(golden.py_seed)
+    got = NativePlanner(cfg, golden.bank).plan_batch(golden.segments)
+    assert random.getstate() == state                      # same MT19937 stream, draw for draw
+    _plans_equal(got, want)
+    assert got.wave_lengths.tolist() == golden.ref_len.tolist()
+
+
+def test_native_planner_large_batch_and_private_rng():
+    from adt_str_b200.native_planner import NativePlanner
+    bank = make_bank(624, max_len=30000)
+    segs = make_segments(300, seed=8) + [make_dense_segment(), make_long_form(20.0)]
+    cfg = setting_1(similarity_threshold=0.4)
+    r1, r2 = random.Random(5), random.Random(5)
+    want = planner.plan_batch(segs, cfg, bank, rng=r1)
+    got = NativePlanner(cfg, bank).plan_batch(segs, rng=r2)
+    assert r1.getstate() == r2.getstate()
+    _plans_equal(got, want)
+
+
+def test_native_planner_errors_and_fallback():
+    from adt_str_b200.native_planner import NativePlanner
+    bank = make_bank(78, min_len=100, max_len=1000)
+    npl = NativePlanner(setting_1(), bank)
+    ok = np.array([[0.1, 0.2, 36, 100]], np.float32)
+    with pytest.raises(ValueError, match="Invalid note"):
+        npl.plan_batch([ok, np.array([[0.1, 0.2, 62, 100]], np.float32)])
+    with pytest.raises(ValueError, match="Invalid note"):
+        npl.plan_batch([np.array([[0.3, 0.2, 36, 100]], np.float32)])
+    with pytest.raises(IndexError):
+        npl.plan_batch([np.array([[0.1, 0.2, 61, 100]], np.float32)])
+    with pytest.raises(KeyError):
+        NativePlanner(setting_1(ADTOF_mapping=True), bank).plan_batch([ok])
+    with pytest.raises(NotImplementedError):
+        NativePlanner(setting_1(use_fx_prob=1.0), bank).plan_batch([ok])
+    # float64 notes take the Python path (float64 index arithmetic, like torch.tensor(float64 array))
+    random.seed(1)
+    p64 = npl.plan_batch([np.array([[0.5, 2.5, 36.0, 100.0]], np.float64)])
+    random.seed(1)
+    p32 = npl.plan_batch([[[0.5, 2.5, 36.0, 100.0]]])
+    assert (int(p64.wave_lengths[0]), int(p32.wave_lengths[0])) == (62400, 62399)
+    assert npl.plan_batch([]).n_seg == 0
