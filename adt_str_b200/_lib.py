@@ -25,12 +25,10 @@ class AdtfeError(RuntimeError):
 
 class Plan(C.Structure):
     """adtfe_plan"""
-    _fields_ = [("events_dev", C.c_void_p), ("mix_len_dev", C.c_void_p), ("group_ptr_dev", C.c_void_p),
-                ("segments_dev", C.c_void_p), ("tile_ptr_dev", C.c_void_p), ("tile_events_dev", C.c_void_p),
-                ("peak_work_dev", C.c_void_p),
-                ("n_events", C.c_int32), ("n_groups", C.c_int32), ("n_seg", C.c_int32),
-                ("tiles_per_seg", C.c_int32), ("n_peak_work", C.c_int32), ("reserved", C.c_int32),
-                ("ld_wav", C.c_int64)]
+    _fields_ = [("events_dev", C.c_void_p), ("segments_dev", C.c_void_p), ("tile_ptr_dev", C.c_void_p),
+                ("tile_events_dev", C.c_void_p), ("peak_work_dev", C.c_void_p),
+                ("n_events", C.c_int32), ("n_seg", C.c_int32), ("tiles_per_seg", C.c_int32),
+                ("n_peak_work", C.c_int32), ("ld_wav", C.c_int64)]
 
 
 _lock = threading.Lock()
@@ -55,9 +53,9 @@ def _declare(lib) -> None:
     lib.adtfe_logmel.argtypes = [vp, vp, i32, i64, i64, vp, vp]
     lib.adtfe_render_logmel.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, vp, vp, sz, vp]
     lib.adtfe_frontend_host.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp]
-    lib.adtfe_plan_blob_layout.argtypes = [C.POINTER(Plan), C.POINTER(sz * 7), C.POINTER(sz)]
-    lib.adtfe_planner_create.argtypes = [i32, C.c_double, C.c_double, C.c_double, i32, vp, i32, vp, vp, vp, vp, vp, vp,
-                                         C.POINTER(vp)]
+    lib.adtfe_plan_blob_layout.argtypes = [C.POINTER(Plan), C.POINTER(sz * 5), C.POINTER(sz)]
+    lib.adtfe_planner_create.argtypes = [i32, C.c_double, C.c_double, C.c_double, i32, vp, vp, i32, vp, vp, vp, vp, vp,
+                                         vp, C.POINTER(vp)]
     lib.adtfe_planner_destroy.argtypes = [vp]
     lib.adtfe_planner_plan.argtypes = [vp, vp, vp, i32, vp, i64, vp, vp]
     lib.adtfe_planner_export.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]

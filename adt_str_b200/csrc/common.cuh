@@ -41,6 +41,7 @@ struct ResolvedEvent {
 static_assert(sizeof(ResolvedEvent) == 48, "ResolvedEvent layout");
 static_assert(sizeof(adtfe_event) == 32, "adtfe_event layout");
 static_assert(sizeof(adtfe_segment) == 16, "adtfe_segment layout");
+static_assert(sizeof(adtfe_peak_item) == 40, "adtfe_peak_item layout");
 
 int device_sm_count(int device);
 

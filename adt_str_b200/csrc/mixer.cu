@@ -6,7 +6,7 @@
 //   instrument_mixer 149-156: wav = sum_i track_i * gain_i ; wav / max|wav| * max_volume
 // and the zero padding of collate_fn (data_modules/train_dataset.py:53).
 //
-// The two data-dependent maxima make it three short kernels:
+// The two data-dependent maxima make it two short kernels:
 //   1. peak_kernel      one CTA per (segment, instrument, 4096-sample chunk): both one-shots are
 //                       read once and max|ca*a + cb*b| is taken for every note of that
 //                       instrument at the same time (each note has its own mixup); chunks meet
@@ -16,8 +16,9 @@
 //                       CSR (tile -> events) and are added in array order into registers,
 //                       so the result is deterministic and needs no atomics; emits the
 //                       tile's |max|.
-//   3. normalise_kernel per-segment max of the tile maxima, then wav / peak * max_volume
-//                       in place (an all-zero mix gives NaN, like the reference's 0/0).
+//                       The last CTA of a segment to finish (atomic ticket) takes the max of the
+//                       tile maxima and normalises the row in place, wav / peak * max_volume
+//                       (an all-zero mix gives NaN, like the reference's 0/0).
 #include "common.cuh"
 
 namespace adtfe {
@@ -73,20 +74,16 @@ __device__ __forceinline__ void peak_chunk(const float4 (&va)[kPeakIters], const
 // Peaks are combined with atomicMax on the float bits (non-negative floats order like ints,
 // and max is order-independent, so the result is deterministic).
 __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
-    const float* __restrict__ pcm, const int64_t* __restrict__ offsets, const int32_t* __restrict__ lengths,
-    const adtfe_event* __restrict__ events, const int32_t* __restrict__ mix_len,
-    const int32_t* __restrict__ group_ptr, const int2* __restrict__ work, ResolvedEvent* __restrict__ resolved,
-    int* __restrict__ peak_bits) {
+    const float* __restrict__ pcm, const adtfe_event* __restrict__ events, const adtfe_peak_item* __restrict__ work,
+    ResolvedEvent* __restrict__ resolved, int* __restrict__ peak_bits) {
     __shared__ float s_red[kPeakChunk][kPeakThreads / 32];
     __shared__ float s_ca[kPeakChunk], s_cb[kPeakChunk];
-    const int2 item = work[blockIdx.x];
-    const int g = item.x, chunk = item.y, tid = threadIdx.x;
-    const int e0 = group_ptr[g], e1 = group_ptr[g + 1];
+    const adtfe_peak_item item = work[blockIdx.x];  // one fetch, then the data loads can start
+    const int chunk = item.chunk, tid = threadIdx.x;
+    const int e0 = item.first_event, e1 = e0 + item.n_events;
     if (e0 >= e1) return;
-    const adtfe_event head = events[e0];
-    const int64_t a_off = offsets[head.main_id], b_off = offsets[head.sub_id];
-    const int la = lengths[head.main_id], lb = lengths[head.sub_id];
-    const int n = mix_len[e0];
+    const int64_t a_off = item.a_off, b_off = item.b_off;
+    const int la = item.la, lb = item.lb, n = item.mix_len;
     // every one-shot is padded to 4 floats, so whole float4s up to the padded length are readable
     const int la4 = (la + 3) >> 2, lb4 = (lb + 3) >> 2;
     const int lo4 = chunk * (kPeakSpan / 4), hi4 = min((n + 3) >> 2, lo4 + kPeakSpan / 4);
@@ -158,10 +155,12 @@ struct SubEvent {
 
 __global__ void __launch_bounds__(kMixThreads) mix_kernel(
     const float* __restrict__ pcm, const ResolvedEvent* __restrict__ resolved, const int* __restrict__ peak_bits,
-    const int32_t* __restrict__ tile_ptr, const int32_t* __restrict__ tile_events, int tiles_per_seg,
-    int64_t ld_wav, float* __restrict__ wav, float* __restrict__ tile_max) {
+    const int32_t* __restrict__ tile_ptr, const int32_t* __restrict__ tile_events,
+    const adtfe_segment* __restrict__ segments, int tiles_per_seg, int64_t ld_wav, float* __restrict__ wav,
+    float* __restrict__ tile_max, int* __restrict__ seg_done) {
     __shared__ __align__(16) SubEvent s_sub[2 * kStage];
     __shared__ float s_red[kMixThreads / 32];
+    __shared__ int s_last;
     const int tile_id = blockIdx.x, tid = threadIdx.x;
     const int seg = tile_id / tiles_per_seg, tile = tile_id - seg * tiles_per_seg;
     const int lo = tile * ADTFE_TILE;
@@ -227,33 +226,36 @@ __global__ void __launch_bounds__(kMixThreads) mix_kernel(
         for (int i = 1; i < kMixThreads / 32; ++i) r = nan_max(r, s_red[i]);
         tile_max[tile_id] = r;
     }
-}
-
-__global__ void __launch_bounds__(kMixThreads) normalise_kernel(
-    const adtfe_segment* __restrict__ segments, const float* __restrict__ tile_max, int tiles_per_seg,
-    int64_t ld_wav, float* __restrict__ wav) {
-    __shared__ float s_peak;
-    const int tile_id = blockIdx.x, tid = threadIdx.x;
-    const int seg = tile_id / tiles_per_seg, tile = tile_id - seg * tiles_per_seg;
+    // ---- the last CTA of a segment to get here normalises the whole row (wav / peak * max_volume,
+    // synthetiser.py:142-144,156).  Release: tile + tile_max written, fence, then the ticket;
+    // acquire: ticket, fence, then read through L2 (__ldcg) what the other CTAs wrote.
     const adtfe_segment sg = segments[seg];
-    if (sg.flags == 0) return;  // empty note list: the mixer already wrote zeros
-    if (tid < 32) {
-        float m = 0.0f;
-        for (int t = tid; t < tiles_per_seg; t += 32) m = nan_max(m, tile_max[seg * tiles_per_seg + t]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = nan_max(m, __shfl_xor_sync(0xffffffffu, m, o));
-        if (tid == 0) s_peak = m;
-    }
+    if (sg.flags == 0) return;  // empty note list: the row is already all zeros
+    __threadfence();
     __syncthreads();
-    const float peak = s_peak, vol = sg.max_volume;
-    float* row = wav + (int64_t)seg * ld_wav;
-    const int lo = tile * ADTFE_TILE;
+    if (tid == 0) s_last = atomicAdd(seg_done + seg, 1) == tiles_per_seg - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    float peak = 0.0f;
+    for (int t = tid; t < tiles_per_seg; t += kMixThreads) peak = nan_max(peak, __ldcg(tile_max + seg * tiles_per_seg + t));
 #pragma unroll
-    for (int j = 0; j < kPerThread; ++j) {
-        const int n = lo + tid + j * kMixThreads;
-        // the reference's row ends at len; beyond it collate_fn pads with exact zeros
-        if (n < sg.len) row[n] = __fmul_rn(__fdiv_rn(row[n], peak), vol);
+    for (int o = 16; o > 0; o >>= 1) peak = nan_max(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+    if ((tid & 31) == 0) s_red[tid >> 5] = peak;
+    __syncthreads();
+    peak = s_red[0];
+    for (int i = 1; i < kMixThreads / 32; ++i) peak = nan_max(peak, s_red[i]);
+    const float vol = sg.max_volume;
+    float4* row4 = reinterpret_cast<float4*>(row);  // ld_wav is a multiple of 4 and the base is 16-byte aligned
+    const int n4 = sg.len >> 2;
+    for (int i = tid; i < n4; i += kMixThreads) {
+        float4 v = __ldcg(row4 + i);
+        v.x = __fmul_rn(__fdiv_rn(v.x, peak), vol); v.y = __fmul_rn(__fdiv_rn(v.y, peak), vol);
+        v.z = __fmul_rn(__fdiv_rn(v.z, peak), vol); v.w = __fmul_rn(__fdiv_rn(v.w, peak), vol);
+        row4[i] = v;
     }
+    // the reference's row ends at len; beyond it collate_fn pads with exact zeros
+    for (int i = 4 * n4 + tid; i < sg.len; i += kMixThreads) row[i] = __fmul_rn(__fdiv_rn(__ldcg(row + i), peak), vol);
 }
 
 }  // namespace adtfe
@@ -264,25 +266,24 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg) {
     if (n_events < 0 || n_seg < 0 || tiles_per_seg < 0) return 0;
-    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_events * 4) +
+    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_events * 4 + (size_t)n_seg * 4) +
            align256((size_t)n_seg * tiles_per_seg * 4) + 256;
 }
 
 extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
                             size_t workspace_bytes, void* stream) {
     ADTFE_REQUIRE(bank && plan, ADTFE_ERR_BAD_ARG, "adtfe_render: null bank or plan");
-    ADTFE_REQUIRE(plan->n_seg >= 0 && plan->n_events >= 0 && plan->n_groups >= 0 && plan->tiles_per_seg >= 0,
+    ADTFE_REQUIRE(plan->n_seg >= 0 && plan->n_events >= 0 && plan->n_peak_work >= 0 && plan->tiles_per_seg >= 0,
                   ADTFE_ERR_BAD_ARG, "adtfe_render: negative count");
     if (plan->n_seg == 0 || plan->tiles_per_seg == 0) return ADTFE_OK;
     ADTFE_REQUIRE(plan->ld_wav > 0 && plan->ld_wav % 4 == 0 &&
                       plan->ld_wav <= (int64_t)plan->tiles_per_seg * ADTFE_TILE,
                   ADTFE_ERR_BAD_ARG, "adtfe_render: ld_wav %lld must be a positive multiple of 4 within %d tiles",
                   (long long)plan->ld_wav, plan->tiles_per_seg);
-    ADTFE_REQUIRE(wav_out_dev && plan->segments_dev && plan->tile_ptr_dev, ADTFE_ERR_BAD_ARG,
-                  "adtfe_render: null buffer");
-    ADTFE_REQUIRE(plan->n_events == 0 || (plan->events_dev && plan->mix_len_dev && plan->group_ptr_dev &&
-                                          plan->tile_events_dev && plan->peak_work_dev && bank->pcm &&
-                                          plan->n_peak_work > 0),
+    ADTFE_REQUIRE(wav_out_dev && ((uintptr_t)wav_out_dev & 15) == 0 && plan->segments_dev && plan->tile_ptr_dev,
+                  ADTFE_ERR_BAD_ARG, "adtfe_render: null or misaligned buffer (wav_out must be 16-byte aligned)");
+    ADTFE_REQUIRE(plan->n_events == 0 || (plan->events_dev && plan->tile_events_dev && plan->peak_work_dev &&
+                                          bank->pcm && plan->n_peak_work > 0),
                   ADTFE_ERR_BAD_ARG, "adtfe_render: null event buffers");
     const size_t need = adtfe_render_workspace_bytes(plan->n_events, plan->n_seg, plan->tiles_per_seg);
     ADTFE_REQUIRE(workspace_dev && workspace_bytes >= need, ADTFE_ERR_WORKSPACE,
@@ -291,21 +292,18 @@ extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, floa
     char* ws = (char*)(((uintptr_t)workspace_dev + 255) & ~(uintptr_t)255);
     ResolvedEvent* resolved = (ResolvedEvent*)ws;
     int* peak_bits = (int*)(ws + align256((size_t)plan->n_events * sizeof(ResolvedEvent)));
-    float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4));
+    int* seg_done = peak_bits + plan->n_events;  // zeroed together with the peaks
+    float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4 + (size_t)plan->n_seg * 4));
     const int n_tiles = plan->n_seg * plan->tiles_per_seg;
+    ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, ((size_t)plan->n_events + plan->n_seg) * 4, st));
     if (plan->n_events > 0) {
-        ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, (size_t)plan->n_events * 4, st));
-        peak_kernel<<<plan->n_peak_work, kPeakThreads, 0, st>>>(
-            bank->pcm, bank->offsets, bank->lengths, plan->events_dev, plan->mix_len_dev, plan->group_ptr_dev,
-            reinterpret_cast<const int2*>(plan->peak_work_dev), resolved, peak_bits);
+        peak_kernel<<<plan->n_peak_work, kPeakThreads, 0, st>>>(bank->pcm, plan->events_dev, plan->peak_work_dev,
+                                                               resolved, peak_bits);
         ADTFE_CUDA(cudaGetLastError());
     }
     mix_kernel<<<n_tiles, kMixThreads, 0, st>>>(bank->pcm, resolved, peak_bits, plan->tile_ptr_dev,
-                                               plan->tile_events_dev, plan->tiles_per_seg, plan->ld_wav, wav_out_dev,
-                                               tile_max);
-    ADTFE_CUDA(cudaGetLastError());
-    normalise_kernel<<<n_tiles, kMixThreads, 0, st>>>(plan->segments_dev, tile_max, plan->tiles_per_seg,
-                                                     plan->ld_wav, wav_out_dev);
+                                               plan->tile_events_dev, plan->segments_dev, plan->tiles_per_seg,
+                                               plan->ld_wav, wav_out_dev, tile_max, seg_done);
     ADTFE_CUDA(cudaGetLastError());
     return ADTFE_OK;
 }

@@ -77,24 +77,27 @@ struct adtfe_planner {
     double input_sec = 2.56, mixup_range = 0.8, use_fx_prob = 0.0;
     int adtof = 0;
     std::vector<int32_t> lengths;                 // one-shot lengths
+    std::vector<int64_t> offsets;                 // one-shot starts in the bank (floats)
     std::vector<GroupRange> groups[27];           // pitch 35..61 -> admitted (first id, count), best group first
     float gain[27];                               // per-pitch mixing gain, < 0 = KeyError in the reference
     std::vector<int32_t> inverse[27];             // ADTOF class -> member pitches (empty = KeyError)
     // last plan
     std::vector<adtfe_event> events;
-    std::vector<int32_t> mix_len, group_ptr, tile_ptr, tile_events, peak_work;
+    std::vector<int32_t> mix_len, group_ptr, tile_ptr, tile_events;
+    std::vector<adtfe_peak_item> peak_work;
     std::vector<adtfe_segment> segments;
     int64_t ld_wav = 0;
     int32_t tiles_per_seg = 0;
 };
 
 extern "C" int adtfe_planner_create(int32_t sample_rate, double input_sec, double mixup_range, double use_fx_prob,
-                                    int32_t adtof_mapping, const int32_t* lengths, int32_t n_oneshots,
+                                    int32_t adtof_mapping, const int32_t* lengths, const int64_t* offsets,
+                                    int32_t n_oneshots,
                                     const int32_t* group_ptr /*28*/, const int32_t* group_first,
                                     const int32_t* group_count, const float* gain /*27*/,
                                     const int32_t* inverse_ptr /*28*/, const int32_t* inverse_pitch,
                                     adtfe_planner** out) {
-    if (!out || !lengths || !group_ptr || !gain || !inverse_ptr || n_oneshots < 0) {
+    if (!out || !lengths || !offsets || !group_ptr || !gain || !inverse_ptr || n_oneshots < 0) {
         adtfe::set_error("adtfe_planner_create: bad argument");
         return ADTFE_ERR_BAD_ARG;
     }
@@ -102,6 +105,7 @@ extern "C" int adtfe_planner_create(int32_t sample_rate, double input_sec, doubl
     p->sample_rate = sample_rate; p->input_sec = input_sec; p->mixup_range = mixup_range;
     p->use_fx_prob = use_fx_prob; p->adtof = adtof_mapping;
     p->lengths.assign(lengths, lengths + n_oneshots);
+    p->offsets.assign(offsets, offsets + n_oneshots);
     for (int i = 0; i < 27; ++i) {
         for (int j = group_ptr[i]; j < group_ptr[i + 1]; ++j) p->groups[i].push_back({group_first[j], group_count[j]});
         p->gain[i] = gain[i];
@@ -260,15 +264,21 @@ extern "C" int adtfe_planner_plan(adtfe_planner* P, const float* notes, const in
     }
     P->peak_work.clear();
     for (int32_t g = 0; g + 1 < (int32_t)P->group_ptr.size(); ++g) {
-        const int32_t mix = P->mix_len[P->group_ptr[g]];
-        const int32_t chunks = std::max(1, (mix + ADTFE_PEAK_SPAN - 1) / ADTFE_PEAK_SPAN);
-        for (int32_t c = 0; c < chunks; ++c) { P->peak_work.push_back(g); P->peak_work.push_back(c); }
+        const int32_t e0 = P->group_ptr[g];
+        const adtfe_event& head = P->events[e0];
+        adtfe_peak_item it;
+        it.a_off = P->offsets[head.main_id]; it.b_off = P->offsets[head.sub_id];
+        it.la = P->lengths[head.main_id]; it.lb = P->lengths[head.sub_id];
+        it.mix_len = P->mix_len[e0];
+        it.first_event = e0; it.n_events = P->group_ptr[g + 1] - e0;
+        const int32_t chunks = std::max(1, (it.mix_len + ADTFE_PEAK_SPAN - 1) / ADTFE_PEAK_SPAN);
+        for (int32_t c = 0; c < chunks; ++c) { it.chunk = c; P->peak_work.push_back(it); }
     }
     out_counts[0] = (int64_t)P->events.size();
     out_counts[1] = (int64_t)P->group_ptr.size() - 1;
     out_counts[2] = n_seg;
     out_counts[3] = P->tiles_per_seg;
-    out_counts[4] = (int64_t)P->peak_work.size() / 2;
+    out_counts[4] = (int64_t)P->peak_work.size();
     out_counts[5] = (int64_t)P->tile_events.size();
     out_counts[6] = ld;
     out_counts[7] = max_len;
@@ -277,7 +287,7 @@ extern "C" int adtfe_planner_plan(adtfe_planner* P, const float* notes, const in
 
 // Copies the last plan into caller arrays (any may be NULL to skip).
 extern "C" int adtfe_planner_export(const adtfe_planner* P, adtfe_event* events, int32_t* mix_len, int32_t* group_ptr,
-                                    adtfe_segment* segments, int32_t* tile_ptr, int32_t* peak_work,
+                                    adtfe_segment* segments, int32_t* tile_ptr, adtfe_peak_item* peak_work,
                                     int32_t* tile_events) {
     if (!P) return ADTFE_ERR_BAD_ARG;
     if (events && !P->events.empty()) memcpy(events, P->events.data(), P->events.size() * sizeof(adtfe_event));
@@ -285,7 +295,8 @@ extern "C" int adtfe_planner_export(const adtfe_planner* P, adtfe_event* events,
     if (group_ptr) memcpy(group_ptr, P->group_ptr.data(), P->group_ptr.size() * 4);
     if (segments && !P->segments.empty()) memcpy(segments, P->segments.data(), P->segments.size() * sizeof(adtfe_segment));
     if (tile_ptr) memcpy(tile_ptr, P->tile_ptr.data(), P->tile_ptr.size() * 4);
-    if (peak_work && !P->peak_work.empty()) memcpy(peak_work, P->peak_work.data(), P->peak_work.size() * 4);
+    if (peak_work && !P->peak_work.empty())
+        memcpy(peak_work, P->peak_work.data(), P->peak_work.size() * sizeof(adtfe_peak_item));
     if (tile_events && !P->tile_events.empty()) memcpy(tile_events, P->tile_events.data(), P->tile_events.size() * 4);
     return ADTFE_OK;
 }

@@ -16,7 +16,7 @@ from . import _lib
 from .bank import OneShotBank
 from .config import SynthDrumConfig
 from .mapping import ADTOF_INVERSE, PITCH_MAX, PITCH_MIN, instrument_gain
-from .planner import EVENT_DTYPE, SEGMENT_DTYPE, RenderPlan, plan_batch, similarity_groups
+from .planner import EVENT_DTYPE, PEAK_ITEM_DTYPE, SEGMENT_DTYPE, RenderPlan, plan_batch, similarity_groups
 
 _ERRORS = {1: ValueError, 2: IndexError, 3: KeyError, 4: NotImplementedError}
 
@@ -41,15 +41,15 @@ class NativePlanner:
             ipitch.extend(ADTOF_INVERSE.get(pitch, []))
             iptr.append(len(ipitch))
         a = lambda x, dt: np.ascontiguousarray(np.asarray(x, dt))  # noqa: E731
-        self._keep = [a(bank.lengths, np.int32), a(gptr, np.int32), a(gfirst, np.int32), a(gcount, np.int32),
+        self._keep = [a(bank.lengths, np.int32), a(bank.offsets, np.int64), a(gptr, np.int32), a(gfirst, np.int32), a(gcount, np.int32),
                       a(gain, np.float32), a(iptr, np.int32), a(ipitch, np.int32)]
         k = self._keep
         h = C.c_void_p()
         _lib.check(lib.adtfe_planner_create(config.sample_rate, float(config.input_sec), float(config.mixup_range),
                                             float(config.use_fx_prob), int(bool(config.ADTOF_mapping)),
-                                            k[0].ctypes.data, len(bank), k[1].ctypes.data, k[2].ctypes.data,
+                                            k[0].ctypes.data, k[1].ctypes.data, len(bank), k[2].ctypes.data,
                                             k[3].ctypes.data, k[4].ctypes.data, k[5].ctypes.data, k[6].ctypes.data,
-                                            C.byref(h)), "adtfe_planner_create")
+                                            k[7].ctypes.data, C.byref(h)), "adtfe_planner_create")
         self.handle, self.lib = h, lib
 
     def __del__(self):
@@ -103,7 +103,7 @@ class NativePlanner:
         group_ptr = np.empty(n_grp + 1, np.int32)
         segments = np.empty(n_seg, SEGMENT_DTYPE)
         tile_ptr = np.empty(n_seg * tps + 1, np.int32)
-        peak_work = np.empty((n_pw, 2), np.int32)
+        peak_work = np.empty(n_pw, PEAK_ITEM_DTYPE)
         tile_events = np.empty(n_te, np.int32)
         _lib.check(self.lib.adtfe_planner_export(self.handle, events.ctypes.data, mix_len.ctypes.data,
                                                  group_ptr.ctypes.data, segments.ctypes.data, tile_ptr.ctypes.data,

@@ -46,6 +46,9 @@ EVENT_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("main_id", "<i4"), ("
                         ("ca", "<f4"), ("cb", "<f4"), ("gain", "<f4"), ("seg", "<i4")])
 #: numpy view of ``adtfe_segment`` (16 bytes)
 SEGMENT_DTYPE = np.dtype([("len", "<i4"), ("flags", "<i4"), ("max_volume", "<f4"), ("first_event", "<i4")])
+#: numpy view of ``adtfe_peak_item`` (40 bytes)
+PEAK_ITEM_DTYPE = np.dtype([("a_off", "<i8"), ("b_off", "<i8"), ("la", "<i4"), ("lb", "<i4"), ("mix_len", "<i4"),
+                            ("first_event", "<i4"), ("n_events", "<i4"), ("chunk", "<i4")])
 SEG_EMPTY = 0      # no notes: all-zero waveform of int(input_sec*sr) samples, no normalisation
 SEG_NORMALISE = 1  # wav / max|wav| * max_volume (NaN when the mix is all zero, like the reference)
 
@@ -187,7 +190,7 @@ class RenderPlan:
     group_ptr: np.ndarray         # int32 (n_groups+1,)
     tile_ptr: np.ndarray          # int32 (n_seg*tiles_per_seg+1,)
     tile_events: np.ndarray       # int32 (n_refs,) event ids, ascending inside a tile
-    peak_work: np.ndarray         # int32 (n_peak_work, 2): (group, chunk) items of the peak pass
+    peak_work: np.ndarray         # PEAK_ITEM_DTYPE (n_peak_work,): (group, chunk) items of the peak pass
     wave_lengths: np.ndarray = field(default=None)  # int64 (n_seg,)
 
     @property
@@ -241,7 +244,7 @@ def bucket_tiles(start: np.ndarray, length: np.ndarray, seg: np.ndarray, n_seg: 
     return np.cumsum(tile_ptr).astype(np.int32), tile_events
 
 
-def assemble(plans: Sequence[SegmentPlan], ld_wav: int | None = None) -> RenderPlan:
+def assemble(plans: Sequence[SegmentPlan], bank: OneShotBank, ld_wav: int | None = None) -> RenderPlan:
     n_seg = len(plans)
     max_len = max((p.wave_length for p in plans), default=0)
     if ld_wav is None:
@@ -265,23 +268,32 @@ def assemble(plans: Sequence[SegmentPlan], ld_wav: int | None = None) -> RenderP
     tile_ptr, tile_events = bucket_tiles(events["start"].astype(np.int64), events["len"].astype(np.int64),
                                          events["seg"], n_seg, tiles_per_seg)
     return RenderPlan(n_seg, ld_wav, tiles_per_seg, segments, events, mix_len, group_ptr, tile_ptr,
-                      tile_events, peak_work_items(mix_len, group_ptr),
+                      tile_events, peak_work_items(events, mix_len, group_ptr, bank),
                       np.array([p.wave_length for p in plans], np.int64))
 
 
-def peak_work_items(mix_len: np.ndarray, group_ptr: np.ndarray) -> np.ndarray:
-    """(group, chunk) for every PEAK_SPAN-sample chunk of every group's mixed one-shot."""
+def peak_work_items(events: np.ndarray, mix_len: np.ndarray, group_ptr: np.ndarray, bank: OneShotBank) -> np.ndarray:
+    """One record per PEAK_SPAN-sample chunk of every group's mixed one-shot, bank lookups resolved."""
     n_groups = len(group_ptr) - 1
     if n_groups <= 0:
-        return np.zeros((0, 2), np.int32)
-    chunks = np.maximum(1, -(-mix_len[group_ptr[:-1]].astype(np.int64) // PEAK_SPAN))
+        return np.zeros(0, PEAK_ITEM_DTYPE)
+    first = group_ptr[:-1].astype(np.int64)
+    chunks = np.maximum(1, -(-mix_len[first].astype(np.int64) // PEAK_SPAN))
     group = np.repeat(np.arange(n_groups, dtype=np.int64), chunks)
-    chunk = np.arange(int(chunks.sum()), dtype=np.int64) - np.repeat(np.cumsum(chunks) - chunks, chunks)
-    return np.stack([group, chunk], axis=1).astype(np.int32)
+    out = np.zeros(int(chunks.sum()), PEAK_ITEM_DTYPE)
+    e0 = first[group]
+    main, sub = events["main_id"][e0], events["sub_id"][e0]
+    out["a_off"], out["b_off"] = bank.offsets[main], bank.offsets[sub]
+    out["la"], out["lb"] = bank.lengths[main], bank.lengths[sub]
+    out["mix_len"] = mix_len[e0]
+    out["first_event"] = e0
+    out["n_events"] = np.diff(group_ptr)[group]
+    out["chunk"] = np.arange(len(out), dtype=np.int64) - np.repeat(np.cumsum(chunks) - chunks, chunks)
+    return out
 
 
 def plan_batch(batch_notes: Sequence, config: SynthDrumConfig, bank: OneShotBank, rng=_random,
                ld_wav: int | None = None) -> RenderPlan:
     """Plan ``len(batch_notes)`` independent ``SynthDrum.__call__``s, in order (the RNG
     stream advances exactly as that many reference calls would advance it)."""
-    return assemble([plan_segment(n, config, bank, rng) for n in batch_notes], ld_wav)
+    return assemble([plan_segment(n, config, bank, rng) for n in batch_notes], bank, ld_wav)

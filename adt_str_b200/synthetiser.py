@@ -57,9 +57,9 @@ class PlanBuffers:
 
     def pack(self, plan: RenderPlan) -> _lib.Plan:
         lib = _lib.load()
-        shape = _lib.Plan(None, None, None, None, None, None, None, plan.n_events, plan.n_groups, plan.n_seg,
-                          plan.tiles_per_seg, len(plan.peak_work), 0, plan.ld_wav)
-        off = (C.c_size_t * 7)()
+        shape = _lib.Plan(None, None, None, None, None, plan.n_events, plan.n_seg, plan.tiles_per_seg,
+                          len(plan.peak_work), plan.ld_wav)
+        off = (C.c_size_t * 5)()
         fixed = C.c_size_t()
         _lib.check(lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(fixed)), "adtfe_plan_blob_layout")
         total = (fixed.value + 4 * len(plan.tile_events) + 15) & ~15
@@ -68,8 +68,7 @@ class PlanBuffers:
             self.host = torch.empty(cap, dtype=torch.uint8).pin_memory()
             self.dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
         h = self.host.numpy()
-        for o, arr in zip(off, (plan.events, plan.mix_len, plan.group_ptr, plan.segments, plan.tile_ptr,
-                                plan.peak_work, plan.tile_events)):
+        for o, arr in zip(off, (plan.events, plan.segments, plan.tile_ptr, plan.peak_work, plan.tile_events)):
             raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
             h[o: o + raw.size] = raw
         self.nbytes = total
@@ -84,9 +83,8 @@ class PlanBuffers:
         self.dev[: self.nbytes].copy_(self.host[: self.nbytes], non_blocking=True)
         base = self.dev.data_ptr()
         o = self.offsets
-        return _lib.Plan(base + o[0], base + o[1], base + o[2], base + o[3], base + o[4], base + o[6], base + o[5],
-                         shape.n_events, shape.n_groups, shape.n_seg, shape.tiles_per_seg, shape.n_peak_work, 0,
-                         shape.ld_wav)
+        return _lib.Plan(base + o[0], base + o[1], base + o[2], base + o[4], base + o[3],
+                         shape.n_events, shape.n_seg, shape.tiles_per_seg, shape.n_peak_work, shape.ld_wav)
 
 
 class SynthDrum:

@@ -71,21 +71,28 @@ typedef struct adtfe_segment {
     int32_t first_event; /* index of the segment's first event */
 } adtfe_segment;
 
+/* One work item of the peak pass (40 bytes): samples [chunk*ADTFE_PEAK_SPAN, (chunk+1)*ADTFE_PEAK_SPAN)
+ * of the mixed one-shot shared by the notes first_event .. first_event+n_events-1 (one instrument of one
+ * segment).  Every group needs chunks 0 .. ceil(mix_len/ADTFE_PEAK_SPAN)-1.  Offsets and lengths are the
+ * bank's, resolved on the host so the kernel starts its loads after a single record fetch. */
+typedef struct adtfe_peak_item {
+    int64_t a_off, b_off; /* float offsets of the main / sub one-shot in the bank */
+    int32_t la, lb;       /* their lengths */
+    int32_t mix_len;      /* max(la, lb) */
+    int32_t first_event, n_events, chunk;
+} adtfe_peak_item;
+
 typedef struct adtfe_bank adtfe_bank; /* one-shot bank resident in HBM */
 typedef struct adtfe_mel adtfe_mel;   /* window, mel filterbank (CSR) and twiddles on device */
 
 /* A planned batch, all arrays in device memory. */
 typedef struct adtfe_plan {
-    const adtfe_event* events_dev;     /* n_events */
-    const int32_t* mix_len_dev;        /* n_events: max(len_main, len_sub), untruncated */
-    const int32_t* group_ptr_dev;      /* n_groups+1: events of one (segment, instrument) */
-    const adtfe_segment* segments_dev; /* n_seg */
-    const int32_t* tile_ptr_dev;       /* n_seg*tiles_per_seg+1: CSR tile -> tile_events */
-    const int32_t* tile_events_dev;    /* event ids, ascending inside a tile */
-    const int32_t* peak_work_dev;      /* n_peak_work pairs (group, chunk): chunk c of group g covers samples
-                                          [c*ADTFE_PEAK_SPAN, (c+1)*ADTFE_PEAK_SPAN) of its mixed one-shot;
-                                          every group needs chunks 0 .. ceil(mix_len/ADTFE_PEAK_SPAN)-1 */
-    int32_t n_events, n_groups, n_seg, tiles_per_seg, n_peak_work, reserved;
+    const adtfe_event* events_dev;        /* n_events */
+    const adtfe_segment* segments_dev;    /* n_seg */
+    const int32_t* tile_ptr_dev;          /* n_seg*tiles_per_seg+1: CSR tile -> tile_events */
+    const int32_t* tile_events_dev;       /* event ids, ascending inside a tile */
+    const adtfe_peak_item* peak_work_dev; /* n_peak_work */
+    int32_t n_events, n_seg, tiles_per_seg, n_peak_work;
     int64_t ld_wav; /* row pitch of the waveform matrix in floats, multiple of 4, <= tiles_per_seg*ADTFE_TILE */
 } adtfe_plan;
 
@@ -105,8 +112,8 @@ int64_t adtfe_bank_bytes(const adtfe_bank* bank);
 /* ---- render ------------------------------------------------------------------------ */
 size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg);
 /* Writes the (n_seg, ld_wav) float32 waveform matrix: every row normalised as the reference
- * does and zero-padded to ld_wav.  Three kernels: per-event peak of the mixed one-shot,
- * tile mixer (+ per-tile |max|), per-segment normalise. */
+ * does and zero-padded to ld_wav.  Two kernels: per-note peak of the mixed one-shot, then the tile
+ * mixer, whose last CTA of every segment normalises the row. */
 int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
                  size_t workspace_bytes, void* stream);
 
@@ -132,7 +139,7 @@ int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel, const adtf
 
 /* ---- host-buffer entry (end to end) ------------------------------------------------ */
 /* Plan blob layout (host, 16-byte aligned sections in this order):
- *   events | mix_len | group_ptr | segments | tile_ptr | peak_work | tile_events
+ *   events | segments | tile_ptr | peak_work | tile_events
  * with the counts in `shape` (a plan whose pointers are ignored).  The blob is copied to
  * `blob_dev` (>= blob_bytes), the batch rendered and featurised, then the log-mel matrix
  * (and the waveform when wav_out_host != NULL) copied back.  Asynchronous on `stream`:
@@ -141,9 +148,9 @@ int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel, const adtf
                         const void* blob_host, size_t blob_bytes, void* blob_dev, float* wav_dev, float* mel_dev,
                         void* workspace_dev, size_t workspace_bytes, float* mel_out_host, float* wav_out_host,
                         void* stream);
-/* Byte offsets of the seven sections inside a plan blob (offsets[7]; *blob_bytes = offsets[6], where
+/* Byte offsets of the five sections inside a plan blob (offsets[5]; *blob_bytes = offsets[4], where
  * tile_events starts - it runs to the end of the blob). */
-int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[7], size_t* blob_bytes);
+int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[5], size_t* blob_bytes);
 
 /* ---- host planner (no GPU work) ------------------------------------------------------ */
 /* C++ restatement of the per-note bookkeeping of SynthDrum.__call__ (modules/synthetiser.py:255-292:
@@ -154,7 +161,8 @@ int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[7], size_t* b
  * per pitch (< 0: the reference raises KeyError); inverse_ptr/inverse_pitch: ADTOF class -> member pitches. */
 typedef struct adtfe_planner adtfe_planner;
 int adtfe_planner_create(int32_t sample_rate, double input_sec, double mixup_range, double use_fx_prob,
-                         int32_t adtof_mapping, const int32_t* lengths, int32_t n_oneshots, const int32_t* group_ptr,
+                         int32_t adtof_mapping, const int32_t* lengths, const int64_t* offsets, int32_t n_oneshots,
+                         const int32_t* group_ptr,
                          const int32_t* group_first, const int32_t* group_count, const float* gain,
                          const int32_t* inverse_ptr, const int32_t* inverse_pitch, adtfe_planner** out);
 int adtfe_planner_destroy(adtfe_planner* planner);
@@ -162,11 +170,12 @@ int adtfe_planner_destroy(adtfe_planner* planner);
  * each.  mt_state[625]: random.getstate()[1], advanced in place.  ld_wav_in: 0 = derive.  Returns 0, a
  * negative adtfe_status, or 1 invalid note (ValueError) / 2 no admitted group (IndexError) / 3 KeyError /
  * 4 FX coin hit (NotImplementedError) with info = {segment, note}.
- * out_counts = {n_events, n_groups, n_seg, tiles_per_seg, n_peak_work, n_tile_events, ld_wav, max_len}. */
+ * out_counts = {n_events, n_groups, n_seg, tiles_per_seg, n_peak_work, n_tile_events, ld_wav, max_len}.
+ * mix_len / group_ptr are exported for inspection only; the device plan does not need them. */
 int adtfe_planner_plan(adtfe_planner* planner, const float* notes, const int32_t* counts, int32_t n_seg,
                        uint32_t* mt_state, int64_t ld_wav_in, int64_t* out_counts, int32_t* info);
 int adtfe_planner_export(const adtfe_planner* planner, adtfe_event* events, int32_t* mix_len, int32_t* group_ptr,
-                         adtfe_segment* segments, int32_t* tile_ptr, int32_t* peak_work, int32_t* tile_events);
+                         adtfe_segment* segments, int32_t* tile_ptr, adtfe_peak_item* peak_work, int32_t* tile_events);
 
 #ifdef __cplusplus
 }

@@ -31,20 +31,20 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_struct_sizes_match_numpy_views():
-    from adt_str_b200.planner import EVENT_DTYPE, SEGMENT_DTYPE
-    assert EVENT_DTYPE.itemsize == 32 and SEGMENT_DTYPE.itemsize == 16
-    assert C.sizeof(_lib.Plan) == 7 * 8 + 6 * 4 + 8
+    from adt_str_b200.planner import EVENT_DTYPE, PEAK_ITEM_DTYPE, SEGMENT_DTYPE
+    assert EVENT_DTYPE.itemsize == 32 and SEGMENT_DTYPE.itemsize == 16 and PEAK_ITEM_DTYPE.itemsize == 40
+    assert C.sizeof(_lib.Plan) == 5 * 8 + 4 * 4 + 8
 
 
 def test_version_and_argument_errors_without_a_device(lib):
     assert lib.adtfe_version() == 1
     assert lib.adtfe_render_workspace_bytes(10, 2, 30) >= 10 * 48 + 2 * 30 * 4
     assert lib.adtfe_render_workspace_bytes(-1, 2, 30) == 0
-    shape = _lib.Plan(None, None, None, None, None, None, None, 100, 7, 4, 31, 9, 0, 63488)
-    off = (C.c_size_t * 7)()
+    shape = _lib.Plan(None, None, None, None, None, 100, 4, 31, 9, 63488)
+    off = (C.c_size_t * 5)()
     total = C.c_size_t()
     assert lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(total)) == 0
-    assert list(off)[:2] == [0, 3200] and all(o % 16 == 0 for o in off) and total.value == off[6] and off[6] - off[5] == 80
+    assert list(off)[:3] == [0, 3200, 3264] and all(o % 16 == 0 for o in off) and total.value == off[4] and off[4] - off[3] == 368
     assert lib.adtfe_plan_blob_layout(None, C.byref(off), C.byref(total)) == -1
     assert b"null" in lib.adtfe_last_error()
     # null handles are rejected before any CUDA call

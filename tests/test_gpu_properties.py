@@ -50,7 +50,7 @@ def test_full_size_overlap_add_is_additive(full):
         e = ev[mask].copy()
         e["seg"] = 0
         gp = np.concatenate([[0], np.flatnonzero(np.diff(e["main_id"].astype(np.int64) * 100003 + e["sub_id"])) + 1, [len(e)]])
-        p = assemble([SegmentPlan(L, SEG_NORMALISE, 1.0, e, ml[mask], gp.astype(np.int32))], ld_wav=plan.ld_wav)
+        p = assemble([SegmentPlan(L, SEG_NORMALISE, 1.0, e, ml[mask], gp.astype(np.int32))], synth.bank, ld_wav=plan.ld_wav)
         w = synth.render_plan(p)[0].double()
         return w, float(w.abs().max())
 
