@@ -13,7 +13,7 @@ EXPORTS = [
     "adtfe_version", "adtfe_last_error", "adtfe_device_ok",
     "adtfe_bank_create", "adtfe_bank_destroy", "adtfe_bank_bytes",
     "adtfe_render_workspace_bytes", "adtfe_render",
-    "adtfe_mel_create", "adtfe_mel_destroy", "adtfe_mel_frames", "adtfe_logmel",
+    "adtfe_mel_create", "adtfe_mel_destroy", "adtfe_mel_frames", "adtfe_mel_fast_path", "adtfe_logmel",
     "adtfe_render_logmel", "adtfe_frontend_host", "adtfe_plan_blob_layout",
     "adtfe_planner_create", "adtfe_planner_destroy", "adtfe_planner_plan", "adtfe_planner_export",
 ]
@@ -49,6 +49,7 @@ def _declare(lib) -> None:
     lib.adtfe_render.argtypes = [vp, C.POINTER(Plan), vp, vp, sz, vp]
     lib.adtfe_mel_create.argtypes = [i32, i32, i32, vp, vp, C.c_int, C.POINTER(vp)]
     lib.adtfe_mel_destroy.argtypes = [vp]
+    lib.adtfe_mel_fast_path.argtypes = [vp]
     lib.adtfe_mel_frames.argtypes = [vp, i64, C.POINTER(i32), C.POINTER(i32)]
     lib.adtfe_logmel.argtypes = [vp, vp, i32, i64, i64, vp, vp]
     lib.adtfe_render_logmel.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, vp, vp, sz, vp]

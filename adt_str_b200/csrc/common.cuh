@@ -66,7 +66,8 @@ struct adtfe_mel {
     float* window = nullptr;   // n_fft
     float2* twiddle = nullptr; // 32 x 32: W_2048^(k1*n2), k1 = 1..32, n2 = lane
     float2* lane_tw = nullptr; // 3 x 32: per-lane twiddles of the cross-lane 32-point DFT
-    float* sched_w = nullptr;  // filter weights packed in mel-phase schedule order (per warp)
-    struct adtfe_mel_tables* tables = nullptr;  // filterbank CSR + warp schedule, passed as a kernel parameter
+    float* weights = nullptr;  // filter weights in mel-phase order (interval pairs, or per filter)
+    int32_t fast_path = 0;     // 1: the filterbank is triangular (<= 2 adjacent filters per bin)
+    struct adtfe_mel_tables* tables = nullptr;  // mel-phase items + warp schedule, passed as a kernel parameter
     size_t smem_bytes = 0;
 };

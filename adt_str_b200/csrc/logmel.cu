@@ -6,25 +6,34 @@
 // clamp[-23, 12], (x + 23) / 35, keep frames wpi .. T-wpi-2.  Only kept frames are
 // computed; their support never reaches the reflect padding.
 //
-// A CTA (16 warps) works in rounds of 32 frames; nothing but the (32 x n_mels) result tile
-// goes to HBM.
-//  FFT phase - one warp owns one frame at a time (two per round):
+// Persistent kernel, one CTA of 16 warps per SM.  A *round* is up to 32 consecutive kept
+// frames of one segment (a segment's frames are split into equal rounds); nothing but the
+// (frames x n_mels) result goes to HBM.
+//
+//  span    the round's samples - (frames-1)*hop + 2048 floats, every sample once although it
+//          feeds 8.5 frames - are brought into shared memory by one TMA bulk copy
+//          (cp.async.bulk + mbarrier) issued a round ahead, so global-load latency never sits
+//          on the critical path and no registers are spent on prefetching.  Rows that are not
+//          16-byte aligned take a cooperative copy instead.
+//  FFT     one warp owns one frame at a time (two per round):
 //   pass 1  lane n2 holds x[32*n1 + n2] * hann, n1 = 0..63, and runs a 64-point real DFT
 //           over n1 in registers (generated straight-line code, tools/gen_fft.py)
 //   twiddle Y[k1][n2] *= W_2048^(k1*n2)
-//   exchange through the warp's private shared tile, real parts then imaginary parts
-//           (row pitch 36 floats: STS.32 rows and LDS.128 columns are both conflict-free)
+//   exchange through the frame's own row of the power matrix (not yet written), as a
+//           32 x 32 tile with an XOR swizzle: STS.32 rows and LDS.128 columns are both
+//           conflict-free, real parts then imaginary parts
 //   pass 2  lane k1 (0..31) runs a 32-point complex DFT over n2 -> X[k1 + 64*k2];
 //           bins above 1024 are the mirror images of bins 64-k1 + 64*(31-k2)
 //   column k1 = 32 (bins 32 + 64*k2) is a 32-point DFT across lanes with shuffles
-//   |X|^2 goes to the CTA's power matrix P[bin][frame] (pitch 33: consecutive bins of one
-//           frame land in distinct banks; only the 16 column-32 bins collide, once per frame)
-//  mel phase - lanes are the 32 frames, each warp owns a contiguous, cost-balanced range of
-//   filters: acc += w * P[bin][lane] is conflict-free, weights are broadcast reads (4 per
-//   LDS.128) from the warp's (now idle) exchange tile; then log / clamp / affine, staged in
-//   the same tile and written out in runs of consecutive filters.
-//  The samples of a warp's next frame are requested before the mel phase, so their latency
-//  hides behind it.
+//   |X|^2 goes to P[frame][bin] (row pitch 1061: consecutive bins / consecutive frames both
+//           land in distinct banks)
+//  mel     lanes are the frames.  A triangular filterbank has at most two adjacent filters per
+//          bin, so bins are walked once: the bins between two filter centres feed the falling
+//          edge of the lower filter and the rising edge of the upper one (two FMAs per loaded
+//          power value, weights by broadcast LDS.128).  Each warp owns a contiguous,
+//          cost-balanced range of such intervals.  Filterbanks without that structure take a
+//          plain per-filter loop over the same P layout.
+//  output  log / clamp / affine on the staged (filter x frame) tile, 128-byte coalesced rows.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -38,29 +47,31 @@ namespace adtfe {
 
 constexpr int kWarps = 16;
 constexpr int kThreads = kWarps * 32;
-constexpr int kRound = 32;                  // frames per CTA round (lanes of the mel phase)
-constexpr int kXPitch = 36;                 // floats per exchange row
-constexpr int kXFloats = 32 * kXPitch;      // 1152 floats per warp
-constexpr int kPPitch = 33;
-constexpr int kPRows = 1025 + 3;               // 3 zero rows: filter weights are padded to groups of 4
-constexpr int kPFloats = kPRows * kPPitch;
-constexpr int kWtsMax = 384;                // packed filter weights one warp parks in its tile ...
-constexpr int kStagePitchMax = 23;          // ... followed by its (32 frames x n filters) result tile
-static_assert(kWtsMax + 32 * kStagePitchMax <= kXFloats, "weights + staging must fit in one exchange tile");
+constexpr int kRound = 32;                   // frames per round (lanes of the mel phase)
+constexpr int kSpanFloats = 9504;            // >= 31*240 + 2048, bytes a multiple of 128
+constexpr int kPPitch = 1061;                // floats per frame row of P: odd mod 32, >= 1025 + 31 + padding
 constexpr int kMaxMels = 128;
+constexpr int kSPitch = 33;
+constexpr int kSideRow = kMaxMels;           // S rows kMaxMels .. kMaxMels+15: boundary sums of the 16 warps
+constexpr int kZeroRow = kMaxMels + kWarps;  // an all-zero S row
+constexpr int kSRows = kZeroRow + 1;
+constexpr int kSFloats = 4800;               // >= kSRows * kSPitch, bytes a multiple of 128
+constexpr int kW4Max = 640;                  // float4 weight groups kept in shared memory (fast path)
+static_assert(kSRows * kSPitch <= kSFloats, "S tile");
+static_assert((kSpanFloats * 4) % 128 == 0 && (kPPitch * 4 * kRound) % 128 == 0, "alignment of the shared carve-up");
 
-__device__ __forceinline__ int p_index(int bin) { return bin * kPPitch; }
-
-// Per-warp schedule of the mel phase, passed by value (kernel-parameter constant bank).  The
-// weights themselves are packed per warp in global memory (adtfe_mel::sched_w) and copied into
-// the warp's idle exchange tile every round, where they are read with broadcast LDS.
-struct MelEntry {
-    int16_t lo, cnt4, woff, pad;  // first bin, weights padded to a multiple of 4, offset in the warp's pack
+// One step of the mel phase.  Fast path: interval j between the centres of filters j-1 and j
+// (first bin, bin pairs, float4 offset of its weights {up0, down0, up1, down1}).  Generic path:
+// filter m (first bin, bins, float offset of its weights in global memory).
+struct MelItem {
+    int16_t b0, n;
+    int32_t woff;
 };
 struct MelTables {
-    MelEntry entry[kMaxMels];
-    int16_t first[kWarps + 1];   // warp w owns the contiguous filters first[w] .. first[w+1]-1
-    int16_t wbase[kWarps + 1];   // its packed weights: sched_w[wbase[w] .. wbase[w+1])
+    MelItem item[kMaxMels + 1];
+    int16_t first[kWarps + 1];   // warp w owns items first[w] .. first[w+1]-1
+    uint8_t side[kMaxMels];      // S row added to filter m by the output stage (a boundary row or kZeroRow)
+    int32_t fast, n_w4;
 };
 
 struct LogmelArgs {
@@ -69,115 +80,135 @@ struct LogmelArgs {
     const float* window;
     const float2* twiddle;
     const float2* lane_tw;
-    const float* sched_w;
-    long long* trace;  // ADTFE_TRACE builds only: per-warp clock64 stamps
+    const float* weights;
     int64_t ld_wav;
     int32_t n_seg, first, count, hop, n_mels;
+    int32_t rounds_per_seg, n_rounds;
+    int32_t frames_base, frames_rem;  // round q of a segment has frames_base + (q < frames_rem) frames
 };
 
-// Mel phase of one warp: lane = frame, the warp owns a contiguous range of filters.
-// acc += w * P[bin][lane]: the P read is conflict-free (pitch 33), four weights come from one
-// broadcast LDS.128 out of the warp's own tile.  Results are staged in the same tile and
-// copied out in runs of n consecutive filters per frame.
-__device__ __forceinline__ void mel_phase(const MelTables& tab, int warp, int lane, const float* __restrict__ pl,
-                                          float* __restrict__ tile, float* __restrict__ out, long long g0,
-                                          long long total, int n_mels) {
-    const int f0 = tab.first[warp], n = tab.first[warp + 1] - f0;
-    const int pitch = n | 1;
-    float* stage = tile + kWtsMax;
-    for (int i = 0; i < n; ++i) {
-        const MelEntry en = tab.entry[f0 + i];
-        const float* pp = pl + p_index(en.lo);
-        const float4* ww = reinterpret_cast<const float4*>(tile + en.woff);
-        float acc0 = 0.0f, acc1 = 0.0f;
-        for (int k = 0; k < en.cnt4; k += 4, pp += 4 * kPPitch) {
-            const float4 w = ww[k >> 2];
-            acc0 = fmaf(w.x, pp[0], acc0);
-            acc1 = fmaf(w.y, pp[kPPitch], acc1);
-            acc0 = fmaf(w.z, pp[2 * kPPitch], acc0);
-            acc1 = fmaf(w.w, pp[3 * kPPitch], acc1);
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct RoundGeom {
+    int seg, j0, nf;
+};
+__device__ __forceinline__ RoundGeom round_geom(const LogmelArgs& p, int r) {
+    RoundGeom g;
+    g.seg = (int)((unsigned)r / (unsigned)p.rounds_per_seg);
+    const int q = r - g.seg * p.rounds_per_seg;
+    g.j0 = q * p.frames_base + min(q, p.frames_rem);
+    g.nf = p.frames_base + (q < p.frames_rem ? 1 : 0);
+    return g;
+}
+
+// Bring the samples of round r into s_span: one TMA bulk copy when source and length are 16-byte
+// aligned, a cooperative copy otherwise.  Called by all threads (the choice is CTA-uniform).
+__device__ __forceinline__ void issue_span(const LogmelArgs& p, int r, float* s_span, uint64_t* bar, int tid) {
+    const RoundGeom g = round_geom(p, r);
+    const float* src = p.wav + (long long)g.seg * p.ld_wav + (long long)(p.first + g.j0) * p.hop - 1024;
+    const int len = (g.nf - 1) * p.hop + 2048;
+    if ((((uintptr_t)src | (uintptr_t)(len * 4)) & 15) == 0) {
+        if (tid == 0) {
+            mbar_expect_tx(bar, (uint32_t)len * 4u);
+            bulk_g2s(s_span, src, (uint32_t)len * 4u, bar);
         }
-        float v = __logf((acc0 + acc1) + 1e-10f);           // |err| ~1e-7 in ln, 35x below the tolerance
-        v = v != v ? v : fminf(fmaxf(v, -23.0f), 12.0f);    // torch.clamp keeps NaN
-        stage[lane * pitch + i] = (v + 23.0f) * (1.0f / 35.0f);
-    }
-    __syncwarp();
-    for (int idx = lane; idx < 32 * n; idx += 32) {
-        const int f = idx / n, i = idx - f * n;
-        const long long g = g0 + f;
-        if (g < total) out[g * n_mels + f0 + i] = stage[f * pitch + i];
+    } else {
+        for (int i = tid; i < len; i += kThreads) s_span[i] = __ldg(src + i);
+        if (tid == 0) mbar_arrive(bar);  // the stores become visible at the CTA barrier that follows
     }
 }
 
 __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p, const __grid_constant__ MelTables tab) {
-    extern __shared__ __align__(16) float smem[];
-    float* s_win = smem;                                           // 2048
-    float2* s_tw = reinterpret_cast<float2*>(s_win + 2048);        // 32*32
-    float2* s_ltw = s_tw + 32 * 32;                                // 3*32
-    float* s_x = reinterpret_cast<float*>(s_ltw + 3 * 32);         // kWarps * kXFloats (also the staging tile)
-    float* s_p = s_x + kWarps * kXFloats;                          // kPFloats
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_span = reinterpret_cast<float*>(smem_raw);               // kSpanFloats
+    float* s_p = s_span + kSpanFloats;                                // kRound * kPPitch
+    float* s_s = s_p + kRound * kPPitch;                              // kSFloats
+    float4* s_w4 = reinterpret_cast<float4*>(s_s + kSFloats);         // kW4Max
+    float* s_win = reinterpret_cast<float*>(s_w4 + kW4Max);           // 2048
+    float2* s_tw = reinterpret_cast<float2*>(s_win + 2048);           // 32*32
+    float2* s_ltw = s_tw + 32 * 32;                                   // 3*32
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ltw + 3 * 32);
 
     const int tid = threadIdx.x, lane = tid & 31;
-    // broadcast from lane 0 so the compiler knows the warp index (and everything the mel phase
-    // derives from it: schedule, filter bounds, weight index) is warp-uniform
+    // broadcast from lane 0 so the compiler knows the warp index is warp-uniform
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+
+    if (tid == 0) mbar_init(s_bar, 1);
     for (int i = tid; i < 2048; i += kThreads) s_win[i] = p.window[i];
     for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = p.twiddle[i];
     for (int i = tid; i < 3 * 32; i += kThreads) s_ltw[i] = p.lane_tw[i];
+    for (int i = tid; i < tab.n_w4; i += kThreads) s_w4[i] = __ldg(reinterpret_cast<const float4*>(p.weights) + i);
+    for (int i = tid; i < kSFloats; i += kThreads) s_s[i] = 0.0f;     // the zero row stays zero
+    for (int i = tid; i < kRound * kPPitch; i += kThreads) s_p[i] = 0.0f;
+    __syncthreads();
+    if ((int)blockIdx.x < p.n_rounds) issue_span(p, blockIdx.x, s_span, s_bar, tid);
     __syncthreads();
 
-#ifdef ADTFE_TRACE
-#define TRACE(slot) do { if (lane == 0 && p.trace && tr_round < 3) p.trace[((blockIdx.x * kWarps + warp) * 3 + tr_round) * 16 + (slot)] = clock64(); } while (0)
-    int tr_round = 0;
-#else
-#define TRACE(slot) do {} while (0)
-#endif
-    float* xw = s_x + warp * kXFloats;
     const int col32_bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);
-    const int wb = tab.wbase[warp], wn = tab.wbase[warp + 1] - wb;
-    for (int i = tid; i < 3 * kPPitch; i += kThreads) s_p[1025 * kPPitch + i] = 0.0f;  // padding rows
-
-    const long long total = (long long)p.n_seg * p.count;
-    const long long n_rounds = (total + kRound - 1) / kRound;
-
-    auto frame_ptr = [&](long long g) -> const float* {
-        const int seg = (int)(g / p.count);
-        const int j = (int)(g - (long long)seg * p.count);
-        return p.wav + (long long)seg * p.ld_wav + (long long)(p.first + j) * p.hop - 1024 + lane;
-    };
-
-    // samples of the warp's first frame of the coming round, fetched one round ahead
-    float v[64];
-    {
-        const long long g = (long long)blockIdx.x * kRound + warp;
-        if (g < total) {
-            const float* x = frame_ptr(g);
+    // output stage: lane handles filters lane + 32*i
+    int side_off[4];
 #pragma unroll
-            for (int n1 = 0; n1 < 64; ++n1) v[n1] = __ldg(x + 32 * n1);
-        }
+    for (int i = 0; i < 4; ++i) {
+        const int m = lane + 32 * i;
+        side_off[i] = (m < p.n_mels ? (int)tab.side[m] : kZeroRow) * kSPitch;
     }
+    uint32_t parity = 0;
 
-    for (long long round = blockIdx.x; round < n_rounds; round += gridDim.x) {
-        const long long g0 = round * kRound;
-        TRACE(0);
-        // ================= FFT phase: frames g0 + warp and g0 + warp + 16 =================
+    for (int round = blockIdx.x; round < p.n_rounds; round += gridDim.x) {
+        const RoundGeom geo = round_geom(p, round);
+        mbar_wait(s_bar, parity);
+        parity ^= 1u;
+
+        // ================= FFT phase: frames warp and warp + 16 of the round =================
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             const int f = warp + half * kWarps;
-            const long long g = g0 + f;
-            if (g >= total) break;  // warp-uniform
-            if (half == 1) {
-                const float* x = frame_ptr(g);
-#pragma unroll
-                for (int n1 = 0; n1 < 64; ++n1) v[n1] = __ldg(x + 32 * n1);
-            }
+            if (f >= geo.nf) break;  // warp-uniform
+            float* pf = s_p + f * kPPitch;
+            // the frame's 32 x 32 exchange tile: 128-byte aligned inside its own (still unwritten) P row
+            // (s_p sits on a 128-byte boundary of the shared window, so the rounding is done on the offset)
+            float* tile = s_p + (((f * (kPPitch * 4) + 127) & ~127) >> 2);
+
             // ---- pass 1: window + 64-point real DFT over n1 (stride-32 samples)
             float yr[33], yi[33];
+            {
+                const float* sp = s_span + f * p.hop + lane;
+                float v[64];
 #pragma unroll
-            for (int n1 = 0; n1 < 64; ++n1) v[n1] *= s_win[32 * n1 + lane];
-            TRACE(1 + half * 5);
-            rdft64(v, yr, yi);
-            TRACE(2 + half * 5);
+                for (int n1 = 0; n1 < 64; ++n1) v[n1] = sp[32 * n1] * s_win[32 * n1 + lane];
+                rdft64(v, yr, yi);
+            }
             // ---- twiddle in place (rows 1..31), column 32 is real before its twiddle
 #pragma unroll
             for (int k1 = 1; k1 < 32; ++k1) {
@@ -192,32 +223,27 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
                 cr = yr[32] * w.x;
                 ci = yr[32] * w.y;
             }
-            // ---- exchange, real parts
+            // ---- exchange: element (k1, n2) lives at k1*32 + (n2 ^ ((k1 & 7) << 2)); the writer is lane
+            // n2 (one row per STS), the reader lane k1 (LDS.128 of n2 = 4q .. 4q+3)
             float zr[32], zi[32];
-#pragma unroll
-            for (int k1 = 0; k1 < 32; ++k1) xw[k1 * kXPitch + lane] = yr[k1];
             __syncwarp();
-            {
-                const float4* row = reinterpret_cast<const float4*>(xw + lane * kXPitch);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 t = row[q];
-                    zr[4 * q] = t.x; zr[4 * q + 1] = t.y; zr[4 * q + 2] = t.z; zr[4 * q + 3] = t.w;
-                }
+            for (int k1 = 0; k1 < 32; ++k1) tile[k1 * 32 + (lane ^ ((k1 & 7) << 2))] = yr[k1];
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(tile + lane * 32 + ((q ^ (lane & 7)) << 2));
+                zr[4 * q] = t.x; zr[4 * q + 1] = t.y; zr[4 * q + 2] = t.z; zr[4 * q + 3] = t.w;
             }
             __syncwarp();
-            // ---- exchange, imaginary parts (row 0 is purely real)
-            xw[lane] = 0.0f;
+            tile[lane] = 0.0f;  // row 0 is purely real
 #pragma unroll
-            for (int k1 = 1; k1 < 32; ++k1) xw[k1 * kXPitch + lane] = yi[k1];
+            for (int k1 = 1; k1 < 32; ++k1) tile[k1 * 32 + (lane ^ ((k1 & 7) << 2))] = yi[k1];
             __syncwarp();
-            {
-                const float4* row = reinterpret_cast<const float4*>(xw + lane * kXPitch);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 t = row[q];
-                    zi[4 * q] = t.x; zi[4 * q + 1] = t.y; zi[4 * q + 2] = t.z; zi[4 * q + 3] = t.w;
-                }
+            for (int q = 0; q < 8; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(tile + lane * 32 + ((q ^ (lane & 7)) << 2));
+                zi[4 * q] = t.x; zi[4 * q + 1] = t.y; zi[4 * q + 2] = t.z; zi[4 * q + 3] = t.w;
             }
             __syncwarp();
 
@@ -245,43 +271,85 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
             }
 
             // ---- pass 2: 32-point complex DFT over n2 for k1 = lane
-            TRACE(3 + half * 5);
             cdft32(zr, zi);
-            TRACE(4 + half * 5);
 
-            // ---- power spectrum into P[bin][f]
-            float* pf = s_p + f;
+            // ---- power spectrum into P[f][bin] (over the dead exchange tile)
 #pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) pf[p_index(lane + 64 * k2)] = zr[k2] * zr[k2] + zi[k2] * zi[k2];
+            for (int k2 = 0; k2 < 16; ++k2) pf[lane + 64 * k2] = zr[k2] * zr[k2] + zi[k2] * zi[k2];
 #pragma unroll
-            for (int k2 = 16; k2 < 32; ++k2)
-                pf[p_index(64 - lane + 64 * (31 - k2))] = zr[k2] * zr[k2] + zi[k2] * zi[k2];
-            if ((lane & 1) == 0) pf[p_index(col32_bin)] = cr * cr + ci * ci;
-            TRACE(5 + half * 5);
+            for (int k2 = 16; k2 < 32; ++k2) pf[64 - lane + 64 * (31 - k2)] = zr[k2] * zr[k2] + zi[k2] * zi[k2];
+            if ((lane & 1) == 0) pf[col32_bin] = cr * cr + ci * ci;
+            if (lane == 1) pf[1025] = 0.0f;  // padded bin pairs read one bin past the spectrum with weight 0
         }
-        // the exchange tile is idle until the next round: park this warp's filter weights in it
-        for (int i = lane; i < wn; i += 32) xw[i] = __ldg(p.sched_w + wb + i);
-        // and start fetching the first frame of the next round; it lands during the mel phase
+        __syncthreads();  // P complete; the span buffer is free
+
+        // the next round's samples arrive while the mel phase runs
+        if (round + (int)gridDim.x < p.n_rounds) issue_span(p, round + gridDim.x, s_span, s_bar, tid);
+
+        // ================= mel phase: lane = frame =================
         {
-            const long long g = (round + gridDim.x) * kRound + warp;
-            if (g < total) {
-                const float* x = frame_ptr(g);
-#pragma unroll
-                for (int n1 = 0; n1 < 64; ++n1) v[n1] = __ldg(x + 32 * n1);
+            const float* pl = s_p + lane * kPPitch;
+            const int i0 = tab.first[warp], i1 = tab.first[warp + 1];
+            if (tab.fast) {
+                float up_prev = 0.0f;
+                for (int j = i0; j < i1; ++j) {
+                    const MelItem it = tab.item[j];
+                    const float* pp = pl + it.b0;
+                    const float4* ww = s_w4 + it.woff;
+                    float u0 = 0.0f, u1 = 0.0f, d0 = 0.0f, d1 = 0.0f;
+                    for (int k = 0; k < it.n; ++k) {
+                        const float4 w = ww[k];
+                        const float p0 = pp[2 * k], p1 = pp[2 * k + 1];
+                        u0 = fmaf(w.x, p0, u0);
+                        d0 = fmaf(w.y, p0, d0);
+                        u1 = fmaf(w.z, p1, u1);
+                        d1 = fmaf(w.w, p1, d1);
+                    }
+                    const float up = u0 + u1, dn = d0 + d1;
+                    // `dn` completes filter j-1: inside the range it joins the rising edge held in up_prev,
+                    // at the start of the range it goes to this warp's boundary row
+                    if (j > i0) s_s[(j - 1) * kSPitch + lane] = up_prev + dn;
+                    else if (j > 0) s_s[(kSideRow + warp) * kSPitch + lane] = dn;
+                    up_prev = up;
+                }
+                if (i1 > i0 && i1 - 1 < p.n_mels) s_s[(i1 - 1) * kSPitch + lane] = up_prev;
+            } else {
+                for (int m = i0; m < i1; ++m) {
+                    const MelItem it = tab.item[m];
+                    const float* pp = pl + it.b0;
+                    const float* ww = p.weights + it.woff;
+                    float a0 = 0.0f, a1 = 0.0f;
+                    int k = 0;
+                    for (; k + 1 < it.n; k += 2) {
+                        a0 = fmaf(__ldg(ww + k), pp[k], a0);
+                        a1 = fmaf(__ldg(ww + k + 1), pp[k + 1], a1);
+                    }
+                    if (k < it.n) a0 = fmaf(__ldg(ww + k), pp[k], a0);
+                    s_s[m * kSPitch + lane] = a0 + a1;
+                }
             }
         }
-        TRACE(11);
-        __syncthreads();
-        TRACE(12);
+        __syncthreads();  // S complete (and a cooperatively copied span visible)
 
-        // ================= mel phase: lane = frame, the warp's own filter range =================
-        mel_phase(tab, warp, lane, s_p + lane, xw, p.out, g0, total, p.n_mels);
-        TRACE(13);
-        __syncthreads();  // P and the exchange tiles are reused by the next round
-        TRACE(14);
-#ifdef ADTFE_TRACE
-        ++tr_round;
-#endif
+        // ================= output: log / clamp / affine, one 128-filter row per warp store =================
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int f = warp + half * kWarps;
+            if (f < geo.nf) {
+                float* row = p.out + ((long long)geo.seg * p.count + geo.j0 + f) * p.n_mels;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int m = lane + 32 * i;
+                    if (m < p.n_mels) {
+                        const float mel = s_s[m * kSPitch + f] + s_s[side_off[i] + f];
+                        float v = __logf(mel + 1e-10f);                     // |err| ~1e-7 in ln, 35x below the tolerance
+                        v = v != v ? v : fminf(fmaxf(v, -23.0f), 12.0f);    // torch.clamp keeps NaN
+                        row[m] = (v + 23.0f) * (1.0f / 35.0f);
+                    }
+                }
+            }
+        }
+        // S is rewritten only after the next round's first barrier, which every warp reaches after this point
     }
 }
 
@@ -289,18 +357,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
 
 using namespace adtfe;
 
-// ADTFE_TRACE builds: a device buffer address handed over in the environment by tools/trace_logmel.py
-static void* getenv_trace() {
-#ifdef ADTFE_TRACE
-    const char* e = getenv("ADTFE_TRACE_PTR");
-    return e ? (void*)strtoull(e, nullptr, 0) : nullptr;
-#else
-    return nullptr;
-#endif
-}
-
 static size_t logmel_smem_bytes() {
-    return ((size_t)2048 + 2 * 32 * 32 + 2 * 3 * 32 + (size_t)kWarps * kXFloats + kPFloats) * 4;
+    return ((size_t)kSpanFloats + (size_t)kRound * kPPitch + kSFloats + 4 * (size_t)kW4Max + 2048 + 2 * 32 * 32 +
+            2 * 3 * 32) * 4 + 16;
 }
 
 struct adtfe_mel_tables {
@@ -325,15 +384,21 @@ extern "C" int adtfe_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t 
     adtfe_mel_frames(mel, n_samples, &first, &count);
     if (n_seg == 0 || count == 0) return ADTFE_OK;
     ADTFE_REQUIRE(wav_dev && out_dev, ADTFE_ERR_BAD_ARG, "adtfe_logmel: null buffer");
+    ADTFE_REQUIRE(((uintptr_t)wav_dev & 3) == 0, ADTFE_ERR_BAD_ARG, "adtfe_logmel: wav_dev must be 4-byte aligned");
     // kept frames stay inside the signal by construction; guard against a caller-made mel
     ADTFE_REQUIRE((int64_t)first * mel->hop >= 1024 &&
                       (int64_t)(first + count - 1) * mel->hop + 1024 <= n_samples,
                   ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: frame support leaves the signal");
+    // frames per round: as many as fit the span buffer, at most 32; a segment's frames are split evenly
+    const int cap = std::min(kRound, (kSpanFloats - 2048) / mel->hop + 1);
+    const int rounds_per_seg = (count + cap - 1) / cap;
+    const long long n_rounds = (long long)n_seg * rounds_per_seg;
+    ADTFE_REQUIRE(n_rounds < (1ll << 30), ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: too many frames for one launch");
     LogmelArgs a;
     a.wav = wav_dev; a.out = out_dev; a.window = mel->window; a.twiddle = mel->twiddle; a.lane_tw = mel->lane_tw;
-    a.sched_w = mel->sched_w; a.trace = (long long*)getenv_trace(); a.ld_wav = ld_wav; a.n_seg = n_seg; a.first = first; a.count = count; a.hop = mel->hop; a.n_mels = mel->n_mels;
-    const long long total = (long long)n_seg * count;
-    const long long n_rounds = (total + kRound - 1) / kRound;
+    a.weights = mel->weights; a.ld_wav = ld_wav; a.n_seg = n_seg; a.first = first; a.count = count;
+    a.hop = mel->hop; a.n_mels = mel->n_mels; a.rounds_per_seg = rounds_per_seg; a.n_rounds = (int32_t)n_rounds;
+    a.frames_base = count / rounds_per_seg; a.frames_rem = count % rounds_per_seg;
     const int grid = (int)(n_rounds < mel->sm_count ? n_rounds : mel->sm_count);
     logmel_kernel<<<grid, kThreads, mel->smem_bytes, (cudaStream_t)stream>>>(a, mel->tables->t);
     ADTFE_CUDA(cudaGetLastError());
@@ -343,12 +408,141 @@ extern "C" int adtfe_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t 
 extern "C" int adtfe_mel_destroy(adtfe_mel* mel) {
     if (!mel) return ADTFE_OK;
     cudaSetDevice(mel->device);
-    cudaFree(mel->window); cudaFree(mel->twiddle); cudaFree(mel->lane_tw); cudaFree(mel->sched_w);
+    cudaFree(mel->window); cudaFree(mel->twiddle); cudaFree(mel->lane_tw); cudaFree(mel->weights);
     delete mel->tables;
     delete mel;
     return ADTFE_OK;
 }
 
+// Triangular structure: every bin feeds at most two adjacent filters and the filter index never
+// decreases with the bin.  Bins are then grouped into intervals j = 0..n_mels (interval j lies
+// between the centres of filters j-1 and j) holding, per bin, the weight towards filter j ("up")
+// and towards filter j-1 ("down").  Returns false when fb does not have that structure (or the
+// packed weights do not fit): the caller then uses the per-filter path.
+static bool build_fast_tables(const float* fb, int n_bins, int n_mels, MelTables& t, std::vector<float>& packed) {
+    std::vector<int> iv(n_bins, -1);
+    std::vector<float> up(n_bins, 0.0f), dn(n_bins, 0.0f);
+    std::vector<int> peak(n_mels, 0);
+    for (int m = 0; m < n_mels; ++m) {
+        float best = -1.0f;
+        for (int k = 0; k < n_bins; ++k)
+            if (fb[(size_t)k * n_mels + m] > best) { best = fb[(size_t)k * n_mels + m]; peak[m] = k; }
+    }
+    int prev = 0;
+    for (int k = 0; k < n_bins; ++k) {
+        int a = -1, cnt = 0;
+        for (int m = 0; m < n_mels; ++m)
+            if (fb[(size_t)k * n_mels + m] != 0.0f) { if (cnt == 0) a = m; ++cnt; if (m - a > 1) return false; }
+        if (cnt == 0) continue;
+        if (cnt > 2) return false;
+        int j;
+        if (cnt == 2) {
+            j = a + 1;
+            dn[k] = fb[(size_t)k * n_mels + a];
+            up[k] = fb[(size_t)k * n_mels + a + 1];
+        } else if (a >= prev && k <= peak[a]) {  // rising edge of filter a
+            j = a;
+            up[k] = fb[(size_t)k * n_mels + a];
+        } else {                                 // falling edge of filter a
+            j = a + 1;
+            dn[k] = fb[(size_t)k * n_mels + a];
+        }
+        if (j < prev) return false;
+        iv[k] = j;
+        prev = j;
+    }
+    packed.clear();
+    memset(&t, 0, sizeof(t));
+    std::vector<double> cost(n_mels + 1, 0.0);
+    for (int j = 0; j <= n_mels; ++j) {
+        int lo = -1, hi = -1;
+        for (int k = 0; k < n_bins; ++k)
+            if (iv[k] == j) { if (lo < 0) lo = k; hi = k; }
+        MelItem it;
+        it.b0 = (int16_t)(lo < 0 ? 0 : lo);
+        const int nb = lo < 0 ? 0 : hi - lo + 1;
+        it.n = (int16_t)((nb + 1) / 2);
+        it.woff = (int32_t)(packed.size() / 4);
+        for (int q = 0; q < it.n; ++q)
+            for (int e = 0; e < 2; ++e) {
+                const int k = lo + 2 * q + e;
+                const bool in = k <= hi && iv[k] == j;  // bins of other intervals inside the range cannot occur
+                if (k <= hi && iv[k] != j && iv[k] >= 0) return false;
+                packed.push_back(in ? up[k] : 0.0f);
+                packed.push_back(in ? dn[k] : 0.0f);
+            }
+        if (it.b0 + 2 * it.n > n_bins + 1) return false;  // reads at most one bin past the spectrum (kept at 0)
+        t.item[j] = it;
+        cost[j] = 4.5 * it.n + 8.0;
+    }
+    if (packed.size() / 4 > (size_t)kW4Max) return false;
+    // verify: the intervals reproduce fb exactly
+    {
+        std::vector<float> chk((size_t)n_bins * n_mels, 0.0f);
+        for (int j = 0; j <= n_mels; ++j) {
+            const MelItem& it = t.item[j];
+            for (int q = 0; q < 2 * it.n; ++q) {
+                const int k = it.b0 + q;
+                const float wu = packed[(size_t)it.woff * 4 + 2 * q], wd = packed[(size_t)it.woff * 4 + 2 * q + 1];
+                if (k >= n_bins) { if (wu != 0.0f || wd != 0.0f) return false; continue; }
+                if (wu != 0.0f) { if (j >= n_mels) return false; chk[(size_t)k * n_mels + j] += wu; }
+                if (wd != 0.0f) { if (j < 1) return false; chk[(size_t)k * n_mels + j - 1] += wd; }
+            }
+        }
+        if (memcmp(chk.data(), fb, chk.size() * 4) != 0) {
+            for (size_t i = 0; i < chk.size(); ++i)
+                if (chk[i] != fb[i]) return false;  // (-0.0 vs 0.0 would differ bytewise only)
+        }
+    }
+    // contiguous interval ranges for the 16 warps, balanced by estimated cost
+    double total = 0;
+    for (int j = 0; j <= n_mels; ++j) total += cost[j];
+    int j = 0;
+    double spent = 0;
+    for (int w = 0; w < kWarps; ++w) {
+        t.first[w] = (int16_t)j;
+        const double target = total * (w + 1) / kWarps;
+        while (j <= n_mels && (w == kWarps - 1 || spent + 0.5 * cost[j] <= target)) spent += cost[j++];
+    }
+    t.first[kWarps] = (int16_t)(n_mels + 1);
+    for (int m = 0; m < kMaxMels; ++m) t.side[m] = (uint8_t)kZeroRow;
+    for (int w = 0; w < kWarps; ++w)
+        if (t.first[w + 1] > t.first[w] && t.first[w] > 0) t.side[t.first[w] - 1] = (uint8_t)(kSideRow + w);
+    t.fast = 1;
+    t.n_w4 = (int32_t)(packed.size() / 4);
+    return true;
+}
+
+static void build_generic_tables(const float* fb, int n_bins, int n_mels, MelTables& t, std::vector<float>& packed) {
+    packed.clear();
+    memset(&t, 0, sizeof(t));
+    std::vector<double> cost(n_mels, 0.0);
+    for (int m = 0; m < n_mels; ++m) {
+        int first = -1, last = -1;
+        for (int k = 0; k < n_bins; ++k)
+            if (fb[(size_t)k * n_mels + m] != 0.0f) { if (first < 0) first = k; last = k; }
+        MelItem it;
+        it.b0 = (int16_t)(first < 0 ? 0 : first);
+        it.n = (int16_t)(first < 0 ? 0 : last - first + 1);
+        it.woff = (int32_t)packed.size();
+        for (int k = first; first >= 0 && k <= last; ++k) packed.push_back(fb[(size_t)k * n_mels + m]);
+        t.item[m] = it;
+        cost[m] = 2.5 * it.n + 8.0;
+    }
+    double total = 0;
+    for (int m = 0; m < n_mels; ++m) total += cost[m];
+    int m = 0;
+    double spent = 0;
+    for (int w = 0; w < kWarps; ++w) {
+        t.first[w] = (int16_t)m;
+        const double target = total * (w + 1) / kWarps;
+        while (m < n_mels && (w == kWarps - 1 || spent + 0.5 * cost[m] <= target)) spent += cost[m++];
+    }
+    t.first[kWarps] = (int16_t)n_mels;
+    for (int i = 0; i < kMaxMels; ++i) t.side[i] = (uint8_t)kZeroRow;
+    t.fast = 0;
+    t.n_w4 = 0;
+}
 
 extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, const float* window_host,
                                 const float* fb_host, int device, adtfe_mel** out) {
@@ -363,19 +557,6 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
     ADTFE_CUDA(cudaSetDevice(device));
 
     const int n_bins = n_fft / 2 + 1;
-    std::vector<float> w;
-    std::vector<int32_t> ptr(n_mels + 1, 0), lo(n_mels, 0);
-    for (int m = 0; m < n_mels; ++m) {
-        int first = -1, last = -1;
-        for (int k = 0; k < n_bins; ++k)
-            if (fb_host[(size_t)k * n_mels + m] != 0.0f) { if (first < 0) first = k; last = k; }
-        ptr[m] = (int32_t)w.size();
-        lo[m] = first < 0 ? 0 : first;
-        if (first >= 0)
-            for (int k = first; k <= last; ++k) w.push_back(fb_host[(size_t)k * n_mels + m]);
-    }
-    ptr[n_mels] = (int32_t)w.size();
-
     std::vector<float2> tw(32 * 32), ltw(3 * 32);
     const double two_pi = 6.283185307179586476925286766559;
     for (int k1 = 1; k1 <= 32; ++k1)
@@ -398,54 +579,18 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
     adtfe_mel* mel = new adtfe_mel();
     mel->device = device; mel->n_fft = n_fft; mel->hop = hop; mel->n_mels = n_mels;
     mel->wpi = (n_fft / 2) / hop + 1;  // int((win/2)//hop + 1), model.py:79
-    mel->nnz = (int32_t)w.size();
     mel->sm_count = device_sm_count(device);
     mel->smem_bytes = logmel_smem_bytes();
     mel->tables = new adtfe_mel_tables();
     std::vector<float> packed;
-    {
-        MelTables& t = mel->tables->t;
-        memset(&t, 0, sizeof(t));
-        // contiguous filter ranges for the 16 warps of the mel phase, balanced by estimated cost
-        auto cost = [&](int m) { return 1.5 * (ptr[m + 1] - ptr[m]) + 14.0; };
-        double total_cost = 0;
-        for (int m = 0; m < n_mels; ++m) total_cost += cost(m);
-        int m = 0;
-        bool fits = true;
-        double spent = 0;
-        for (int wv = 0; wv < kWarps; ++wv) {
-            t.first[wv] = (int16_t)m;
-            t.wbase[wv] = (int16_t)packed.size();
-            const size_t base = packed.size();
-            const double target = total_cost * (wv + 1) / kWarps;
-            int taken = 0;
-            while (m < n_mels && taken < kStagePitchMax &&
-                   (wv == kWarps - 1 || taken == 0 || spent + 0.5 * cost(m) <= target)) {
-                MelEntry en;
-                const int cnt = ptr[m + 1] - ptr[m];
-                en.lo = (int16_t)lo[m]; en.cnt4 = (int16_t)((cnt + 3) & ~3);
-                en.woff = (int16_t)(packed.size() - base); en.pad = 0;
-                t.entry[m] = en;
-                packed.insert(packed.end(), w.begin() + ptr[m], w.begin() + ptr[m + 1]);
-                packed.resize(base + en.woff + en.cnt4, 0.0f);
-                fits = fits && lo[m] + en.cnt4 <= kPRows;
-                spent += cost(m);
-                ++m; ++taken;
-            }
-            fits = fits && packed.size() - base <= (size_t)kWtsMax;
-        }
-        t.first[kWarps] = (int16_t)m;
-        t.wbase[kWarps] = (int16_t)packed.size();
-        if (!fits || m != n_mels || packed.size() > 32000) {
-            set_error("adtfe_mel_create: filterbank does not fit the mel-phase tiles (%zu stored weights, %d of %d "
-                      "filters placed)", packed.size(), m, n_mels);
-            adtfe_mel_destroy(mel);
-            return ADTFE_ERR_UNSUPPORTED;
-        }
-    }
+    if (!build_fast_tables(fb_host, n_bins, n_mels, mel->tables->t, packed))
+        build_generic_tables(fb_host, n_bins, n_mels, mel->tables->t, packed);
+    mel->fast_path = mel->tables->t.fast;
+    mel->nnz = 0;
+    for (size_t i = 0; i < (size_t)n_bins * n_mels; ++i) mel->nnz += fb_host[i] != 0.0f;
     auto fail = [&](int status) { adtfe_mel_destroy(mel); return status; };
 #define MEL_UPLOAD(dst, src, bytes)                                                                  \
-    if (cudaMalloc((void**)&(dst), (bytes) ? (bytes) : 4) != cudaSuccess ||                          \
+    if (cudaMalloc((void**)&(dst), (bytes) ? (bytes) : 16) != cudaSuccess ||                         \
         cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice) != cudaSuccess) {                  \
         set_error("adtfe_mel_create: upload failed: %s", cudaGetErrorString(cudaGetLastError()));    \
         return fail(ADTFE_ERR_CUDA);                                                                 \
@@ -453,7 +598,7 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
     MEL_UPLOAD(mel->window, window_host, (size_t)n_fft * 4);
     MEL_UPLOAD(mel->twiddle, tw.data(), tw.size() * sizeof(float2));
     MEL_UPLOAD(mel->lane_tw, ltw.data(), ltw.size() * sizeof(float2));
-    MEL_UPLOAD(mel->sched_w, packed.data(), packed.size() * 4);
+    MEL_UPLOAD(mel->weights, packed.data(), packed.size() * 4);
 #undef MEL_UPLOAD
     if (cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel->smem_bytes) !=
         cudaSuccess) {
@@ -464,3 +609,5 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
     *out = mel;
     return ADTFE_OK;
 }
+
+extern "C" int adtfe_mel_fast_path(const adtfe_mel* mel) { return mel ? mel->fast_path : -1; }

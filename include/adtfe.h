@@ -126,6 +126,9 @@ int adtfe_mel_destroy(adtfe_mel* mel);
 /* Frames the reference keeps for an n_samples-long input: t = *first .. *first+*count-1 of
  * the centred STFT (model.py:79,95-97). */
 int adtfe_mel_frames(const adtfe_mel* mel, int64_t n_samples, int32_t* first, int32_t* count);
+/* 1 when the filterbank has the triangular structure (at most two adjacent filters per bin) the fast
+ * mel phase needs, 0 when the per-filter path is used (any fb works), < 0 on a null handle. */
+int adtfe_mel_fast_path(const adtfe_mel* mel);
 /* wav_dev: (n_seg, ld_wav) rows of n_samples valid floats; out_dev: (n_seg, count, n_mels). */
 int adtfe_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav, int64_t n_samples,
                  float* out_dev, void* stream);

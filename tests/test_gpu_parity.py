@@ -189,6 +189,45 @@ def test_mel_input_variants_and_state_dict():
         mel(torch.zeros(61440).cuda())
 
 
+def test_mel_fast_and_generic_filterbank_paths():
+    """The triangular fast path and the per-filter path (any fb) against the float64 oracle."""
+    from adt_str_b200 import ComputeMelSpectrogram, _lib
+    lib = _lib.load()
+    mel = ComputeMelSpectrogram(24000, 2048, 0.01, 128)
+    x = (torch.randn(2, 30000, generator=torch.Generator().manual_seed(3)) * 0.1)
+    assert lib.adtfe_mel_fast_path(mel._handle(torch.device("cuda", 0)).handle) == 1
+    fb0 = mel.state_dict()["compute_spec.mel_scale.fb"].clone()
+    want = mel_oracle.logmel_direct(x.numpy(), 24000, 2048, 0.01, 128, np.float64, fb=fb0.numpy())
+    assert_logmel_close(mel(x.cuda()).cpu().numpy(), want, atol=2e-6)
+    # a filterbank with three filters on some bins and a dense filter cannot use the interval walk
+    g = torch.Generator().manual_seed(4)
+    fb = fb0.clone()
+    fb[:, 5] += 0.25 * fb0[:, 9]
+    fb[:, 127] = torch.rand(1025, generator=g) * 0.01
+    fb[100:140, 40] = torch.rand(40, generator=g)
+    mel.load_state_dict({"compute_spec.spectrogram.window": mel.state_dict()["compute_spec.spectrogram.window"],
+                         "compute_spec.mel_scale.fb": fb}, strict=True)
+    got = mel(x.cuda()).cpu().numpy()
+    assert lib.adtfe_mel_fast_path(mel._handle(torch.device("cuda", 0)).handle) == 0
+    want = mel_oracle.logmel_direct(x.numpy(), 24000, 2048, 0.01, 128, np.float64, fb=fb.numpy())
+    assert_logmel_close(got, want, atol=2e-6)
+
+
+@pytest.mark.parametrize("sr,n,n_mels", [(44100, 30001, 128), (22050, 25003, 80), (16000, 40960, 128),
+                                          (24000, 61441, 64), (204800, 9000, 32)])
+def test_mel_odd_hops_unaligned_rows_and_small_banks(sr, n, n_mels):
+    """hop 441 (span length not a multiple of 4 -> cooperative copy), odd row lengths (rows not 16-byte
+    aligned), fewer mel bands, and hop 2048 (4 frames per round)."""
+    from adt_str_b200 import ComputeMelSpectrogram
+    mel = ComputeMelSpectrogram(sr, 2048, 0.01, n_mels)
+    x = torch.randn(3, n, generator=torch.Generator().manual_seed(n)) * 0.3
+    got = mel(x.cuda()).cpu().numpy()
+    fb = mel.state_dict()["compute_spec.mel_scale.fb"].numpy()
+    want = mel_oracle.logmel_direct(x.numpy(), sr, 2048, 0.01, n_mels, np.float64, fb=fb)
+    assert got.shape == want.shape and got.shape[1] > 0
+    assert_logmel_close(got, want, atol=2e-6)
+
+
 def test_abi_status_codes_on_device():
     from adt_str_b200 import _lib
     from adt_str_b200.config import setting_1
