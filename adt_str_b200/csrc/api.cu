@@ -74,6 +74,7 @@ extern "C" int adtfe_bank_create(const float* pcm_host, int64_t total_floats, co
     ADTFE_CUDA(cudaSetDevice(device));
     adtfe_bank* b = new adtfe_bank();
     b->device = device;
+    b->sm_count = device_sm_count(device);
     b->n = n_oneshots;
     b->total = total_floats;
     auto up = [&](void** dst, const void* src, size_t bytes) -> bool {

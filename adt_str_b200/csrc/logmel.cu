@@ -87,39 +87,6 @@ struct LogmelArgs {
     int32_t frames_base, frames_rem;  // round q of a segment has frames_base + (q < frames_rem) frames
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("{ .reg .b64 t; mbarrier.arrive.shared::cta.b64 t, [%0]; }" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("{ .reg .b64 t; mbarrier.arrive.expect_tx.shared::cta.b64 t, [%0], %1; }" ::"r"(smem_u32(bar)),
-                 "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 struct RoundGeom {
     int seg, j0, nf;
 };
@@ -292,18 +259,34 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
             const int i0 = tab.first[warp], i1 = tab.first[warp + 1];
             if (tab.fast) {
                 float up_prev = 0.0f;
+#define MEL_PAIR(q)                                                     \
+    {                                                                   \
+        const float4 w = ww[q];                                         \
+        const float p0 = pp[2 * (q)], p1 = pp[2 * (q) + 1];             \
+        u0 = fmaf(w.x, p0, u0); d0 = fmaf(w.y, p0, d0);                 \
+        u1 = fmaf(w.z, p1, u1); d1 = fmaf(w.w, p1, d1);                 \
+    }
+#pragma unroll 1
                 for (int j = i0; j < i1; ++j) {
                     const MelItem it = tab.item[j];
                     const float* pp = pl + it.b0;
                     const float4* ww = s_w4 + it.woff;
                     float u0 = 0.0f, u1 = 0.0f, d0 = 0.0f, d1 = 0.0f;
-                    for (int k = 0; k < it.n; ++k) {
-                        const float4 w = ww[k];
-                        const float p0 = pp[2 * k], p1 = pp[2 * k + 1];
-                        u0 = fmaf(w.x, p0, u0);
-                        d0 = fmaf(w.y, p0, d0);
-                        u1 = fmaf(w.z, p1, u1);
-                        d1 = fmaf(w.w, p1, d1);
+                    int n = it.n;
+#pragma unroll 1
+                    for (; n > 8; n -= 8, pp += 16, ww += 8) {
+                        MEL_PAIR(0) MEL_PAIR(1) MEL_PAIR(2) MEL_PAIR(3) MEL_PAIR(4) MEL_PAIR(5) MEL_PAIR(6) MEL_PAIR(7)
+                    }
+                    switch (n) {  // the last 0..8 pairs: one jump into straight-line code
+                        case 8: MEL_PAIR(7)
+                        case 7: MEL_PAIR(6)
+                        case 6: MEL_PAIR(5)
+                        case 5: MEL_PAIR(4)
+                        case 4: MEL_PAIR(3)
+                        case 3: MEL_PAIR(2)
+                        case 2: MEL_PAIR(1)
+                        case 1: MEL_PAIR(0)
+                        default: break;
                     }
                     const float up = u0 + u1, dn = d0 + d1;
                     // `dn` completes filter j-1: inside the range it joins the rising edge held in up_prev,
@@ -312,6 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
                     else if (j > 0) s_s[(kSideRow + warp) * kSPitch + lane] = dn;
                     up_prev = up;
                 }
+#undef MEL_PAIR
                 if (i1 > i0 && i1 - 1 < p.n_mels) s_s[(i1 - 1) * kSPitch + lane] = up_prev;
             } else {
                 for (int m = i0; m < i1; ++m) {
@@ -473,7 +457,7 @@ static bool build_fast_tables(const float* fb, int n_bins, int n_mels, MelTables
             }
         if (it.b0 + 2 * it.n > n_bins + 1) return false;  // reads at most one bin past the spectrum (kept at 0)
         t.item[j] = it;
-        cost[j] = 4.5 * it.n + 8.0;
+        cost[j] = 7.0 * it.n + 24.0;
     }
     if (packed.size() / 4 > (size_t)kW4Max) return false;
     // verify: the intervals reproduce fb exactly

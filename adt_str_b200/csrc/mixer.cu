@@ -19,6 +19,8 @@
 //                       The last CTA of a segment to finish (atomic ticket) takes the max of the
 //                       tile maxima and normalises the row in place, wav / peak * max_volume
 //                       (an all-zero mix gives NaN, like the reference's 0/0).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace adtfe {
@@ -28,9 +30,6 @@ constexpr int kPeakChunk = 8;   // notes of one instrument handled per sweep ove
 constexpr int kPeakSpan = ADTFE_PEAK_SPAN;  // samples of the mixed one-shot per peak work item
 constexpr int kPeakIters = kPeakSpan / 4 / kPeakThreads;  // float4 per thread per one-shot
 static_assert(kPeakIters * kPeakThreads * 4 == kPeakSpan, "peak span must be a multiple of 4 * threads");
-constexpr int kMixThreads = 256;
-constexpr int kPerThread = ADTFE_TILE / kMixThreads;  // 8 samples, stride kMixThreads
-constexpr int kStage = 64;      // resolved events staged in shared memory per round
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -145,117 +144,218 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
     }
 }
 
-// One source of one note inside one tile: acc[n] += coef * src[n - start] for start <= n < start+len.
-struct SubEvent {
-    const float* src;
-    int32_t start, len;
+// ---------------------------------------------------------------------------------------------
+// Tile mixer.  Persistent CTAs: one producer warp stages the one-shot slices a tile needs through a
+// ring of shared-memory buffers with TMA bulk copies (cp.async.bulk + mbarrier), eight consumer
+// warps accumulate them in arrival (= event) order into registers.  Tiles are handed out by an
+// atomic counter, so long and short tiles balance.
+constexpr int kMixConsumers = 8;                         // warps; 256 threads x 8 samples = one tile
+constexpr int kMixThreads = (kMixConsumers + 1) * 32;    // + the producer warp
+constexpr int kPerThread = ADTFE_TILE / (kMixConsumers * 32);
+constexpr int kStages = 6;
+constexpr int kStageFloats = 2080;                       // >= 2048 + 2*3 alignment slack, bytes a multiple of 128
+static_assert(kPerThread == 8, "tile / consumer threads");
+
+struct __align__(16) StageDesc {   // written by the producer lane, read (broadcast) by every consumer
+    int32_t kind;                  // 0: data, 1: a new tile begins (tile id in `tile`, < 0: no more work)
+    int32_t tile;
+    int32_t base;                  // sample i of the tile sits at buffer index i + base
+    int32_t vlo, vhi;              // samples vlo <= i < vhi of the tile are covered
     float coef;
-    int32_t pad;
+    int32_t pad0, pad1;
 };
 
-__global__ void __launch_bounds__(kMixThreads) mix_kernel(
-    const float* __restrict__ pcm, const ResolvedEvent* __restrict__ resolved, const int* __restrict__ peak_bits,
-    const int32_t* __restrict__ tile_ptr, const int32_t* __restrict__ tile_events,
-    const adtfe_segment* __restrict__ segments, int tiles_per_seg, int64_t ld_wav, float* __restrict__ wav,
-    float* __restrict__ tile_max, int* __restrict__ seg_done) {
-    __shared__ __align__(16) SubEvent s_sub[2 * kStage];
-    __shared__ float s_red[kMixThreads / 32];
-    __shared__ int s_last;
-    const int tile_id = blockIdx.x, tid = threadIdx.x;
-    const int seg = tile_id / tiles_per_seg, tile = tile_id - seg * tiles_per_seg;
-    const int lo = tile * ADTFE_TILE;
-    float acc[kPerThread];
-#pragma unroll
-    for (int j = 0; j < kPerThread; ++j) acc[j] = 0.0f;
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kMixConsumers * 32) : "memory"); }
 
-    const int p0 = tile_ptr[tile_id], p1 = tile_ptr[tile_id + 1];
-    for (int base = p0; base < p1; base += kStage) {
-        const int nst = min(kStage, p1 - base);
-        __syncthreads();
-        // (1 - mixup) * a and mixup * b become two independent sources, each scaled by
-        // gain / peak: o = (ca*a + cb*b) / peak * vol * gain up to float rounding (1e-7 relative)
-        if (tid < nst) {
-            const int e = tile_events[base + tid];
-            const ResolvedEvent ev = resolved[e];
-            // an all-zero one-shot has peak 0: gain/0 = inf (or NaN), and 0 * inf = NaN over the whole
-            // note - the reference's o / 0 (synthetiser.py:225)
-            const float scale = ev.gain / __int_as_float(peak_bits[e]);
-            SubEvent a, b;
-            a.src = pcm + ev.a_off; a.start = ev.start; a.len = ev.la; a.coef = ev.ca * scale; a.pad = 0;
-            b.src = pcm + ev.b_off; b.start = ev.start; b.len = ev.lb; b.coef = ev.cb * scale; b.pad = 0;
-            s_sub[2 * tid] = a;
-            s_sub[2 * tid + 1] = b;
-        }
-        __syncthreads();
-        // the two sources of one note are processed together: 16 loads in flight per thread
-        for (int k = 0; k < 2 * nst; k += 2) {
-            const SubEvent ea = s_sub[k], eb = s_sub[k + 1];
-            const int r0 = lo + tid - ea.start;  // same start for both
-            const float* sa = ea.src + r0;
-            const float* sb = eb.src + r0;
-            float va[kPerThread], vb[kPerThread];
-#pragma unroll
-            for (int j = 0; j < kPerThread; ++j) {
-                const unsigned r = (unsigned)(r0 + j * kMixThreads);
-                va[j] = r < (unsigned)ea.len ? __ldg(sa + j * kMixThreads) : 0.0f;
-                vb[j] = r < (unsigned)eb.len ? __ldg(sb + j * kMixThreads) : 0.0f;
-            }
-#pragma unroll
-            for (int j = 0; j < kPerThread; ++j) {
-                const unsigned r = (unsigned)(r0 + j * kMixThreads);
-                // samples outside the note stay untouched even when coef is inf / NaN
-                if (r < (unsigned)ea.len) acc[j] = fmaf(va[j], ea.coef, acc[j]);
-                if (r < (unsigned)eb.len) acc[j] = fmaf(vb[j], eb.coef, acc[j]);
-            }
-        }
-    }
+struct MixArgs {
+    const float* pcm;
+    const ResolvedEvent* resolved;
+    const int* peak_bits;
+    const int32_t* tile_ptr;
+    const int32_t* tile_events;
+    const adtfe_segment* segments;
+    float* wav;
+    float* tile_max;
+    int* tile_counter;
+    int64_t ld_wav;
+    int32_t tiles_per_seg, n_tiles;
+};
+
+// Writes the finished (not yet normalised) tile and publishes its |max|.
+__device__ __forceinline__ void finish_tile(const MixArgs& a, int tile_id, const float (&acc)[kPerThread], int tid,
+                                            float* s_red) {
+    const int seg = tile_id / a.tiles_per_seg, lo = (tile_id - seg * a.tiles_per_seg) * ADTFE_TILE;
     float m = 0.0f;
-    float* row = wav + (int64_t)seg * ld_wav;
+    float* row = a.wav + (int64_t)seg * a.ld_wav;
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
-        const int n = lo + tid + j * kMixThreads;
-        if (n < ld_wav) row[n] = acc[j];
+        const int n = lo + tid + j * (kMixConsumers * 32);
+        if (n < a.ld_wav) row[n] = acc[j];
         m = nan_max(m, fabsf(acc[j]));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) m = nan_max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    consumer_sync();  // s_red of the previous tile is no longer read
     if ((tid & 31) == 0) s_red[tid >> 5] = m;
-    __syncthreads();
+    consumer_sync();
     if (tid == 0) {
         float r = s_red[0];
-        for (int i = 1; i < kMixThreads / 32; ++i) r = nan_max(r, s_red[i]);
-        tile_max[tile_id] = r;
+        for (int i = 1; i < kMixConsumers; ++i) r = nan_max(r, s_red[i]);
+        a.tile_max[tile_id] = r;
     }
-    // ---- the last CTA of a segment to get here normalises the whole row (wav / peak * max_volume,
-    // synthetiser.py:142-144,156).  Release: tile + tile_max written, fence, then the ticket;
-    // acquire: ticket, fence, then read through L2 (__ldcg) what the other CTAs wrote.
+}
+
+__global__ void __launch_bounds__(kMixThreads, 4) mix_kernel(const MixArgs a) {
+    extern __shared__ __align__(128) unsigned char mix_smem[];
+    float* s_buf = reinterpret_cast<float*>(mix_smem);                               // kStages * kStageFloats
+    StageDesc* s_desc = reinterpret_cast<StageDesc*>(s_buf + kStages * kStageFloats);
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_desc + kStages);
+    uint64_t* s_empty = s_full + kStages;
+    float* s_red = reinterpret_cast<float*>(s_empty + kStages);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) { mbar_init(s_full + s, 1); mbar_init(s_empty + s, kMixConsumers); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int stage = 0;
+    uint32_t phase = 0;
+
+    if (warp == kMixConsumers) {
+        // ================= producer warp =================
+        for (;;) {
+            int tile = 0;
+            if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
+            tile = __shfl_sync(0xffffffffu, tile, 0);
+            const bool done = tile >= a.n_tiles;
+            mbar_wait(s_empty + stage, phase ^ 1u);
+            if (lane == 0) {
+                StageDesc d;
+                d.kind = 1; d.tile = done ? -1 : tile; d.base = 0; d.vlo = 0; d.vhi = 0; d.coef = 0.0f; d.pad0 = d.pad1 = 0;
+                s_desc[stage] = d;
+                mbar_arrive(s_full + stage);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            if (done) break;
+            const int seg = tile / a.tiles_per_seg;
+            const int lo = (tile - seg * a.tiles_per_seg) * ADTFE_TILE;
+            const int p0 = __ldg(a.tile_ptr + tile), p1 = __ldg(a.tile_ptr + tile + 1);
+            for (int base = p0; base < p1; base += 32) {
+                const int n = min(32, p1 - base);
+                // lane i owns event base + i: both of its sources, clipped to this tile
+                int64_t off[2] = {0, 0};
+                int r_lo[2] = {0, 0}, r_hi[2] = {0, 0}, rel = 0;
+                float coef[2] = {0.0f, 0.0f};
+                if (lane < n) {
+                    const int e = __ldg(a.tile_events + base + lane);
+                    const ResolvedEvent ev = a.resolved[e];
+                    // an all-zero one-shot has peak 0: gain/0 = inf (or NaN), and 0 * inf = NaN over the
+                    // whole note - the reference's o / 0 (synthetiser.py:225)
+                    const float scale = ev.gain / __int_as_float(a.peak_bits[e]);
+                    rel = lo - ev.start;  // tile sample i is source sample i + rel
+                    off[0] = ev.a_off; off[1] = ev.b_off;
+                    coef[0] = ev.ca * scale; coef[1] = ev.cb * scale;
+                    r_lo[0] = r_lo[1] = max(0, rel);
+                    r_hi[0] = min(ev.la, rel + ADTFE_TILE);
+                    r_hi[1] = min(ev.lb, rel + ADTFE_TILE);
+                }
+                for (int i = 0; i < n; ++i) {
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const bool live = r_hi[s] > r_lo[s];
+                        if (!__shfl_sync(0xffffffffu, (int)live, i)) continue;  // warp-uniform
+                        mbar_wait(s_empty + stage, phase ^ 1u);
+                        if (lane == i) {
+                            const int g_lo = r_lo[s] & ~3, g_hi = (r_hi[s] + 3) & ~3;  // storage is padded to 4 floats
+                            StageDesc d;
+                            d.kind = 0; d.tile = tile; d.base = rel - g_lo; d.vlo = r_lo[s] - rel; d.vhi = r_hi[s] - rel;
+                            d.coef = coef[s]; d.pad0 = d.pad1 = 0;
+                            s_desc[stage] = d;
+                            const uint32_t bytes = (uint32_t)(g_hi - g_lo) * 4u;
+                            mbar_expect_tx(s_full + stage, bytes);
+                            bulk_g2s(s_buf + stage * kStageFloats, a.pcm + off[s] + g_lo, bytes, s_full + stage);
+                        }
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ================= consumer warps =================
+    float acc[kPerThread];
+#pragma unroll
+    for (int j = 0; j < kPerThread; ++j) acc[j] = 0.0f;
+    int tile = -1;
+    for (;;) {
+        mbar_wait(s_full + stage, phase);
+        const int4 d0 = *reinterpret_cast<const int4*>(s_desc + stage);
+        if (d0.x != 0) {  // a new tile begins
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty + stage);
+            if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            if (tile >= 0) finish_tile(a, tile, acc, tid, s_red);
+            tile = d0.y;
+            if (tile < 0) break;
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j) acc[j] = 0.0f;
+            continue;
+        }
+        const int4 d1 = *reinterpret_cast<const int4*>(reinterpret_cast<const char*>(s_desc + stage) + 16);
+        const int vlo = d0.w, vhi = d1.x;
+        const float coef = __int_as_float(d1.y);
+        const float* src = s_buf + stage * kStageFloats + d0.z + tid;
+        if (vlo == 0 && vhi == ADTFE_TILE) {
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j) acc[j] = fmaf(src[j * (kMixConsumers * 32)], coef, acc[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPerThread; ++j) {
+                const int i = tid + j * (kMixConsumers * 32);
+                // samples outside the note stay untouched even when coef is inf / NaN
+                if (i >= vlo && i < vhi) acc[j] = fmaf(src[j * (kMixConsumers * 32)], coef, acc[j]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_empty + stage);
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+    }
+}
+
+
+// Row normalisation (wav / peak * max_volume, synthetiser.py:142-144,156): one CTA per tile; the
+// segment peak is the max of its tile maxima.  An all-zero mix gives NaN (the reference's 0/0),
+// samples beyond the segment's length stay exact zeros (collate_fn pads with 0.0).
+constexpr int kNormThreads = 256;
+__global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_segment* __restrict__ segments,
+                                                                 const float* __restrict__ tile_max, int tiles_per_seg,
+                                                                 int64_t ld_wav, float* __restrict__ wav) {
+    const int tile_id = blockIdx.x, tid = threadIdx.x;
+    const int seg = tile_id / tiles_per_seg, lo = (tile_id - seg * tiles_per_seg) * ADTFE_TILE;
     const adtfe_segment sg = segments[seg];
-    if (sg.flags == 0) return;  // empty note list: the row is already all zeros
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = atomicAdd(seg_done + seg, 1) == tiles_per_seg - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
+    if (sg.flags == 0 || lo >= sg.len) return;
     float peak = 0.0f;
-    for (int t = tid; t < tiles_per_seg; t += kMixThreads) peak = nan_max(peak, __ldcg(tile_max + seg * tiles_per_seg + t));
+    for (int t = tid & 31; t < tiles_per_seg; t += 32) peak = nan_max(peak, __ldg(tile_max + seg * tiles_per_seg + t));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) peak = nan_max(peak, __shfl_xor_sync(0xffffffffu, peak, o));
-    if ((tid & 31) == 0) s_red[tid >> 5] = peak;
-    __syncthreads();
-    peak = s_red[0];
-    for (int i = 1; i < kMixThreads / 32; ++i) peak = nan_max(peak, s_red[i]);
     const float vol = sg.max_volume;
-    float4* row4 = reinterpret_cast<float4*>(row);  // ld_wav is a multiple of 4 and the base is 16-byte aligned
-    const int n4 = sg.len >> 2;
-    for (int i = tid; i < n4; i += kMixThreads) {
-        float4 v = __ldcg(row4 + i);
+    float* row = wav + (int64_t)seg * ld_wav + lo;  // ld_wav is a multiple of 4 and the base is 16-byte aligned
+    const int n = min(ADTFE_TILE, sg.len - lo);
+    float4* row4 = reinterpret_cast<float4*>(row);
+    const int n4 = n >> 2;
+    for (int i = tid; i < n4; i += kNormThreads) {
+        float4 v = row4[i];
         v.x = __fmul_rn(__fdiv_rn(v.x, peak), vol); v.y = __fmul_rn(__fdiv_rn(v.y, peak), vol);
         v.z = __fmul_rn(__fdiv_rn(v.z, peak), vol); v.w = __fmul_rn(__fdiv_rn(v.w, peak), vol);
         row4[i] = v;
     }
-    // the reference's row ends at len; beyond it collate_fn pads with exact zeros
-    for (int i = 4 * n4 + tid; i < sg.len; i += kMixThreads) row[i] = __fmul_rn(__fdiv_rn(__ldcg(row + i), peak), vol);
+    for (int i = 4 * n4 + tid; i < n; i += kNormThreads) row[i] = __fmul_rn(__fdiv_rn(row[i], peak), vol);
+}
+
+static size_t mix_smem_bytes() {
+    return (size_t)kStages * kStageFloats * 4 + kStages * sizeof(StageDesc) + 2 * kStages * 8 + kMixConsumers * 4 + 16;
 }
 
 }  // namespace adtfe
@@ -266,7 +366,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg) {
     if (n_events < 0 || n_seg < 0 || tiles_per_seg < 0) return 0;
-    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_events * 4 + (size_t)n_seg * 4) +
+    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_events * 4 + (size_t)n_seg * 4 + 4) +
            align256((size_t)n_seg * tiles_per_seg * 4) + 256;
 }
 
@@ -293,17 +393,30 @@ extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, floa
     ResolvedEvent* resolved = (ResolvedEvent*)ws;
     int* peak_bits = (int*)(ws + align256((size_t)plan->n_events * sizeof(ResolvedEvent)));
     int* seg_done = peak_bits + plan->n_events;  // zeroed together with the peaks
-    float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4 + (size_t)plan->n_seg * 4));
+    int* tile_counter = seg_done + plan->n_seg;   // the mixer's work queue head
+    float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4 + (size_t)plan->n_seg * 4 + 4));
     const int n_tiles = plan->n_seg * plan->tiles_per_seg;
-    ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, ((size_t)plan->n_events + plan->n_seg) * 4, st));
+    ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, ((size_t)plan->n_events + plan->n_seg + 1) * 4, st));
     if (plan->n_events > 0) {
         peak_kernel<<<plan->n_peak_work, kPeakThreads, 0, st>>>(bank->pcm, plan->events_dev, plan->peak_work_dev,
                                                                resolved, peak_bits);
         ADTFE_CUDA(cudaGetLastError());
     }
-    mix_kernel<<<n_tiles, kMixThreads, 0, st>>>(bank->pcm, resolved, peak_bits, plan->tile_ptr_dev,
-                                               plan->tile_events_dev, plan->segments_dev, plan->tiles_per_seg,
-                                               plan->ld_wav, wav_out_dev, tile_max, seg_done);
+    static bool smem_set[64] = {};
+    if (bank->device < 64 && !smem_set[bank->device]) {
+        ADTFE_CUDA(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mix_smem_bytes()));
+        smem_set[bank->device] = true;
+    }
+    MixArgs a;
+    a.pcm = bank->pcm; a.resolved = resolved; a.peak_bits = peak_bits; a.tile_ptr = plan->tile_ptr_dev;
+    a.tile_events = plan->tile_events_dev; a.segments = plan->segments_dev; a.wav = wav_out_dev; a.tile_max = tile_max;
+    a.tile_counter = tile_counter; a.ld_wav = plan->ld_wav; a.tiles_per_seg = plan->tiles_per_seg;
+    a.n_tiles = n_tiles;
+    const int grid = std::min(n_tiles, 4 * bank->sm_count);
+    mix_kernel<<<grid, kMixThreads, mix_smem_bytes(), st>>>(a);
+    ADTFE_CUDA(cudaGetLastError());
+    normalise_kernel<<<n_tiles, kNormThreads, 0, st>>>(plan->segments_dev, tile_max, plan->tiles_per_seg, plan->ld_wav,
+                                                      wav_out_dev);
     ADTFE_CUDA(cudaGetLastError());
     return ADTFE_OK;
 }
