@@ -13,7 +13,7 @@ EXPORTS = [
     "adtfe_version", "adtfe_last_error", "adtfe_device_ok",
     "adtfe_bank_create", "adtfe_bank_destroy", "adtfe_bank_bytes",
     "adtfe_render_workspace_bytes", "adtfe_render",
-    "adtfe_mel_create", "adtfe_mel_destroy", "adtfe_mel_frames", "adtfe_mel_fast_path", "adtfe_logmel",
+    "adtfe_mel_create", "adtfe_mel_destroy", "adtfe_mel_frames", "adtfe_mel_fast_path", "adtfe_logmel", "adtfe_logmel_rows",
     "adtfe_render_logmel", "adtfe_frontend_host", "adtfe_plan_blob_layout",
     "adtfe_planner_create", "adtfe_planner_destroy", "adtfe_planner_plan", "adtfe_planner_export",
 ]
@@ -28,7 +28,9 @@ class Plan(C.Structure):
     _fields_ = [("events_dev", C.c_void_p), ("segments_dev", C.c_void_p), ("tile_ptr_dev", C.c_void_p),
                 ("tile_events_dev", C.c_void_p), ("peak_work_dev", C.c_void_p),
                 ("n_events", C.c_int32), ("n_seg", C.c_int32), ("tiles_per_seg", C.c_int32),
-                ("n_peak_work", C.c_int32), ("ld_wav", C.c_int64)]
+                ("n_peak_work", C.c_int32), ("ld_wav", C.c_int64),
+                ("mel_rows_dev", C.c_void_p), ("mel_total_rows", C.c_int64), ("mel_max_count", C.c_int32),
+                ("n_chunks", C.c_int32), ("chunks_host", C.c_void_p)]
 
 
 _lock = threading.Lock()
@@ -52,9 +54,10 @@ def _declare(lib) -> None:
     lib.adtfe_mel_fast_path.argtypes = [vp]
     lib.adtfe_mel_frames.argtypes = [vp, i64, C.POINTER(i32), C.POINTER(i32)]
     lib.adtfe_logmel.argtypes = [vp, vp, i32, i64, i64, vp, vp]
+    lib.adtfe_logmel_rows.argtypes = [vp, vp, i32, i64, vp, i32, vp, vp]
     lib.adtfe_render_logmel.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, vp, vp, sz, vp]
     lib.adtfe_frontend_host.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp]
-    lib.adtfe_plan_blob_layout.argtypes = [C.POINTER(Plan), C.POINTER(sz * 5), C.POINTER(sz)]
+    lib.adtfe_plan_blob_layout.argtypes = [C.POINTER(Plan), C.POINTER(sz * 6), C.POINTER(sz)]
     lib.adtfe_planner_create.argtypes = [i32, C.c_double, C.c_double, C.c_double, i32, vp, vp, i32, vp, vp, vp, vp, vp,
                                          vp, C.POINTER(vp)]
     lib.adtfe_planner_destroy.argtypes = [vp]

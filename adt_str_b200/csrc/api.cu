@@ -47,6 +47,11 @@ extern "C" int adtfe_bank_destroy(adtfe_bank* bank) {
     cudaFree(bank->pcm);
     cudaFree(bank->offsets);
     cudaFree(bank->lengths);
+    for (int k = 0; k < bank->n_streams; ++k) {
+        if (bank->streams[k]) cudaStreamDestroy(bank->streams[k]);
+        if (bank->join_events[k]) cudaEventDestroy(bank->join_events[k]);
+    }
+    if (bank->fork_event) cudaEventDestroy(bank->fork_event);
     delete bank;
     return ADTFE_OK;
 }
@@ -88,6 +93,17 @@ extern "C" int adtfe_bank_create(const float* pcm_host, int64_t total_floats, co
         adtfe_bank_destroy(b);
         return ADTFE_ERR_CUDA;
     }
+    bool ok = cudaEventCreateWithFlags(&b->fork_event, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; ok && k < kBankStreams; ++k) {
+        ok = cudaStreamCreateWithFlags(&b->streams[k], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&b->join_events[k], cudaEventDisableTiming) == cudaSuccess;
+        if (ok) b->n_streams = k + 1;
+    }
+    if (!ok) {
+        set_error("adtfe_bank_create: cannot create streams: %s", cudaGetErrorString(cudaGetLastError()));
+        adtfe_bank_destroy(b);
+        return ADTFE_ERR_CUDA;
+    }
     *out = b;
     return ADTFE_OK;
 }
@@ -95,16 +111,19 @@ extern "C" int adtfe_bank_create(const float* pcm_host, int64_t total_floats, co
 extern "C" int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel, const adtfe_plan* plan,
                                    int64_t n_samples, float* wav_out_dev, float* mel_out_dev, void* workspace_dev,
                                    size_t workspace_bytes, void* stream) {
-    ADTFE_REQUIRE(plan && n_samples <= plan->ld_wav, ADTFE_ERR_BAD_ARG,
+    ADTFE_REQUIRE(plan && (plan->mel_rows_dev || n_samples <= plan->ld_wav), ADTFE_ERR_BAD_ARG,
                   "adtfe_render_logmel: n_samples exceeds the row pitch");
     int rc = adtfe_render(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream);
     if (rc != ADTFE_OK) return rc;
+    if (plan->mel_rows_dev)
+        return adtfe_logmel_rows(mel, wav_out_dev, plan->n_seg, plan->ld_wav, plan->mel_rows_dev, plan->mel_max_count,
+                                 mel_out_dev, stream);
     return adtfe_logmel(mel, wav_out_dev, plan->n_seg, plan->ld_wav, n_samples, mel_out_dev, stream);
 }
 
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-extern "C" int adtfe_plan_blob_layout(const adtfe_plan* s, size_t offsets[5], size_t* blob_bytes) {
+extern "C" int adtfe_plan_blob_layout(const adtfe_plan* s, size_t offsets[6], size_t* blob_bytes) {
     ADTFE_REQUIRE(s && offsets && blob_bytes, ADTFE_ERR_BAD_ARG, "adtfe_plan_blob_layout: null pointer");
     ADTFE_REQUIRE(s->n_events >= 0 && s->n_seg >= 0 && s->tiles_per_seg >= 0 && s->n_peak_work >= 0,
                   ADTFE_ERR_BAD_ARG, "adtfe_plan_blob_layout: negative count");
@@ -113,7 +132,8 @@ extern "C" int adtfe_plan_blob_layout(const adtfe_plan* s, size_t offsets[5], si
     offsets[1] = o; o = align16(o + (size_t)s->n_seg * sizeof(adtfe_segment));
     offsets[2] = o; o = align16(o + ((size_t)s->n_seg * s->tiles_per_seg + 1) * 4);
     offsets[3] = o; o = align16(o + (size_t)s->n_peak_work * sizeof(adtfe_peak_item));
-    offsets[4] = o;  // tile_events runs to the end of the blob; its length is tile_ptr's last entry
+    offsets[4] = o; o = align16(o + (s->mel_total_rows > 0 ? (size_t)s->n_seg * sizeof(adtfe_mel_row) : 0));
+    offsets[5] = o;  // tile_events runs to the end of the blob; its length is tile_ptr's last entry
     *blob_bytes = o;
     return ADTFE_OK;
 }
@@ -124,7 +144,7 @@ extern "C" int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel,
                                    float* mel_out_host, float* wav_out_host, void* stream) {
     ADTFE_REQUIRE(bank && mel && shape && blob_host && blob_dev && mel_out_host, ADTFE_ERR_BAD_ARG,
                   "adtfe_frontend_host: null pointer");
-    size_t off[5], fixed = 0;
+    size_t off[6], fixed = 0;
     int rc = adtfe_plan_blob_layout(shape, off, &fixed);
     if (rc != ADTFE_OK) return rc;
     ADTFE_REQUIRE(blob_bytes >= fixed, ADTFE_ERR_BAD_ARG, "adtfe_frontend_host: plan blob %zu B < %zu B", blob_bytes,
@@ -137,12 +157,14 @@ extern "C" int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel,
     p.segments_dev = (const adtfe_segment*)(d + off[1]);
     p.tile_ptr_dev = (const int32_t*)(d + off[2]);
     p.peak_work_dev = (const adtfe_peak_item*)(d + off[3]);
-    p.tile_events_dev = (const int32_t*)(d + off[4]);
+    p.mel_rows_dev = shape->mel_total_rows > 0 ? (const adtfe_mel_row*)(d + off[4]) : nullptr;
+    p.tile_events_dev = (const int32_t*)(d + off[5]);
     rc = adtfe_render_logmel(bank, mel, &p, n_samples, wav_dev, mel_dev, workspace_dev, workspace_bytes, stream);
     if (rc != ADTFE_OK) return rc;
     int32_t first = 0, count = 0;
     adtfe_mel_frames(mel, n_samples, &first, &count);
-    const size_t mel_bytes = (size_t)p.n_seg * count * mel->n_mels * 4;
+    const size_t mel_bytes = p.mel_rows_dev ? (size_t)p.mel_total_rows * mel->n_mels * 4
+                                            : (size_t)p.n_seg * count * mel->n_mels * 4;
     if (mel_bytes) ADTFE_CUDA(cudaMemcpyAsync(mel_out_host, mel_dev, mel_bytes, cudaMemcpyDeviceToHost, st));
     if (wav_out_host && p.n_seg)
         ADTFE_CUDA(cudaMemcpyAsync(wav_out_host, wav_dev, (size_t)p.n_seg * p.ld_wav * 4, cudaMemcpyDeviceToHost, st));

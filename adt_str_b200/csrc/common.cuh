@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <mutex>
 #include <string>
 
 #include "../../include/adtfe.h"
@@ -85,6 +86,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 struct adtfe_mel_tables;
 
+constexpr int kBankStreams = 4;
 struct adtfe_bank {
     int device = 0;
     int sm_count = 148;
@@ -93,6 +95,11 @@ struct adtfe_bank {
     float* pcm = nullptr;
     int64_t* offsets = nullptr;
     int32_t* lengths = nullptr;
+    // internal streams for chunked plans: forked from / joined into the caller's stream
+    int n_streams = 0;
+    cudaStream_t streams[kBankStreams] = {};
+    cudaEvent_t fork_event = nullptr, join_events[kBankStreams] = {};
+    mutable std::mutex mu;
 };
 
 struct adtfe_mel {
@@ -102,8 +109,9 @@ struct adtfe_mel {
     int32_t nnz = 0;        // stored filter weights (first..last non-zero bin of every filter)
     float* window = nullptr;   // n_fft
     float2* twiddle = nullptr; // 32 x 32: W_2048^(k1*n2), k1 = 1..32, n2 = lane
-    float2* lane_tw = nullptr; // 3 x 32: per-lane twiddles of the cross-lane 32-point DFT
-    float* weights = nullptr;  // filter weights in mel-phase order (interval pairs, or per filter)
+    float2* lane_tw = nullptr; // 4 x 32: per-lane twiddles of the cross-lane 32-point DFT (stages 0..3)
+    float* weights = nullptr;  // filter weights in mel-phase order (groups of (up, down) pairs, or per filter)
+    void* groups = nullptr;    // fast path: MelGroup records {first bin, S row to flush into}
     int32_t fast_path = 0;     // 1: the filterbank is triangular (<= 2 adjacent filters per bin)
     struct adtfe_mel_tables* tables = nullptr;  // mel-phase items + warp schedule, passed as a kernel parameter
     size_t smem_bytes = 0;

@@ -6,33 +6,41 @@
 // clamp[-23, 12], (x + 23) / 35, keep frames wpi .. T-wpi-2.  Only kept frames are
 // computed; their support never reaches the reflect padding.
 //
-// Persistent kernel, one CTA of 16 warps per SM.  A *round* is up to 32 consecutive kept
-// frames of one segment (a segment's frames are split into equal rounds); nothing but the
-// (frames x n_mels) result goes to HBM.
+// Persistent kernel, one CTA of 8 warps per SM, up to 255 registers per thread.  A *round* is up
+// to 32 consecutive kept frames of one segment (a segment's frames are split into equal rounds);
+// nothing but the (frames x n_mels) result goes to HBM.
+//
+// The fp32 pipe of sm_100a retires one scalar FFMA/FADD/FMUL per clock per scheduler, and a packed
+// FFMA2/FADD2/FMUL2 (two results per lane) every two clocks - same arithmetic rate, half the issue
+// slots (tools/microbench/fp32_pipe.cu).  The scalar kernel was issue-bound, so every warp now
+// transforms TWO frames at once: all values are float2 = (frame f, frame f+1), every butterfly,
+// twiddle and power is one packed instruction, and window / twiddle loads and all address
+// arithmetic are shared by the two frames.
 //
 //  span    the round's samples - (frames-1)*hop + 2048 floats, every sample once although it
 //          feeds 8.5 frames - are brought into shared memory by one TMA bulk copy
 //          (cp.async.bulk + mbarrier) issued a round ahead, so global-load latency never sits
 //          on the critical path and no registers are spent on prefetching.  Rows that are not
 //          16-byte aligned take a cooperative copy instead.
-//  FFT     one warp owns one frame at a time (two per round):
+//  FFT     one warp owns one frame pair at a time (two pairs per round):
 //   pass 1  lane n2 holds x[32*n1 + n2] * hann, n1 = 0..63, and runs a 64-point real DFT
 //           over n1 in registers (generated straight-line code, tools/gen_fft.py)
 //   twiddle Y[k1][n2] *= W_2048^(k1*n2)
-//   exchange through the frame's own row of the power matrix (not yet written), as a
-//           32 x 32 tile with an XOR swizzle: STS.32 rows and LDS.128 columns are both
-//           conflict-free, real parts then imaginary parts
+//   exchange through the pair's own two columns of the power matrix P[bin][frame] (not yet
+//           written): element (k1, n2) sits in row 33*k1 + n2, so the writer (lane n2, one k1 per
+//           STS.64) and the reader (lane k1, one n2 per LDS.64) are both conflict-free with
+//           immediate offsets only; real parts, then imaginary parts
 //   pass 2  lane k1 (0..31) runs a 32-point complex DFT over n2 -> X[k1 + 64*k2];
 //           bins above 1024 are the mirror images of bins 64-k1 + 64*(31-k2)
 //   column k1 = 32 (bins 32 + 64*k2) is a 32-point DFT across lanes with shuffles
-//   |X|^2 goes to P[frame][bin] (row pitch 1061: consecutive bins / consecutive frames both
-//           land in distinct banks)
+//   |X|^2 goes to P[bin][f .. f+1] (row pitch 34: STS.64 of consecutive bins and LDS.32 of
+//           consecutive frames are conflict-free)
 //  mel     lanes are the frames.  A triangular filterbank has at most two adjacent filters per
 //          bin, so bins are walked once: the bins between two filter centres feed the falling
-//          edge of the lower filter and the rising edge of the upper one (two FMAs per loaded
-//          power value, weights by broadcast LDS.128).  Each warp owns a contiguous,
-//          cost-balanced range of such intervals.  Filterbanks without that structure take a
-//          plain per-filter loop over the same P layout.
+//          edge of the lower filter and the rising edge of the upper one - one packed FFMA2 per
+//          loaded power value on the (up, down) weight pair, weights by broadcast LDS.128.  Each
+//          warp owns a contiguous, cost-balanced range of such intervals.  Filterbanks without
+//          that structure take a plain per-filter loop over the same P layout.
 //  output  log / clamp / affine on the staged (filter x frame) tile, 128-byte coalesced rows.
 #include <algorithm>
 #include <cmath>
@@ -45,33 +53,50 @@
 
 namespace adtfe {
 
-constexpr int kWarps = 16;
+constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kRound = 32;                   // frames per round (lanes of the mel phase)
+constexpr int kPairsPerWarp = kRound / 2 / kWarps;
 constexpr int kSpanFloats = 9504;            // >= 31*240 + 2048, bytes a multiple of 128
-constexpr int kPPitch = 1061;                // floats per frame row of P: odd mod 32, >= 1025 + 31 + padding
+constexpr int kPPitch = 34;                  // floats per bin row of P[bin][frame]: 32 frames + 2, pitch/2 odd
+constexpr int kXPitch = 33;                  // exchange element (k1, n2) lives in row 33*k1 + n2 of the pair's columns
+constexpr int kPRows = 1056;                 // 1025 bins + the zero pad row 1025; exchange rows up to 33*31 + 31
+constexpr int kWinPitch = 68;                // window, transposed: lane n2 reads n1 = 4q..4q+3 with one LDS.128
 constexpr int kMaxMels = 128;
 constexpr int kSPitch = 33;
-constexpr int kSideRow = kMaxMels;           // S rows kMaxMels .. kMaxMels+15: boundary sums of the 16 warps
+constexpr int kSideRow = kMaxMels;           // S rows kMaxMels .. kMaxMels+kWarps-1: boundary sums of the warps
 constexpr int kZeroRow = kMaxMels + kWarps;  // an all-zero S row
-constexpr int kSRows = kZeroRow + 1;
-constexpr int kSFloats = 4800;               // >= kSRows * kSPitch, bytes a multiple of 128
-constexpr int kW4Max = 640;                  // float4 weight groups kept in shared memory (fast path)
+constexpr int kDummyRow = kZeroRow + 1;      // sink for sums nobody reads
+constexpr int kSRows = kDummyRow + 1;
+constexpr int kSFloats = 4576;               // >= kSRows * kSPitch, bytes a multiple of 128
+constexpr int kGroupBins = 4;                // bins per mel group (fast path): two float4 of (up, down) weights
+constexpr int kGroupsMax = 320;              // groups kept in shared memory (fast path)
+constexpr int kW4Max = 2 * kGroupsMax;
 static_assert(kSRows * kSPitch <= kSFloats, "S tile");
-static_assert((kSpanFloats * 4) % 128 == 0 && (kPPitch * 4 * kRound) % 128 == 0, "alignment of the shared carve-up");
+static_assert((kSpanFloats * 4) % 128 == 0 && (kPPitch * 4 * kPRows) % 128 == 0 && (kSFloats * 4) % 128 == 0,
+              "alignment of the shared carve-up");
+static_assert(kXPitch * 31 + 31 < kPRows, "exchange rows");
+static_assert(kPairsPerWarp * 2 * kWarps == kRound, "pairs per warp");
 
-// One step of the mel phase.  Fast path: interval j between the centres of filters j-1 and j
-// (first bin, bin pairs, float4 offset of its weights {up0, down0, up1, down1}).  Generic path:
-// filter m (first bin, bins, float offset of its weights in global memory).
+// Mel phase tables.  Fast path (triangular filterbank): the bins between the centres of filters j-1
+// and j form interval j; it is cut into groups of kGroupBins bins {first bin, S row to flush into or -1}
+// with two float4 of weights {up0, down0, up1, down1} each (zero for bins outside the interval), kept in
+// global memory and staged into shared memory by every CTA.  Generic path: filter m (first bin, bins,
+// float offset of its weights in global memory).
 struct MelItem {
     int16_t b0, n;
     int32_t woff;
 };
+struct MelGroup {
+    int32_t b0;   // first of the group's kGroupBins power rows (b0 + kGroupBins - 1 <= n_bins: the pad row)
+    int32_t row;  // >= 0: last group of its interval - S[row] = (rising-edge sum carried) + (falling-edge sum)
+};
 struct MelTables {
-    MelItem item[kMaxMels + 1];
-    int16_t first[kWarps + 1];   // warp w owns items first[w] .. first[w+1]-1
+    MelItem item[kMaxMels + 1];  // generic path only
+    int16_t first[kWarps + 1];   // warp w owns items (generic) / groups (fast) first[w] .. first[w+1]-1
+    uint8_t last_row[kWarps];    // fast path: S row of the rising edge a warp is left with (or kDummyRow)
     uint8_t side[kMaxMels];      // S row added to filter m by the output stage (a boundary row or kZeroRow)
-    int32_t fast, n_w4;
+    int32_t fast, n_groups;
 };
 
 struct LogmelArgs {
@@ -81,31 +106,46 @@ struct LogmelArgs {
     const float2* twiddle;
     const float2* lane_tw;
     const float* weights;
+    const MelGroup* groups;
+    const adtfe_mel_row* rows;  // ragged form: per-segment frame count and first output row (else NULL)
     int64_t ld_wav;
     int32_t n_seg, first, count, hop, n_mels;
     int32_t rounds_per_seg, n_rounds;
-    int32_t frames_base, frames_rem;  // round q of a segment has frames_base + (q < frames_rem) frames
 };
 
+// Round r = part q of segment seg: a segment's `count` frames are split evenly over rounds_per_seg rounds,
+// round q has count / rounds_per_seg + (q < count % rounds_per_seg) frames starting at kept frame j0.
 struct RoundGeom {
     int seg, j0, nf;
+    long long out_row;  // output row of the round's first frame
 };
 __device__ __forceinline__ RoundGeom round_geom(const LogmelArgs& p, int r) {
     RoundGeom g;
     g.seg = (int)((unsigned)r / (unsigned)p.rounds_per_seg);
     const int q = r - g.seg * p.rounds_per_seg;
-    g.j0 = q * p.frames_base + min(q, p.frames_rem);
-    g.nf = p.frames_base + (q < p.frames_rem ? 1 : 0);
+    int count = p.count;
+    long long base = (long long)g.seg * p.count;
+    if (p.rows) {
+        const int4 row = __ldg(reinterpret_cast<const int4*>(p.rows + g.seg));  // {out_row lo, hi, count, -}
+        base = (long long)(((unsigned long long)(unsigned)row.y << 32) | (unsigned)row.x);
+        count = row.z;
+    }
+    const int fb = count / p.rounds_per_seg, rem = count - fb * p.rounds_per_seg;
+    g.j0 = q * fb + min(q, rem);
+    g.nf = fb + (q < rem ? 1 : 0);
+    g.out_row = base + g.j0;
     return g;
 }
 
 // Bring the samples of round r into s_span: one TMA bulk copy when source and length are 16-byte
 // aligned, a cooperative copy otherwise.  Called by all threads (the choice is CTA-uniform).
-__device__ __forceinline__ void issue_span(const LogmelArgs& p, int r, float* s_span, uint64_t* bar, int tid) {
-    const RoundGeom g = round_geom(p, r);
+__device__ __forceinline__ void issue_span(const LogmelArgs& p, const RoundGeom& g, float* s_span, uint64_t* bar,
+                                           int tid) {
     const float* src = p.wav + (long long)g.seg * p.ld_wav + (long long)(p.first + g.j0) * p.hop - 1024;
     const int len = (g.nf - 1) * p.hop + 2048;
-    if ((((uintptr_t)src | (uintptr_t)(len * 4)) & 15) == 0) {
+    if (g.nf <= 0) {  // a segment with fewer frames than rounds: nothing to fetch
+        if (tid == 0) mbar_arrive(bar);
+    } else if ((((uintptr_t)src | (uintptr_t)(len * 4)) & 15) == 0) {
         if (tid == 0) {
             mbar_expect_tx(bar, (uint32_t)len * 4u);
             bulk_g2s(s_span, src, (uint32_t)len * 4u, bar);
@@ -116,30 +156,47 @@ __device__ __forceinline__ void issue_span(const LogmelArgs& p, int r, float* s_
     }
 }
 
+__device__ __forceinline__ float2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
+    return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+// (ar + i ai) * (w.x + i w.y), both halves of the pair by the same w: 4 packed instructions
+__device__ __forceinline__ void cmul2(float2& ar, float2& ai, const float2 w) {
+    const float2 t = __fmul2_rn(ai, bc2(w.y));
+    const float2 u = __fmul2_rn(ai, bc2(w.x));
+    ai = __ffma2_rn(ar, bc2(w.y), u);
+    ar = __ffma2_rn(ar, bc2(w.x), neg2(t));
+}
+
 __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p, const __grid_constant__ MelTables tab) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_span = reinterpret_cast<float*>(smem_raw);               // kSpanFloats
-    float* s_p = s_span + kSpanFloats;                                // kRound * kPPitch
-    float* s_s = s_p + kRound * kPPitch;                              // kSFloats
+    float* s_p = s_span + kSpanFloats;                                // kPRows * kPPitch
+    float* s_s = s_p + kPRows * kPPitch;                              // kSFloats
     float4* s_w4 = reinterpret_cast<float4*>(s_s + kSFloats);         // kW4Max
-    float* s_win = reinterpret_cast<float*>(s_w4 + kW4Max);           // 2048
-    float2* s_tw = reinterpret_cast<float2*>(s_win + 2048);           // 32*32
-    float2* s_ltw = s_tw + 32 * 32;                                   // 3*32
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ltw + 3 * 32);
+    float* s_win = reinterpret_cast<float*>(s_w4 + kW4Max + 2);       // 32 * kWinPitch (two spare weight slots: prefetch)
+    float2* s_tw = reinterpret_cast<float2*>(s_win + 32 * kWinPitch); // 32*32
+    float2* s_ltw = s_tw + 32 * 32;                                   // 4*32
+    int2* s_grp = reinterpret_cast<int2*>(s_ltw + 4 * 32);            // kGroupsMax + 1
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_grp + kGroupsMax + 2);
 
     const int tid = threadIdx.x, lane = tid & 31;
     // broadcast from lane 0 so the compiler knows the warp index is warp-uniform
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
     if (tid == 0) mbar_init(s_bar, 1);
-    for (int i = tid; i < 2048; i += kThreads) s_win[i] = p.window[i];
+    for (int i = tid; i < 2048; i += kThreads) s_win[(i & 31) * kWinPitch + (i >> 5)] = p.window[i];
     for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = p.twiddle[i];
-    for (int i = tid; i < 3 * 32; i += kThreads) s_ltw[i] = p.lane_tw[i];
-    for (int i = tid; i < tab.n_w4; i += kThreads) s_w4[i] = __ldg(reinterpret_cast<const float4*>(p.weights) + i);
+    for (int i = tid; i < 4 * 32; i += kThreads) s_ltw[i] = p.lane_tw[i];
+    for (int i = tid; i < 2 * tab.n_groups; i += kThreads) s_w4[i] = __ldg(reinterpret_cast<const float4*>(p.weights) + i);
+    for (int i = tid; i <= kGroupsMax; i += kThreads)  // the entry after the last group is prefetched, never used
+        s_grp[i] = i < tab.n_groups ? __ldg(reinterpret_cast<const int2*>(p.groups) + i) : make_int2(0, -1);
     for (int i = tid; i < kSFloats; i += kThreads) s_s[i] = 0.0f;     // the zero row stays zero
-    for (int i = tid; i < kRound * kPPitch; i += kThreads) s_p[i] = 0.0f;
+    for (int i = tid; i < kPRows * kPPitch; i += kThreads) s_p[i] = 0.0f;
     __syncthreads();
-    if ((int)blockIdx.x < p.n_rounds) issue_span(p, blockIdx.x, s_span, s_bar, tid);
+    RoundGeom geo_next = round_geom(p, min((int)blockIdx.x, p.n_rounds - 1));
+    if ((int)blockIdx.x < p.n_rounds) issue_span(p, geo_next, s_span, s_bar, tid);
     __syncthreads();
 
     const int col32_bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);
@@ -153,162 +210,148 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
     uint32_t parity = 0;
 
     for (int round = blockIdx.x; round < p.n_rounds; round += gridDim.x) {
-        const RoundGeom geo = round_geom(p, round);
+        const RoundGeom geo = geo_next;
         mbar_wait(s_bar, parity);
         parity ^= 1u;
 
-        // ================= FFT phase: frames warp and warp + 16 of the round =================
+        // ================= FFT phase: frame pairs warp and warp + 8 of the round =================
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const int f = warp + half * kWarps;
+        for (int half = 0; half < kPairsPerWarp; ++half) {
+            const int f = 2 * (warp + half * kWarps);
             if (f >= geo.nf) break;  // warp-uniform
-            float* pf = s_p + f * kPPitch;
-            // the frame's 32 x 32 exchange tile: 128-byte aligned inside its own (still unwritten) P row
-            // (s_p sits on a 128-byte boundary of the shared window, so the rounding is done on the offset)
-            float* tile = s_p + (((f * (kPPitch * 4) + 127) & ~127) >> 2);
+            // an odd frame count leaves the last pair half empty: its second half repeats the first
+            const int hop_b = (f + 1 < geo.nf) ? p.hop : 0;
 
-            // ---- pass 1: window + 64-point real DFT over n1 (stride-32 samples)
-            float yr[33], yi[33];
+            // ---- pass 1: window + 64-point real DFT over n1 (stride-32 samples), both frames
+            float2 yr[33], yi[33];
             {
-                const float* sp = s_span + f * p.hop + lane;
-                float v[64];
+                const float* sa = s_span + f * p.hop + lane;
+                const float* sb = sa + hop_b;
+                const float4* wt = reinterpret_cast<const float4*>(s_win + lane * kWinPitch);
+                float2 v[64];
 #pragma unroll
-                for (int n1 = 0; n1 < 64; ++n1) v[n1] = sp[32 * n1] * s_win[32 * n1 + lane];
+                for (int q = 0; q < 16; ++q) {
+                    const float4 w = wt[q];
+                    v[4 * q + 0] = __fmul2_rn(make_float2(sa[32 * (4 * q + 0)], sb[32 * (4 * q + 0)]), bc2(w.x));
+                    v[4 * q + 1] = __fmul2_rn(make_float2(sa[32 * (4 * q + 1)], sb[32 * (4 * q + 1)]), bc2(w.y));
+                    v[4 * q + 2] = __fmul2_rn(make_float2(sa[32 * (4 * q + 2)], sb[32 * (4 * q + 2)]), bc2(w.z));
+                    v[4 * q + 3] = __fmul2_rn(make_float2(sa[32 * (4 * q + 3)], sb[32 * (4 * q + 3)]), bc2(w.w));
+                }
                 rdft64(v, yr, yi);
             }
             // ---- twiddle in place (rows 1..31), column 32 is real before its twiddle
 #pragma unroll
-            for (int k1 = 1; k1 < 32; ++k1) {
-                const float2 w = s_tw[(k1 - 1) * 32 + lane];
-                const float a = yr[k1] * w.x - yi[k1] * w.y;
-                yi[k1] = yr[k1] * w.y + yi[k1] * w.x;
-                yr[k1] = a;
-            }
-            float cr, ci;
+            for (int k1 = 1; k1 < 32; ++k1) cmul2(yr[k1], yi[k1], s_tw[(k1 - 1) * 32 + lane]);
+            float2 cr, ci;
             {
                 const float2 w = s_tw[31 * 32 + lane];
-                cr = yr[32] * w.x;
-                ci = yr[32] * w.y;
+                cr = __fmul2_rn(yr[32], bc2(w.x));
+                ci = __fmul2_rn(yr[32], bc2(w.y));
             }
-            // ---- exchange: element (k1, n2) lives at k1*32 + (n2 ^ ((k1 & 7) << 2)); the writer is lane
-            // n2 (one row per STS), the reader lane k1 (LDS.128 of n2 = 4q .. 4q+3)
-            float zr[32], zi[32];
+            // ---- exchange through columns f, f+1 of P: writer lane n2 -> row 33*k1 + n2, reader lane k1
+            float* xw = s_p + lane * kPPitch + f;
+            const float* xr = s_p + lane * (kXPitch * kPPitch) + f;
+            float2 zr[32], zi[32];
             __syncwarp();
 #pragma unroll
-            for (int k1 = 0; k1 < 32; ++k1) tile[k1 * 32 + (lane ^ ((k1 & 7) << 2))] = yr[k1];
+            for (int k1 = 0; k1 < 32; ++k1) *reinterpret_cast<float2*>(xw + k1 * (kXPitch * kPPitch)) = yr[k1];
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 t = *reinterpret_cast<const float4*>(tile + lane * 32 + ((q ^ (lane & 7)) << 2));
-                zr[4 * q] = t.x; zr[4 * q + 1] = t.y; zr[4 * q + 2] = t.z; zr[4 * q + 3] = t.w;
-            }
+            for (int n2 = 0; n2 < 32; ++n2) zr[n2] = *reinterpret_cast<const float2*>(xr + n2 * kPPitch);
             __syncwarp();
-            tile[lane] = 0.0f;  // row 0 is purely real
+            *reinterpret_cast<float2*>(xw) = make_float2(0.0f, 0.0f);  // row 0 is purely real
 #pragma unroll
-            for (int k1 = 1; k1 < 32; ++k1) tile[k1 * 32 + (lane ^ ((k1 & 7) << 2))] = yi[k1];
+            for (int k1 = 1; k1 < 32; ++k1) *reinterpret_cast<float2*>(xw + k1 * (kXPitch * kPPitch)) = yi[k1];
             __syncwarp();
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const float4 t = *reinterpret_cast<const float4*>(tile + lane * 32 + ((q ^ (lane & 7)) << 2));
-                zi[4 * q] = t.x; zi[4 * q + 1] = t.y; zi[4 * q + 2] = t.z; zi[4 * q + 3] = t.w;
-            }
+            for (int n2 = 0; n2 < 32; ++n2) zi[n2] = *reinterpret_cast<const float2*>(xr + n2 * kPPitch);
             __syncwarp();
 
-            // ---- 32-point DFT across lanes for column 32 (decimation in frequency, bit-reversed)
+            // ---- 32-point DFT across lanes for column 32 (decimation in frequency, bit-reversed):
+            // d = other + sign * own (sign -1 on the upper half), then the per-lane twiddle of the stage
+            // (1 on the lower half; W_{2*hb}^(lane mod hb), -i or 1 on the upper half)
 #pragma unroll
             for (int s = 0; s < 5; ++s) {
                 const int hb = 16 >> s;
-                const float orr = __shfl_xor_sync(0xffffffffu, cr, hb);
-                const float oi = __shfl_xor_sync(0xffffffffu, ci, hb);
-                const bool upper = (lane & hb) != 0;
-                const float dr = upper ? orr - cr : cr + orr;
-                const float di = upper ? oi - ci : ci + oi;
-                if (s < 3) {            // W_{2*hb}^(lane mod hb) on the upper half, 1 on the lower
-                    const float2 w = s_ltw[s * 32 + lane];
-                    cr = dr * w.x - di * w.y;
-                    ci = dr * w.y + di * w.x;
-                } else if (s == 3) {    // hb = 2: twiddle is 1 or -i
-                    const bool rot = upper && (lane & 1);
-                    cr = rot ? di : dr;
-                    ci = rot ? -dr : di;
-                } else {
-                    cr = dr;
-                    ci = di;
-                }
+                const float2 orr = shfl_xor2(cr, hb), oi = shfl_xor2(ci, hb);
+                const float sg = (lane & hb) ? -1.0f : 1.0f;
+                cr = __ffma2_rn(cr, bc2(sg), orr);
+                ci = __ffma2_rn(ci, bc2(sg), oi);
+                if (s < 4) cmul2(cr, ci, s_ltw[s * 32 + lane]);
             }
 
             // ---- pass 2: 32-point complex DFT over n2 for k1 = lane
             cdft32(zr, zi);
 
-            // ---- power spectrum into P[f][bin] (over the dead exchange tile)
+            // ---- power spectrum into P[bin][f .. f+1] (over the dead exchange rows)
+            float* pc = s_p + f;
 #pragma unroll
-            for (int k2 = 0; k2 < 16; ++k2) pf[lane + 64 * k2] = zr[k2] * zr[k2] + zi[k2] * zi[k2];
+            for (int k2 = 0; k2 < 16; ++k2)
+                *reinterpret_cast<float2*>(pc + (lane + 64 * k2) * kPPitch) =
+                    __ffma2_rn(zi[k2], zi[k2], __fmul2_rn(zr[k2], zr[k2]));
 #pragma unroll
-            for (int k2 = 16; k2 < 32; ++k2) pf[64 - lane + 64 * (31 - k2)] = zr[k2] * zr[k2] + zi[k2] * zi[k2];
-            if ((lane & 1) == 0) pf[col32_bin] = cr * cr + ci * ci;
-            if (lane == 1) pf[1025] = 0.0f;  // padded bin pairs read one bin past the spectrum with weight 0
+            for (int k2 = 16; k2 < 32; ++k2)
+                *reinterpret_cast<float2*>(pc + (64 - lane + 64 * (31 - k2)) * kPPitch) =
+                    __ffma2_rn(zi[k2], zi[k2], __fmul2_rn(zr[k2], zr[k2]));
+            if ((lane & 1) == 0)
+                *reinterpret_cast<float2*>(pc + col32_bin * kPPitch) = __ffma2_rn(ci, ci, __fmul2_rn(cr, cr));
+            // padded bin pairs read one bin past the spectrum with weight 0: keep it finite
+            if (lane == 1) *reinterpret_cast<float2*>(pc + 1025 * kPPitch) = make_float2(0.0f, 0.0f);
         }
         __syncthreads();  // P complete; the span buffer is free
 
         // the next round's samples arrive while the mel phase runs
-        if (round + (int)gridDim.x < p.n_rounds) issue_span(p, round + gridDim.x, s_span, s_bar, tid);
+        if (round + (int)gridDim.x < p.n_rounds) {
+            geo_next = round_geom(p, round + gridDim.x);
+            issue_span(p, geo_next, s_span, s_bar, tid);
+        }
 
         // ================= mel phase: lane = frame =================
         {
-            const float* pl = s_p + lane * kPPitch;
+            const float* pl = s_p + lane;
             const int i0 = tab.first[warp], i1 = tab.first[warp + 1];
             if (tab.fast) {
+                // groups i0 .. i1-1 of this warp, software-pipelined: the next group's record, power values and
+                // weights are requested before the current group's four packed FMAs.  a0 / a1 hold the
+                // (rising-edge, falling-edge) sums of the interval's even / odd bins.
                 float up_prev = 0.0f;
-#define MEL_PAIR(q)                                                     \
-    {                                                                   \
-        const float4 w = ww[q];                                         \
-        const float p0 = pp[2 * (q)], p1 = pp[2 * (q) + 1];             \
-        u0 = fmaf(w.x, p0, u0); d0 = fmaf(w.y, p0, d0);                 \
-        u1 = fmaf(w.z, p1, u1); d1 = fmaf(w.w, p1, d1);                 \
-    }
-#pragma unroll 1
-                for (int j = i0; j < i1; ++j) {
-                    const MelItem it = tab.item[j];
-                    const float* pp = pl + it.b0;
-                    const float4* ww = s_w4 + it.woff;
-                    float u0 = 0.0f, u1 = 0.0f, d0 = 0.0f, d1 = 0.0f;
-                    int n = it.n;
-#pragma unroll 1
-                    for (; n > 8; n -= 8, pp += 16, ww += 8) {
-                        MEL_PAIR(0) MEL_PAIR(1) MEL_PAIR(2) MEL_PAIR(3) MEL_PAIR(4) MEL_PAIR(5) MEL_PAIR(6) MEL_PAIR(7)
+                float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
+                int2 g = s_grp[i0];
+                const float* pp = pl + g.x * kPPitch;
+                float q0 = pp[0], q1 = pp[kPPitch], q2 = pp[2 * kPPitch], q3 = pp[3 * kPPitch];
+                float4 w0 = s_w4[2 * i0], w1 = s_w4[2 * i0 + 1];
+#pragma unroll 2
+                for (int i = i0; i < i1; ++i) {
+                    const int2 gn = s_grp[i + 1];
+                    const float* pn = pl + gn.x * kPPitch;
+                    const float n0 = pn[0], n1 = pn[kPPitch], n2 = pn[2 * kPPitch], n3 = pn[3 * kPPitch];
+                    const float4 v0 = s_w4[2 * i + 2], v1 = s_w4[2 * i + 3];
+                    a0 = __ffma2_rn(make_float2(w0.x, w0.y), bc2(q0), a0);
+                    a1 = __ffma2_rn(make_float2(w0.z, w0.w), bc2(q1), a1);
+                    a0 = __ffma2_rn(make_float2(w1.x, w1.y), bc2(q2), a0);
+                    a1 = __ffma2_rn(make_float2(w1.z, w1.w), bc2(q3), a1);
+                    if (g.y >= 0) {  // warp-uniform: the interval ends here
+                        const float2 a = __fadd2_rn(a0, a1);
+                        s_s[g.y * kSPitch + lane] = up_prev + a.y;  // falling edge completes the filter below
+                        up_prev = a.x;                              // rising edge waits for the next interval
+                        a0 = make_float2(0.0f, 0.0f);
+                        a1 = make_float2(0.0f, 0.0f);
                     }
-                    switch (n) {  // the last 0..8 pairs: one jump into straight-line code
-                        case 8: MEL_PAIR(7)
-                        case 7: MEL_PAIR(6)
-                        case 6: MEL_PAIR(5)
-                        case 5: MEL_PAIR(4)
-                        case 4: MEL_PAIR(3)
-                        case 3: MEL_PAIR(2)
-                        case 2: MEL_PAIR(1)
-                        case 1: MEL_PAIR(0)
-                        default: break;
-                    }
-                    const float up = u0 + u1, dn = d0 + d1;
-                    // `dn` completes filter j-1: inside the range it joins the rising edge held in up_prev,
-                    // at the start of the range it goes to this warp's boundary row
-                    if (j > i0) s_s[(j - 1) * kSPitch + lane] = up_prev + dn;
-                    else if (j > 0) s_s[(kSideRow + warp) * kSPitch + lane] = dn;
-                    up_prev = up;
+                    g = gn; q0 = n0; q1 = n1; q2 = n2; q3 = n3; w0 = v0; w1 = v1;
                 }
-#undef MEL_PAIR
-                if (i1 > i0 && i1 - 1 < p.n_mels) s_s[(i1 - 1) * kSPitch + lane] = up_prev;
+                s_s[(int)tab.last_row[warp] * kSPitch + lane] = up_prev;
             } else {
                 for (int m = i0; m < i1; ++m) {
                     const MelItem it = tab.item[m];
-                    const float* pp = pl + it.b0;
+                    const float* pp = pl + it.b0 * kPPitch;
                     const float* ww = p.weights + it.woff;
                     float a0 = 0.0f, a1 = 0.0f;
                     int k = 0;
                     for (; k + 1 < it.n; k += 2) {
-                        a0 = fmaf(__ldg(ww + k), pp[k], a0);
-                        a1 = fmaf(__ldg(ww + k + 1), pp[k + 1], a1);
+                        a0 = fmaf(__ldg(ww + k), pp[k * kPPitch], a0);
+                        a1 = fmaf(__ldg(ww + k + 1), pp[(k + 1) * kPPitch], a1);
                     }
-                    if (k < it.n) a0 = fmaf(__ldg(ww + k), pp[k], a0);
+                    if (k < it.n) a0 = fmaf(__ldg(ww + k), pp[k * kPPitch], a0);
                     s_s[m * kSPitch + lane] = a0 + a1;
                 }
             }
@@ -317,10 +360,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
 
         // ================= output: log / clamp / affine, one 128-filter row per warp store =================
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int f = warp + half * kWarps;
+        for (int h = 0; h < kRound / kWarps; ++h) {
+            const int f = warp + h * kWarps;
             if (f < geo.nf) {
-                float* row = p.out + ((long long)geo.seg * p.count + geo.j0 + f) * p.n_mels;
+                float* row = p.out + (geo.out_row + f) * p.n_mels;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int m = lane + 32 * i;
@@ -342,8 +385,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
 using namespace adtfe;
 
 static size_t logmel_smem_bytes() {
-    return ((size_t)kSpanFloats + (size_t)kRound * kPPitch + kSFloats + 4 * (size_t)kW4Max + 2048 + 2 * 32 * 32 +
-            2 * 3 * 32) * 4 + 16;
+    return ((size_t)kSpanFloats + (size_t)kPRows * kPPitch + kSFloats + 4 * (size_t)(kW4Max + 2) + 32 * kWinPitch +
+            2 * 32 * 32 + 2 * 4 * 32 + 2 * (kGroupsMax + 2)) * 4 + 16;
 }
 
 struct adtfe_mel_tables {
@@ -356,6 +399,24 @@ extern "C" int adtfe_mel_frames(const adtfe_mel* mel, int64_t n_samples, int32_t
     const int64_t c = t_total - 2 * (int64_t)mel->wpi - 1;
     *first = mel->wpi;
     *count = (int32_t)(c > 0 ? c : 0);
+    return ADTFE_OK;
+}
+
+static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav, int32_t first,
+                         int32_t count, const adtfe_mel_row* rows_dev, float* out_dev, void* stream) {
+    // frames per round: as many as fit the span buffer, at most 32; a segment's frames are split evenly
+    const int cap = std::min(kRound, (kSpanFloats - 2048) / mel->hop + 1);
+    const int rounds_per_seg = (count + cap - 1) / cap;
+    const long long n_rounds = (long long)n_seg * rounds_per_seg;
+    ADTFE_REQUIRE(n_rounds < (1ll << 30), ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: too many frames for one launch");
+    LogmelArgs a;
+    a.wav = wav_dev; a.out = out_dev; a.window = mel->window; a.twiddle = mel->twiddle; a.lane_tw = mel->lane_tw;
+    a.weights = mel->weights; a.groups = (const MelGroup*)mel->groups; a.rows = rows_dev; a.ld_wav = ld_wav;
+    a.n_seg = n_seg; a.first = first; a.count = count;
+    a.hop = mel->hop; a.n_mels = mel->n_mels; a.rounds_per_seg = rounds_per_seg; a.n_rounds = (int32_t)n_rounds;
+    const int grid = (int)(n_rounds < mel->sm_count ? n_rounds : mel->sm_count);
+    logmel_kernel<<<grid, kThreads, mel->smem_bytes, (cudaStream_t)stream>>>(a, mel->tables->t);
+    ADTFE_CUDA(cudaGetLastError());
     return ADTFE_OK;
 }
 
@@ -373,26 +434,29 @@ extern "C" int adtfe_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t 
     ADTFE_REQUIRE((int64_t)first * mel->hop >= 1024 &&
                       (int64_t)(first + count - 1) * mel->hop + 1024 <= n_samples,
                   ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: frame support leaves the signal");
-    // frames per round: as many as fit the span buffer, at most 32; a segment's frames are split evenly
-    const int cap = std::min(kRound, (kSpanFloats - 2048) / mel->hop + 1);
-    const int rounds_per_seg = (count + cap - 1) / cap;
-    const long long n_rounds = (long long)n_seg * rounds_per_seg;
-    ADTFE_REQUIRE(n_rounds < (1ll << 30), ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: too many frames for one launch");
-    LogmelArgs a;
-    a.wav = wav_dev; a.out = out_dev; a.window = mel->window; a.twiddle = mel->twiddle; a.lane_tw = mel->lane_tw;
-    a.weights = mel->weights; a.ld_wav = ld_wav; a.n_seg = n_seg; a.first = first; a.count = count;
-    a.hop = mel->hop; a.n_mels = mel->n_mels; a.rounds_per_seg = rounds_per_seg; a.n_rounds = (int32_t)n_rounds;
-    a.frames_base = count / rounds_per_seg; a.frames_rem = count % rounds_per_seg;
-    const int grid = (int)(n_rounds < mel->sm_count ? n_rounds : mel->sm_count);
-    logmel_kernel<<<grid, kThreads, mel->smem_bytes, (cudaStream_t)stream>>>(a, mel->tables->t);
-    ADTFE_CUDA(cudaGetLastError());
-    return ADTFE_OK;
+    return launch_logmel(mel, wav_dev, n_seg, ld_wav, first, count, nullptr, out_dev, stream);
+}
+
+extern "C" int adtfe_logmel_rows(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
+                                 const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream) {
+    ADTFE_REQUIRE(mel && n_seg >= 0 && max_count >= 0 && ld_wav >= 0, ADTFE_ERR_BAD_ARG,
+                  "adtfe_logmel_rows: bad argument (n_seg=%d ld_wav=%lld max_count=%d)", n_seg, (long long)ld_wav,
+                  max_count);
+    if (n_seg == 0 || max_count == 0) return ADTFE_OK;
+    ADTFE_REQUIRE(wav_dev && out_dev && rows_dev, ADTFE_ERR_BAD_ARG, "adtfe_logmel_rows: null buffer");
+    ADTFE_REQUIRE(((uintptr_t)wav_dev & 3) == 0 && ((uintptr_t)rows_dev & 15) == 0, ADTFE_ERR_BAD_ARG,
+                  "adtfe_logmel_rows: wav_dev must be 4-byte and rows_dev 16-byte aligned");
+    const int32_t first = mel->wpi;
+    // the longest row must stay inside the pitch (the per-row counts live on the device: the caller's contract)
+    ADTFE_REQUIRE((int64_t)first * mel->hop >= 1024 && (int64_t)(first + max_count - 1) * mel->hop + 1024 <= ld_wav,
+                  ADTFE_ERR_UNSUPPORTED, "adtfe_logmel_rows: frame support leaves the row");
+    return launch_logmel(mel, wav_dev, n_seg, ld_wav, first, max_count, rows_dev, out_dev, stream);
 }
 
 extern "C" int adtfe_mel_destroy(adtfe_mel* mel) {
     if (!mel) return ADTFE_OK;
     cudaSetDevice(mel->device);
-    cudaFree(mel->window); cudaFree(mel->twiddle); cudaFree(mel->lane_tw); cudaFree(mel->weights);
+    cudaFree(mel->window); cudaFree(mel->twiddle); cudaFree(mel->lane_tw); cudaFree(mel->weights); cudaFree(mel->groups);
     delete mel->tables;
     delete mel;
     return ADTFE_OK;
@@ -401,9 +465,10 @@ extern "C" int adtfe_mel_destroy(adtfe_mel* mel) {
 // Triangular structure: every bin feeds at most two adjacent filters and the filter index never
 // decreases with the bin.  Bins are then grouped into intervals j = 0..n_mels (interval j lies
 // between the centres of filters j-1 and j) holding, per bin, the weight towards filter j ("up")
-// and towards filter j-1 ("down").  Returns false when fb does not have that structure (or the
+// and towards filter j-1 ("down"); intervals are cut into groups of kGroupBins bins.  Returns false when fb does not have that structure (or the
 // packed weights do not fit): the caller then uses the per-filter path.
-static bool build_fast_tables(const float* fb, int n_bins, int n_mels, MelTables& t, std::vector<float>& packed) {
+static bool build_fast_tables(const float* fb, int n_bins, int n_mels, MelTables& t, std::vector<float>& packed,
+                              std::vector<MelGroup>& groups) {
     std::vector<int> iv(n_bins, -1);
     std::vector<float> up(n_bins, 0.0f), dn(n_bins, 0.0f);
     std::vector<int> peak(n_mels, 0);
@@ -435,65 +500,85 @@ static bool build_fast_tables(const float* fb, int n_bins, int n_mels, MelTables
         iv[k] = j;
         prev = j;
     }
+    // intervals -> groups of kGroupBins bins; an interval without bins still gets one (all-zero) group,
+    // because its end is where the filter below it is completed
     packed.clear();
+    groups.clear();
     memset(&t, 0, sizeof(t));
-    std::vector<double> cost(n_mels + 1, 0.0);
+    std::vector<int> iv_first(n_mels + 2, 0);  // first group of every interval
     for (int j = 0; j <= n_mels; ++j) {
+        iv_first[j] = (int)groups.size();
         int lo = -1, hi = -1;
         for (int k = 0; k < n_bins; ++k)
             if (iv[k] == j) { if (lo < 0) lo = k; hi = k; }
-        MelItem it;
-        it.b0 = (int16_t)(lo < 0 ? 0 : lo);
-        const int nb = lo < 0 ? 0 : hi - lo + 1;
-        it.n = (int16_t)((nb + 1) / 2);
-        it.woff = (int32_t)(packed.size() / 4);
-        for (int q = 0; q < it.n; ++q)
-            for (int e = 0; e < 2; ++e) {
-                const int k = lo + 2 * q + e;
-                const bool in = k <= hi && iv[k] == j;  // bins of other intervals inside the range cannot occur
-                if (k <= hi && iv[k] != j && iv[k] >= 0) return false;
+        for (int k = lo; k <= hi; ++k)
+            if (lo >= 0 && iv[k] != j && iv[k] >= 0) return false;  // bins of another interval inside the range
+        int g0 = lo < 0 ? 0 : lo;
+        do {
+            MelGroup g;
+            g.b0 = std::min(g0, n_bins + 1 - kGroupBins);  // rows 0 .. n_bins exist (row n_bins is kept at zero)
+            g.row = -1;
+            for (int e = 0; e < kGroupBins; ++e) {
+                const int k = g.b0 + e;
+                const bool in = lo >= 0 && k >= g0 && k < g0 + kGroupBins && k <= hi && iv[k] == j;
                 packed.push_back(in ? up[k] : 0.0f);
                 packed.push_back(in ? dn[k] : 0.0f);
             }
-        if (it.b0 + 2 * it.n > n_bins + 1) return false;  // reads at most one bin past the spectrum (kept at 0)
-        t.item[j] = it;
-        cost[j] = 7.0 * it.n + 24.0;
+            groups.push_back(g);
+            g0 += kGroupBins;
+        } while (lo >= 0 && g0 <= hi);
     }
-    if (packed.size() / 4 > (size_t)kW4Max) return false;
-    // verify: the intervals reproduce fb exactly
+    iv_first[n_mels + 1] = (int)groups.size();
+    if (groups.size() > (size_t)kGroupsMax) return false;
+    // verify: the groups reproduce fb exactly
     {
         std::vector<float> chk((size_t)n_bins * n_mels, 0.0f);
-        for (int j = 0; j <= n_mels; ++j) {
-            const MelItem& it = t.item[j];
-            for (int q = 0; q < 2 * it.n; ++q) {
-                const int k = it.b0 + q;
-                const float wu = packed[(size_t)it.woff * 4 + 2 * q], wd = packed[(size_t)it.woff * 4 + 2 * q + 1];
-                if (k >= n_bins) { if (wu != 0.0f || wd != 0.0f) return false; continue; }
-                if (wu != 0.0f) { if (j >= n_mels) return false; chk[(size_t)k * n_mels + j] += wu; }
-                if (wd != 0.0f) { if (j < 1) return false; chk[(size_t)k * n_mels + j - 1] += wd; }
-            }
-        }
-        if (memcmp(chk.data(), fb, chk.size() * 4) != 0) {
-            for (size_t i = 0; i < chk.size(); ++i)
-                if (chk[i] != fb[i]) return false;  // (-0.0 vs 0.0 would differ bytewise only)
-        }
+        for (int j = 0; j <= n_mels; ++j)
+            for (int gi = iv_first[j]; gi < iv_first[j + 1]; ++gi)
+                for (int e = 0; e < kGroupBins; ++e) {
+                    const int k = groups[gi].b0 + e;
+                    const float wu = packed[((size_t)gi * kGroupBins + e) * 2], wd = packed[((size_t)gi * kGroupBins + e) * 2 + 1];
+                    if (k >= n_bins) { if (wu != 0.0f || wd != 0.0f) return false; continue; }
+                    if (wu != 0.0f) { if (j >= n_mels) return false; chk[(size_t)k * n_mels + j] += wu; }
+                    if (wd != 0.0f) { if (j < 1) return false; chk[(size_t)k * n_mels + j - 1] += wd; }
+                }
+        for (size_t i = 0; i < chk.size(); ++i)
+            if (chk[i] != fb[i]) return false;
     }
-    // contiguous interval ranges for the 16 warps, balanced by estimated cost
+    // contiguous interval ranges for the warps, balanced by estimated cost (a group ~16 issue slots, an
+    // interval end ~10 more)
+    std::vector<double> cost(n_mels + 1, 0.0);
     double total = 0;
-    for (int j = 0; j <= n_mels; ++j) total += cost[j];
+    for (int j = 0; j <= n_mels; ++j) total += cost[j] = 16.0 * (iv_first[j + 1] - iv_first[j]) + 10.0;
     int j = 0;
     double spent = 0;
+    std::vector<int> iv_of_warp(kWarps + 1, 0);
     for (int w = 0; w < kWarps; ++w) {
-        t.first[w] = (int16_t)j;
+        iv_of_warp[w] = j;
         const double target = total * (w + 1) / kWarps;
         while (j <= n_mels && (w == kWarps - 1 || spent + 0.5 * cost[j] <= target)) spent += cost[j++];
     }
-    t.first[kWarps] = (int16_t)(n_mels + 1);
+    iv_of_warp[kWarps] = n_mels + 1;
     for (int m = 0; m < kMaxMels; ++m) t.side[m] = (uint8_t)kZeroRow;
-    for (int w = 0; w < kWarps; ++w)
-        if (t.first[w + 1] > t.first[w] && t.first[w] > 0) t.side[t.first[w] - 1] = (uint8_t)(kSideRow + w);
+    for (int w = 0; w < kWarps; ++w) {
+        const int j0 = iv_of_warp[w], j1 = iv_of_warp[w + 1];
+        t.first[w] = (int16_t)iv_first[j0];
+        t.last_row[w] = (uint8_t)kDummyRow;
+        for (int jj = j0; jj < j1; ++jj) {
+            // the end of interval jj completes filter jj-1: inside the warp's range with the rising edge the
+            // warp carries, at the start of the range through the warp's boundary row
+            int row = jj - 1;
+            if (jj == j0) row = jj > 0 ? kSideRow + w : kDummyRow;
+            groups[iv_first[jj + 1] - 1].row = row;
+        }
+        if (j1 > j0) {
+            if (j0 > 0) t.side[j0 - 1] = (uint8_t)(kSideRow + w);
+            if (j1 - 1 < n_mels) t.last_row[w] = (uint8_t)(j1 - 1);
+        }
+    }
+    t.first[kWarps] = (int16_t)groups.size();
     t.fast = 1;
-    t.n_w4 = (int32_t)(packed.size() / 4);
+    t.n_groups = (int32_t)groups.size();
     return true;
 }
 
@@ -525,7 +610,7 @@ static void build_generic_tables(const float* fb, int n_bins, int n_mels, MelTab
     t.first[kWarps] = (int16_t)n_mels;
     for (int i = 0; i < kMaxMels; ++i) t.side[i] = (uint8_t)kZeroRow;
     t.fast = 0;
-    t.n_w4 = 0;
+    t.n_groups = 0;
 }
 
 extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, const float* window_host,
@@ -541,17 +626,19 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
     ADTFE_CUDA(cudaSetDevice(device));
 
     const int n_bins = n_fft / 2 + 1;
-    std::vector<float2> tw(32 * 32), ltw(3 * 32);
+    std::vector<float2> tw(32 * 32), ltw(4 * 32);
     const double two_pi = 6.283185307179586476925286766559;
     for (int k1 = 1; k1 <= 32; ++k1)
         for (int n2 = 0; n2 < 32; ++n2) {
             const double a = -two_pi * (double)(k1 * n2) / 2048.0;
             tw[(k1 - 1) * 32 + n2] = make_float2((float)std::cos(a), (float)std::sin(a));
         }
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < 4; ++s) {  // stage 3 (half = 2): 1 or -i, exact
         const int half = 16 >> s;
         for (int l = 0; l < 32; ++l) {
-            if (l & half) {
+            if (s == 3) {
+                ltw[s * 32 + l] = ((l & half) && (l & 1)) ? make_float2(0.0f, -1.0f) : make_float2(1.0f, 0.0f);
+            } else if (l & half) {
                 const double a = -two_pi * (double)(l & (half - 1)) / (double)(2 * half);
                 ltw[s * 32 + l] = make_float2((float)std::cos(a), (float)std::sin(a));
             } else {
@@ -567,8 +654,11 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
     mel->smem_bytes = logmel_smem_bytes();
     mel->tables = new adtfe_mel_tables();
     std::vector<float> packed;
-    if (!build_fast_tables(fb_host, n_bins, n_mels, mel->tables->t, packed))
+    std::vector<MelGroup> groups;
+    if (!build_fast_tables(fb_host, n_bins, n_mels, mel->tables->t, packed, groups)) {
+        groups.clear();
         build_generic_tables(fb_host, n_bins, n_mels, mel->tables->t, packed);
+    }
     mel->fast_path = mel->tables->t.fast;
     mel->nnz = 0;
     for (size_t i = 0; i < (size_t)n_bins * n_mels; ++i) mel->nnz += fb_host[i] != 0.0f;
@@ -583,6 +673,7 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
     MEL_UPLOAD(mel->twiddle, tw.data(), tw.size() * sizeof(float2));
     MEL_UPLOAD(mel->lane_tw, ltw.data(), ltw.size() * sizeof(float2));
     MEL_UPLOAD(mel->weights, packed.data(), packed.size() * 4);
+    MEL_UPLOAD(mel->groups, groups.data(), groups.size() * sizeof(MelGroup));
 #undef MEL_UPLOAD
     if (cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel->smem_bytes) !=
         cudaSuccess) {

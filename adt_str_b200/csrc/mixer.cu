@@ -20,6 +20,7 @@
 //                       tile maxima and normalises the row in place, wav / peak * max_volume
 //                       (an all-zero mix gives NaN, like the reference's 0/0).
 #include <algorithm>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -388,35 +389,70 @@ extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, floa
     const size_t need = adtfe_render_workspace_bytes(plan->n_events, plan->n_seg, plan->tiles_per_seg);
     ADTFE_REQUIRE(workspace_dev && workspace_bytes >= need, ADTFE_ERR_WORKSPACE,
                   "adtfe_render: workspace %zu B < %zu B", workspace_bytes, need);
-    cudaStream_t st = (cudaStream_t)stream;
+    // chunk boundaries: the plan's, or one chunk covering everything
+    const adtfe_chunk whole[2] = {{0, 0, 0}, {plan->n_seg, plan->n_events, plan->n_peak_work}};
+    const adtfe_chunk* ch = whole;
+    int n_chunks = 1;
+    if (plan->chunks_host && plan->n_chunks > 0) {
+        ch = plan->chunks_host;
+        n_chunks = plan->n_chunks;
+        ADTFE_REQUIRE(n_chunks <= plan->n_seg && ch[0].seg == 0 && ch[0].event == 0 && ch[0].peak_work == 0 &&
+                          ch[n_chunks].seg == plan->n_seg && ch[n_chunks].event == plan->n_events &&
+                          ch[n_chunks].peak_work == plan->n_peak_work,
+                      ADTFE_ERR_BAD_ARG, "adtfe_render: chunk boundaries do not cover the plan");
+        for (int c = 0; c < n_chunks; ++c)
+            ADTFE_REQUIRE(ch[c + 1].seg > ch[c].seg && ch[c + 1].event >= ch[c].event &&
+                              ch[c + 1].peak_work >= ch[c].peak_work,
+                          ADTFE_ERR_BAD_ARG, "adtfe_render: chunk %d is empty or out of order", c);
+    }
+    cudaStream_t user = (cudaStream_t)stream;
     char* ws = (char*)(((uintptr_t)workspace_dev + 255) & ~(uintptr_t)255);
     ResolvedEvent* resolved = (ResolvedEvent*)ws;
     int* peak_bits = (int*)(ws + align256((size_t)plan->n_events * sizeof(ResolvedEvent)));
-    int* seg_done = peak_bits + plan->n_events;  // zeroed together with the peaks
-    int* tile_counter = seg_done + plan->n_seg;   // the mixer's work queue head
+    int* counters = peak_bits + plan->n_events;  // one work-queue head per chunk (n_chunks <= n_seg)
     float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4 + (size_t)plan->n_seg * 4 + 4));
-    const int n_tiles = plan->n_seg * plan->tiles_per_seg;
-    ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, ((size_t)plan->n_events + plan->n_seg + 1) * 4, st));
-    if (plan->n_events > 0) {
-        peak_kernel<<<plan->n_peak_work, kPeakThreads, 0, st>>>(bank->pcm, plan->events_dev, plan->peak_work_dev,
-                                                               resolved, peak_bits);
-        ADTFE_CUDA(cudaGetLastError());
-    }
     static bool smem_set[64] = {};
     if (bank->device < 64 && !smem_set[bank->device]) {
         ADTFE_CUDA(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mix_smem_bytes()));
         smem_set[bank->device] = true;
     }
-    MixArgs a;
-    a.pcm = bank->pcm; a.resolved = resolved; a.peak_bits = peak_bits; a.tile_ptr = plan->tile_ptr_dev;
-    a.tile_events = plan->tile_events_dev; a.segments = plan->segments_dev; a.wav = wav_out_dev; a.tile_max = tile_max;
-    a.tile_counter = tile_counter; a.ld_wav = plan->ld_wav; a.tiles_per_seg = plan->tiles_per_seg;
-    a.n_tiles = n_tiles;
-    const int grid = std::min(n_tiles, 4 * bank->sm_count);
-    mix_kernel<<<grid, kMixThreads, mix_smem_bytes(), st>>>(a);
-    ADTFE_CUDA(cudaGetLastError());
-    normalise_kernel<<<n_tiles, kNormThreads, 0, st>>>(plan->segments_dev, tile_max, plan->tiles_per_seg, plan->ld_wav,
-                                                      wav_out_dev);
-    ADTFE_CUDA(cudaGetLastError());
+    // zero the peaks and the queue heads once, then fork the chunks over the bank's streams
+    ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, ((size_t)plan->n_events + plan->n_seg + 1) * 4, user));
+    const bool fork = n_chunks > 1 && bank->n_streams > 0;
+    std::unique_lock<std::mutex> lock(bank->mu, std::defer_lock);
+    if (fork) {
+        lock.lock();
+        ADTFE_CUDA(cudaEventRecord(bank->fork_event, user));
+        for (int k = 0; k < bank->n_streams && k < n_chunks; ++k)
+            ADTFE_CUDA(cudaStreamWaitEvent(bank->streams[k], bank->fork_event, 0));
+    }
+    const int tps = plan->tiles_per_seg;
+    for (int c = 0; c < n_chunks; ++c) {
+        cudaStream_t st = fork ? bank->streams[c % bank->n_streams] : user;
+        const int s0 = ch[c].seg, n_seg = ch[c + 1].seg - s0;
+        const int pw0 = ch[c].peak_work, n_pw = ch[c + 1].peak_work - pw0;
+        if (n_pw > 0) {
+            peak_kernel<<<n_pw, kPeakThreads, 0, st>>>(bank->pcm, plan->events_dev, plan->peak_work_dev + pw0, resolved,
+                                                      peak_bits);
+            ADTFE_CUDA(cudaGetLastError());
+        }
+        MixArgs a;
+        a.pcm = bank->pcm; a.resolved = resolved; a.peak_bits = peak_bits;
+        a.tile_ptr = plan->tile_ptr_dev + (size_t)s0 * tps; a.tile_events = plan->tile_events_dev;
+        a.segments = plan->segments_dev + s0; a.wav = wav_out_dev + (size_t)s0 * plan->ld_wav;
+        a.tile_max = tile_max + (size_t)s0 * tps; a.tile_counter = counters + c; a.ld_wav = plan->ld_wav;
+        a.tiles_per_seg = tps; a.n_tiles = n_seg * tps;
+        const int grid = std::min(a.n_tiles, 4 * bank->sm_count);
+        mix_kernel<<<grid, kMixThreads, mix_smem_bytes(), st>>>(a);
+        ADTFE_CUDA(cudaGetLastError());
+        normalise_kernel<<<a.n_tiles, kNormThreads, 0, st>>>(a.segments, a.tile_max, tps, plan->ld_wav, a.wav);
+        ADTFE_CUDA(cudaGetLastError());
+    }
+    if (fork) {
+        for (int k = 0; k < bank->n_streams && k < n_chunks; ++k) {
+            ADTFE_CUDA(cudaEventRecord(bank->join_events[k], bank->streams[k]));
+            ADTFE_CUDA(cudaStreamWaitEvent(user, bank->join_events[k], 0));
+        }
+    }
     return ADTFE_OK;
 }

@@ -29,7 +29,10 @@ class FrontEnd:
         dev = self.synth.device
         n_mels = self.mel.compute_spec.n_mels
         wav = torch.empty((plan.n_seg, plan.ld_wav), dtype=torch.float32, device=dev)
-        feat = torch.empty((plan.n_seg, self.mel.n_frames(n_samples), n_mels), dtype=torch.float32, device=dev)
+        if plan.mel_rows is not None:  # several batches: flat (rows, n_mels), split per batch by plan.split
+            feat = torch.empty((plan.mel_total_rows, n_mels), dtype=torch.float32, device=dev)
+        else:
+            feat = torch.empty((plan.n_seg, self.mel.n_frames(n_samples), n_mels), dtype=torch.float32, device=dev)
         return wav, feat
 
     def run_plan(self, plan: RenderPlan, buffers: Optional[PlanBuffers] = None, wav: Optional[torch.Tensor] = None,
@@ -58,6 +61,17 @@ class FrontEnd:
     def __call__(self, batch_notes: Sequence, rng=_random) -> Tuple[torch.Tensor, torch.Tensor]:
         """``[notes, ...] -> (wav (B, Lmax) cuda, logmel (B, T, n_mels) cuda)``."""
         return self.run_plan(self.synth.plan(batch_notes, rng))
+
+    def plan_batches(self, batches: Sequence[Sequence], rng=_random) -> RenderPlan:
+        return self.synth.plan_batches(batches, self.mel.n_frames, rng)
+
+    def run_batches(self, batches: Sequence[Sequence], rng=_random):
+        """Several batches through one plan: one H2D copy and one launch per kernel for all of them
+        (what a prefetching loader hands over).  Returns ``[(wav_b, logmel_b), ...]``, each pair
+        what ``__call__`` would return for that batch."""
+        plan = self.plan_batches(batches, rng)
+        wav, feat = self.run_plan(plan)
+        return plan.split(wav, feat)
 
     def run_plan_host(self, plan: RenderPlan, mel_out_host: torch.Tensor, wav_out_host: Optional[torch.Tensor] = None,
                       buffers: Optional[PlanBuffers] = None, wav: Optional[torch.Tensor] = None,

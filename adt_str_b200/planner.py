@@ -49,6 +49,10 @@ SEGMENT_DTYPE = np.dtype([("len", "<i4"), ("flags", "<i4"), ("max_volume", "<f4"
 #: numpy view of ``adtfe_peak_item`` (40 bytes)
 PEAK_ITEM_DTYPE = np.dtype([("a_off", "<i8"), ("b_off", "<i8"), ("la", "<i4"), ("lb", "<i4"), ("mix_len", "<i4"),
                             ("first_event", "<i4"), ("n_events", "<i4"), ("chunk", "<i4")])
+#: numpy view of ``adtfe_mel_row`` (16 bytes)
+MEL_ROW_DTYPE = np.dtype([("out_row", "<i8"), ("count", "<i4"), ("reserved", "<i4")])
+#: numpy view of ``adtfe_chunk`` (12 bytes)
+CHUNK_DTYPE = np.dtype([("seg", "<i4"), ("event", "<i4"), ("peak_work", "<i4")])
 SEG_EMPTY = 0      # no notes: all-zero waveform of int(input_sec*sr) samples, no normalisation
 SEG_NORMALISE = 1  # wav / max|wav| * max_volume (NaN when the mix is all zero, like the reference)
 
@@ -192,6 +196,50 @@ class RenderPlan:
     tile_events: np.ndarray       # int32 (n_refs,) event ids, ascending inside a tile
     peak_work: np.ndarray         # PEAK_ITEM_DTYPE (n_peak_work,): (group, chunk) items of the peak pass
     wave_lengths: np.ndarray = field(default=None)  # int64 (n_seg,)
+    # ---- several collated batches in one plan (set_batches): ragged log-mel rows + render chunks
+    batch_ptr: np.ndarray = field(default=None)      # int64 (n_batches+1,): segments of batch b
+    batch_samples: np.ndarray = field(default=None)  # int64 (n_batches,): collated width of batch b
+    batch_frames: np.ndarray = field(default=None)   # int64 (n_batches,): log-mel frames of batch b
+    mel_rows: np.ndarray = field(default=None)       # MEL_ROW_DTYPE (n_seg,)
+    mel_total_rows: int = 0
+    chunks: np.ndarray = field(default=None)         # CHUNK_DTYPE (n_chunks+1,)
+
+    def set_batches(self, sizes: Sequence[int], n_frames) -> "RenderPlan":
+        """Mark the plan as ``len(sizes)`` collated batches laid end to end (``sizes[b]`` segments
+        each).  Every batch keeps its own width - the longest of *its* segments, as
+        ``collate_fn``'s ``pad_sequence`` gives (train_dataset.py:53) - and therefore its own
+        frame count ``n_frames(width)`` (model.py:95-97).  One chunk of the render per batch."""
+        sizes = np.asarray(sizes, np.int64)
+        if sizes.sum() != self.n_seg or (sizes <= 0).any():
+            raise ValueError("batch sizes must be positive and add up to the number of segments")
+        ptr = np.concatenate([[0], np.cumsum(sizes)])
+        width = np.maximum.reduceat(self.wave_lengths, ptr[:-1]) if self.n_seg else np.zeros(0, np.int64)
+        frames = np.array([n_frames(int(w)) for w in width], np.int64)
+        rows = np.zeros(self.n_seg, MEL_ROW_DTYPE)
+        row0 = np.concatenate([[0], np.cumsum(sizes * frames)])
+        batch_of = np.repeat(np.arange(len(sizes)), sizes)
+        rows["count"] = frames[batch_of]
+        rows["out_row"] = row0[batch_of] + (np.arange(self.n_seg) - ptr[batch_of]) * frames[batch_of]
+        chunks = np.zeros(len(sizes) + 1, CHUNK_DTYPE)
+        chunks["seg"] = ptr
+        first_event = np.concatenate([self.segments["first_event"].astype(np.int64), [self.n_events]])
+        chunks["event"] = first_event[ptr]
+        chunks["peak_work"] = np.searchsorted(self.peak_work["first_event"], chunks["event"], side="left")
+        self.batch_ptr, self.batch_samples, self.batch_frames = ptr, width.astype(np.int64), frames
+        self.mel_rows, self.mel_total_rows, self.chunks = rows, int(row0[-1]), chunks
+        return self
+
+    def split(self, wav, feat):
+        """Per-batch views of the outputs of a plan with batches: ``[(wav_b (B, Lmax_b), mel_b (B, T_b, n_mels))]``."""
+        out = []
+        row0 = 0
+        for b in range(len(self.batch_frames)):
+            s0, s1 = int(self.batch_ptr[b]), int(self.batch_ptr[b + 1])
+            t = int(self.batch_frames[b])
+            n = (s1 - s0) * t
+            out.append((wav[s0:s1, : int(self.batch_samples[b])], feat[row0: row0 + n].view(s1 - s0, t, -1)))
+            row0 += n
+        return out
 
     @property
     def n_events(self) -> int:

@@ -57,9 +57,15 @@ class PlanBuffers:
 
     def pack(self, plan: RenderPlan) -> _lib.Plan:
         lib = _lib.load()
+        batched = plan.mel_rows is not None
+        self._chunks = np.ascontiguousarray(plan.chunks) if batched else None  # host memory the library reads
         shape = _lib.Plan(None, None, None, None, None, plan.n_events, plan.n_seg, plan.tiles_per_seg,
-                          len(plan.peak_work), plan.ld_wav)
-        off = (C.c_size_t * 5)()
+                          len(plan.peak_work), plan.ld_wav, None,
+                          plan.mel_total_rows if batched else 0,
+                          int(plan.batch_frames.max()) if batched and len(plan.batch_frames) else 0,
+                          len(self._chunks) - 1 if batched else 0,
+                          self._chunks.ctypes.data if batched else None)
+        off = (C.c_size_t * 6)()
         fixed = C.c_size_t()
         _lib.check(lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(fixed)), "adtfe_plan_blob_layout")
         total = (fixed.value + 4 * len(plan.tile_events) + 15) & ~15
@@ -68,7 +74,8 @@ class PlanBuffers:
             self.host = torch.empty(cap, dtype=torch.uint8).pin_memory()
             self.dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
         h = self.host.numpy()
-        for o, arr in zip(off, (plan.events, plan.segments, plan.tile_ptr, plan.peak_work, plan.tile_events)):
+        rows = plan.mel_rows if batched else np.zeros(0, np.uint8)
+        for o, arr in zip(off, (plan.events, plan.segments, plan.tile_ptr, plan.peak_work, rows, plan.tile_events)):
             raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
             h[o: o + raw.size] = raw
         self.nbytes = total
@@ -83,8 +90,10 @@ class PlanBuffers:
         self.dev[: self.nbytes].copy_(self.host[: self.nbytes], non_blocking=True)
         base = self.dev.data_ptr()
         o = self.offsets
-        return _lib.Plan(base + o[0], base + o[1], base + o[2], base + o[4], base + o[3],
-                         shape.n_events, shape.n_seg, shape.tiles_per_seg, shape.n_peak_work, shape.ld_wav)
+        return _lib.Plan(base + o[0], base + o[1], base + o[2], base + o[5], base + o[3],
+                         shape.n_events, shape.n_seg, shape.tiles_per_seg, shape.n_peak_work, shape.ld_wav,
+                         base + o[4] if shape.mel_total_rows > 0 else None, shape.mel_total_rows,
+                         shape.mel_max_count, shape.n_chunks, shape.chunks_host)
 
 
 class SynthDrum:
@@ -144,6 +153,14 @@ class SynthDrum:
             from .native_planner import NativePlanner
             self._native_planner = NativePlanner(self.config, self.bank)
         return self._native_planner.plan_batch(batch_notes, rng, ld_wav)
+
+    def plan_batches(self, batches: Sequence[Sequence], n_frames, rng=_random) -> RenderPlan:
+        """Plan several batches as ONE device plan (one H2D copy, one launch per kernel): the segments
+        of all batches in order - the RNG stream advances exactly as planning them one by one would -
+        with per-batch collated widths and frame counts (``RenderPlan.set_batches``).
+        ``n_frames`` is ``ComputeMelSpectrogram.n_frames``."""
+        flat = [notes for b in batches for notes in b]
+        return self.plan(flat, rng).set_batches([len(b) for b in batches], n_frames)
 
     # ---------------------------------------------------------------- render
     def render_plan(self, plan: RenderPlan, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -9,8 +9,10 @@ Workload (BASELINE.json configs[1], "training-shape batch"): setting-1 shapes - 
 x 2.56 s @ 24 kHz per batch (configs/train/setting-1.yaml:6-11,29-33), random MIDI event
 streams and a synthetic 10 000 one-shot bank.  One batch is only ~100 us of GPU
 work, so a *step* is ``--batches-per-step`` (256) distinct batches run back to back, each
-through its own ``adtfe_render_logmel`` call (SURVEY §8d "config 2").  Per rank the work is
-fixed (weak scaling); ranks share nothing but the final statistics.
+planned into ONE device plan and run by one ``adtfe_render_logmel`` call - the render chunk by chunk
+(one chunk per batch, over the library's internal streams), the log-mel kernel as a single persistent
+launch with per-batch frame counts (SURVEY §8d "config 2": persistent launch over >=256 batches).  Per
+rank the work is fixed (weak scaling); ranks share nothing but the final statistics.
 
 value  : audio-seconds rendered+featurised per second, plans already resident in HBM.
 e2e    : the same through the public API (FrontEnd.__call__ semantics): host planning of the
@@ -55,7 +57,7 @@ def parse_args():
     p.add_argument("--e2e-steps", type=int, default=2)
     p.add_argument("--cpu-segments", type=int, default=0, help="cpu_baseline sample size (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--streams", type=int, default=int(os.environ.get("ADTFE_BENCH_STREAMS", "1")))
+    p.add_argument("--e2e-group", type=int, default=32, help="batches per end-to-end plan")
     return p.parse_args()
 
 
@@ -234,41 +236,29 @@ def run_b200(args):
     mel = ComputeMelSpectrogram(SR, 2048, 0.01, 128)
     fe = FrontEnd(synth, mel)
 
-    # ---- plan every batch once and make the plans resident (not timed for `value`)
+    # ---- plan the step once and make the plan resident (not timed for `value`): all batches of the
+    # step in ONE device plan - one launch of the log-mel kernel, the render chunked per batch
     rng = random.Random(1234 + rank)
     batches = [segs[b * BATCH:(b + 1) * BATCH] for b in range(n_batches)]
     t0 = time.perf_counter()
-    plans = [synth.plan(b, rng) for b in batches]
+    plan = fe.plan_batches(batches, rng)
     plan_s = time.perf_counter() - t0
-    bufs = [PlanBuffers(dev) for _ in plans]
-    outs = []
-    for p, buf in zip(plans, bufs):
-        buf._dplan = buf.upload(buf.pack(p))
-        buf._resident = p
-        n_samples = int(p.wave_lengths.max())
-        outs.append((torch.empty((p.n_seg, p.ld_wav), dtype=torch.float32, device=dev),
-                     torch.empty((p.n_seg, mel.n_frames(n_samples), 128), dtype=torch.float32, device=dev)))
+    buf = PlanBuffers(dev)
+    buf._dplan = buf.upload(buf.pack(plan))
+    buf._resident = plan
+    wav, feat = fe._outputs(plan, 0)
     torch.cuda.synchronize(dev)
 
-    audio_s_step = float(sum(int(p.wave_lengths.sum()) for p in plans)) / SR
-    bytes_alg_step = sum(p.bytes_alg(bank, o[1].shape[1], 128) for p, o in zip(plans, outs))
-    launches_per_step = sum(3 + (1 if p.n_groups else 0) for p in plans)
-
-    streams = [torch.cuda.Stream(dev) for _ in range(max(1, args.streams))] if args.streams > 1 else [torch.cuda.current_stream(dev)]
+    audio_s_step = float(int(plan.wave_lengths.sum())) / SR
+    n_frames_seg = np.repeat(plan.batch_frames, np.diff(plan.batch_ptr))
+    bytes_alg_step = (4 * int(plan.wave_lengths.sum()) + 4 * 128 * int(n_frames_seg.sum()) + plan.bank_bytes(bank)
+                      + 32 * plan.n_events)
+    n_chunks = len(plan.chunks) - 1
+    # OUR kernels per step: peak (when the chunk has notes) + mix + normalise per chunk, one log-mel launch
+    launches_per_step = int(2 * n_chunks + (np.diff(plan.chunks["peak_work"]) > 0).sum() + 1)
 
     def step():
-        if len(streams) == 1:
-            for p, buf, (w, f) in zip(plans, bufs, outs):
-                fe.run_plan(p, buffers=buf, wav=w, feat=f, upload=False)
-        else:
-            main = torch.cuda.current_stream(dev)
-            for s in streams:
-                s.wait_stream(main)
-            for i, (p, buf, (w, f)) in enumerate(zip(plans, bufs, outs)):
-                with torch.cuda.stream(streams[i % len(streams)]):
-                    fe.run_plan(p, buffers=buf, wav=w, feat=f, upload=False)
-            for s in streams:
-                main.wait_stream(s)
+        fe.run_plan(plan, buffers=buf, wav=wav, feat=feat, upload=False)
 
     def barrier():
         if world > 1:
@@ -302,36 +292,47 @@ def run_b200(args):
         return a.elapsed_time(b) / reps
 
     def render_all():
-        for p, buf, (w, _f) in zip(plans, bufs, outs):
-            _lib.check(lib.adtfe_render(bh, C.byref(buf._dplan), w.data_ptr(), buf.workspace.data_ptr(),
-                                        buf.workspace.numel(), st))
+        _lib.check(lib.adtfe_render(bh, C.byref(buf._dplan), wav.data_ptr(), buf.workspace.data_ptr(),
+                                    buf.workspace.numel(), st))
 
     def logmel_all():
-        for p, (w, f) in zip(plans, outs):
-            _lib.check(lib.adtfe_logmel(mh, w.data_ptr(), p.n_seg, p.ld_wav, int(p.wave_lengths.max()), f.data_ptr(), st))
+        _lib.check(lib.adtfe_logmel_rows(mh, wav.data_ptr(), plan.n_seg, plan.ld_wav, buf._dplan.mel_rows_dev,
+                                         buf._dplan.mel_max_count, feat.data_ptr(), st))
 
     render_ms, logmel_ms = time_loop(render_all), time_loop(logmel_all)
-    one = time_loop(lambda: fe.run_plan(plans[0], buffers=bufs[0], wav=outs[0][0], feat=outs[0][1], upload=False), reps=20)
+    # latency of ONE training batch through the same entry (its own plan, resident)
+    one_plan = synth.plan(batches[0], random.Random(5))
+    one_buf = PlanBuffers(dev)
+    one_buf._dplan = one_buf.upload(one_buf.pack(one_plan)); one_buf._resident = one_plan
+    one_w, one_f = fe._outputs(one_plan, int(one_plan.wave_lengths.max()))
+    one = time_loop(lambda: fe.run_plan(one_plan, buffers=one_buf, wav=one_w, feat=one_f, upload=False), reps=20)
 
-    # ---- end to end: host notes -> plan -> pinned blob -> H2D -> kernels -> D2H log-mel (pinned)
-    mel_host = [torch.empty(o[1].shape, dtype=torch.float32).pin_memory() for o in outs[:4]]
+    # ---- end to end: host notes -> plan -> pinned blob -> H2D -> kernels -> D2H log-mel (pinned), in groups of
+    # batches; planning of group g+1 (host) overlaps the GPU work and copies of group g (all asynchronous)
+    group = max(1, min(args.e2e_group, n_batches))
+    groups = [batches[i:i + group] for i in range(0, n_batches, group)]
+    n_sets = 3
+    sets = [dict(buf=PlanBuffers(dev), wav=None, feat=None, host=None, done=torch.cuda.Event()) for _ in range(n_sets)]
     e2e_rng = random.Random(99 + rank)
     h2d = d2h = 0
 
     def e2e_step():
         nonlocal h2d, d2h
         h2d = d2h = 0
-        for i, (b, buf, (w, f)) in enumerate(zip(batches, bufs, outs)):
-            p = synth.plan(b, e2e_rng)
-            if (p.n_seg, p.ld_wav) != tuple(w.shape) or mel.n_frames(int(p.wave_lengths.max())) != f.shape[1]:
-                w = torch.empty((p.n_seg, p.ld_wav), dtype=torch.float32, device=dev)
-                f = torch.empty((p.n_seg, mel.n_frames(int(p.wave_lengths.max())), 128), dtype=torch.float32, device=dev)
-            host = mel_host[i % len(mel_host)]
-            if host.numel() < f.numel():
-                host = mel_host[i % len(mel_host)] = torch.empty(f.shape, dtype=torch.float32).pin_memory()
-            fe.run_plan_host(p, host, None, buffers=buf, wav=w, feat=f)
-            h2d += buf.nbytes
-            d2h += f.numel() * 4
+        for i, g in enumerate(groups):
+            s = sets[i % n_sets]
+            s["done"].synchronize()                         # the set's previous use has left the GPU
+            p = fe.plan_batches(g, e2e_rng)
+            if s["wav"] is None or s["wav"].shape != (p.n_seg, p.ld_wav):
+                s["wav"] = torch.empty((p.n_seg, p.ld_wav), dtype=torch.float32, device=dev)
+            if s["feat"] is None or s["feat"].shape[0] < p.mel_total_rows:
+                rows = int(p.mel_total_rows * 1.02) + 64
+                s["feat"] = torch.empty((rows, 128), dtype=torch.float32, device=dev)
+                s["host"] = torch.empty((rows, 128), dtype=torch.float32).pin_memory()
+            fe.run_plan_host(p, s["host"], None, buffers=s["buf"], wav=s["wav"], feat=s["feat"])
+            s["done"].record()
+            h2d += s["buf"].nbytes
+            d2h += p.mel_total_rows * 128 * 4
         torch.cuda.synchronize(dev)
 
     e2e_step()  # warm-up (allocations, pinned buffers)
@@ -355,7 +356,8 @@ def run_b200(args):
 
     peak, peak_src = measured_peak()
     n_seg_step = n_batches * BATCH
-    logmel_bytes = sum(4 * p.n_seg * int(p.wave_lengths.max()) + 4 * o[1].numel() for p, o in zip(plans, outs))
+    width_seg = np.repeat(plan.batch_samples, np.diff(plan.batch_ptr))
+    logmel_bytes = 4 * int(width_seg.sum()) + 4 * 128 * int(n_frames_seg.sum())   # collated rows read + log-mel written
     logmel_gbs = logmel_bytes / (logmel_ms * 1e-3) / 1e9
     path_gbs = (total_bytes / world) / (max_ms / args.steps * 1e-3) / 1e9
     line = {
@@ -363,17 +365,18 @@ def run_b200(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": max_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "segments_per_step_per_gpu": n_seg_step,
-                   "audio_s_per_step_per_gpu": audio_s_step, "streams": len(streams),
+                   "audio_s_per_step_per_gpu": audio_s_step,
+                   "launch": f"one plan per step: render in {n_chunks} chunks over 4 internal streams, one log-mel launch",
                    "l2": "no flush needed: per step 0.5 GB bank + ~6 GB of distinct outputs >> 126 MB L2",
                    "single_batch_latency_ms": one, "plan_ms_per_batch_host": 1e3 * plan_s / n_batches},
         "clocks": clocks,
         "e2e": {"value": total_audio_e2e / (max_e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": max(1, args.e2e_steps),
-                "includes": "host planning of note lists, plan blob H2D, 4 kernels per batch, log-mel D2H"},
+                "includes": f"host planning of note lists, plan blob H2D, kernels, log-mel D2H; groups of {group} batches"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": "logmel_kernel", "achieved": logmel_gbs, "peak": peak, "unit": "GB/s",
                      "frac": logmel_gbs / peak, "traffic": None, "peak_source": peak_src,
-                     "bytes_per_launch": logmel_bytes / n_batches, "avg_launch_ms": logmel_ms / n_batches,
+                     "bytes_per_launch": logmel_bytes, "avg_launch_ms": logmel_ms,
                      "share_of_step": logmel_ms / (max_ms / args.steps),
                      "render_ms_per_step": render_ms, "logmel_ms_per_step": logmel_ms,
                      "path": {"bytes_alg_per_step": total_bytes / world, "achieved": path_gbs, "frac": path_gbs / peak,

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define ADTFE_VERSION 1
+#define ADTFE_VERSION 2
 #define ADTFE_TILE 2048      /* output samples owned by one mixer CTA */
 #define ADTFE_PEAK_SPAN 4096 /* samples of a mixed one-shot scanned by one peak work item */
 
@@ -82,6 +82,22 @@ typedef struct adtfe_peak_item {
     int32_t first_event, n_events, chunk;
 } adtfe_peak_item;
 
+/* Ragged log-mel: segment s writes `count` frames (the first kept frame is always the window-pad index)
+ * to rows out_row .. out_row+count-1 of the (rows, n_mels) output matrix.  Lets one launch featurise many
+ * collated batches at once - each batch has its own width, hence its own frame count (model.py:95-97). */
+typedef struct adtfe_mel_row {
+    int64_t out_row;
+    int32_t count; /* >= 0; the frames must lie inside the row: (first+count-1)*hop + n_fft/2 <= ld_wav */
+    int32_t reserved;
+} adtfe_mel_row;
+
+/* A chunk of a plan: segments, events and peak work items [x[c], x[c+1]) are rendered together, chunks
+ * are independent and run on the library's internal streams (so that a chunk's one-shots are still in L2
+ * when its tile mixer re-reads them, and small kernels of different chunks overlap). */
+typedef struct adtfe_chunk {
+    int32_t seg, event, peak_work;
+} adtfe_chunk;
+
 typedef struct adtfe_bank adtfe_bank; /* one-shot bank resident in HBM */
 typedef struct adtfe_mel adtfe_mel;   /* window, mel filterbank (CSR) and twiddles on device */
 
@@ -94,6 +110,12 @@ typedef struct adtfe_plan {
     const adtfe_peak_item* peak_work_dev; /* n_peak_work */
     int32_t n_events, n_seg, tiles_per_seg, n_peak_work;
     int64_t ld_wav; /* row pitch of the waveform matrix in floats, multiple of 4, <= tiles_per_seg*ADTFE_TILE */
+    /* optional (NULL / 0 = absent) */
+    const adtfe_mel_row* mel_rows_dev;   /* n_seg rows: ragged log-mel output (several collated batches per plan) */
+    int64_t mel_total_rows;              /* rows of the log-mel matrix when mel_rows_dev is given */
+    int32_t mel_max_count;               /* largest count in mel_rows_dev */
+    int32_t n_chunks;                    /* boundaries in chunks_host: n_chunks + 1 records, first all-zero, */
+    const adtfe_chunk* chunks_host;      /* last = {n_seg, n_events, n_peak_work}; HOST memory */
 } adtfe_plan;
 
 int adtfe_version(void);
@@ -112,8 +134,10 @@ int64_t adtfe_bank_bytes(const adtfe_bank* bank);
 /* ---- render ------------------------------------------------------------------------ */
 size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg);
 /* Writes the (n_seg, ld_wav) float32 waveform matrix: every row normalised as the reference
- * does and zero-padded to ld_wav.  Two kernels: per-note peak of the mixed one-shot, then the tile
- * mixer, whose last CTA of every segment normalises the row. */
+ * does and zero-padded to ld_wav.  Three kernels per chunk: per-note peak of the mixed one-shot, the tile
+ * mixer, the row normalisation.  A plan with chunks (plan->chunks_host) is rendered chunk by chunk on the
+ * bank's internal streams, forked from and joined back into `stream`; calls on one bank handle must not
+ * be made from several host threads at once. */
 int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
                  size_t workspace_bytes, void* stream);
 
@@ -132,18 +156,23 @@ int adtfe_mel_fast_path(const adtfe_mel* mel);
 /* wav_dev: (n_seg, ld_wav) rows of n_samples valid floats; out_dev: (n_seg, count, n_mels). */
 int adtfe_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav, int64_t n_samples,
                  float* out_dev, void* stream);
+/* Ragged form: one launch over rows with their own frame counts (rows_dev[n_seg], max_count = the largest). */
+int adtfe_logmel_rows(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
+                      const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream);
 
 /* ---- fused call -------------------------------------------------------------------- */
 /* adtfe_render then adtfe_logmel over the first n_samples (<= plan->ld_wav) floats of every
- * row: n_samples is the collated batch width (longest segment), which sets the frame count. */
+ * row: n_samples is the collated batch width (longest segment), which sets the frame count.
+ * With plan->mel_rows_dev the ragged form is used instead and n_samples is ignored. */
 int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel, const adtfe_plan* plan, int64_t n_samples,
                         float* wav_out_dev, float* mel_out_dev, void* workspace_dev, size_t workspace_bytes,
                         void* stream);
 
 /* ---- host-buffer entry (end to end) ------------------------------------------------ */
 /* Plan blob layout (host, 16-byte aligned sections in this order):
- *   events | segments | tile_ptr | peak_work | tile_events
- * with the counts in `shape` (a plan whose pointers are ignored).  The blob is copied to
+ *   events | segments | tile_ptr | peak_work | mel_rows | tile_events
+ * with the counts in `shape` (a plan whose device pointers are ignored; mel_rows is n_seg records when
+ * shape->mel_total_rows > 0, else empty; shape->chunks_host is used as given).  The blob is copied to
  * `blob_dev` (>= blob_bytes), the batch rendered and featurised, then the log-mel matrix
  * (and the waveform when wav_out_host != NULL) copied back.  Asynchronous on `stream`:
  * the host buffers must be pinned and stay alive until the stream is synchronised. */
@@ -151,9 +180,9 @@ int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel, const adtf
                         const void* blob_host, size_t blob_bytes, void* blob_dev, float* wav_dev, float* mel_dev,
                         void* workspace_dev, size_t workspace_bytes, float* mel_out_host, float* wav_out_host,
                         void* stream);
-/* Byte offsets of the five sections inside a plan blob (offsets[5]; *blob_bytes = offsets[4], where
+/* Byte offsets of the six sections inside a plan blob (offsets[6]; *blob_bytes = offsets[5], where
  * tile_events starts - it runs to the end of the blob). */
-int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[5], size_t* blob_bytes);
+int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[6], size_t* blob_bytes);
 
 /* ---- host planner (no GPU work) ------------------------------------------------------ */
 /* C++ restatement of the per-note bookkeeping of SynthDrum.__call__ (modules/synthetiser.py:255-292:

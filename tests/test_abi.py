@@ -33,18 +33,24 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_sizes_match_numpy_views():
     from adt_str_b200.planner import EVENT_DTYPE, PEAK_ITEM_DTYPE, SEGMENT_DTYPE
     assert EVENT_DTYPE.itemsize == 32 and SEGMENT_DTYPE.itemsize == 16 and PEAK_ITEM_DTYPE.itemsize == 40
-    assert C.sizeof(_lib.Plan) == 5 * 8 + 4 * 4 + 8
+    assert C.sizeof(_lib.Plan) == 5 * 8 + 4 * 4 + 8 + 8 + 8 + 4 + 4 + 8
+    from adt_str_b200.planner import CHUNK_DTYPE, MEL_ROW_DTYPE
+    assert MEL_ROW_DTYPE.itemsize == 16 and CHUNK_DTYPE.itemsize == 12
 
 
 def test_version_and_argument_errors_without_a_device(lib):
-    assert lib.adtfe_version() == 1
+    assert lib.adtfe_version() == 2
     assert lib.adtfe_render_workspace_bytes(10, 2, 30) >= 10 * 48 + 2 * 30 * 4
     assert lib.adtfe_render_workspace_bytes(-1, 2, 30) == 0
     shape = _lib.Plan(None, None, None, None, None, 100, 4, 31, 9, 63488)
-    off = (C.c_size_t * 5)()
+    off = (C.c_size_t * 6)()
     total = C.c_size_t()
     assert lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(total)) == 0
-    assert list(off)[:3] == [0, 3200, 3264] and all(o % 16 == 0 for o in off) and total.value == off[4] and off[4] - off[3] == 368
+    assert list(off)[:3] == [0, 3200, 3264] and all(o % 16 == 0 for o in off) and total.value == off[5]
+    assert off[4] - off[3] == 368 and off[5] == off[4]          # no mel rows section without batches
+    shape.mel_total_rows = 1000
+    assert lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(total)) == 0
+    assert off[5] - off[4] == 4 * 16                            # one adtfe_mel_row per segment
     assert lib.adtfe_plan_blob_layout(None, C.byref(off), C.byref(total)) == -1
     assert b"null" in lib.adtfe_last_error()
     # null handles are rejected before any CUDA call

@@ -228,6 +228,56 @@ def test_mel_odd_hops_unaligned_rows_and_small_banks(sr, n, n_mels):
     assert_logmel_close(got, want, atol=2e-6)
 
 
+def test_batches_in_one_plan_equal_batch_by_batch():
+    """Several collated batches through one plan (ragged log-mel rows, chunked multi-stream render) give
+    bit for bit what the same batches give one call at a time."""
+    from adt_str_b200.config import setting_1
+    from adt_str_b200.synthetic import make_bank, make_segments
+    bank = make_bank(390, 24000, seed=12)
+    _, _, fe = _objects(setting_1(), bank)
+    segs = make_segments(40, seed=21, empty_fraction=0.1)
+    batches = [segs[:9], segs[9:10], segs[10:26], segs[26:33], segs[33:]]
+    rng = random.Random(4321)
+    got = fe.run_batches(batches, rng)
+    torch.cuda.synchronize()
+    rng = random.Random(4321)
+    for (wav, feat), b in zip(got, batches):
+        w1, f1 = fe(b, rng)
+        assert wav.shape == w1.shape and feat.shape == f1.shape
+        assert torch.equal(wav, w1) and torch.equal(feat, f1)
+    # and twice the same plan: deterministic across the internal streams
+    rng = random.Random(4321)
+    again = fe.run_batches(batches, rng)
+    for (w0, f0), (w1, f1) in zip(got, again):
+        assert torch.equal(w0, w1) and torch.equal(f0, f1)
+
+
+def test_logmel_rows_with_short_and_empty_rows():
+    """adtfe_logmel_rows: rows with their own frame counts, including 0 and counts below the rounds per row."""
+    from adt_str_b200 import ComputeMelSpectrogram, _lib
+    from adt_str_b200.planner import MEL_ROW_DTYPE
+    mel = ComputeMelSpectrogram(24000, 2048, 0.01, 128)
+    g = torch.Generator().manual_seed(3)
+    n = 61440
+    x = torch.randn(6, n, generator=g).cuda()
+    full = mel(x)
+    counts = [full.shape[1], 0, 3, 40, 1, 100]
+    rows = np.zeros(6, MEL_ROW_DTYPE)
+    rows["count"] = counts
+    rows["out_row"] = np.concatenate([[0], np.cumsum(counts)[:-1]])
+    rows_dev = torch.from_numpy(rows.view(np.uint8)).cuda()
+    out = torch.full((sum(counts) + 1, 128), -7.0, device="cuda")
+    native = mel._handle(x.device)
+    _lib.check(native.lib.adtfe_logmel_rows(native.handle, x.data_ptr(), 6, n, rows_dev.data_ptr(), max(counts),
+                                            out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    r = 0
+    for i, c in enumerate(counts):
+        assert torch.equal(out[r:r + c], full[i, :c])
+        r += c
+    assert (out[r:] == -7.0).all()
+
+
 def test_abi_status_codes_on_device():
     from adt_str_b200 import _lib
     from adt_str_b200.config import setting_1

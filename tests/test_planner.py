@@ -236,3 +236,43 @@ def test_native_planner_errors_and_fallback():
     p32 = npl.plan_batch([[[0.5, 2.5, 36.0, 100.0]]])
     assert (int(p64.wave_lengths[0]), int(p32.wave_lengths[0])) == (62400, 62399)
     assert npl.plan_batch([]).n_seg == 0
+
+
+def test_batches_in_one_plan_match_plans_one_by_one():
+    """plan_batches = the same events / indices as planning batch by batch with the same RNG
+    stream, plus per-batch widths, frame counts, ragged log-mel rows and render chunks."""
+    from adt_str_b200 import ComputeMelSpectrogram, SynthDrum
+    from adt_str_b200.config import setting_1
+    from adt_str_b200.synthetic import make_bank, make_segments
+    bank = make_bank(260, 24000, seed=4)
+    segs = make_segments(14, seed=8, empty_fraction=0.2)
+    batches = [segs[:5], segs[5:6], segs[6:11], segs[11:]]
+    synth = SynthDrum(setting_1(), bank=bank)
+    mel = ComputeMelSpectrogram(24000, 2048, 0.01, 128)
+    rng = random.Random(77)
+    big = synth.plan_batches(batches, mel.n_frames, rng)
+    state_after = rng.getstate()
+    rng = random.Random(77)
+    singles = [synth.plan(b, rng) for b in batches]
+    assert rng.getstate() == state_after
+    assert big.n_seg == 14 and big.ld_wav == max(p.ld_wav for p in singles)
+    e0 = r0 = pw0 = s0 = 0
+    for b, p in enumerate(singles):
+        ev = big.events[e0:e0 + p.n_events]
+        for f in ("start", "len", "main_id", "sub_id", "ca", "cb", "gain"):
+            assert np.array_equal(ev[f], p.events[f])
+        assert np.array_equal(ev["seg"], p.events["seg"] + s0)
+        assert np.array_equal(big.wave_lengths[s0:s0 + p.n_seg], p.wave_lengths)
+        assert big.batch_samples[b] == p.wave_lengths.max()
+        t = mel.n_frames(int(p.wave_lengths.max()))
+        assert big.batch_frames[b] == t
+        rows = big.mel_rows[s0:s0 + p.n_seg]
+        assert np.array_equal(rows["count"], np.full(p.n_seg, t))
+        assert np.array_equal(rows["out_row"], r0 + t * np.arange(p.n_seg))
+        assert tuple(big.chunks[b]) == (s0, e0, pw0)
+        pw = big.peak_work[pw0:pw0 + len(p.peak_work)]
+        assert np.array_equal(pw["first_event"], p.peak_work["first_event"] + e0)
+        e0 += p.n_events; r0 += t * p.n_seg; pw0 += len(p.peak_work); s0 += p.n_seg
+    assert tuple(big.chunks[-1]) == (14, big.n_events, len(big.peak_work)) and big.mel_total_rows == r0
+    with pytest.raises(ValueError):
+        big.set_batches([7, 6], mel.n_frames)

@@ -3,10 +3,16 @@
 
 Writes ``adt_str_b200/csrc/fft_gen.cuh`` with
 
-* ``rdft64(const float (&x)[64], float (&re)[33], float (&im)[33])`` - real-input
+* ``rdft64<V>(const V (&x)[64], V (&re)[33], V (&im)[33])`` - real-input
   64-point DFT, outputs bins 0..32 (im[0] = im[32] = 0), and
-* ``cdft32(float (&re)[32], float (&im)[32])`` - complex 32-point DFT, in place,
+* ``cdft32<V>(V (&re)[32], V (&im)[32])`` - complex 32-point DFT, in place,
   natural order in and out.
+
+``V`` is ``float`` or ``float2``: with ``float2`` every operation is one packed
+sm_100a instruction (FADD2 / FMUL2 / FFMA2) working on two independent transforms
+at once - the log-mel kernel runs two frames per warp that way.  Negations,
+constant broadcasts and half swaps are operand modifiers in SASS, so the packed
+body has exactly the instruction count of the scalar one.
 
 Both are radix-2 decimation-in-time recursions executed *symbolically*: every
 value is a signed reference to a C variable (or a known zero), so negations,
@@ -38,7 +44,7 @@ class Emitter:
         name = f"t{self.n}"
         self.n += 1
         self.ops += 1
-        self.lines.append(f"    const float {name} = {expr};")
+        self.lines.append(f"    const V {name} = {expr};")
         return Val(name, 1)
 
 
@@ -70,12 +76,12 @@ def add(em: Emitter, a: Val, b: Val) -> Val:
     if b.zero:
         return a
     if a.sign > 0 and b.sign > 0:
-        return em.new(f"{a.name} + {b.name}")
+        return em.new(f"vadd({a.name}, {b.name})")
     if a.sign > 0:
-        return em.new(f"{a.name} - {b.name}")
+        return em.new(f"vsub({a.name}, {b.name})")
     if b.sign > 0:
-        return em.new(f"{b.name} - {a.name}")
-    return em.new(f"{a.name} + {b.name}").neg()
+        return em.new(f"vsub({b.name}, {a.name})")
+    return em.new(f"vadd({a.name}, {b.name})").neg()
 
 
 def sub(em, a, b):
@@ -88,10 +94,10 @@ def fma(em: Emitter, c: float, x: Val, y: Val) -> Val:
         return y
     c = c * x.sign
     if y.zero:
-        return em.new(f"{lit(c)} * {x.name}")
+        return em.new(f"vmul({lit(c)}, {x.name})")
     if y.sign > 0:
-        return em.new(f"fmaf({lit(c)}, {x.name}, {y.name})")
-    return em.new(f"fmaf({lit(-c)}, {x.name}, {y.name})").neg()
+        return em.new(f"vfma({lit(c)}, {x.name}, {y.name})")
+    return em.new(f"vfma({lit(-c)}, {x.name}, {y.name})").neg()
 
 
 def butterfly(em, E, O, wr, wi, need2=True):
@@ -150,8 +156,8 @@ def rfft(em, xs):
 
 def store(v: Val) -> str:
     if v.zero:
-        return "0.0f"
-    return v.name if v.sign > 0 else f"-{v.name}"
+        return "vzero<V>()"
+    return v.name if v.sign > 0 else f"vneg({v.name})"
 
 
 def gen_rdft64() -> tuple[str, int]:
@@ -162,7 +168,7 @@ def gen_rdft64() -> tuple[str, int]:
     for k in range(33):
         body.append(f"    re[{k}] = {store(X[k][0])};")
         body.append(f"    im[{k}] = {store(X[k][1])};")
-    src = ("__device__ __forceinline__ void rdft64(const float (&x)[64], float (&re)[33], float (&im)[33]) {\n"
+    src = ("template <typename V>\n__device__ __forceinline__ void rdft64(const V (&x)[64], V (&re)[33], V (&im)[33]) {\n"
            + "\n".join(body) + "\n}\n")
     return src, em.ops
 
@@ -172,16 +178,36 @@ def gen_cdft32() -> tuple[str, int]:
     head = []
     xs = []
     for i in range(32):
-        head.append(f"    const float xr{i} = re[{i}], xi{i} = im[{i}];")
+        head.append(f"    const V xr{i} = re[{i}], xi{i} = im[{i}];")
         xs.append((Val(f"xr{i}"), Val(f"xi{i}")))
     X = cfft(em, xs)
     body = head + list(em.lines)
     for k in range(32):
         body.append(f"    re[{k}] = {store(X[k][0])};")
         body.append(f"    im[{k}] = {store(X[k][1])};")
-    src = ("__device__ __forceinline__ void cdft32(float (&re)[32], float (&im)[32]) {\n"
+    src = ("template <typename V>\n__device__ __forceinline__ void cdft32(V (&re)[32], V (&im)[32]) {\n"
            + "\n".join(body) + "\n}\n")
     return src, em.ops
+
+
+PRELUDE = r"""
+// Element operations: float, or float2 = two independent transforms per thread in packed
+// FADD2 / FMUL2 / FFMA2 instructions (sm_100a).  Negation and constant broadcast fold into
+// SASS operand modifiers.
+template <typename V> __device__ __forceinline__ V vzero();
+template <> __device__ __forceinline__ float vzero<float>() { return 0.0f; }
+template <> __device__ __forceinline__ float2 vzero<float2>() { return make_float2(0.0f, 0.0f); }
+__device__ __forceinline__ float vneg(float a) { return -a; }
+__device__ __forceinline__ float vadd(float a, float b) { return a + b; }
+__device__ __forceinline__ float vsub(float a, float b) { return a - b; }
+__device__ __forceinline__ float vmul(float c, float a) { return c * a; }
+__device__ __forceinline__ float vfma(float c, float a, float b) { return fmaf(c, a, b); }
+__device__ __forceinline__ float2 vneg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 vadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 vsub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 vmul(float c, float2 a) { return __fmul2_rn(a, make_float2(c, c)); }
+__device__ __forceinline__ float2 vfma(float c, float2 a, float2 b) { return __ffma2_rn(a, make_float2(c, c), b); }
+"""
 
 
 def main():
@@ -191,7 +217,7 @@ def main():
     with open(out, "w") as f:
         f.write("// GENERATED by tools/gen_fft.py - do not edit.\n"
                 f"// rdft64: {r_ops} float ops per thread, cdft32: {c_ops} float ops per thread.\n"
-                "#pragma once\n\nnamespace adtfe {\n\n" + r_src + "\n" + c_src + "\n}  // namespace adtfe\n")
+                "#pragma once\n\nnamespace adtfe {\n" + PRELUDE + "\n" + r_src + "\n" + c_src + "\n}  // namespace adtfe\n")
     print(f"wrote {os.path.normpath(out)}: rdft64 {r_ops} ops, cdft32 {c_ops} ops", file=sys.stderr)
 
 
