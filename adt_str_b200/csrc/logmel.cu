@@ -64,13 +64,11 @@ constexpr int kPRows = 1056;                 // 1025 bins + the zero pad row 102
 constexpr int kWinPitch = 68;                // window, transposed: lane n2 reads n1 = 4q..4q+3 with one LDS.128
 constexpr int kMaxMels = 128;
 constexpr int kSPitch = 33;
-constexpr int kSideRow = kMaxMels;           // S rows kMaxMels .. kMaxMels+kWarps-1: boundary sums of the warps
-constexpr int kZeroRow = kMaxMels + kWarps;  // an all-zero S row
-constexpr int kDummyRow = kZeroRow + 1;      // sink for sums nobody reads
+constexpr int kDummyRow = kMaxMels;          // S row kMaxMels: sink for sums nobody reads
 constexpr int kSRows = kDummyRow + 1;
-constexpr int kSFloats = 4576;               // >= kSRows * kSPitch, bytes a multiple of 128
+constexpr int kSFloats = 4288;               // >= kSRows * kSPitch, bytes a multiple of 128
 constexpr int kGroupBins = 4;                // bins per mel group (fast path): two float4 of (up, down) weights
-constexpr int kGroupsMax = 320;              // groups kept in shared memory (fast path)
+constexpr int kGroupsMax = 360;              // groups kept in shared memory (fast path)
 constexpr int kW4Max = 2 * kGroupsMax;
 static_assert(kSRows * kSPitch <= kSFloats, "S tile");
 static_assert((kSpanFloats * 4) % 128 == 0 && (kPPitch * 4 * kPRows) % 128 == 0 && (kSFloats * 4) % 128 == 0,
@@ -94,8 +92,6 @@ struct MelGroup {
 struct MelTables {
     MelItem item[kMaxMels + 1];  // generic path only
     int16_t first[kWarps + 1];   // warp w owns items (generic) / groups (fast) first[w] .. first[w+1]-1
-    uint8_t last_row[kWarps];    // fast path: S row of the rising edge a warp is left with (or kDummyRow)
-    uint8_t side[kMaxMels];      // S row added to filter m by the output stage (a boundary row or kZeroRow)
     int32_t fast, n_groups;
 };
 
@@ -192,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
     for (int i = tid; i < 2 * tab.n_groups; i += kThreads) s_w4[i] = __ldg(reinterpret_cast<const float4*>(p.weights) + i);
     for (int i = tid; i <= kGroupsMax; i += kThreads)  // the entry after the last group is prefetched, never used
         s_grp[i] = i < tab.n_groups ? __ldg(reinterpret_cast<const int2*>(p.groups) + i) : make_int2(0, -1);
-    for (int i = tid; i < kSFloats; i += kThreads) s_s[i] = 0.0f;     // the zero row stays zero
+    for (int i = tid; i < kSFloats; i += kThreads) s_s[i] = 0.0f;
     for (int i = tid; i < kPRows * kPPitch; i += kThreads) s_p[i] = 0.0f;
     __syncthreads();
     RoundGeom geo_next = round_geom(p, min((int)blockIdx.x, p.n_rounds - 1));
@@ -200,13 +196,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
     __syncthreads();
 
     const int col32_bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);
-    // output stage: lane handles filters lane + 32*i
-    int side_off[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int m = lane + 32 * i;
-        side_off[i] = (m < p.n_mels ? (int)tab.side[m] : kZeroRow) * kSPitch;
-    }
     uint32_t parity = 0;
 
     for (int round = blockIdx.x; round < p.n_rounds; round += gridDim.x) {
@@ -311,35 +300,47 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
             const float* pl = s_p + lane;
             const int i0 = tab.first[warp], i1 = tab.first[warp + 1];
             if (tab.fast) {
-                // groups i0 .. i1-1 of this warp, software-pipelined: the next group's record, power values and
-                // weights are requested before the current group's four packed FMAs.  a0 / a1 hold the
-                // (rising-edge, falling-edge) sums of the interval's even / odd bins.
+                // groups i0 .. i1-1 of this warp, software-pipelined two at a time: while one group's four
+                // packed FMAs run, the other's record, power values and weights are in flight.  a0 / a1 hold
+                // the (rising-edge, falling-edge) sums of the interval's even / odd bins.  A warp's range
+                // starts with the interval whose rising edge it needs (that flush goes to the dummy row) and
+                // ends with the interval that completes its last filter, so no sum crosses warps.
                 float up_prev = 0.0f;
                 float2 a0 = make_float2(0.0f, 0.0f), a1 = make_float2(0.0f, 0.0f);
-                int2 g = s_grp[i0];
-                const float* pp = pl + g.x * kPPitch;
-                float q0 = pp[0], q1 = pp[kPPitch], q2 = pp[2 * kPPitch], q3 = pp[3 * kPPitch];
-                float4 w0 = s_w4[2 * i0], w1 = s_w4[2 * i0 + 1];
-#pragma unroll 2
-                for (int i = i0; i < i1; ++i) {
-                    const int2 gn = s_grp[i + 1];
-                    const float* pn = pl + gn.x * kPPitch;
-                    const float n0 = pn[0], n1 = pn[kPPitch], n2 = pn[2 * kPPitch], n3 = pn[3 * kPPitch];
-                    const float4 v0 = s_w4[2 * i + 2], v1 = s_w4[2 * i + 3];
-                    a0 = __ffma2_rn(make_float2(w0.x, w0.y), bc2(q0), a0);
-                    a1 = __ffma2_rn(make_float2(w0.z, w0.w), bc2(q1), a1);
-                    a0 = __ffma2_rn(make_float2(w1.x, w1.y), bc2(q2), a0);
-                    a1 = __ffma2_rn(make_float2(w1.z, w1.w), bc2(q3), a1);
-                    if (g.y >= 0) {  // warp-uniform: the interval ends here
-                        const float2 a = __fadd2_rn(a0, a1);
-                        s_s[g.y * kSPitch + lane] = up_prev + a.y;  // falling edge completes the filter below
-                        up_prev = a.x;                              // rising edge waits for the next interval
-                        a0 = make_float2(0.0f, 0.0f);
-                        a1 = make_float2(0.0f, 0.0f);
-                    }
-                    g = gn; q0 = n0; q1 = n1; q2 = n2; q3 = n3; w0 = v0; w1 = v1;
+#define MEL_LOAD(G, Q0, Q1, Q2, Q3, W0, W1, idx)                                           \
+    G = s_grp[idx];                                                                        \
+    {                                                                                      \
+        const float* pp_ = pl + G.x * kPPitch;                                             \
+        Q0 = pp_[0]; Q1 = pp_[kPPitch]; Q2 = pp_[2 * kPPitch]; Q3 = pp_[3 * kPPitch];      \
+        W0 = s_w4[2 * (idx)]; W1 = s_w4[2 * (idx) + 1];                                    \
+    }
+#define MEL_GROUP(G, Q0, Q1, Q2, Q3, W0, W1)                                               \
+    a0 = __ffma2_rn(make_float2(W0.x, W0.y), bc2(Q0), a0);                                 \
+    a1 = __ffma2_rn(make_float2(W0.z, W0.w), bc2(Q1), a1);                                 \
+    a0 = __ffma2_rn(make_float2(W1.x, W1.y), bc2(Q2), a0);                                 \
+    a1 = __ffma2_rn(make_float2(W1.z, W1.w), bc2(Q3), a1);                                 \
+    if (G.y >= 0) { /* warp-uniform: the interval ends here */                             \
+        const float2 a_ = __fadd2_rn(a0, a1);                                              \
+        s_s[G.y * kSPitch + lane] = up_prev + a_.y; /* falling edge completes the filter below */ \
+        up_prev = a_.x;                             /* rising edge waits for the next interval */ \
+        a0 = make_float2(0.0f, 0.0f);                                                      \
+        a1 = make_float2(0.0f, 0.0f);                                                      \
+    }
+                int2 ga, gb;
+                float pa0, pa1, pa2, pa3, pb0, pb1, pb2, pb3;
+                float4 wa0, wa1, wb0, wb1;
+                int i = i0;
+                MEL_LOAD(ga, pa0, pa1, pa2, pa3, wa0, wa1, i)
+#pragma unroll 1
+                for (; i + 1 < i1; i += 2) {
+                    MEL_LOAD(gb, pb0, pb1, pb2, pb3, wb0, wb1, i + 1)
+                    MEL_GROUP(ga, pa0, pa1, pa2, pa3, wa0, wa1)
+                    MEL_LOAD(ga, pa0, pa1, pa2, pa3, wa0, wa1, i + 2)   // one past the range at the end: a valid slot
+                    MEL_GROUP(gb, pb0, pb1, pb2, pb3, wb0, wb1)
                 }
-                s_s[(int)tab.last_row[warp] * kSPitch + lane] = up_prev;
+                if (i < i1) { MEL_GROUP(ga, pa0, pa1, pa2, pa3, wa0, wa1) }
+#undef MEL_LOAD
+#undef MEL_GROUP
             } else {
                 for (int m = i0; m < i1; ++m) {
                     const MelItem it = tab.item[m];
@@ -359,20 +360,21 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
         __syncthreads();  // S complete (and a cooperatively copied span visible)
 
         // ================= output: log / clamp / affine, one 128-filter row per warp store =================
+        {
+            float mel[kRound / kWarps][4];
 #pragma unroll
-        for (int h = 0; h < kRound / kWarps; ++h) {
-            const int f = warp + h * kWarps;
-            if (f < geo.nf) {
+            for (int h = 0; h < kRound / kWarps; ++h)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mel[h][i] = s_s[(lane + 32 * i) * kSPitch + warp + h * kWarps];
+#pragma unroll
+            for (int h = 0; h < kRound / kWarps; ++h) {
+                const int f = warp + h * kWarps;
                 float* row = p.out + (geo.out_row + f) * p.n_mels;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const int m = lane + 32 * i;
-                    if (m < p.n_mels) {
-                        const float mel = s_s[m * kSPitch + f] + s_s[side_off[i] + f];
-                        float v = __logf(mel + 1e-10f);                     // |err| ~1e-7 in ln, 35x below the tolerance
-                        v = v != v ? v : fminf(fmaxf(v, -23.0f), 12.0f);    // torch.clamp keeps NaN
-                        row[m] = (v + 23.0f) * (1.0f / 35.0f);
-                    }
+                    float v = __logf(mel[h][i] + 1e-10f);               // |err| ~1e-7 in ln, 35x below the tolerance
+                    v = v != v ? v : fminf(fmaxf(v, -23.0f), 12.0f);    // torch.clamp keeps NaN
+                    if (f < geo.nf && lane + 32 * i < p.n_mels) row[lane + 32 * i] = (v + 23.0f) * (1.0f / 35.0f);
                 }
             }
         }
@@ -500,83 +502,70 @@ static bool build_fast_tables(const float* fb, int n_bins, int n_mels, MelTables
         iv[k] = j;
         prev = j;
     }
+    // warp ranges over the filters: warp w completes filters m0 .. m1-1, i.e. walks intervals m0 .. m1 (interval
+    // m0 only for its rising edge, interval m1 only for its falling edge); the boundary intervals are walked
+    // twice so that no sum crosses warps.  Balanced by the bins per range.
+    std::vector<int> iv_bins(n_mels + 2, 0);
+    for (int k = 0; k < n_bins; ++k)
+        if (iv[k] >= 0) ++iv_bins[iv[k]];
+    auto iv_groups = [&](int j) { return std::max(1, (iv_bins[j] + kGroupBins - 1) / kGroupBins); };
+    std::vector<int> m_of_warp(kWarps + 1, 0);
+    {
+        std::vector<double> cost(n_mels, 0.0);
+        double total = 0;
+        for (int m = 0; m < n_mels; ++m) total += cost[m] = 16.0 * iv_groups(m + 1) + 10.0;
+        int m = 0;
+        double spent = 0;
+        for (int w = 0; w < kWarps; ++w) {
+            m_of_warp[w] = m;
+            const double target = total * (w + 1) / kWarps;
+            while (m < n_mels && (w == kWarps - 1 || spent + 0.5 * cost[m] <= target)) spent += cost[m++];
+        }
+        m_of_warp[kWarps] = n_mels;
+    }
     // intervals -> groups of kGroupBins bins; an interval without bins still gets one (all-zero) group,
     // because its end is where the filter below it is completed
     packed.clear();
     groups.clear();
     memset(&t, 0, sizeof(t));
-    std::vector<int> iv_first(n_mels + 2, 0);  // first group of every interval
-    for (int j = 0; j <= n_mels; ++j) {
-        iv_first[j] = (int)groups.size();
-        int lo = -1, hi = -1;
-        for (int k = 0; k < n_bins; ++k)
-            if (iv[k] == j) { if (lo < 0) lo = k; hi = k; }
-        for (int k = lo; k <= hi; ++k)
-            if (lo >= 0 && iv[k] != j && iv[k] >= 0) return false;  // bins of another interval inside the range
-        int g0 = lo < 0 ? 0 : lo;
-        do {
-            MelGroup g;
-            g.b0 = std::min(g0, n_bins + 1 - kGroupBins);  // rows 0 .. n_bins exist (row n_bins is kept at zero)
-            g.row = -1;
-            for (int e = 0; e < kGroupBins; ++e) {
-                const int k = g.b0 + e;
-                const bool in = lo >= 0 && k >= g0 && k < g0 + kGroupBins && k <= hi && iv[k] == j;
-                packed.push_back(in ? up[k] : 0.0f);
-                packed.push_back(in ? dn[k] : 0.0f);
-            }
-            groups.push_back(g);
-            g0 += kGroupBins;
-        } while (lo >= 0 && g0 <= hi);
-    }
-    iv_first[n_mels + 1] = (int)groups.size();
-    if (groups.size() > (size_t)kGroupsMax) return false;
-    // verify: the groups reproduce fb exactly
-    {
-        std::vector<float> chk((size_t)n_bins * n_mels, 0.0f);
-        for (int j = 0; j <= n_mels; ++j)
-            for (int gi = iv_first[j]; gi < iv_first[j + 1]; ++gi)
+    std::vector<float> chk((size_t)n_bins * n_mels, 0.0f);
+    for (int w = 0; w < kWarps; ++w) {
+        t.first[w] = (int16_t)groups.size();
+        const int m0 = m_of_warp[w], m1 = m_of_warp[w + 1];
+        for (int j = m0; m1 > m0 && j <= m1; ++j) {
+            int lo = -1, hi = -1;
+            for (int k = 0; k < n_bins; ++k)
+                if (iv[k] == j) { if (lo < 0) lo = k; hi = k; }
+            for (int k = lo; k <= hi; ++k)
+                if (lo >= 0 && iv[k] != j && iv[k] >= 0) return false;  // bins of another interval inside the range
+            int g0 = lo < 0 ? 0 : lo;
+            do {
+                MelGroup g;
+                g.b0 = std::min(g0, n_bins + 1 - kGroupBins);  // rows 0 .. n_bins exist (row n_bins is kept at zero)
+                g.row = -1;
                 for (int e = 0; e < kGroupBins; ++e) {
-                    const int k = groups[gi].b0 + e;
-                    const float wu = packed[((size_t)gi * kGroupBins + e) * 2], wd = packed[((size_t)gi * kGroupBins + e) * 2 + 1];
-                    if (k >= n_bins) { if (wu != 0.0f || wd != 0.0f) return false; continue; }
-                    if (wu != 0.0f) { if (j >= n_mels) return false; chk[(size_t)k * n_mels + j] += wu; }
-                    if (wd != 0.0f) { if (j < 1) return false; chk[(size_t)k * n_mels + j - 1] += wd; }
+                    const int k = g.b0 + e;
+                    const bool in = lo >= 0 && k >= g0 && k < g0 + kGroupBins && k <= hi && iv[k] == j;
+                    const float wu = in ? up[k] : 0.0f, wd = in ? dn[k] : 0.0f;
+                    packed.push_back(wu);
+                    packed.push_back(wd);
+                    // what the kernel will use of this group: the rising edge unless it is the range's last
+                    // interval, the falling edge unless it is the range's first
+                    if (in && wu != 0.0f && j < m1) { if (j >= n_mels) return false; chk[(size_t)k * n_mels + j] += wu; }
+                    if (in && wd != 0.0f && j > m0) chk[(size_t)k * n_mels + j - 1] += wd;
+                    if (in && wd != 0.0f && j == 0) return false;
                 }
-        for (size_t i = 0; i < chk.size(); ++i)
-            if (chk[i] != fb[i]) return false;
-    }
-    // contiguous interval ranges for the warps, balanced by estimated cost (a group ~16 issue slots, an
-    // interval end ~10 more)
-    std::vector<double> cost(n_mels + 1, 0.0);
-    double total = 0;
-    for (int j = 0; j <= n_mels; ++j) total += cost[j] = 16.0 * (iv_first[j + 1] - iv_first[j]) + 10.0;
-    int j = 0;
-    double spent = 0;
-    std::vector<int> iv_of_warp(kWarps + 1, 0);
-    for (int w = 0; w < kWarps; ++w) {
-        iv_of_warp[w] = j;
-        const double target = total * (w + 1) / kWarps;
-        while (j <= n_mels && (w == kWarps - 1 || spent + 0.5 * cost[j] <= target)) spent += cost[j++];
-    }
-    iv_of_warp[kWarps] = n_mels + 1;
-    for (int m = 0; m < kMaxMels; ++m) t.side[m] = (uint8_t)kZeroRow;
-    for (int w = 0; w < kWarps; ++w) {
-        const int j0 = iv_of_warp[w], j1 = iv_of_warp[w + 1];
-        t.first[w] = (int16_t)iv_first[j0];
-        t.last_row[w] = (uint8_t)kDummyRow;
-        for (int jj = j0; jj < j1; ++jj) {
-            // the end of interval jj completes filter jj-1: inside the warp's range with the rising edge the
-            // warp carries, at the start of the range through the warp's boundary row
-            int row = jj - 1;
-            if (jj == j0) row = jj > 0 ? kSideRow + w : kDummyRow;
-            groups[iv_first[jj + 1] - 1].row = row;
-        }
-        if (j1 > j0) {
-            if (j0 > 0) t.side[j0 - 1] = (uint8_t)(kSideRow + w);
-            if (j1 - 1 < n_mels) t.last_row[w] = (uint8_t)(j1 - 1);
+                groups.push_back(g);
+                g0 += kGroupBins;
+            } while (lo >= 0 && g0 <= hi);
+            groups.back().row = j > m0 ? j - 1 : kDummyRow;  // the end of interval j completes filter j-1
         }
     }
     t.first[kWarps] = (int16_t)groups.size();
+    if (groups.size() > (size_t)kGroupsMax) return false;
+    // verify: the groups reproduce fb exactly
+    for (size_t i = 0; i < chk.size(); ++i)
+        if (chk[i] != fb[i]) return false;
     t.fast = 1;
     t.n_groups = (int32_t)groups.size();
     return true;
@@ -608,7 +597,6 @@ static void build_generic_tables(const float* fb, int n_bins, int n_mels, MelTab
         while (m < n_mels && (w == kWarps - 1 || spent + 0.5 * cost[m] <= target)) spent += cost[m++];
     }
     t.first[kWarps] = (int16_t)n_mels;
-    for (int i = 0; i < kMaxMels; ++i) t.side[i] = (uint8_t)kZeroRow;
     t.fast = 0;
     t.n_groups = 0;
 }

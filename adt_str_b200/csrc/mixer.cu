@@ -42,11 +42,22 @@ __device__ __forceinline__ float nan_max(float a, float b) {  // torch.max propa
     return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b);
 }
 
-// max|ca*a + cb*b| over the float4s held in registers, for NC notes at once
+// (ca*a.x + cb*b.x, ca*a.y + cb*b.y) for two samples in two packed sm_100a instructions: fl(cb*b + fl(ca*a)).
+// torch rounds both products before the sum (mul, mul, add, synthetiser.py:223); this form skips the rounding
+// of the second product, so a peak can differ from the reference's in its last bit (<= 6e-8 relative, two
+// orders below the 1e-5 waveform tolerance).  ptxas contracts packed mul + add into FFMA2 whatever the source
+// says (even explicit .rn PTX under --fmad=false), so the contraction is spelled out rather than left to it.
+__device__ __forceinline__ float2 mix2(float ax, float ay, float bx, float by, float ca, float cb) {
+    return __ffma2_rn(make_float2(bx, by), make_float2(cb, cb), __fmul2_rn(make_float2(ax, ay), make_float2(ca, ca)));
+}
+
+// max|ca*a + cb*b| over the float4s held in registers, for NC notes at once: per pair of samples two
+// packed fp32 instructions and one three-input FMNMX; the warp's maximum by one REDUX on the float bits
+// (non-negative floats order like unsigned integers), the CTA's through a shared-memory atomicMax.
 template <int NC>
 __device__ __forceinline__ void peak_chunk(const float4 (&va)[kPeakIters], const float4 (&vb)[kPeakIters],
                                            const float* __restrict__ s_ca, const float* __restrict__ s_cb,
-                                           float (*s_red)[kPeakThreads / 32], int tid) {
+                                           unsigned* s_peak, int tid) {
     float ca[NC], cb[NC], m[NC];
 #pragma unroll
     for (int i = 0; i < NC; ++i) { ca[i] = s_ca[i]; cb[i] = s_cb[i]; m[i] = 0.0f; }
@@ -54,17 +65,16 @@ __device__ __forceinline__ void peak_chunk(const float4 (&va)[kPeakIters], const
     for (int it = 0; it < kPeakIters; ++it) {
 #pragma unroll
         for (int i = 0; i < NC; ++i) {
-            // separate roundings, as torch's mul, mul, add (synthetiser.py:223)
-            m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va[it].x, ca[i]), __fmul_rn(cb[i], vb[it].x))));
-            m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va[it].y, ca[i]), __fmul_rn(cb[i], vb[it].y))));
-            m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va[it].z, ca[i]), __fmul_rn(cb[i], vb[it].z))));
-            m[i] = fmaxf(m[i], fabsf(__fadd_rn(__fmul_rn(va[it].w, ca[i]), __fmul_rn(cb[i], vb[it].w))));
+            const float2 lo = mix2(va[it].x, va[it].y, vb[it].x, vb[it].y, ca[i], cb[i]);
+            const float2 hi = mix2(va[it].z, va[it].w, vb[it].z, vb[it].w, ca[i], cb[i]);
+            m[i] = fmaxf(fmaxf(m[i], fabsf(lo.x)), fabsf(lo.y));
+            m[i] = fmaxf(fmaxf(m[i], fabsf(hi.x)), fabsf(hi.y));
         }
     }
 #pragma unroll
     for (int i = 0; i < NC; ++i) {
-        const float w = warp_max(m[i]);
-        if ((tid & 31) == 0) s_red[i][tid >> 5] = w;
+        const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(m[i]));
+        if ((tid & 31) == 0 && w != 0u) atomicMax(s_peak + i, w);
     }
 }
 
@@ -76,7 +86,7 @@ __device__ __forceinline__ void peak_chunk(const float4 (&va)[kPeakIters], const
 __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
     const float* __restrict__ pcm, const adtfe_event* __restrict__ events, const adtfe_peak_item* __restrict__ work,
     ResolvedEvent* __restrict__ resolved, int* __restrict__ peak_bits) {
-    __shared__ float s_red[kPeakChunk][kPeakThreads / 32];
+    __shared__ unsigned s_peak[kPeakChunk];
     __shared__ float s_ca[kPeakChunk], s_cb[kPeakChunk];
     const adtfe_peak_item item = work[blockIdx.x];  // one fetch, then the data loads can start
     const int chunk = item.chunk, tid = threadIdx.x;
@@ -124,24 +134,26 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
     }
     for (int c0 = e0; c0 < e1; c0 += kPeakChunk) {
         const int nc = min(kPeakChunk, e1 - c0);
-        __syncthreads();
+        __syncthreads();  // the previous sweep's peaks have been published
         if (tid < kPeakChunk) {
             const bool live = tid < nc;
             s_ca[tid] = live ? events[c0 + tid].ca : 0.0f;
             s_cb[tid] = live ? events[c0 + tid].cb : 0.0f;
+            s_peak[tid] = 0u;
         }
         __syncthreads();
-        if (nc <= 1) peak_chunk<1>(va, vb, s_ca, s_cb, s_red, tid);
-        else if (nc <= 2) peak_chunk<2>(va, vb, s_ca, s_cb, s_red, tid);
-        else if (nc <= 4) peak_chunk<4>(va, vb, s_ca, s_cb, s_red, tid);
-        else peak_chunk<8>(va, vb, s_ca, s_cb, s_red, tid);
-        __syncthreads();
-        if (tid < nc) {
-            float peak = 0.0f;
-#pragma unroll
-            for (int w = 0; w < kPeakThreads / 32; ++w) peak = fmaxf(peak, s_red[tid][w]);
-            if (peak > 0.0f) atomicMax(peak_bits + c0 + tid, __float_as_int(peak));
+        switch (nc) {
+            case 1: peak_chunk<1>(va, vb, s_ca, s_cb, s_peak, tid); break;
+            case 2: peak_chunk<2>(va, vb, s_ca, s_cb, s_peak, tid); break;
+            case 3: peak_chunk<3>(va, vb, s_ca, s_cb, s_peak, tid); break;
+            case 4: peak_chunk<4>(va, vb, s_ca, s_cb, s_peak, tid); break;
+            case 5: peak_chunk<5>(va, vb, s_ca, s_cb, s_peak, tid); break;
+            case 6: peak_chunk<6>(va, vb, s_ca, s_cb, s_peak, tid); break;
+            case 7: peak_chunk<7>(va, vb, s_ca, s_cb, s_peak, tid); break;
+            default: peak_chunk<8>(va, vb, s_ca, s_cb, s_peak, tid); break;
         }
+        __syncthreads();
+        if (tid < nc && s_peak[tid] != 0u) atomicMax(peak_bits + c0 + tid, (int)s_peak[tid]);
     }
 }
 
