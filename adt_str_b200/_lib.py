@@ -7,7 +7,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libadtfe.so")
+#: ``ADTFE_LIB`` selects a tuning variant built by ``build.py --out=...`` (same ABI, same sources)
+LIB_PATH = os.environ.get("ADTFE_LIB") or os.path.join(_HERE, "libadtfe.so")
 
 EXPORTS = [
     "adtfe_version", "adtfe_last_error", "adtfe_device_ok",

@@ -29,19 +29,24 @@ def stale() -> bool:
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """``defines`` / ``out``: tuning variants (``-DADTFE_MIX_CONSUMERS=2`` ...) built next to the product
+    library and selected with the ``ADTFE_LIB`` environment variable (see ``_lib.py``)."""
     gen = os.path.join(CSRC, "fft_gen.cuh")
     if not os.path.exists(gen):
         subprocess.check_call([sys.executable, os.path.join(HERE, "..", "tools", "gen_fft.py")])
-    if not force and not stale():
+    if out == LIB and not defines and not force and not stale():
         return LIB
     flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
-    cmd = [_nvcc(), *flags, *(["-Xptxas", "-v"] if verbose else []), "-o", LIB + ".tmp",
+    cmd = [_nvcc(), *flags, *[f"-D{d}" for d in defines], *(["-Xptxas", "-v"] if verbose else []), "-o", out + ".tmp",
            *[os.path.join(CSRC, s) for s in SOURCES]]
     subprocess.check_call(cmd, cwd=CSRC)
-    os.replace(LIB + ".tmp", LIB)
-    return LIB
+    os.replace(out + ".tmp", out)
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, defines=defs,
+                out=os.path.join(HERE, outs[0]) if outs else LIB))

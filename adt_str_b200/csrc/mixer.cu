@@ -159,15 +159,28 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
 
 // ---------------------------------------------------------------------------------------------
 // Tile mixer.  Persistent CTAs: one producer warp stages the one-shot slices a tile needs through a
-// ring of shared-memory buffers with TMA bulk copies (cp.async.bulk + mbarrier), eight consumer
+// ring of shared-memory buffers with TMA bulk copies (cp.async.bulk + mbarrier), the consumer
 // warps accumulate them in arrival (= event) order into registers.  Tiles are handed out by an
-// atomic counter, so long and short tiles balance.
-constexpr int kMixConsumers = 8;                         // warps; 256 threads x 8 samples = one tile
+// atomic counter, so long and short tiles balance.  Measured on B200 (tools/gpu_variants.sh): the
+// kernel is bound by the latency chain of a tile (queue head -> tile_ptr -> events -> records -> TMA),
+// so many small CTAs (4 consumer warps x 16 samples per thread, a 2-slot ring, 8 CTAs per SM) beat
+// few large ones (8 x 8, 6 slots, 4 per SM) by 12 % on the whole render.
+#ifndef ADTFE_MIX_CONSUMERS
+#define ADTFE_MIX_CONSUMERS 4
+#endif
+#ifndef ADTFE_MIX_STAGES
+#define ADTFE_MIX_STAGES 2
+#endif
+#ifndef ADTFE_MIX_CTAS
+#define ADTFE_MIX_CTAS 8
+#endif
+constexpr int kMixConsumers = ADTFE_MIX_CONSUMERS;       // warps; each thread owns tile / (32 * warps) samples
 constexpr int kMixThreads = (kMixConsumers + 1) * 32;    // + the producer warp
 constexpr int kPerThread = ADTFE_TILE / (kMixConsumers * 32);
-constexpr int kStages = 6;
+constexpr int kStages = ADTFE_MIX_STAGES;
+constexpr int kMixCtasPerSm = ADTFE_MIX_CTAS;
 constexpr int kStageFloats = 2080;                       // >= 2048 + 2*3 alignment slack, bytes a multiple of 128
-static_assert(kPerThread == 8, "tile / consumer threads");
+static_assert(kPerThread * kMixConsumers * 32 == ADTFE_TILE, "tile / consumer threads");
 
 struct __align__(16) StageDesc {   // written by the producer lane, read (broadcast) by every consumer
     int32_t kind;                  // 0: data, 1: a new tile begins (tile id in `tile`, < 0: no more work)
@@ -178,7 +191,19 @@ struct __align__(16) StageDesc {   // written by the producer lane, read (broadc
     int32_t pad0, pad1;
 };
 
+struct __align__(16) SliceMsg {    // producer-private list entry: the StageDesc words + what the TMA copy needs
+    int4 d0;                       // kind, tile, base, vlo
+    int4 d1;                       // vhi, coef bits, -, -
+    int4 d2;                       // source float offset (lo, hi), bytes (0: no copy, plain arrive), -
+};
+constexpr int kListMax = 65;       // a tile marker + two sources of 32 notes
+constexpr int kIssue = kStages / 2 > 0 ? kStages / 2 : 1;  // messages issued per producer pass
+
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kMixConsumers * 32) : "memory"); }
+
+__host__ __device__ constexpr size_t mix_list_offset() {
+    return (((size_t)kStages * kStageFloats * 4 + kStages * 32 + 2 * kStages * 8 + kMixConsumers * 4) + 15) & ~(size_t)15;
+}
 
 struct MixArgs {
     const float* pcm;
@@ -218,13 +243,14 @@ __device__ __forceinline__ void finish_tile(const MixArgs& a, int tile_id, const
     }
 }
 
-__global__ void __launch_bounds__(kMixThreads, 4) mix_kernel(const MixArgs a) {
+__global__ void __launch_bounds__(kMixThreads, kMixCtasPerSm) mix_kernel(const MixArgs a) {
     extern __shared__ __align__(128) unsigned char mix_smem[];
     float* s_buf = reinterpret_cast<float*>(mix_smem);                               // kStages * kStageFloats
     StageDesc* s_desc = reinterpret_cast<StageDesc*>(s_buf + kStages * kStageFloats);
     uint64_t* s_full = reinterpret_cast<uint64_t*>(s_desc + kStages);
     uint64_t* s_empty = s_full + kStages;
     float* s_red = reinterpret_cast<float*>(s_empty + kStages);
+    SliceMsg* s_list = reinterpret_cast<SliceMsg*>(mix_smem + mix_list_offset());
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -237,28 +263,30 @@ __global__ void __launch_bounds__(kMixThreads, 4) mix_kernel(const MixArgs a) {
 
     if (warp == kMixConsumers) {
         // ================= producer warp =================
+        // Per tile: a marker message, then one message per live (note, source) slice in event order.  The
+        // messages of up to 32 notes are first laid out in a warp-private list (ballot + popcount give every
+        // lane its slots); then lane j takes the j-th next message: it waits for ring slot stage + j to drain,
+        // publishes the descriptor and starts the TMA copy - kStages slots are refilled per pass instead of one.
+        SliceMsg* list = s_list;
         for (;;) {
             int tile = 0;
             if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
             tile = __shfl_sync(0xffffffffu, tile, 0);
             const bool done = tile >= a.n_tiles;
-            mbar_wait(s_empty + stage, phase ^ 1u);
-            if (lane == 0) {
-                StageDesc d;
-                d.kind = 1; d.tile = done ? -1 : tile; d.base = 0; d.vlo = 0; d.vhi = 0; d.coef = 0.0f; d.pad0 = d.pad1 = 0;
-                s_desc[stage] = d;
-                mbar_arrive(s_full + stage);
+            int p0 = 0, p1 = 0, lo = 0;
+            if (!done) {
+                const int seg = tile / a.tiles_per_seg;
+                lo = (tile - seg * a.tiles_per_seg) * ADTFE_TILE;
+                p0 = __ldg(a.tile_ptr + tile);
+                p1 = __ldg(a.tile_ptr + tile + 1);
             }
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            if (done) break;
-            const int seg = tile / a.tiles_per_seg;
-            const int lo = (tile - seg * a.tiles_per_seg) * ADTFE_TILE;
-            const int p0 = __ldg(a.tile_ptr + tile), p1 = __ldg(a.tile_ptr + tile + 1);
-            for (int base = p0; base < p1; base += 32) {
+            bool first = true;
+            int base = p0;
+            do {
                 const int n = min(32, p1 - base);
                 // lane i owns event base + i: both of its sources, clipped to this tile
                 int64_t off[2] = {0, 0};
-                int r_lo[2] = {0, 0}, r_hi[2] = {0, 0}, rel = 0;
+                int r_lo = 0, r_hi[2] = {0, 0}, rel = 0;
                 float coef[2] = {0.0f, 0.0f};
                 if (lane < n) {
                     const int e = __ldg(a.tile_events + base + lane);
@@ -269,30 +297,62 @@ __global__ void __launch_bounds__(kMixThreads, 4) mix_kernel(const MixArgs a) {
                     rel = lo - ev.start;  // tile sample i is source sample i + rel
                     off[0] = ev.a_off; off[1] = ev.b_off;
                     coef[0] = ev.ca * scale; coef[1] = ev.cb * scale;
-                    r_lo[0] = r_lo[1] = max(0, rel);
+                    r_lo = max(0, rel);
                     r_hi[0] = min(ev.la, rel + ADTFE_TILE);
                     r_hi[1] = min(ev.lb, rel + ADTFE_TILE);
                 }
-                for (int i = 0; i < n; ++i) {
+                const bool live0 = r_hi[0] > r_lo, live1 = r_hi[1] > r_lo;
+                const unsigned m0 = __ballot_sync(0xffffffffu, live0), m1 = __ballot_sync(0xffffffffu, live1);
+                const unsigned below = (1u << lane) - 1u;
+                int slot = (first ? 1 : 0) + __popc(m0 & below) + __popc(m1 & below);
+                const int total = (first ? 1 : 0) + __popc(m0) + __popc(m1);
+                if (first && lane == 0) {
+                    SliceMsg m;
+                    m.d0 = make_int4(1, done ? -1 : tile, 0, 0);
+                    m.d1 = make_int4(0, 0, 0, 0);
+                    m.d2 = make_int4(0, 0, 0, 0);
+                    list[0] = m;
+                }
 #pragma unroll
-                    for (int s = 0; s < 2; ++s) {
-                        const bool live = r_hi[s] > r_lo[s];
-                        if (!__shfl_sync(0xffffffffu, (int)live, i)) continue;  // warp-uniform
-                        mbar_wait(s_empty + stage, phase ^ 1u);
-                        if (lane == i) {
-                            const int g_lo = r_lo[s] & ~3, g_hi = (r_hi[s] + 3) & ~3;  // storage is padded to 4 floats
-                            StageDesc d;
-                            d.kind = 0; d.tile = tile; d.base = rel - g_lo; d.vlo = r_lo[s] - rel; d.vhi = r_hi[s] - rel;
-                            d.coef = coef[s]; d.pad0 = d.pad1 = 0;
-                            s_desc[stage] = d;
-                            const uint32_t bytes = (uint32_t)(g_hi - g_lo) * 4u;
-                            mbar_expect_tx(s_full + stage, bytes);
-                            bulk_g2s(s_buf + stage * kStageFloats, a.pcm + off[s] + g_lo, bytes, s_full + stage);
-                        }
-                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                for (int sidx = 0; sidx < 2; ++sidx) {
+                    if (sidx == 0 ? live0 : live1) {
+                        const int g_lo = r_lo & ~3, g_hi = (r_hi[sidx] + 3) & ~3;  // storage is padded to 4 floats
+                        const long long src = off[sidx] + g_lo;
+                        SliceMsg m;
+                        m.d0 = make_int4(0, tile, rel - g_lo, r_lo - rel);
+                        m.d1 = make_int4(r_hi[sidx] - rel, __float_as_int(coef[sidx]), 0, 0);
+                        m.d2 = make_int4((int)(unsigned)(src & 0xffffffffll), (int)(src >> 32), (g_hi - g_lo) * 4, 0);
+                        list[slot++] = m;
                     }
                 }
-            }
+                __syncwarp();
+                for (int k0 = 0; k0 < total; k0 += kIssue) {
+                    const int k = k0 + lane;
+                    if (lane < kIssue && k < total) {
+                        int st = stage + lane;
+                        uint32_t ph = phase;
+                        if (st >= kStages) { st -= kStages; ph ^= 1u; }
+                        const SliceMsg m = list[k];
+                        mbar_wait(s_empty + st, ph ^ 1u);
+                        int4* d = reinterpret_cast<int4*>(s_desc + st);
+                        d[0] = m.d0;
+                        d[1] = m.d1;
+                        if (m.d2.z > 0) {
+                            const long long src = (long long)(((unsigned long long)(unsigned)m.d2.y << 32) | (unsigned)m.d2.x);
+                            mbar_expect_tx(s_full + st, (uint32_t)m.d2.z);
+                            bulk_g2s(s_buf + st * kStageFloats, a.pcm + src, (uint32_t)m.d2.z, s_full + st);
+                        } else {
+                            mbar_arrive(s_full + st);
+                        }
+                    }
+                    stage += min(kIssue, total - k0);
+                    if (stage >= kStages) { stage -= kStages; phase ^= 1u; }
+                }
+                __syncwarp();  // the list is rewritten by the next batch
+                first = false;
+                base += 32;
+            } while (base < p1);
+            if (done) break;
         }
         return;
     }
@@ -367,9 +427,7 @@ __global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_seg
     for (int i = 4 * n4 + tid; i < n; i += kNormThreads) row[i] = __fmul_rn(__fdiv_rn(row[i], peak), vol);
 }
 
-static size_t mix_smem_bytes() {
-    return (size_t)kStages * kStageFloats * 4 + kStages * sizeof(StageDesc) + 2 * kStages * 8 + kMixConsumers * 4 + 16;
-}
+static size_t mix_smem_bytes() { return mix_list_offset() + kListMax * sizeof(SliceMsg); }
 
 }  // namespace adtfe
 
@@ -454,7 +512,7 @@ extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, floa
         a.segments = plan->segments_dev + s0; a.wav = wav_out_dev + (size_t)s0 * plan->ld_wav;
         a.tile_max = tile_max + (size_t)s0 * tps; a.tile_counter = counters + c; a.ld_wav = plan->ld_wav;
         a.tiles_per_seg = tps; a.n_tiles = n_seg * tps;
-        const int grid = std::min(a.n_tiles, 4 * bank->sm_count);
+        const int grid = std::min(a.n_tiles, kMixCtasPerSm * bank->sm_count);
         mix_kernel<<<grid, kMixThreads, mix_smem_bytes(), st>>>(a);
         ADTFE_CUDA(cudaGetLastError());
         normalise_kernel<<<a.n_tiles, kNormThreads, 0, st>>>(a.segments, a.tile_max, tps, plan->ld_wav, a.wav);

@@ -62,8 +62,8 @@ class FrontEnd:
         """``[notes, ...] -> (wav (B, Lmax) cuda, logmel (B, T, n_mels) cuda)``."""
         return self.run_plan(self.synth.plan(batch_notes, rng))
 
-    def plan_batches(self, batches: Sequence[Sequence], rng=_random) -> RenderPlan:
-        return self.synth.plan_batches(batches, self.mel.n_frames, rng)
+    def plan_batches(self, batches: Sequence[Sequence], rng=_random, chunk_batches: int = 1) -> RenderPlan:
+        return self.synth.plan_batches(batches, self.mel.n_frames, rng, chunk_batches)
 
     def run_batches(self, batches: Sequence[Sequence], rng=_random):
         """Several batches through one plan: one H2D copy and one launch per kernel for all of them

@@ -204,11 +204,12 @@ class RenderPlan:
     mel_total_rows: int = 0
     chunks: np.ndarray = field(default=None)         # CHUNK_DTYPE (n_chunks+1,)
 
-    def set_batches(self, sizes: Sequence[int], n_frames) -> "RenderPlan":
+    def set_batches(self, sizes: Sequence[int], n_frames, chunk_batches: int = 1) -> "RenderPlan":
         """Mark the plan as ``len(sizes)`` collated batches laid end to end (``sizes[b]`` segments
         each).  Every batch keeps its own width - the longest of *its* segments, as
         ``collate_fn``'s ``pad_sequence`` gives (train_dataset.py:53) - and therefore its own
-        frame count ``n_frames(width)`` (model.py:95-97).  One chunk of the render per batch."""
+        frame count ``n_frames(width)`` (model.py:95-97).  One chunk of the render per
+        ``chunk_batches`` batches."""
         sizes = np.asarray(sizes, np.int64)
         if sizes.sum() != self.n_seg or (sizes <= 0).any():
             raise ValueError("batch sizes must be positive and add up to the number of segments")
@@ -220,10 +221,11 @@ class RenderPlan:
         batch_of = np.repeat(np.arange(len(sizes)), sizes)
         rows["count"] = frames[batch_of]
         rows["out_row"] = row0[batch_of] + (np.arange(self.n_seg) - ptr[batch_of]) * frames[batch_of]
-        chunks = np.zeros(len(sizes) + 1, CHUNK_DTYPE)
-        chunks["seg"] = ptr
+        cptr = np.unique(np.concatenate([ptr[::max(1, int(chunk_batches))], ptr[-1:]]))
+        chunks = np.zeros(len(cptr), CHUNK_DTYPE)
+        chunks["seg"] = cptr
         first_event = np.concatenate([self.segments["first_event"].astype(np.int64), [self.n_events]])
-        chunks["event"] = first_event[ptr]
+        chunks["event"] = first_event[cptr]
         chunks["peak_work"] = np.searchsorted(self.peak_work["first_event"], chunks["event"], side="left")
         self.batch_ptr, self.batch_samples, self.batch_frames = ptr, width.astype(np.int64), frames
         self.mel_rows, self.mel_total_rows, self.chunks = rows, int(row0[-1]), chunks

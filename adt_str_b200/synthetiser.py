@@ -154,13 +154,13 @@ class SynthDrum:
             self._native_planner = NativePlanner(self.config, self.bank)
         return self._native_planner.plan_batch(batch_notes, rng, ld_wav)
 
-    def plan_batches(self, batches: Sequence[Sequence], n_frames, rng=_random) -> RenderPlan:
+    def plan_batches(self, batches: Sequence[Sequence], n_frames, rng=_random, chunk_batches: int = 1) -> RenderPlan:
         """Plan several batches as ONE device plan (one H2D copy, one launch per kernel): the segments
         of all batches in order - the RNG stream advances exactly as planning them one by one would -
         with per-batch collated widths and frame counts (``RenderPlan.set_batches``).
         ``n_frames`` is ``ComputeMelSpectrogram.n_frames``."""
         flat = [notes for b in batches for notes in b]
-        return self.plan(flat, rng).set_batches([len(b) for b in batches], n_frames)
+        return self.plan(flat, rng).set_batches([len(b) for b in batches], n_frames, chunk_batches)
 
     # ---------------------------------------------------------------- render
     def render_plan(self, plan: RenderPlan, out: Optional[torch.Tensor] = None) -> torch.Tensor:

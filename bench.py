@@ -58,6 +58,7 @@ def parse_args():
     p.add_argument("--cpu-segments", type=int, default=0, help="cpu_baseline sample size (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--e2e-group", type=int, default=32, help="batches per end-to-end plan")
+    p.add_argument("--chunk-batches", type=int, default=4, help="batches rendered together as one chunk")
     return p.parse_args()
 
 
@@ -241,7 +242,7 @@ def run_b200(args):
     rng = random.Random(1234 + rank)
     batches = [segs[b * BATCH:(b + 1) * BATCH] for b in range(n_batches)]
     t0 = time.perf_counter()
-    plan = fe.plan_batches(batches, rng)
+    plan = fe.plan_batches(batches, rng, args.chunk_batches)
     plan_s = time.perf_counter() - t0
     buf = PlanBuffers(dev)
     buf._dplan = buf.upload(buf.pack(plan))
@@ -322,7 +323,7 @@ def run_b200(args):
         for i, g in enumerate(groups):
             s = sets[i % n_sets]
             s["done"].synchronize()                         # the set's previous use has left the GPU
-            p = fe.plan_batches(g, e2e_rng)
+            p = fe.plan_batches(g, e2e_rng, args.chunk_batches)
             if s["wav"] is None or s["wav"].shape != (p.n_seg, p.ld_wav):
                 s["wav"] = torch.empty((p.n_seg, p.ld_wav), dtype=torch.float32, device=dev)
             if s["feat"] is None or s["feat"].shape[0] < p.mel_total_rows:
