@@ -5,7 +5,7 @@ from .config import SharedConfig, SynthDrumConfig, setting_1, config_default  # 
 from .bank import OneShotBank  # noqa: F401
 
 __all__ = ["SharedConfig", "SynthDrumConfig", "OneShotBank", "setting_1", "config_default",
-           "SynthDrum", "ComputeMelSpectrogram", "FrontEnd"]
+           "SynthDrum", "ComputeMelSpectrogram", "FrontEnd", "HostPipeline"]
 
 
 def __getattr__(name):  # lazy: importing the package must not need the CUDA library
@@ -18,4 +18,7 @@ def __getattr__(name):  # lazy: importing the package must not need the CUDA lib
     if name == "FrontEnd":
         from .frontend import FrontEnd
         return FrontEnd
+    if name == "HostPipeline":
+        from .pipeline import HostPipeline
+        return HostPipeline
     raise AttributeError(name)

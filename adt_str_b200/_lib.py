@@ -57,7 +57,7 @@ def _declare(lib) -> None:
     lib.adtfe_logmel.argtypes = [vp, vp, i32, i64, i64, vp, vp]
     lib.adtfe_logmel_rows.argtypes = [vp, vp, i32, i64, vp, i32, vp, vp]
     lib.adtfe_render_logmel.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, vp, vp, sz, vp]
-    lib.adtfe_frontend_host.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp]
+    lib.adtfe_frontend_host.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp, vp]
     lib.adtfe_plan_blob_layout.argtypes = [C.POINTER(Plan), C.POINTER(sz * 6), C.POINTER(sz)]
     lib.adtfe_planner_create.argtypes = [i32, C.c_double, C.c_double, C.c_double, i32, vp, vp, i32, vp, vp, vp, vp, vp,
                                          vp, C.POINTER(vp)]

@@ -141,7 +141,7 @@ extern "C" int adtfe_plan_blob_layout(const adtfe_plan* s, size_t offsets[6], si
 extern "C" int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel, const adtfe_plan* shape,
                                    int64_t n_samples, const void* blob_host, size_t blob_bytes, void* blob_dev,
                                    float* wav_dev, float* mel_dev, void* workspace_dev, size_t workspace_bytes,
-                                   float* mel_out_host, float* wav_out_host, void* stream) {
+                                   float* mel_out_host, float* wav_out_host, void* stream, void* copy_stream) {
     ADTFE_REQUIRE(bank && mel && shape && blob_host && blob_dev && mel_out_host, ADTFE_ERR_BAD_ARG,
                   "adtfe_frontend_host: null pointer");
     size_t off[6], fixed = 0;
@@ -165,8 +165,15 @@ extern "C" int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel,
     adtfe_mel_frames(mel, n_samples, &first, &count);
     const size_t mel_bytes = p.mel_rows_dev ? (size_t)p.mel_total_rows * mel->n_mels * 4
                                             : (size_t)p.n_seg * count * mel->n_mels * 4;
-    if (mel_bytes) ADTFE_CUDA(cudaMemcpyAsync(mel_out_host, mel_dev, mel_bytes, cudaMemcpyDeviceToHost, st));
+    cudaStream_t cs = st;
+    if (copy_stream && copy_stream != stream) {  // results leave on their own stream, after the kernels
+        cs = (cudaStream_t)copy_stream;
+        std::lock_guard<std::mutex> lock(bank->mu);
+        ADTFE_CUDA(cudaEventRecord(bank->fork_event, st));
+        ADTFE_CUDA(cudaStreamWaitEvent(cs, bank->fork_event, 0));
+    }
+    if (mel_bytes) ADTFE_CUDA(cudaMemcpyAsync(mel_out_host, mel_dev, mel_bytes, cudaMemcpyDeviceToHost, cs));
     if (wav_out_host && p.n_seg)
-        ADTFE_CUDA(cudaMemcpyAsync(wav_out_host, wav_dev, (size_t)p.n_seg * p.ld_wav * 4, cudaMemcpyDeviceToHost, st));
+        ADTFE_CUDA(cudaMemcpyAsync(wav_out_host, wav_dev, (size_t)p.n_seg * p.ld_wav * 4, cudaMemcpyDeviceToHost, cs));
     return ADTFE_OK;
 }

@@ -75,10 +75,13 @@ class FrontEnd:
 
     def run_plan_host(self, plan: RenderPlan, mel_out_host: torch.Tensor, wav_out_host: Optional[torch.Tensor] = None,
                       buffers: Optional[PlanBuffers] = None, wav: Optional[torch.Tensor] = None,
-                      feat: Optional[torch.Tensor] = None) -> None:
-        """End-to-end entry with HOST buffers: packs the plan into pinned memory, then one
+                      feat: Optional[torch.Tensor] = None, packed: bool = False,
+                      copy_stream: Optional[torch.cuda.Stream] = None) -> None:
+        """End-to-end entry with HOST buffers: packs the plan into pinned memory (unless ``packed``:
+        ``buffers.pack(plan)`` was already called, e.g. by a planning thread), then one
         ``adtfe_frontend_host`` call does H2D(plan) -> render -> log-mel -> D2H(log-mel[, wav]).
-        Asynchronous; synchronise the current stream before reading ``mel_out_host``."""
+        Asynchronous; synchronise the current stream (``copy_stream`` when given: the D2H copies then
+        run there, overlapping the next call's kernels) before reading ``mel_out_host``."""
         dev = self.synth.device
         n_samples = int(plan.wave_lengths.max()) if plan.n_seg else 0
         if not mel_out_host.is_pinned() or (wav_out_host is not None and not wav_out_host.is_pinned()):
@@ -87,14 +90,16 @@ class FrontEnd:
             bank = self.synth.device_bank()
             native = self.mel._handle(dev)
             buf = buffers or self.synth.buffers()
-            shape = buf.pack(plan)
+            shape = buf.shape if packed else buf.pack(plan)
             if wav is None or feat is None:
                 wav, feat = self._outputs(plan, n_samples)
-            if mel_out_host.numel() < feat.numel() or (wav_out_host is not None and wav_out_host.numel() < wav.numel()):
+            need = plan.mel_total_rows * feat.shape[-1] if plan.mel_rows is not None else feat.numel()
+            if mel_out_host.numel() < need or (wav_out_host is not None and wav_out_host.numel() < wav.numel()):
                 raise ValueError("host output buffer too small")
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(bank.lib.adtfe_frontend_host(
                 bank.handle, native.handle, C.byref(shape), n_samples, buf.host.data_ptr(), buf.nbytes,
                 buf.dev.data_ptr(), wav.data_ptr(), feat.data_ptr(), buf.workspace.data_ptr(), buf.workspace.numel(),
-                mel_out_host.data_ptr(), wav_out_host.data_ptr() if wav_out_host is not None else None, stream),
+                mel_out_host.data_ptr(), wav_out_host.data_ptr() if wav_out_host is not None else None, stream,
+                copy_stream.cuda_stream if copy_stream is not None else None),
                 "adtfe_frontend_host")

@@ -1,0 +1,152 @@
+"""Host-side pipeline: note lists in host memory -> log-mel in pinned host memory.
+
+The reference renders inside forked DataLoader workers, each with its own ``random``
+state (``train.py:235-237``, ``data_modules/train_dataset.py:213-229``).  Here the
+workers are *threads* that only plan - the C++ planner runs without the GIL - each with
+its own ``random.Random`` stream and planner handle; the main thread enqueues one
+``adtfe_frontend_host`` call per group of batches (plan blob H2D -> render -> log-mel on the
+current stream, the D2H on a copy stream so that it overlaps the next group's kernels).
+``n_sets`` rotating buffer sets (pinned blob, device blob, workspace, device outputs, pinned
+log-mel) let planning of the next groups, the GPU work of the current one and the copies of
+the previous one overlap.
+
+    pipe = HostPipeline(frontend, workers=8, seed=0)
+    for result in pipe.run(groups):          # groups: iterable of [batch, ...]; batch: [notes, ...]
+        for wav_len, logmel in result.batches():   # logmel: pinned (B, T, n_mels) float32 view
+            ...
+        result.release()                     # the set may be reused from here on
+"""
+from __future__ import annotations
+
+import random
+import threading
+from collections import deque
+from concurrent.futures import ThreadPoolExecutor
+from typing import Iterable, Iterator, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .frontend import FrontEnd
+from .planner import RenderPlan
+from .synthetiser import PlanBuffers
+
+
+class _Set:
+    """One rotating buffer set."""
+
+    def __init__(self, device: torch.device):
+        self.buf = PlanBuffers(device)
+        self.wav: Optional[torch.Tensor] = None
+        self.feat: Optional[torch.Tensor] = None
+        self.host: Optional[torch.Tensor] = None
+        self.done = torch.cuda.Event()
+        self.free = threading.Event()
+        self.free.set()
+
+
+class GroupResult:
+    """Outputs of one group of batches; valid until ``release()``."""
+
+    def __init__(self, plan: RenderPlan, s: _Set, n_mels: int):
+        self.plan, self._set, self._n_mels = plan, s, n_mels
+        self.h2d_bytes = s.buf.nbytes
+        self.d2h_bytes = plan.mel_total_rows * n_mels * 4
+
+    def wait(self) -> "GroupResult":
+        self._set.done.synchronize()
+        return self
+
+    def batches(self):
+        """``[(lengths (B,), logmel (B, T, n_mels) pinned host view)]`` - call after ``wait()``."""
+        p, out, row0 = self.plan, [], 0
+        for b in range(len(p.batch_frames)):
+            s0, s1, t = int(p.batch_ptr[b]), int(p.batch_ptr[b + 1]), int(p.batch_frames[b])
+            n = (s1 - s0) * t
+            out.append((p.wave_lengths[s0:s1], self._set.host[row0:row0 + n].view(s1 - s0, t, self._n_mels)))
+            row0 += n
+        return out
+
+    def release(self) -> None:
+        self._set.free.set()
+
+
+class HostPipeline:
+    def __init__(self, frontend: FrontEnd, workers: int = 4, n_sets: int = 4, seed: int = 0, chunk_batches: int = 4):
+        self.fe = frontend
+        self.workers = max(1, int(workers))
+        self.n_sets = max(2, int(n_sets))
+        self.chunk_batches = chunk_batches
+        self.device = frontend.synth.device
+        self.n_mels = frontend.mel.compute_spec.n_mels
+        self._sets = [_Set(self.device) for _ in range(self.n_sets)]
+        self._local = threading.local()
+        self._seed = seed
+        self._next_worker = 0
+        self._lock = threading.Lock()
+        self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="adtfe-plan")
+        self._copy_stream = torch.cuda.Stream(self.device)   # D2H of group g overlaps the kernels of group g+1
+
+    # ---- worker side: plan + pack into the set's pinned blob (no CUDA calls besides the event wait)
+    def _worker_state(self):
+        st = getattr(self._local, "st", None)
+        if st is None:
+            from .native_planner import NativePlanner
+            with self._lock:
+                wid = self._next_worker
+                self._next_worker += 1
+            st = self._local.st = dict(rng=random.Random(self._seed * 1_000_003 + wid),
+                                       planner=NativePlanner(self.fe.synth.config, self.fe.synth.bank))
+        return st
+
+    def _plan(self, group: Sequence[Sequence], s: _Set):
+        st = self._worker_state()
+        flat = [notes for b in group for notes in b]
+        plan = st["planner"].plan_batch(flat, st["rng"]).set_batches([len(b) for b in group], self.fe.mel.n_frames,
+                                                                     self.chunk_batches)
+        s.free.wait()          # the consumer released the set ...
+        s.free.clear()
+        s.done.synchronize()   # ... and the GPU has left it
+        shape = s.buf.pack(plan)
+        return plan, shape
+
+    # ---- main thread: enqueue in order
+    def run(self, groups: Iterable[Sequence[Sequence]]) -> Iterator[GroupResult]:
+        """Yields a ``GroupResult`` per group, in order, as soon as its work is *enqueued*;
+        ``result.wait()`` blocks until the log-mel is in host memory."""
+        pending = deque()
+        it = iter(groups)
+        k = 0
+        exhausted = False
+        while True:
+            while not exhausted and len(pending) < self.n_sets:
+                try:
+                    g = next(it)
+                except StopIteration:
+                    exhausted = True
+                    break
+                s = self._sets[k % self.n_sets]
+                pending.append((self._pool.submit(self._plan, g, s), s))
+                k += 1
+            if not pending:
+                return
+            fut, s = pending.popleft()
+            plan, _shape = fut.result()
+            self._enqueue(plan, s)
+            yield GroupResult(plan, s, self.n_mels)
+
+    def _enqueue(self, plan: RenderPlan, s: _Set) -> None:
+        dev = self.device
+        if s.wav is None or s.wav.numel() < plan.n_seg * plan.ld_wav:   # flat, grown on demand, viewed per plan
+            s.wav = torch.empty(int(plan.n_seg * plan.ld_wav * 1.02) + 64, dtype=torch.float32, device=dev)
+        if s.feat is None or s.feat.shape[0] < plan.mel_total_rows:
+            rows = int(plan.mel_total_rows * 1.02) + 64
+            s.feat = torch.empty((rows, self.n_mels), dtype=torch.float32, device=dev)
+            s.host = torch.empty((rows, self.n_mels), dtype=torch.float32).pin_memory()
+        wav = s.wav[: plan.n_seg * plan.ld_wav].view(plan.n_seg, plan.ld_wav)
+        self.fe.run_plan_host(plan, s.host, None, buffers=s.buf, wav=wav, feat=s.feat, packed=True,
+                              copy_stream=self._copy_stream)
+        s.done.record(self._copy_stream)
+
+    def close(self) -> None:
+        self._pool.shutdown(wait=True)

@@ -83,6 +83,7 @@ class PlanBuffers:
         if self.workspace.numel() < need:
             self.workspace = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=self.device)
         self.offsets = [int(o) for o in off]
+        self.shape = shape
         return shape
 
     def upload(self, shape: _lib.Plan) -> _lib.Plan:

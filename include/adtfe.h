@@ -175,11 +175,13 @@ int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel, const adtf
  * shape->mel_total_rows > 0, else empty; shape->chunks_host is used as given).  The blob is copied to
  * `blob_dev` (>= blob_bytes), the batch rendered and featurised, then the log-mel matrix
  * (and the waveform when wav_out_host != NULL) copied back.  Asynchronous on `stream`:
- * the host buffers must be pinned and stay alive until the stream is synchronised. */
+ * the host buffers must be pinned and stay alive until the stream is synchronised.
+ * copy_stream: NULL, or a second stream for the device->host copies - they then wait for the kernels through
+ * an event and overlap the next call's work on `stream`; synchronise copy_stream before reading the results. */
 int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel, const adtfe_plan* shape, int64_t n_samples,
                         const void* blob_host, size_t blob_bytes, void* blob_dev, float* wav_dev, float* mel_dev,
                         void* workspace_dev, size_t workspace_bytes, float* mel_out_host, float* wav_out_host,
-                        void* stream);
+                        void* stream, void* copy_stream);
 /* Byte offsets of the six sections inside a plan blob (offsets[6]; *blob_bytes = offsets[5], where
  * tile_events starts - it runs to the end of the blob). */
 int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[6], size_t* blob_bytes);

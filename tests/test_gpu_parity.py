@@ -252,6 +252,39 @@ def test_batches_in_one_plan_equal_batch_by_batch():
         assert torch.equal(w0, w1) and torch.equal(f0, f1)
 
 
+def test_host_pipeline_equals_direct_calls():
+    """HostPipeline (planner threads, rotating pinned buffer sets, host log-mel) returns what the direct
+    device calls return for the same RNG stream; with several workers it stays self-consistent."""
+    from adt_str_b200 import HostPipeline
+    from adt_str_b200.config import setting_1
+    from adt_str_b200.synthetic import make_bank, make_segments
+    bank = make_bank(390, 24000, seed=14)
+    _, _, fe = _objects(setting_1(), bank)
+    segs = make_segments(60, seed=22, empty_fraction=0.1)
+    groups = [[segs[0:6], segs[6:10]], [segs[10:25]], [segs[25:31], segs[31:32], segs[32:40]], [segs[40:50], segs[50:60]],
+              [segs[3:9]], [segs[20:44], segs[1:2]]]
+    pipe = HostPipeline(fe, workers=1, n_sets=2, seed=7)
+    rng = random.Random(7 * 1_000_003)
+    for res, group in zip(pipe.run(groups), groups):
+        got = [(l.copy(), m.clone()) for l, m in res.wait().batches()]
+        res.release()
+        want = fe.run_batches(group, rng)
+        assert len(got) == len(want)
+        for (lengths, mel_host), (wav, feat), b in zip(got, want, group):
+            assert not mel_host.is_cuda and lengths.shape == (len(b),)
+            assert torch.equal(mel_host, feat.cpu())
+    pipe.close()
+    pipe = HostPipeline(fe, workers=3, n_sets=3, seed=7)
+    shapes = []
+    for res, group in zip(pipe.run(groups), groups):
+        shapes.append([tuple(m.shape) for _, m in res.wait().batches()])
+        for (_, m), b in zip(res.batches(), group):
+            assert m.shape[0] == len(b) and torch.isfinite(m).all() and float(m.max()) <= 1.0
+        res.release()
+    pipe.close()
+    assert len(shapes) == len(groups)
+
+
 def test_logmel_rows_with_short_and_empty_rows():
     """adtfe_logmel_rows: rows with their own frame counts, including 0 and counts below the rounds per row."""
     from adt_str_b200 import ComputeMelSpectrogram, _lib
