@@ -355,6 +355,12 @@ def run_b200(args):
         return 0
 
     peak, peak_src = measured_peak()
+    traffic = None
+    try:  # DRAM bytes of the log-mel kernel per segment, from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = float(json.load(f)["dram_bytes_per_segment"]) * plan.n_seg
+    except Exception:
+        pass
     n_seg_step = n_batches * BATCH
     width_seg = np.repeat(plan.batch_samples, np.diff(plan.batch_ptr))
     logmel_bytes = 4 * int(width_seg.sum()) + 4 * 128 * int(n_frames_seg.sum())   # collated rows read + log-mel written
@@ -376,7 +382,9 @@ def run_b200(args):
                             f"log-mel D2H into pinned host memory; groups of {group} batches, 4 buffer sets"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": "logmel_kernel", "achieved": logmel_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": logmel_gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "frac": logmel_gbs / peak, "traffic": traffic,
+                     "traffic_source": "profiles/r01_traffic.json: dram bytes per segment of an ncu --set full capture x segments",
+                     "peak_source": peak_src,
                      "bytes_per_launch": logmel_bytes, "avg_launch_ms": logmel_ms,
                      "share_of_step": logmel_ms / (max_ms / args.steps),
                      "render_ms_per_step": render_ms, "logmel_ms_per_step": logmel_ms,
