@@ -112,6 +112,10 @@ struct adtfe_mel {
     float2* lane_tw = nullptr; // 4 x 32: per-lane twiddles of the cross-lane 32-point DFT (stages 0..3)
     float* weights = nullptr;  // filter weights in mel-phase order (groups of (up, down) pairs, or per filter)
     void* groups = nullptr;    // fast path: MelGroup records {first bin, S row to flush into}
+    // warp-autonomous kernel (v6): lane-walk weights, per-lane masks, per-filter partial-sum lists
+    int32_t v6_ok = 0;
+    void *w6 = nullptr, *lane6 = nullptr, *comb6 = nullptr;
+    size_t smem6_bytes = 0;
     int32_t fast_path = 0;     // 1: the filterbank is triangular (<= 2 adjacent filters per bin)
     struct adtfe_mel_tables* tables = nullptr;  // mel-phase items + warp schedule, passed as a kernel parameter
     size_t smem_bytes = 0;

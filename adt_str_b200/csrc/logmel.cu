@@ -382,6 +382,263 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
     }
 }
 
+
+// =============================================================================================
+// v6: warp-autonomous kernel.  Same arithmetic for the transform; what changes is the organisation:
+// nothing is shared between the warps of a CTA after set-up - no CTA barrier, no common power matrix.
+// A warp owns a *unit* of up to four consecutive kept frames of one segment (two packed pairs):
+//  span    the unit's samples (3*hop + 2048 floats) arrive in the warp's own buffer by a TMA bulk copy
+//          that the warp itself issues for its NEXT unit as soon as the last pass-1 loads of the current
+//          one are consumed, so the load latency is hidden behind more than half a unit of work
+//  FFT     as in v5, but the exchange tile and then the pair's power spectrum Q[bin] (float2 = the two
+//          frames) live in an 8.4 KB warp-private buffer
+//  mel     lanes are BIN RANGES: lane l walks bins 33*l .. 33*l+32 of Q once (conflict-free: stride 33)
+//          with two running packed sums - `hi` for the filter whose rising edge the current interval is,
+//          `lo` for the filter below (falling edge).  Where the interval changes inside the lane's range
+//          (a per-lane bit mask) `lo` is complete for this lane and goes to the lane's next slot of a small
+//          partial-sum array M, `lo <- hi`, `hi <- 0`.  A filter gets at most three such partial sums (its
+//          two intervals span <= 48 bins), listed per filter in a table
+//  output  lanes are filters (4 each): sum the partial sums in lane order, log / clamp / affine, store
+// Warps drift apart freely, so the load-heavy and the FMA-heavy stretches of different warps overlap, which
+// the lock-step phases of v5 prevented.  Used when hop % 4 == 0, hop <= 256 and the filterbank is triangular
+// with non-empty intervals (both shipped configurations); everything else takes the v5 kernel above.
+constexpr int kW6Span = 2816;                 // floats of a warp's span buffer: 3*hop + 2048 <= 2816
+constexpr int kLaneBins = 33;                 // bins walked by one lane: 32 * 33 = 1056 >= n_bins
+constexpr int kQ2 = 32 * kLaneBins;           // float2 entries of a warp's exchange / power buffer
+constexpr int kMMax = 224;                    // float2 partial sums per warp
+constexpr int kUnitFrames = 4;
+
+struct Lane6 {        // the mel walk of one lane
+    uint32_t mask_lo, mask_hi;   // bit i: the interval changes after the lane's i-th bin
+    int32_t base;                // first M slot of the lane
+    int32_t n_out;               // slots used (boundaries + 2)
+};
+struct Comb6 {        // one filter: its partial sums in lane order
+    int16_t idx[3];
+    int16_t n;
+};
+struct Logmel6Tables {
+    const float2* w;      // [kLaneBins][32]: (rising, falling) weight of lane l's i-th bin
+    const Lane6* lane;    // [32]
+    const Comb6* comb;    // [4][32]: filter lane + 32*k
+};
+
+struct Unit6 {
+    int seg, j0, nf;
+    long long out_row;
+};
+__device__ __forceinline__ Unit6 unit6_geom(const LogmelArgs& p, int u, int units_per_seg) {
+    Unit6 g;
+    g.seg = (int)((unsigned)u / (unsigned)units_per_seg);
+    g.j0 = (u - g.seg * units_per_seg) * kUnitFrames;
+    int count = p.count;
+    long long base = (long long)g.seg * p.count;
+    if (p.rows) {
+        const int4 row = __ldg(reinterpret_cast<const int4*>(p.rows + g.seg));  // {out_row lo, hi, count, -}
+        base = (long long)(((unsigned long long)(unsigned)row.y << 32) | (unsigned)row.x);
+        count = row.z;
+    }
+    g.nf = max(0, min(kUnitFrames, count - g.j0));
+    g.out_row = base + g.j0;
+    return g;
+}
+__device__ __forceinline__ void issue_span6(const LogmelArgs& p, const Unit6& g, float* span, uint64_t* bar, int lane) {
+    if (lane == 0) {
+        if (g.nf <= 0) {
+            mbar_arrive(bar);
+        } else {
+            const float* src = p.wav + (long long)g.seg * p.ld_wav + (long long)(p.first + g.j0) * p.hop - 1024;
+            const uint32_t bytes = (uint32_t)((g.nf - 1) * p.hop + 2048) * 4u;
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(span, src, bytes, bar);
+        }
+    }
+}
+
+// `tma`: every unit's samples start on a 16-byte boundary (aligned base, row pitch a multiple of 4 floats); otherwise the
+// warp copies its span itself at the start of the unit (no prefetch) - same arithmetic, so results do not depend on it.
+__global__ void __launch_bounds__(kThreads, 1) logmel6_kernel(const LogmelArgs p, const Logmel6Tables t6, int n_units,
+                                                              int units_per_seg, int tma) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* s_win = reinterpret_cast<float*>(smem_raw);                    // 32 * kWinPitch
+    float2* s_tw = reinterpret_cast<float2*>(s_win + 32 * kWinPitch);     // 32*32
+    float2* s_ltw = s_tw + 32 * 32;                                       // 4*32
+    float2* s_w = s_ltw + 4 * 32;                                         // kLaneBins*32
+    Lane6* s_lane = reinterpret_cast<Lane6*>(s_w + kLaneBins * 32);       // 32
+    Comb6* s_comb = reinterpret_cast<Comb6*>(s_lane + 32);                // 128
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_comb + 128);          // kWarps (+ pad to 128 B)
+    float* s_warp = reinterpret_cast<float*>(s_bar + 16);                 // per warp: span | Q | M
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    float* span = s_warp + warp * (kW6Span + 2 * kQ2 + 2 * kMMax);
+    float2* qb = reinterpret_cast<float2*>(span + kW6Span);
+    float2* mb = qb + kQ2;
+    uint64_t* bar = s_bar + warp;
+
+    if (lane == 0) mbar_init(bar, 1);
+    for (int i = tid; i < 2048; i += kThreads) s_win[(i & 31) * kWinPitch + (i >> 5)] = p.window[i];
+    for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = p.twiddle[i];
+    for (int i = tid; i < 4 * 32; i += kThreads) s_ltw[i] = p.lane_tw[i];
+    for (int i = tid; i < kLaneBins * 32; i += kThreads) s_w[i] = t6.w[i];
+    for (int i = tid; i < 32; i += kThreads) s_lane[i] = t6.lane[i];
+    for (int i = tid; i < 128; i += kThreads) s_comb[i] = t6.comb[i];
+    __syncthreads();  // the only CTA-wide barrier
+
+    const int col32_bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);
+    const int gstride = (int)gridDim.x * kWarps;
+    int u = (int)blockIdx.x * kWarps + warp;
+    Unit6 g = unit6_geom(p, min(u, n_units - 1), units_per_seg);
+    if (tma && u < n_units) issue_span6(p, g, span, bar, lane);
+    uint32_t parity = 0;
+
+#pragma unroll 1
+    for (; u < n_units; u += gstride) {
+        const bool more = u + gstride < n_units;
+        Unit6 gn = g;
+        if (more) gn = unit6_geom(p, u + gstride, units_per_seg);
+        if (tma) {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        } else if (g.nf > 0) {
+            const float* src = p.wav + (long long)g.seg * p.ld_wav + (long long)(p.first + g.j0) * p.hop - 1024;
+            const int len = (g.nf - 1) * p.hop + 2048;
+            __syncwarp();
+            for (int i = lane; i < len; i += 32) span[i] = __ldg(src + i);
+            __syncwarp();
+        }
+        const int n_pairs = (g.nf + 1) >> 1;
+        if (tma && n_pairs == 0 && more) { __syncwarp(); issue_span6(p, gn, span, bar, lane); }
+#pragma unroll 1
+        for (int pr = 0; pr < n_pairs; ++pr) {
+            const int f = 2 * pr;
+            const int hop_b = (f + 1 < g.nf) ? p.hop : 0;  // an odd count: the last pair's second half repeats the first
+            // ---- pass 1: window + 64-point real DFT over n1 (stride-32 samples), both frames
+            float2 yr[33], yi[33];
+            {
+                const float* sa = span + f * p.hop + lane;
+                const float* sb = sa + hop_b;
+                const float4* wt = reinterpret_cast<const float4*>(s_win + lane * kWinPitch);
+                float2 v[64];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const float4 w = wt[q];
+                    v[4 * q + 0] = __fmul2_rn(make_float2(sa[32 * (4 * q + 0)], sb[32 * (4 * q + 0)]), bc2(w.x));
+                    v[4 * q + 1] = __fmul2_rn(make_float2(sa[32 * (4 * q + 1)], sb[32 * (4 * q + 1)]), bc2(w.y));
+                    v[4 * q + 2] = __fmul2_rn(make_float2(sa[32 * (4 * q + 2)], sb[32 * (4 * q + 2)]), bc2(w.z));
+                    v[4 * q + 3] = __fmul2_rn(make_float2(sa[32 * (4 * q + 3)], sb[32 * (4 * q + 3)]), bc2(w.w));
+                }
+                rdft64(v, yr, yi);
+            }
+            // ---- twiddle in place (rows 1..31), column 32 is real before its twiddle
+#pragma unroll
+            for (int k1 = 1; k1 < 32; ++k1) cmul2(yr[k1], yi[k1], s_tw[(k1 - 1) * 32 + lane]);
+            float2 cr, ci;
+            {
+                const float2 w = s_tw[31 * 32 + lane];
+                cr = __fmul2_rn(yr[32], bc2(w.x));
+                ci = __fmul2_rn(yr[32], bc2(w.y));
+            }
+            // the unit's last span reads are consumed: fetch the next unit's samples behind the rest of this one
+            if (tma && pr == n_pairs - 1 && more) { __syncwarp(); issue_span6(p, gn, span, bar, lane); }
+            // ---- exchange through the warp's buffer: element (k1, n2) at 33*k1 + n2
+            float2* xw = qb + lane;
+            const float2* xr = qb + lane * kLaneBins;
+            float2 zr[32], zi[32];
+            __syncwarp();
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) xw[k1 * kLaneBins] = yr[k1];
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) zr[n2] = xr[n2];
+            __syncwarp();
+            xw[0] = make_float2(0.0f, 0.0f);  // row 0 is purely real
+#pragma unroll
+            for (int k1 = 1; k1 < 32; ++k1) xw[k1 * kLaneBins] = yi[k1];
+            __syncwarp();
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) zi[n2] = xr[n2];
+            __syncwarp();
+            // ---- 32-point DFT across lanes for column 32
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                const int hb = 16 >> s;
+                const float2 orr = shfl_xor2(cr, hb), oi = shfl_xor2(ci, hb);
+                const float sg = (lane & hb) ? -1.0f : 1.0f;
+                cr = __ffma2_rn(cr, bc2(sg), orr);
+                ci = __ffma2_rn(ci, bc2(sg), oi);
+                if (s < 4) cmul2(cr, ci, s_ltw[s * 32 + lane]);
+            }
+            // ---- pass 2: 32-point complex DFT over n2 for k1 = lane
+            cdft32(zr, zi);
+            // ---- power spectrum of the pair into Q[bin] (over the dead exchange tile)
+#pragma unroll
+            for (int k2 = 0; k2 < 16; ++k2) qb[lane + 64 * k2] = __ffma2_rn(zi[k2], zi[k2], __fmul2_rn(zr[k2], zr[k2]));
+#pragma unroll
+            for (int k2 = 16; k2 < 32; ++k2)
+                qb[64 - lane + 64 * (31 - k2)] = __ffma2_rn(zi[k2], zi[k2], __fmul2_rn(zr[k2], zr[k2]));
+            if ((lane & 1) == 0) qb[col32_bin] = __ffma2_rn(ci, ci, __fmul2_rn(cr, cr));
+            if (lane < kQ2 - 1025) qb[1025 + lane] = make_float2(0.0f, 0.0f);  // bins past the spectrum: weight 0, keep finite
+            __syncwarp();
+            // ---- mel: lane walks its 33 bins.  All power values and weights are requested first (the transform's
+            // registers are dead by now), so the walk itself is a chain of packed FMAs without load stalls.
+            {
+                const float2* q = qb + lane * kLaneBins;
+                const float2* w = s_w + lane;
+                const Lane6 ln = s_lane[lane];
+                float2 pw[kLaneBins], wt[kLaneBins];
+#pragma unroll
+                for (int i = 0; i < kLaneBins; ++i) { pw[i] = q[i]; wt[i] = w[i * 32]; }
+                float2* mp = mb + ln.base;
+                float2 lo = make_float2(0.0f, 0.0f), hi = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int i = 0; i < kLaneBins; ++i) {
+                    hi = __ffma2_rn(pw[i], bc2(wt[i].x), hi);
+                    lo = __ffma2_rn(pw[i], bc2(wt[i].y), lo);
+                    const bool cut = i < 32 ? ((ln.mask_lo >> i) & 1u) : ((ln.mask_hi >> (i - 32)) & 1u);
+                    if (cut) {
+                        *mp++ = lo;
+                        lo = hi;
+                        hi = make_float2(0.0f, 0.0f);
+                    }
+                }
+                mp[0] = lo;
+                mp[1] = hi;
+                if (lane == 0) mb[kMMax - 1] = make_float2(0.0f, 0.0f);  // the slot unused list entries point to
+            }
+            __syncwarp();
+            // ---- output: lane = filter (4 each): partial sums in lane order (missing ones read the zero slot),
+            // log / clamp / affine on eight independent values
+            {
+                float* row_a = p.out + (g.out_row + f) * p.n_mels;
+                const bool ok_a = f < g.nf, ok_b = f + 1 < g.nf;
+                Comb6 c[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) c[k] = s_comb[k * 32 + lane];
+                float2 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 m0 = mb[c[k].idx[0]], m1 = mb[c[k].idx[1]], m2 = mb[c[k].idx[2]];
+                    v[k] = __fadd2_rn(__fadd2_rn(m0, m1), m2);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int m = lane + 32 * k;
+                    float a = __logf(v[k].x + 1e-10f), b = __logf(v[k].y + 1e-10f);
+                    a = a != a ? a : fminf(fmaxf(a, -23.0f), 12.0f);    // torch.clamp keeps NaN
+                    b = b != b ? b : fminf(fmaxf(b, -23.0f), 12.0f);
+                    if (m < p.n_mels) {
+                        if (ok_a) row_a[m] = (a + 23.0f) * (1.0f / 35.0f);
+                        if (ok_b) row_a[p.n_mels + m] = (b + 23.0f) * (1.0f / 35.0f);
+                    }
+                }
+            }
+            __syncwarp();  // Q and M are rewritten by the next pair
+        }
+        g = gn;
+    }
+}
+
 }  // namespace adtfe
 
 using namespace adtfe;
@@ -416,6 +673,20 @@ static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_s
     a.weights = mel->weights; a.groups = (const MelGroup*)mel->groups; a.rows = rows_dev; a.ld_wav = ld_wav;
     a.n_seg = n_seg; a.first = first; a.count = count;
     a.hop = mel->hop; a.n_mels = mel->n_mels; a.rounds_per_seg = rounds_per_seg; a.n_rounds = (int32_t)n_rounds;
+    if (mel->v6_ok && !getenv("ADTFE_LOGMEL_V5")) {
+        // TMA needs 16-byte aligned unit starts; other rows are copied by the warps (same results)
+        const int tma = ((uintptr_t)wav_dev & 15) == 0 && ld_wav % 4 == 0;
+        const int units_per_seg = (count + kUnitFrames - 1) / kUnitFrames;
+        const long long n_units = (long long)n_seg * units_per_seg;
+        ADTFE_REQUIRE(n_units < (1ll << 30), ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: too many frames for one launch");
+        Logmel6Tables t6;
+        t6.w = (const float2*)mel->w6; t6.lane = (const Lane6*)mel->lane6; t6.comb = (const Comb6*)mel->comb6;
+        const long long ctas = (n_units + kWarps - 1) / kWarps;
+        const int grid6 = (int)(ctas < mel->sm_count ? ctas : mel->sm_count);
+        logmel6_kernel<<<grid6, kThreads, mel->smem6_bytes, (cudaStream_t)stream>>>(a, t6, (int)n_units, units_per_seg, tma);
+        ADTFE_CUDA(cudaGetLastError());
+        return ADTFE_OK;
+    }
     const int grid = (int)(n_rounds < mel->sm_count ? n_rounds : mel->sm_count);
     logmel_kernel<<<grid, kThreads, mel->smem_bytes, (cudaStream_t)stream>>>(a, mel->tables->t);
     ADTFE_CUDA(cudaGetLastError());
@@ -459,6 +730,7 @@ extern "C" int adtfe_mel_destroy(adtfe_mel* mel) {
     if (!mel) return ADTFE_OK;
     cudaSetDevice(mel->device);
     cudaFree(mel->window); cudaFree(mel->twiddle); cudaFree(mel->lane_tw); cudaFree(mel->weights); cudaFree(mel->groups);
+    cudaFree(mel->w6); cudaFree(mel->lane6); cudaFree(mel->comb6);
     delete mel->tables;
     delete mel;
     return ADTFE_OK;
@@ -469,10 +741,11 @@ extern "C" int adtfe_mel_destroy(adtfe_mel* mel) {
 // between the centres of filters j-1 and j) holding, per bin, the weight towards filter j ("up")
 // and towards filter j-1 ("down"); intervals are cut into groups of kGroupBins bins.  Returns false when fb does not have that structure (or the
 // packed weights do not fit): the caller then uses the per-filter path.
-static bool build_fast_tables(const float* fb, int n_bins, int n_mels, MelTables& t, std::vector<float>& packed,
-                              std::vector<MelGroup>& groups) {
-    std::vector<int> iv(n_bins, -1);
-    std::vector<float> up(n_bins, 0.0f), dn(n_bins, 0.0f);
+static bool triangular_structure(const float* fb, int n_bins, int n_mels, std::vector<int>& iv, std::vector<float>& up,
+                                 std::vector<float>& dn) {
+    iv.assign(n_bins, -1);
+    up.assign(n_bins, 0.0f);
+    dn.assign(n_bins, 0.0f);
     std::vector<int> peak(n_mels, 0);
     for (int m = 0; m < n_mels; ++m) {
         float best = -1.0f;
@@ -502,6 +775,14 @@ static bool build_fast_tables(const float* fb, int n_bins, int n_mels, MelTables
         iv[k] = j;
         prev = j;
     }
+    return true;
+}
+
+static bool build_fast_tables(const float* fb, int n_bins, int n_mels, MelTables& t, std::vector<float>& packed,
+                              std::vector<MelGroup>& groups) {
+    std::vector<int> iv;
+    std::vector<float> up, dn;
+    if (!triangular_structure(fb, n_bins, n_mels, iv, up, dn)) return false;
     // warp ranges over the filters: warp w completes filters m0 .. m1-1, i.e. walks intervals m0 .. m1 (interval
     // m0 only for its rising edge, interval m1 only for its falling edge); the boundary intervals are walked
     // twice so that no sum crosses warps.  Balanced by the bins per range.
@@ -601,6 +882,95 @@ static void build_generic_tables(const float* fb, int n_bins, int n_mels, MelTab
     t.n_groups = 0;
 }
 
+// Tables of the warp-autonomous kernel (v6): per lane the (rising, falling) weights of its 33 bins, the bit mask
+// of interval changes and its first partial-sum slot; per filter the slots that add up to it.  Returns false
+// when the filterbank does not fit (not triangular, an interval without bins, too many partial sums).
+static bool build_lane_tables(const float* fb, int n_bins, int n_mels, std::vector<float2>& w, std::vector<Lane6>& lanes,
+                              std::vector<Comb6>& comb) {
+    if (n_bins > kQ2 - 1 || n_mels > kMaxMels) return false;
+    std::vector<int> iv;
+    std::vector<float> up, dn;
+    if (!triangular_structure(fb, n_bins, n_mels, iv, up, dn)) return false;
+    // bins without weights take the interval of their neighbour, so that they never cut a run
+    std::vector<int> j_of(kQ2, -1);
+    int last = -1;
+    for (int k = 0; k < n_bins; ++k) { if (iv[k] >= 0) last = iv[k]; j_of[k] = last; }
+    if (last < 0) return false;
+    int first_valid = 0;
+    while (j_of[first_valid] < 0) ++first_valid;
+    for (int k = 0; k < first_valid; ++k) j_of[k] = j_of[first_valid];
+    for (int k = n_bins; k < kQ2; ++k) j_of[k] = last;
+    w.assign((size_t)kLaneBins * 32, make_float2(0.0f, 0.0f));
+    lanes.assign(32, Lane6{0u, 0u, 0, 0});
+    std::vector<std::vector<int>> slots_of(n_mels);  // filter -> M slots, in lane order
+    int n_slots = 0;
+    for (int l = 0; l < 32; ++l) {
+        Lane6& ln = lanes[l];
+        ln.base = n_slots;
+        int filt = j_of[l * kLaneBins] - 1;  // the filter `lo` stands for
+        for (int i = 0; i < kLaneBins; ++i) {
+            const int k = l * kLaneBins + i;
+            if (k < n_bins) w[(size_t)i * 32 + l] = make_float2(up[k], dn[k]);
+            if (i + 1 < kLaneBins && j_of[k + 1] != j_of[k]) {
+                if (j_of[k + 1] != j_of[k] + 1) return false;  // an interval without bins
+                if (i < 32) ln.mask_lo |= 1u << i; else ln.mask_hi |= 1u << (i - 32);
+                if (filt >= 0 && filt < n_mels) slots_of[filt].push_back(n_slots);
+                ++n_slots;
+                ++filt;
+            }
+        }
+        for (int e = 0; e < 2; ++e, ++filt, ++n_slots)  // what is left at the end of the range: lo, then hi
+            if (filt >= 0 && filt < n_mels) slots_of[filt].push_back(n_slots);
+        ln.n_out = n_slots - ln.base;
+    }
+    if (n_slots > kMMax - 1) return false;  // the last slot is kept at zero for unused list entries
+    comb.assign(128, Comb6{{(int16_t)(kMMax - 1), (int16_t)(kMMax - 1), (int16_t)(kMMax - 1)}, 0});
+    for (int m = 0; m < n_mels; ++m) {
+        if (slots_of[m].empty() || slots_of[m].size() > 3) return false;
+        Comb6& c = comb[(size_t)(m >> 5) * 32 + (m & 31)];
+        c.n = (int16_t)slots_of[m].size();
+        for (size_t e = 0; e < slots_of[m].size(); ++e) c.idx[e] = (int16_t)slots_of[m][e];
+    }
+    // verify by replaying the walk symbolically: every weight must land on the filter fb has it on
+    std::vector<float> chk((size_t)n_bins * n_mels, 0.0f);
+    std::vector<int> filter_of_slot(n_slots, -1);
+    for (int m = 0; m < n_mels; ++m)
+        for (int sl : slots_of[m]) filter_of_slot[sl] = m;
+    for (int l = 0; l < 32; ++l) {
+        int slot = lanes[l].base;
+        std::vector<int> lo_bins, hi_bins;  // bins currently summed in lo (with dn) / hi (with up)
+        auto emit = [&](const std::vector<int>& dnb, const std::vector<int>& upb) {
+            const int m = filter_of_slot[slot];
+            for (int k : dnb) { if (dn[k] != 0.0f) { if (m < 0) return false; chk[(size_t)k * n_mels + m] += dn[k]; } }
+            for (int k : upb) { if (up[k] != 0.0f) { if (m < 0) return false; chk[(size_t)k * n_mels + m] += up[k]; } }
+            ++slot;
+            return true;
+        };
+        std::vector<int> lo_up;  // bins whose `up` weight moved from hi into lo at a cut
+        for (int i = 0; i < kLaneBins; ++i) {
+            const int k = l * kLaneBins + i;
+            if (k < n_bins) { hi_bins.push_back(k); lo_bins.push_back(k); }
+            const bool cut = i < 32 ? (lanes[l].mask_lo >> i) & 1u : (lanes[l].mask_hi >> (i - 32)) & 1u;
+            if (cut) {
+                if (!emit(lo_bins, lo_up)) return false;
+                lo_up = hi_bins;     // lo <- hi: the rising-edge sums so far
+                lo_bins.clear();     // and no falling-edge sums yet for the new lo
+                hi_bins.clear();
+            }
+        }
+        if (!emit(lo_bins, lo_up)) return false;
+        if (!emit(std::vector<int>(), hi_bins)) return false;
+    }
+    for (size_t i = 0; i < chk.size(); ++i)
+        if (chk[i] != fb[i]) return false;
+    return true;
+}
+
+static size_t logmel6_smem_bytes() {
+    return (size_t)(32 * kWinPitch + 2 * 32 * 32 + 2 * 4 * 32 + 2 * kLaneBins * 32) * 4 + 32 * sizeof(Lane6) +
+           128 * sizeof(Comb6) + 128 + (size_t)kWarps * (kW6Span + 2 * kQ2 + 2 * kMMax) * 4;
+}
+
 extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, const float* window_host,
                                 const float* fb_host, int device, adtfe_mel** out) {
     ADTFE_REQUIRE(out && window_host && fb_host, ADTFE_ERR_BAD_ARG, "adtfe_mel_create: null pointer");
@@ -662,6 +1032,24 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
     MEL_UPLOAD(mel->lane_tw, ltw.data(), ltw.size() * sizeof(float2));
     MEL_UPLOAD(mel->weights, packed.data(), packed.size() * 4);
     MEL_UPLOAD(mel->groups, groups.data(), groups.size() * sizeof(MelGroup));
+    {
+        std::vector<float2> w6;
+        std::vector<Lane6> lane6;
+        std::vector<Comb6> comb6;
+        mel->v6_ok = hop % 4 == 0 && (kUnitFrames - 1) * hop + 2048 <= kW6Span && ((n_fft / 2) / hop + 1) * hop >= 1024 &&
+                     build_lane_tables(fb_host, n_bins, n_mels, w6, lane6, comb6);
+        if (mel->v6_ok) {
+            MEL_UPLOAD(mel->w6, w6.data(), w6.size() * sizeof(float2));
+            MEL_UPLOAD(mel->lane6, lane6.data(), lane6.size() * sizeof(Lane6));
+            MEL_UPLOAD(mel->comb6, comb6.data(), comb6.size() * sizeof(Comb6));
+            mel->smem6_bytes = logmel6_smem_bytes();
+            if (cudaFuncSetAttribute(logmel6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)mel->smem6_bytes) != cudaSuccess) {
+                cudaGetLastError();
+                mel->v6_ok = 0;
+            }
+        }
+    }
 #undef MEL_UPLOAD
     if (cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mel->smem_bytes) !=
         cudaSuccess) {

@@ -58,7 +58,8 @@ def parse_args():
     p.add_argument("--cpu-segments", type=int, default=0, help="cpu_baseline sample size (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--e2e-group", type=int, default=8, help="batches per end-to-end plan")
-    p.add_argument("--e2e-workers", type=int, default=8, help="planner threads of the end-to-end pipeline")
+    p.add_argument("--e2e-workers", type=int, default=0,
+                   help="planner threads of the end-to-end pipeline (0 = host cores / ranks, at most 8)")
     p.add_argument("--chunk-batches", type=int, default=4, help="batches rendered together as one chunk")
     return p.parse_args()
 
@@ -233,6 +234,7 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     synth = SynthDrum(setting_1(), bank=bank, device=dev)
     mel = ComputeMelSpectrogram(SR, 2048, 0.01, 128)
@@ -315,6 +317,8 @@ def run_b200(args):
     from adt_str_b200 import HostPipeline
     group = max(1, min(args.e2e_group, n_batches))
     groups = [batches[i:i + group] for i in range(0, n_batches, group)]
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    args.e2e_workers = args.e2e_workers or max(1, min(8, cores // max(1, world)))
     pipe = HostPipeline(fe, workers=args.e2e_workers, n_sets=4, seed=99 + rank, chunk_batches=args.chunk_batches)
     h2d = d2h = 0
     e2e_checksum = 0.0

@@ -285,6 +285,25 @@ def test_host_pipeline_equals_direct_calls():
     assert len(shapes) == len(groups)
 
 
+def test_logmel_warp_autonomous_kernel_agrees_with_the_round_kernel(monkeypatch):
+    """Both log-mel kernels (v6: warp-autonomous units, lane-walk mel; v5: CTA rounds, frame-lane mel) see the same
+    spectra; they differ only in the order the mel sums are taken, i.e. by float32 rounding of the filter sums."""
+    from adt_str_b200 import ComputeMelSpectrogram
+    g = torch.Generator().manual_seed(11)
+    for sr, n in ((24000, 63840), (16000, 40960), (24000, 61440 + 240 * 3)):
+        mel = ComputeMelSpectrogram(sr, 2048, 0.01, 128)
+        x = (torch.randn(5, n, generator=g) * torch.logspace(-3, 0, 5).unsqueeze(1)).cuda()
+        monkeypatch.delenv("ADTFE_LOGMEL_V5", raising=False)
+        a = mel(x)
+        monkeypatch.setenv("ADTFE_LOGMEL_V5", "1")
+        b = mel(x)
+        monkeypatch.delenv("ADTFE_LOGMEL_V5", raising=False)
+        assert a.shape == b.shape and a.shape[1] == mel.n_frames(n)
+        assert float((a - b).abs().max()) <= 2e-6
+        want = mel_oracle.logmel_direct(x.cpu().numpy(), sr, 2048, 0.01, 128, np.float64)
+        assert_logmel_close(a.cpu().numpy(), want, atol=2e-6)
+
+
 def test_logmel_rows_with_short_and_empty_rows():
     """adtfe_logmel_rows: rows with their own frame counts, including 0 and counts below the rounds per row."""
     from adt_str_b200 import ComputeMelSpectrogram, _lib
