@@ -386,10 +386,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
 // =============================================================================================
 // v6: warp-autonomous kernel.  Same arithmetic for the transform; what changes is the organisation:
 // nothing is shared between the warps of a CTA after set-up - no CTA barrier, no common power matrix.
-// A warp owns a *unit* of up to four consecutive kept frames of one segment (two packed pairs):
-//  span    the unit's samples (3*hop + 2048 floats) arrive in the warp's own buffer by a TMA bulk copy
-//          that the warp itself issues for its NEXT unit as soon as the last pass-1 loads of the current
-//          one are consumed, so the load latency is hidden behind more than half a unit of work
+// A warp owns a *unit* of kUnitFrames consecutive kept frames of one segment (packed pairs, one after the other):
+//  span    the unit's samples ((kUnitFrames-1)*hop + 2048 floats) arrive in the warp's own buffer by a TMA bulk
+//          copy that the warp itself issues for its NEXT unit as soon as the last pass-1 loads of the current one
+//          are consumed.  Longer units re-read less of the overlapping frames from L2 (measured: 2 frames per
+//          unit 9.05 ms per step, 4 frames 8.27 ms)
 //  FFT     as in v5, but the exchange tile and then the pair's power spectrum Q[bin] (float2 = the two
 //          frames) live in an 8.4 KB warp-private buffer
 //  mel     lanes are BIN RANGES: lane l walks bins 33*l .. 33*l+32 of Q once (conflict-free: stride 33)
@@ -400,13 +401,26 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
 //          two intervals span <= 48 bins), listed per filter in a table
 //  output  lanes are filters (4 each): sum the partial sums in lane order, log / clamp / affine, store
 // Warps drift apart freely, so the load-heavy and the FMA-heavy stretches of different warps overlap, which
-// the lock-step phases of v5 prevented.  Used when hop % 4 == 0, hop <= 256 and the filterbank is triangular
+// the lock-step phases of v5 prevented.  More warps do not help (8, 10 and 12 per SM measure the same): the
+// kernel is bound by the shared-memory and fp32 pipes, not by latency.  Used when hop % 4 == 0, hop <= 256 and the filterbank is triangular
 // with non-empty intervals (both shipped configurations); everything else takes the v5 kernel above.
-constexpr int kW6Span = 2816;                 // floats of a warp's span buffer: 3*hop + 2048 <= 2816
+#ifndef ADTFE_LM6_DIRECT
+#define ADTFE_LM6_DIRECT 0    // 1: pass 1 reads the samples straight from global memory (no span buffer, no TMA)
+#endif
+#ifndef ADTFE_LM6_WARPS
+#define ADTFE_LM6_WARPS 8
+#endif
+#ifndef ADTFE_LM6_UNIT
+#define ADTFE_LM6_UNIT 6      // frames per unit (even): the span of a unit is (UNIT-1)*hop + 2048 samples
+#endif
+constexpr bool kDirect6 = ADTFE_LM6_DIRECT != 0;
+constexpr int kWarps6 = ADTFE_LM6_WARPS;
+constexpr int kThreads6 = kWarps6 * 32;
+constexpr int kUnitFrames = ADTFE_LM6_UNIT;
+constexpr int kW6Span = kDirect6 ? 0 : (kUnitFrames - 1) * 256 + 2048;  // floats of a warp's span buffer: hop <= 256
 constexpr int kLaneBins = 33;                 // bins walked by one lane: 32 * 33 = 1056 >= n_bins
 constexpr int kQ2 = 32 * kLaneBins;           // float2 entries of a warp's exchange / power buffer
-constexpr int kMMax = 224;                    // float2 partial sums per warp
-constexpr int kUnitFrames = 4;
+constexpr int kMMax = 200;                    // float2 partial sums per warp
 
 struct Lane6 {        // the mel walk of one lane
     uint32_t mask_lo, mask_hi;   // bit i: the interval changes after the lane's i-th bin
@@ -457,7 +471,7 @@ __device__ __forceinline__ void issue_span6(const LogmelArgs& p, const Unit6& g,
 
 // `tma`: every unit's samples start on a 16-byte boundary (aligned base, row pitch a multiple of 4 floats); otherwise the
 // warp copies its span itself at the start of the unit (no prefetch) - same arithmetic, so results do not depend on it.
-__global__ void __launch_bounds__(kThreads, 1) logmel6_kernel(const LogmelArgs p, const Logmel6Tables t6, int n_units,
+__global__ void __launch_bounds__(kThreads6, 1) logmel6_kernel(const LogmelArgs p, const Logmel6Tables t6, int n_units,
                                                               int units_per_seg, int tma) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_win = reinterpret_cast<float*>(smem_raw);                    // 32 * kWinPitch
@@ -466,7 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel6_kernel(const LogmelArgs p
     float2* s_w = s_ltw + 4 * 32;                                         // kLaneBins*32
     Lane6* s_lane = reinterpret_cast<Lane6*>(s_w + kLaneBins * 32);       // 32
     Comb6* s_comb = reinterpret_cast<Comb6*>(s_lane + 32);                // 128
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_comb + 128);          // kWarps (+ pad to 128 B)
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_comb + 128);          // kWarps6 (+ pad to 128 B)
     float* s_warp = reinterpret_cast<float*>(s_bar + 16);                 // per warp: span | Q | M
 
     const int tid = threadIdx.x, lane = tid & 31;
@@ -477,18 +491,19 @@ __global__ void __launch_bounds__(kThreads, 1) logmel6_kernel(const LogmelArgs p
     uint64_t* bar = s_bar + warp;
 
     if (lane == 0) mbar_init(bar, 1);
-    for (int i = tid; i < 2048; i += kThreads) s_win[(i & 31) * kWinPitch + (i >> 5)] = p.window[i];
-    for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = p.twiddle[i];
-    for (int i = tid; i < 4 * 32; i += kThreads) s_ltw[i] = p.lane_tw[i];
-    for (int i = tid; i < kLaneBins * 32; i += kThreads) s_w[i] = t6.w[i];
-    for (int i = tid; i < 32; i += kThreads) s_lane[i] = t6.lane[i];
-    for (int i = tid; i < 128; i += kThreads) s_comb[i] = t6.comb[i];
+    for (int i = tid; i < 2048; i += kThreads6) s_win[(i & 31) * kWinPitch + (i >> 5)] = p.window[i];
+    for (int i = tid; i < 32 * 32; i += kThreads6) s_tw[i] = p.twiddle[i];
+    for (int i = tid; i < 4 * 32; i += kThreads6) s_ltw[i] = p.lane_tw[i];
+    for (int i = tid; i < kLaneBins * 32; i += kThreads6) s_w[i] = t6.w[i];
+    for (int i = tid; i < 32; i += kThreads6) s_lane[i] = t6.lane[i];
+    for (int i = tid; i < 128; i += kThreads6) s_comb[i] = t6.comb[i];
     __syncthreads();  // the only CTA-wide barrier
 
     const int col32_bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);
-    const int gstride = (int)gridDim.x * kWarps;
-    int u = (int)blockIdx.x * kWarps + warp;
+    const int gstride = (int)gridDim.x * kWarps6;
+    int u = (int)blockIdx.x * kWarps6 + warp;
     Unit6 g = unit6_geom(p, min(u, n_units - 1), units_per_seg);
+    if (kDirect6) tma = 0;
     if (tma && u < n_units) issue_span6(p, g, span, bar, lane);
     uint32_t parity = 0;
 
@@ -500,7 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel6_kernel(const LogmelArgs p
         if (tma) {
             mbar_wait(bar, parity);
             parity ^= 1u;
-        } else if (g.nf > 0) {
+        } else if (!kDirect6 && g.nf > 0) {
             const float* src = p.wav + (long long)g.seg * p.ld_wav + (long long)(p.first + g.j0) * p.hop - 1024;
             const int len = (g.nf - 1) * p.hop + 2048;
             __syncwarp();
@@ -516,17 +531,33 @@ __global__ void __launch_bounds__(kThreads, 1) logmel6_kernel(const LogmelArgs p
             // ---- pass 1: window + 64-point real DFT over n1 (stride-32 samples), both frames
             float2 yr[33], yi[33];
             {
-                const float* sa = span + f * p.hop + lane;
+                const float* sa = kDirect6 ? p.wav + (long long)g.seg * p.ld_wav +
+                                                 (long long)(p.first + g.j0 + f) * p.hop - 1024 + lane
+                                           : span + f * p.hop + lane;
                 const float* sb = sa + hop_b;
                 const float4* wt = reinterpret_cast<const float4*>(s_win + lane * kWinPitch);
                 float2 v[64];
+                if (kDirect6) {  // all 128 global loads in flight, then the window
+                    float xa[64], xb[64];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const float4 w = wt[q];
-                    v[4 * q + 0] = __fmul2_rn(make_float2(sa[32 * (4 * q + 0)], sb[32 * (4 * q + 0)]), bc2(w.x));
-                    v[4 * q + 1] = __fmul2_rn(make_float2(sa[32 * (4 * q + 1)], sb[32 * (4 * q + 1)]), bc2(w.y));
-                    v[4 * q + 2] = __fmul2_rn(make_float2(sa[32 * (4 * q + 2)], sb[32 * (4 * q + 2)]), bc2(w.z));
-                    v[4 * q + 3] = __fmul2_rn(make_float2(sa[32 * (4 * q + 3)], sb[32 * (4 * q + 3)]), bc2(w.w));
+                    for (int n1 = 0; n1 < 64; ++n1) { xa[n1] = __ldg(sa + 32 * n1); xb[n1] = __ldg(sb + 32 * n1); }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const float4 w = wt[q];
+                        v[4 * q + 0] = __fmul2_rn(make_float2(xa[4 * q + 0], xb[4 * q + 0]), bc2(w.x));
+                        v[4 * q + 1] = __fmul2_rn(make_float2(xa[4 * q + 1], xb[4 * q + 1]), bc2(w.y));
+                        v[4 * q + 2] = __fmul2_rn(make_float2(xa[4 * q + 2], xb[4 * q + 2]), bc2(w.z));
+                        v[4 * q + 3] = __fmul2_rn(make_float2(xa[4 * q + 3], xb[4 * q + 3]), bc2(w.w));
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const float4 w = wt[q];
+                        v[4 * q + 0] = __fmul2_rn(make_float2(sa[32 * (4 * q + 0)], sb[32 * (4 * q + 0)]), bc2(w.x));
+                        v[4 * q + 1] = __fmul2_rn(make_float2(sa[32 * (4 * q + 1)], sb[32 * (4 * q + 1)]), bc2(w.y));
+                        v[4 * q + 2] = __fmul2_rn(make_float2(sa[32 * (4 * q + 2)], sb[32 * (4 * q + 2)]), bc2(w.z));
+                        v[4 * q + 3] = __fmul2_rn(make_float2(sa[32 * (4 * q + 3)], sb[32 * (4 * q + 3)]), bc2(w.w));
+                    }
                 }
                 rdft64(v, yr, yi);
             }
@@ -681,9 +712,9 @@ static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_s
         ADTFE_REQUIRE(n_units < (1ll << 30), ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: too many frames for one launch");
         Logmel6Tables t6;
         t6.w = (const float2*)mel->w6; t6.lane = (const Lane6*)mel->lane6; t6.comb = (const Comb6*)mel->comb6;
-        const long long ctas = (n_units + kWarps - 1) / kWarps;
+        const long long ctas = (n_units + kWarps6 - 1) / kWarps6;
         const int grid6 = (int)(ctas < mel->sm_count ? ctas : mel->sm_count);
-        logmel6_kernel<<<grid6, kThreads, mel->smem6_bytes, (cudaStream_t)stream>>>(a, t6, (int)n_units, units_per_seg, tma);
+        logmel6_kernel<<<grid6, kThreads6, mel->smem6_bytes, (cudaStream_t)stream>>>(a, t6, (int)n_units, units_per_seg, tma);
         ADTFE_CUDA(cudaGetLastError());
         return ADTFE_OK;
     }
@@ -968,7 +999,7 @@ static bool build_lane_tables(const float* fb, int n_bins, int n_mels, std::vect
 
 static size_t logmel6_smem_bytes() {
     return (size_t)(32 * kWinPitch + 2 * 32 * 32 + 2 * 4 * 32 + 2 * kLaneBins * 32) * 4 + 32 * sizeof(Lane6) +
-           128 * sizeof(Comb6) + 128 + (size_t)kWarps * (kW6Span + 2 * kQ2 + 2 * kMMax) * 4;
+           128 * sizeof(Comb6) + 128 + (size_t)kWarps6 * (kW6Span + 2 * kQ2 + 2 * kMMax) * 4;
 }
 
 extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, const float* window_host,
