@@ -73,6 +73,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// the same, letting the hardware park the thread for up to `ns` nanoseconds per try: a waiter that expects a
+// long wait (data still on its way from L2) then leaves the issue slots to the other warps of the SM
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITR_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONER_%=;\n\t"
+        "bra WAITR_%=;\n\t"
+        "DONER_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(ns)
+        : "memory");
+}
 // TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

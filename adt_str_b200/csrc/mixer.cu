@@ -102,11 +102,22 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
 
     float4 va[kPeakIters], vb[kPeakIters];
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    // interior chunks (both one-shots reach past the chunk) need neither load predicates nor tail masks
+    const bool interior = lo4 + kPeakSpan / 4 <= (la >> 2) && lo4 + kPeakSpan / 4 <= (lb >> 2);
+    if (interior) {
 #pragma unroll
-    for (int it = 0; it < kPeakIters; ++it) {
-        const int i4 = lo4 + tid + it * kPeakThreads;
-        va[it] = (i4 < hi4 && i4 < la4) ? __ldg(a4 + i4) : z;
-        vb[it] = (i4 < hi4 && i4 < lb4) ? __ldg(b4 + i4) : z;
+        for (int it = 0; it < kPeakIters; ++it) {
+            const int i4 = lo4 + tid + it * kPeakThreads;
+            va[it] = __ldg(a4 + i4);
+            vb[it] = __ldg(b4 + i4);
+        }
+    } else {
+#pragma unroll
+        for (int it = 0; it < kPeakIters; ++it) {
+            const int i4 = lo4 + tid + it * kPeakThreads;
+            va[it] = (i4 < hi4 && i4 < la4) ? __ldg(a4 + i4) : z;
+            vb[it] = (i4 < hi4 && i4 < lb4) ? __ldg(b4 + i4) : z;
+        }
     }
     if (chunk == 0) {  // resolve the bank lookups once per note for the tile mixer
         for (int e = e0 + tid; e < e1; e += kPeakThreads) {
@@ -118,18 +129,20 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
             resolved[e] = r;
         }
     }
+    if (!interior) {
 #pragma unroll
-    for (int it = 0; it < kPeakIters; ++it) {  // last float4 of a one-shot: ignore whatever pads it
-        const int i4 = lo4 + tid + it * kPeakThreads;
-        if (4 * i4 + 3 >= la) {
-            if (4 * i4 + 1 >= la) va[it].y = 0.f;
-            if (4 * i4 + 2 >= la) va[it].z = 0.f;
-            va[it].w = 0.f;
-        }
-        if (4 * i4 + 3 >= lb) {
-            if (4 * i4 + 1 >= lb) vb[it].y = 0.f;
-            if (4 * i4 + 2 >= lb) vb[it].z = 0.f;
-            vb[it].w = 0.f;
+        for (int it = 0; it < kPeakIters; ++it) {  // last float4 of a one-shot: ignore whatever pads it
+            const int i4 = lo4 + tid + it * kPeakThreads;
+            if (4 * i4 + 3 >= la) {
+                if (4 * i4 + 1 >= la) va[it].y = 0.f;
+                if (4 * i4 + 2 >= la) va[it].z = 0.f;
+                va[it].w = 0.f;
+            }
+            if (4 * i4 + 3 >= lb) {
+                if (4 * i4 + 1 >= lb) vb[it].y = 0.f;
+                if (4 * i4 + 2 >= lb) vb[it].z = 0.f;
+                vb[it].w = 0.f;
+            }
         }
     }
     for (int c0 = e0; c0 < e1; c0 += kPeakChunk) {
@@ -333,7 +346,7 @@ __global__ void __launch_bounds__(kMixThreads, kMixCtasPerSm) mix_kernel(const M
                         uint32_t ph = phase;
                         if (st >= kStages) { st -= kStages; ph ^= 1u; }
                         const SliceMsg m = list[k];
-                        mbar_wait(s_empty + st, ph ^ 1u);
+                        mbar_wait_relaxed(s_empty + st, ph ^ 1u, 2000u);
                         int4* d = reinterpret_cast<int4*>(s_desc + st);
                         d[0] = m.d0;
                         d[1] = m.d1;
@@ -363,7 +376,7 @@ __global__ void __launch_bounds__(kMixThreads, kMixCtasPerSm) mix_kernel(const M
     for (int j = 0; j < kPerThread; ++j) acc[j] = 0.0f;
     int tile = -1;
     for (;;) {
-        mbar_wait(s_full + stage, phase);
+        mbar_wait_relaxed(s_full + stage, phase, 2000u);
         const int4 d0 = *reinterpret_cast<const int4*>(s_desc + stage);
         if (d0.x != 0) {  // a new tile begins
             __syncwarp();
@@ -418,13 +431,21 @@ __global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_seg
     const int n = min(ADTFE_TILE, sg.len - lo);
     float4* row4 = reinterpret_cast<float4*>(row);
     const int n4 = n >> 2;
+    // v / peak * vol with the division by an invariant done the way the hardware sequence does it: q = v*r,
+    // one residual correction (correctly rounded for normal operands, i.e. everything a mix can hold), r = 1/peak
+    // rounded to nearest once per thread.  peak = 0 (all-zero mix) or NaN still gives NaN everywhere.
+    const float r = __frcp_rn(peak);
+    auto norm = [&](float v) {
+        const float q = __fmul_rn(v, r);
+        const float rem = __fmaf_rn(-q, peak, v);
+        return __fmul_rn(__fmaf_rn(rem, r, q), vol);
+    };
     for (int i = tid; i < n4; i += kNormThreads) {
         float4 v = row4[i];
-        v.x = __fmul_rn(__fdiv_rn(v.x, peak), vol); v.y = __fmul_rn(__fdiv_rn(v.y, peak), vol);
-        v.z = __fmul_rn(__fdiv_rn(v.z, peak), vol); v.w = __fmul_rn(__fdiv_rn(v.w, peak), vol);
+        v.x = norm(v.x); v.y = norm(v.y); v.z = norm(v.z); v.w = norm(v.w);
         row4[i] = v;
     }
-    for (int i = 4 * n4 + tid; i < n; i += kNormThreads) row[i] = __fmul_rn(__fdiv_rn(row[i], peak), vol);
+    for (int i = 4 * n4 + tid; i < n; i += kNormThreads) row[i] = norm(row[i]);
 }
 
 static size_t mix_smem_bytes() { return mix_list_offset() + kListMax * sizeof(SliceMsg); }

@@ -385,7 +385,7 @@ def run_b200(args):
                 "includes": f"host planning of note lists ({args.e2e_workers} planner threads), plan blob H2D, kernels, "
                             f"log-mel D2H into pinned host memory; groups of {group} batches, 4 buffer sets"},
         "gpu_launches": launches_per_step * args.steps,
-        "roofline": {"bound": "hbm", "kernel": "logmel_kernel", "achieved": logmel_gbs, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "logmel6_kernel", "achieved": logmel_gbs, "peak": peak, "unit": "GB/s",
                      "frac": logmel_gbs / peak, "traffic": traffic,
                      "traffic_source": "profiles/r01_traffic.json: dram bytes per segment of an ncu --set full capture x segments",
                      "peak_source": peak_src,
