@@ -16,6 +16,7 @@ EXPORTS = [
     "adtfe_render_workspace_bytes", "adtfe_render",
     "adtfe_mel_create", "adtfe_mel_destroy", "adtfe_mel_frames", "adtfe_mel_fast_path", "adtfe_logmel", "adtfe_logmel_rows",
     "adtfe_render_logmel", "adtfe_frontend_host", "adtfe_plan_blob_layout",
+    "adtfe_trace_begin", "adtfe_trace_dump",
     "adtfe_planner_create", "adtfe_planner_destroy", "adtfe_planner_plan", "adtfe_planner_export",
 ]
 
@@ -59,6 +60,7 @@ def _declare(lib) -> None:
     lib.adtfe_render_logmel.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, vp, vp, sz, vp]
     lib.adtfe_frontend_host.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp, vp]
     lib.adtfe_plan_blob_layout.argtypes = [C.POINTER(Plan), C.POINTER(sz * 6), C.POINTER(sz)]
+    lib.adtfe_trace_dump.argtypes = [C.c_char_p]
     lib.adtfe_planner_create.argtypes = [i32, C.c_double, C.c_double, C.c_double, i32, vp, vp, i32, vp, vp, vp, vp, vp,
                                          vp, C.POINTER(vp)]
     lib.adtfe_planner_destroy.argtypes = [vp]

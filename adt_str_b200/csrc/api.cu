@@ -1,5 +1,8 @@
 // libadtfe: error state, device checks, bank, fused and host-buffer entry points.
 #include <stdarg.h>
+#include <stdlib.h>
+
+#include <vector>
 
 #include "common.cuh"
 
@@ -14,6 +17,30 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---- launch trace: cudaEvent pairs around the kernels of adtfe_render / adtfe_render_logmel --------------------
+struct TraceRec {
+    const char* kernel;
+    int index;
+    cudaEvent_t a, b;
+};
+static std::vector<TraceRec> g_trace;
+static bool g_trace_on = false;
+static std::mutex g_trace_mu;
+
+void trace_open(const char* kernel, int index, cudaStream_t st) {
+    if (!g_trace_on) return;
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    TraceRec r = {kernel, index, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    g_trace.push_back(r);
+}
+void trace_close(cudaStream_t st) {
+    if (!g_trace_on) return;
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    if (!g_trace.empty()) cudaEventRecord(g_trace.back().b, st);
+}
+
 int device_sm_count(int device) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || n <= 0) n = 148;
@@ -24,8 +51,42 @@ int device_sm_count(int device) {
 
 using namespace adtfe;
 
+#ifndef ADTFE_CO_GROUP_DEFAULT
+#define ADTFE_CO_GROUP_DEFAULT 0
+#endif
+constexpr int kCoGroupDefault = ADTFE_CO_GROUP_DEFAULT;
+
 extern "C" int adtfe_version(void) { return ADTFE_VERSION; }
 extern "C" const char* adtfe_last_error(void) { return g_error; }
+
+extern "C" int adtfe_trace_begin(void) {
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    for (auto& r : g_trace) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_trace.clear();
+    g_trace_on = true;
+    return ADTFE_OK;
+}
+
+extern "C" int adtfe_trace_dump(const char* path) {
+    ADTFE_REQUIRE(path, ADTFE_ERR_BAD_ARG, "adtfe_trace_dump: null path");
+    ADTFE_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    g_trace_on = false;
+    FILE* f = fopen(path, "w");
+    ADTFE_REQUIRE(f, ADTFE_ERR_BAD_ARG, "adtfe_trace_dump: cannot write %s", path);
+    fprintf(f, "kernel,index,start_ms,end_ms\n");
+    for (auto& r : g_trace) {
+        float t0 = 0.f, t1 = 0.f;
+        if (cudaEventElapsedTime(&t0, g_trace.front().a, r.a) == cudaSuccess &&
+            cudaEventElapsedTime(&t1, g_trace.front().a, r.b) == cudaSuccess)
+            fprintf(f, "%s,%d,%.4f,%.4f\n", r.kernel, r.index, t0, t1);
+    }
+    for (auto& r : g_trace) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    cudaGetLastError();
+    g_trace.clear();
+    fclose(f);
+    return ADTFE_OK;
+}
 
 extern "C" int adtfe_device_ok(int device) {
     int count = 0;
@@ -52,6 +113,8 @@ extern "C" int adtfe_bank_destroy(adtfe_bank* bank) {
         if (bank->join_events[k]) cudaEventDestroy(bank->join_events[k]);
     }
     if (bank->fork_event) cudaEventDestroy(bank->fork_event);
+    if (bank->mel_stream) cudaStreamDestroy(bank->mel_stream);
+    if (bank->mel_event) cudaEventDestroy(bank->mel_event);
     delete bank;
     return ADTFE_OK;
 }
@@ -99,6 +162,12 @@ extern "C" int adtfe_bank_create(const float* pcm_host, int64_t total_floats, co
              cudaEventCreateWithFlags(&b->join_events[k], cudaEventDisableTiming) == cudaSuccess;
         if (ok) b->n_streams = k + 1;
     }
+    if (ok) {
+        int least = 0, greatest = 0;
+        ok = cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess &&
+             cudaStreamCreateWithPriority(&b->mel_stream, cudaStreamNonBlocking, greatest) == cudaSuccess &&
+             cudaEventCreateWithFlags(&b->mel_event, cudaEventDisableTiming) == cudaSuccess;
+    }
     if (!ok) {
         set_error("adtfe_bank_create: cannot create streams: %s", cudaGetErrorString(cudaGetLastError()));
         adtfe_bank_destroy(b);
@@ -113,11 +182,26 @@ extern "C" int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel,
                                    size_t workspace_bytes, void* stream) {
     ADTFE_REQUIRE(plan && (plan->mel_rows_dev || n_samples <= plan->ld_wav), ADTFE_ERR_BAD_ARG,
                   "adtfe_render_logmel: n_samples exceeds the row pitch");
+    // A chunked plan with ragged rows can be pipelined: the log-mel of a finished group of chunks runs beside the
+    // render of the following ones (ADTFE_CO_GROUP chunks per group; 0 = render everything first, the default:
+    // on B200 the co-running kernels take as long as they do one after the other - the render saturates L2 and
+    // leaves the log-mel CTAs no room to keep their rate, see DESIGN.md "Pipelined front end").
+    const char* co_env = getenv("ADTFE_CO_GROUP");
+    const int co_group = co_env ? atoi(co_env) : kCoGroupDefault;
+    if (co_group > 0 && mel && mel->v6co_ok && plan->mel_rows_dev && plan->chunks_host && plan->n_chunks > co_group &&
+        bank && bank->n_streams > 0 && mel_out_dev) {
+        const MelStage ms = {mel, mel_out_dev, co_group};
+        return render_impl(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream, &ms);
+    }
     int rc = adtfe_render(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream);
     if (rc != ADTFE_OK) return rc;
-    if (plan->mel_rows_dev)
-        return adtfe_logmel_rows(mel, wav_out_dev, plan->n_seg, plan->ld_wav, plan->mel_rows_dev, plan->mel_max_count,
-                                 mel_out_dev, stream);
+    if (plan->mel_rows_dev) {
+        trace_open("logmel", -1, (cudaStream_t)stream);
+        rc = adtfe_logmel_rows(mel, wav_out_dev, plan->n_seg, plan->ld_wav, plan->mel_rows_dev, plan->mel_max_count,
+                               mel_out_dev, stream);
+        trace_close((cudaStream_t)stream);
+        return rc;
+    }
     return adtfe_logmel(mel, wav_out_dev, plan->n_seg, plan->ld_wav, n_samples, mel_out_dev, stream);
 }
 

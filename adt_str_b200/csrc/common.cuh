@@ -99,7 +99,27 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 struct adtfe_mel_tables;
 
-constexpr int kBankStreams = 4;
+namespace adtfe {
+// Log-mel stage of the pipelined front end: after every `group_chunks` render chunks the finished rows are
+// featurised on the bank's mel stream while the following chunks render.
+struct MelStage {
+    const adtfe_mel* mel;
+    float* out_dev;
+    int group_chunks;
+};
+int render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
+                size_t workspace_bytes, void* stream, const MelStage* mel_stage);
+// Diagnostics (adtfe_trace_begin / adtfe_trace_dump): a pair of timing events around every kernel launch.
+void trace_open(const char* kernel, int index, cudaStream_t st);
+void trace_close(cudaStream_t st);
+int logmel_rows_co(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
+                   const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream);
+}  // namespace adtfe
+
+#ifndef ADTFE_BANK_STREAMS
+#define ADTFE_BANK_STREAMS 4
+#endif
+constexpr int kBankStreams = ADTFE_BANK_STREAMS;
 struct adtfe_bank {
     int device = 0;
     int sm_count = 148;
@@ -112,6 +132,10 @@ struct adtfe_bank {
     int n_streams = 0;
     cudaStream_t streams[kBankStreams] = {};
     cudaEvent_t fork_event = nullptr, join_events[kBankStreams] = {};
+    // pipelined front end: the log-mel of finished chunk groups runs here (highest priority, so that its
+    // CTAs are placed before the pending render CTAs of later chunks) beside the render of the next groups
+    cudaStream_t mel_stream = nullptr;
+    cudaEvent_t mel_event = nullptr;
     mutable std::mutex mu;
 };
 
@@ -129,6 +153,8 @@ struct adtfe_mel {
     int32_t v6_ok = 0;
     void *w6 = nullptr, *lane6 = nullptr, *comb6 = nullptr;
     size_t smem6_bytes = 0;
+    int32_t v6co_ok = 0;       // the co-resident shape of the v6 kernel can run (see adtfe_render_logmel)
+    size_t smem6co_bytes = 0;
     int32_t fast_path = 0;     // 1: the filterbank is triangular (<= 2 adjacent filters per bin)
     struct adtfe_mel_tables* tables = nullptr;  // mel-phase items + warp schedule, passed as a kernel parameter
     size_t smem_bytes = 0;

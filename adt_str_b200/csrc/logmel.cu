@@ -413,11 +413,21 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
 #ifndef ADTFE_LM6_UNIT
 #define ADTFE_LM6_UNIT 6      // frames per unit (even): the span of a unit is (UNIT-1)*hop + 2048 samples
 #endif
+// The co-resident shape: the same kernel with fewer warps and shorter units, so that its CTA leaves room on the SM
+// (shared memory and registers) for the render kernels of later chunks - see adtfe_render_logmel (mixer.cu).
+#ifndef ADTFE_CO_WARPS
+#define ADTFE_CO_WARPS 6
+#endif
+#ifndef ADTFE_CO_UNIT
+#define ADTFE_CO_UNIT 4
+#endif
 constexpr bool kDirect6 = ADTFE_LM6_DIRECT != 0;
 constexpr int kWarps6 = ADTFE_LM6_WARPS;
-constexpr int kThreads6 = kWarps6 * 32;
 constexpr int kUnitFrames = ADTFE_LM6_UNIT;
-constexpr int kW6Span = kDirect6 ? 0 : (kUnitFrames - 1) * 256 + 2048;  // floats of a warp's span buffer: hop <= 256
+constexpr int kCoWarps = ADTFE_CO_WARPS;
+constexpr int kCoUnit = ADTFE_CO_UNIT;
+// floats of a warp's span buffer for units of `unit` frames: hop <= 256
+__host__ __device__ constexpr int w6_span(int unit) { return kDirect6 ? 0 : (unit - 1) * 256 + 2048; }
 constexpr int kLaneBins = 33;                 // bins walked by one lane: 32 * 33 = 1056 >= n_bins
 constexpr int kQ2 = 32 * kLaneBins;           // float2 entries of a warp's exchange / power buffer
 constexpr int kMMax = 200;                    // float2 partial sums per warp
@@ -441,6 +451,7 @@ struct Unit6 {
     int seg, j0, nf;
     long long out_row;
 };
+template <int kUnitFrames>
 __device__ __forceinline__ Unit6 unit6_geom(const LogmelArgs& p, int u, int units_per_seg) {
     Unit6 g;
     g.seg = (int)((unsigned)u / (unsigned)units_per_seg);
@@ -471,8 +482,11 @@ __device__ __forceinline__ void issue_span6(const LogmelArgs& p, const Unit6& g,
 
 // `tma`: every unit's samples start on a 16-byte boundary (aligned base, row pitch a multiple of 4 floats); otherwise the
 // warp copies its span itself at the start of the unit (no prefetch) - same arithmetic, so results do not depend on it.
-__global__ void __launch_bounds__(kThreads6, 1) logmel6_kernel(const LogmelArgs p, const Logmel6Tables t6, int n_units,
-                                                              int units_per_seg, int tma) {
+template <int kWarps6, int kUnitFrames>
+__global__ void __launch_bounds__(kWarps6 * 32, 1) logmel6_kernel(const LogmelArgs p, const Logmel6Tables t6, int n_units,
+                                                                int units_per_seg, int tma) {
+    constexpr int kThreads6 = kWarps6 * 32;
+    constexpr int kW6Span = w6_span(kUnitFrames);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* s_win = reinterpret_cast<float*>(smem_raw);                    // 32 * kWinPitch
     float2* s_tw = reinterpret_cast<float2*>(s_win + 32 * kWinPitch);     // 32*32
@@ -502,7 +516,7 @@ __global__ void __launch_bounds__(kThreads6, 1) logmel6_kernel(const LogmelArgs 
     const int col32_bin = 32 + 64 * (int)(__brev((unsigned)lane) >> 27);
     const int gstride = (int)gridDim.x * kWarps6;
     int u = (int)blockIdx.x * kWarps6 + warp;
-    Unit6 g = unit6_geom(p, min(u, n_units - 1), units_per_seg);
+    Unit6 g = unit6_geom<kUnitFrames>(p, min(u, n_units - 1), units_per_seg);
     if (kDirect6) tma = 0;
     if (tma && u < n_units) issue_span6(p, g, span, bar, lane);
     uint32_t parity = 0;
@@ -511,7 +525,7 @@ __global__ void __launch_bounds__(kThreads6, 1) logmel6_kernel(const LogmelArgs 
     for (; u < n_units; u += gstride) {
         const bool more = u + gstride < n_units;
         Unit6 gn = g;
-        if (more) gn = unit6_geom(p, u + gstride, units_per_seg);
+        if (more) gn = unit6_geom<kUnitFrames>(p, u + gstride, units_per_seg);
         if (tma) {
             mbar_wait(bar, parity);
             parity ^= 1u;
@@ -692,8 +706,15 @@ extern "C" int adtfe_mel_frames(const adtfe_mel* mel, int64_t n_samples, int32_t
     return ADTFE_OK;
 }
 
+static size_t logmel6_smem_bytes(int warps, int unit) {
+    return (size_t)(32 * kWinPitch + 2 * 32 * 32 + 2 * 4 * 32 + 2 * kLaneBins * 32) * 4 + 32 * sizeof(Lane6) +
+           128 * sizeof(Comb6) + 128 + (size_t)warps * (w6_span(unit) + 2 * kQ2 + 2 * kMMax) * 4;
+}
+
+// `co`: the co-resident shape of the v6 kernel (kCoWarps warps, units of kCoUnit frames) - same arithmetic per frame
+// pair, so the results are bit-identical to the stand-alone shape.
 static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav, int32_t first,
-                         int32_t count, const adtfe_mel_row* rows_dev, float* out_dev, void* stream) {
+                         int32_t count, const adtfe_mel_row* rows_dev, float* out_dev, void* stream, bool co = false) {
     // frames per round: as many as fit the span buffer, at most 32; a segment's frames are split evenly
     const int cap = std::min(kRound, (kSpanFloats - 2048) / mel->hop + 1);
     const int rounds_per_seg = (count + cap - 1) / cap;
@@ -707,14 +728,20 @@ static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_s
     if (mel->v6_ok && !getenv("ADTFE_LOGMEL_V5")) {
         // TMA needs 16-byte aligned unit starts; other rows are copied by the warps (same results)
         const int tma = ((uintptr_t)wav_dev & 15) == 0 && ld_wav % 4 == 0;
-        const int units_per_seg = (count + kUnitFrames - 1) / kUnitFrames;
+        const int unit = co ? kCoUnit : kUnitFrames, warps = co ? kCoWarps : kWarps6;
+        const int units_per_seg = (count + unit - 1) / unit;
         const long long n_units = (long long)n_seg * units_per_seg;
         ADTFE_REQUIRE(n_units < (1ll << 30), ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: too many frames for one launch");
         Logmel6Tables t6;
         t6.w = (const float2*)mel->w6; t6.lane = (const Lane6*)mel->lane6; t6.comb = (const Comb6*)mel->comb6;
-        const long long ctas = (n_units + kWarps6 - 1) / kWarps6;
+        const long long ctas = (n_units + warps - 1) / warps;
         const int grid6 = (int)(ctas < mel->sm_count ? ctas : mel->sm_count);
-        logmel6_kernel<<<grid6, kThreads6, mel->smem6_bytes, (cudaStream_t)stream>>>(a, t6, (int)n_units, units_per_seg, tma);
+        if (co)
+            logmel6_kernel<kCoWarps, kCoUnit><<<grid6, kCoWarps * 32, mel->smem6co_bytes, (cudaStream_t)stream>>>(
+                a, t6, (int)n_units, units_per_seg, tma);
+        else
+            logmel6_kernel<kWarps6, kUnitFrames><<<grid6, kWarps6 * 32, mel->smem6_bytes, (cudaStream_t)stream>>>(
+                a, t6, (int)n_units, units_per_seg, tma);
         ADTFE_CUDA(cudaGetLastError());
         return ADTFE_OK;
     }
@@ -741,8 +768,8 @@ extern "C" int adtfe_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t 
     return launch_logmel(mel, wav_dev, n_seg, ld_wav, first, count, nullptr, out_dev, stream);
 }
 
-extern "C" int adtfe_logmel_rows(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
-                                 const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream) {
+static int logmel_rows_checked(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
+                               const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream, bool co) {
     ADTFE_REQUIRE(mel && n_seg >= 0 && max_count >= 0 && ld_wav >= 0, ADTFE_ERR_BAD_ARG,
                   "adtfe_logmel_rows: bad argument (n_seg=%d ld_wav=%lld max_count=%d)", n_seg, (long long)ld_wav,
                   max_count);
@@ -754,8 +781,23 @@ extern "C" int adtfe_logmel_rows(const adtfe_mel* mel, const float* wav_dev, int
     // the longest row must stay inside the pitch (the per-row counts live on the device: the caller's contract)
     ADTFE_REQUIRE((int64_t)first * mel->hop >= 1024 && (int64_t)(first + max_count - 1) * mel->hop + 1024 <= ld_wav,
                   ADTFE_ERR_UNSUPPORTED, "adtfe_logmel_rows: frame support leaves the row");
-    return launch_logmel(mel, wav_dev, n_seg, ld_wav, first, max_count, rows_dev, out_dev, stream);
+    return launch_logmel(mel, wav_dev, n_seg, ld_wav, first, max_count, rows_dev, out_dev, stream, co);
 }
+
+extern "C" int adtfe_logmel_rows(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
+                                 const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream) {
+    // ADTFE_LOGMEL_CO=1: the co-resident kernel shape on its own (tuning aid, same results)
+    const bool co = mel && mel->v6co_ok && getenv("ADTFE_LOGMEL_CO") != nullptr;
+    return logmel_rows_checked(mel, wav_dev, n_seg, ld_wav, rows_dev, max_count, out_dev, stream, co);
+}
+
+namespace adtfe {
+int logmel_rows_co(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
+                   const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream) {
+    return logmel_rows_checked(mel, wav_dev, n_seg, ld_wav, rows_dev, max_count, out_dev, stream,
+                               mel && mel->v6co_ok);
+}
+}  // namespace adtfe
 
 extern "C" int adtfe_mel_destroy(adtfe_mel* mel) {
     if (!mel) return ADTFE_OK;
@@ -997,11 +1039,6 @@ static bool build_lane_tables(const float* fb, int n_bins, int n_mels, std::vect
     return true;
 }
 
-static size_t logmel6_smem_bytes() {
-    return (size_t)(32 * kWinPitch + 2 * 32 * 32 + 2 * 4 * 32 + 2 * kLaneBins * 32) * 4 + 32 * sizeof(Lane6) +
-           128 * sizeof(Comb6) + 128 + (size_t)kWarps6 * (kW6Span + 2 * kQ2 + 2 * kMMax) * 4;
-}
-
 extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, const float* window_host,
                                 const float* fb_host, int device, adtfe_mel** out) {
     ADTFE_REQUIRE(out && window_host && fb_host, ADTFE_ERR_BAD_ARG, "adtfe_mel_create: null pointer");
@@ -1067,18 +1104,24 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
         std::vector<float2> w6;
         std::vector<Lane6> lane6;
         std::vector<Comb6> comb6;
-        mel->v6_ok = hop % 4 == 0 && (kUnitFrames - 1) * hop + 2048 <= kW6Span && ((n_fft / 2) / hop + 1) * hop >= 1024 &&
+        mel->v6_ok = hop % 4 == 0 && (kUnitFrames - 1) * hop + 2048 <= w6_span(kUnitFrames) && ((n_fft / 2) / hop + 1) * hop >= 1024 &&
                      build_lane_tables(fb_host, n_bins, n_mels, w6, lane6, comb6);
         if (mel->v6_ok) {
             MEL_UPLOAD(mel->w6, w6.data(), w6.size() * sizeof(float2));
             MEL_UPLOAD(mel->lane6, lane6.data(), lane6.size() * sizeof(Lane6));
             MEL_UPLOAD(mel->comb6, comb6.data(), comb6.size() * sizeof(Comb6));
-            mel->smem6_bytes = logmel6_smem_bytes();
-            if (cudaFuncSetAttribute(logmel6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            mel->smem6_bytes = logmel6_smem_bytes(kWarps6, kUnitFrames);
+            mel->smem6co_bytes = logmel6_smem_bytes(kCoWarps, kCoUnit);
+            if (cudaFuncSetAttribute(logmel6_kernel<kWarps6, kUnitFrames>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)mel->smem6_bytes) != cudaSuccess) {
                 cudaGetLastError();
                 mel->v6_ok = 0;
             }
+            mel->v6co_ok = mel->v6_ok && (kCoUnit - 1) * hop + 2048 <= w6_span(kCoUnit) &&
+                           cudaFuncSetAttribute(logmel6_kernel<kCoWarps, kCoUnit>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)mel->smem6co_bytes) == cudaSuccess;
+            cudaGetLastError();
         }
     }
 #undef MEL_UPLOAD

@@ -26,7 +26,10 @@
 
 namespace adtfe {
 
-constexpr int kPeakThreads = 256;
+#ifndef ADTFE_PEAK_THREADS
+#define ADTFE_PEAK_THREADS 128   // 128 x 96 registers: 6 % faster render than 256 x 64 (more CTAs fit beside the mixer)
+#endif
+constexpr int kPeakThreads = ADTFE_PEAK_THREADS;
 constexpr int kPeakChunk = 8;   // notes of one instrument handled per sweep over the one-shots
 constexpr int kPeakSpan = ADTFE_PEAK_SPAN;  // samples of the mixed one-shot per peak work item
 constexpr int kPeakIters = kPeakSpan / 4 / kPeakThreads;  // float4 per thread per one-shot
@@ -464,6 +467,11 @@ extern "C" size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, 
 
 extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
                             size_t workspace_bytes, void* stream) {
+    return render_impl(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream, nullptr);
+}
+
+int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
+                       size_t workspace_bytes, void* stream, const MelStage* ms) {
     ADTFE_REQUIRE(bank && plan, ADTFE_ERR_BAD_ARG, "adtfe_render: null bank or plan");
     ADTFE_REQUIRE(plan->n_seg >= 0 && plan->n_events >= 0 && plan->n_peak_work >= 0 && plan->tiles_per_seg >= 0,
                   ADTFE_ERR_BAD_ARG, "adtfe_render: negative count");
@@ -517,14 +525,19 @@ extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, floa
         for (int k = 0; k < bank->n_streams && k < n_chunks; ++k)
             ADTFE_CUDA(cudaStreamWaitEvent(bank->streams[k], bank->fork_event, 0));
     }
+    const bool staged = ms && fork && plan->mel_rows_dev;  // log-mel of finished chunk groups beside the render
+    if (staged) ADTFE_CUDA(cudaStreamWaitEvent(bank->mel_stream, bank->fork_event, 0));
+    int group_first = 0;  // first chunk of the group being rendered
     const int tps = plan->tiles_per_seg;
     for (int c = 0; c < n_chunks; ++c) {
         cudaStream_t st = fork ? bank->streams[c % bank->n_streams] : user;
         const int s0 = ch[c].seg, n_seg = ch[c + 1].seg - s0;
         const int pw0 = ch[c].peak_work, n_pw = ch[c + 1].peak_work - pw0;
         if (n_pw > 0) {
+            trace_open("peak", c, st);
             peak_kernel<<<n_pw, kPeakThreads, 0, st>>>(bank->pcm, plan->events_dev, plan->peak_work_dev + pw0, resolved,
                                                       peak_bits);
+            trace_close(st);
             ADTFE_CUDA(cudaGetLastError());
         }
         MixArgs a;
@@ -534,10 +547,34 @@ extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, floa
         a.tile_max = tile_max + (size_t)s0 * tps; a.tile_counter = counters + c; a.ld_wav = plan->ld_wav;
         a.tiles_per_seg = tps; a.n_tiles = n_seg * tps;
         const int grid = std::min(a.n_tiles, kMixCtasPerSm * bank->sm_count);
+        trace_open("mix", c, st);
         mix_kernel<<<grid, kMixThreads, mix_smem_bytes(), st>>>(a);
+        trace_close(st);
         ADTFE_CUDA(cudaGetLastError());
+        trace_open("normalise", c, st);
         normalise_kernel<<<a.n_tiles, kNormThreads, 0, st>>>(a.segments, a.tile_max, tps, plan->ld_wav, a.wav);
+        trace_close(st);
         ADTFE_CUDA(cudaGetLastError());
+        if (staged && (c + 1 - group_first >= ms->group_chunks || c + 1 == n_chunks)) {
+            // the group's chunks sit on the streams (group_first .. c) % n_streams: the mel stream waits for them
+            const int used = std::min(c + 1 - group_first, bank->n_streams);
+            for (int j = 0; j < used; ++j) {
+                const int k = (c - j) % bank->n_streams;
+                ADTFE_CUDA(cudaEventRecord(bank->join_events[k], bank->streams[k]));
+                ADTFE_CUDA(cudaStreamWaitEvent(bank->mel_stream, bank->join_events[k], 0));
+            }
+            const int g0 = ch[group_first].seg, g1 = ch[c + 1].seg;
+            trace_open("logmel", group_first, bank->mel_stream);
+            const int rc = logmel_rows_co(ms->mel, wav_out_dev + (size_t)g0 * plan->ld_wav, g1 - g0, plan->ld_wav,
+                                          plan->mel_rows_dev + g0, plan->mel_max_count, ms->out_dev, bank->mel_stream);
+            trace_close(bank->mel_stream);
+            if (rc != ADTFE_OK) return rc;
+            group_first = c + 1;
+        }
+    }
+    if (staged) {
+        ADTFE_CUDA(cudaEventRecord(bank->mel_event, bank->mel_stream));
+        ADTFE_CUDA(cudaStreamWaitEvent(user, bank->mel_event, 0));
     }
     if (fork) {
         for (int k = 0; k < bank->n_streams && k < n_chunks; ++k) {

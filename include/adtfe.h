@@ -186,6 +186,14 @@ int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel, const adtf
  * tile_events starts - it runs to the end of the blob). */
 int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[6], size_t* blob_bytes);
 
+/* ---- diagnostics ----------------------------------------------------------------------- */
+/* Launch trace: after adtfe_trace_begin every kernel launched by adtfe_render / adtfe_render_logmel is bracketed
+ * by a pair of timing events on its stream; adtfe_trace_dump synchronises the device, writes
+ * "kernel,index,start_ms,end_ms" lines (times relative to the first launch; index = chunk or group) and stops
+ * tracing.  Shows how the chunks' kernels and the log-mel groups overlap across the internal streams. */
+int adtfe_trace_begin(void);
+int adtfe_trace_dump(const char* path);
+
 /* ---- host planner (no GPU work) ------------------------------------------------------ */
 /* C++ restatement of the per-note bookkeeping of SynthDrum.__call__ (modules/synthetiser.py:255-292:
  * RNG draws in the reference's order from Python's MT19937 stream, float32 index rules, velocity

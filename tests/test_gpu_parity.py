@@ -252,6 +252,36 @@ def test_batches_in_one_plan_equal_batch_by_batch():
         assert torch.equal(w0, w1) and torch.equal(f0, f1)
 
 
+def test_pipelined_front_end_equals_render_then_logmel(monkeypatch):
+    """adtfe_render_logmel on a chunked plan featurises finished chunk groups (co-resident log-mel shape on the
+    bank's mel stream) while later chunks render; whatever the group size, the waveforms and the log-mel are bit for
+    bit those of render-everything-then-one-log-mel-launch (ADTFE_CO_GROUP=0)."""
+    from adt_str_b200.config import setting_1
+    from adt_str_b200.synthetic import make_bank, make_segments
+    bank = make_bank(390, 24000, seed=16)
+    _, _, fe = _objects(setting_1(), bank)
+    segs = make_segments(90, seed=23, empty_fraction=0.1)
+    cuts = [0, 7, 8, 20, 26, 33, 41, 42, 50, 57, 63, 70, 78, 84, 90]
+    batches = [segs[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    results = {}
+    for group, chunk_batches in (("0", 1), ("1", 1), ("3", 1), ("5", 2), (None, 1)):
+        if group is None:
+            monkeypatch.delenv("ADTFE_CO_GROUP", raising=False)
+        else:
+            monkeypatch.setenv("ADTFE_CO_GROUP", group)
+        plan = fe.plan_batches(batches, random.Random(99), chunk_batches)
+        for _ in range(2):     # twice: the second run overlaps the first one's tail on the internal streams
+            wav, feat = fe.run_plan(plan)
+        torch.cuda.synchronize()
+        results[(group, chunk_batches)] = (wav.clone(), feat.clone())
+    monkeypatch.delenv("ADTFE_CO_GROUP", raising=False)
+    w0, f0 = results[("0", 1)]
+    assert torch.isfinite(f0).all()
+    for key, (w, f) in results.items():
+        assert torch.equal(w, w0), key
+        assert torch.equal(f, f0), key
+
+
 def test_host_pipeline_equals_direct_calls():
     """HostPipeline (planner threads, rotating pinned buffer sets, host log-mel) returns what the direct
     device calls return for the same RNG stream; with several workers it stays self-consistent."""
