@@ -5,7 +5,7 @@ from .config import SharedConfig, SynthDrumConfig, setting_1, config_default  # 
 from .bank import OneShotBank  # noqa: F401
 
 __all__ = ["SharedConfig", "SynthDrumConfig", "OneShotBank", "setting_1", "config_default",
-           "SynthDrum", "ComputeMelSpectrogram", "FrontEnd", "HostPipeline"]
+           "SynthDrum", "ComputeMelSpectrogram", "FrontEnd", "HostPipeline", "Resample", "LongFormFrontEnd"]
 
 
 def __getattr__(name):  # lazy: importing the package must not need the CUDA library
@@ -21,4 +21,10 @@ def __getattr__(name):  # lazy: importing the package must not need the CUDA lib
     if name == "HostPipeline":
         from .pipeline import HostPipeline
         return HostPipeline
+    if name == "Resample":
+        from .audio_utils import Resample
+        return Resample
+    if name == "LongFormFrontEnd":
+        from .inference_front import LongFormFrontEnd
+        return LongFormFrontEnd
     raise AttributeError(name)

@@ -16,6 +16,8 @@ EXPORTS = [
     "adtfe_render_workspace_bytes", "adtfe_render",
     "adtfe_mel_create", "adtfe_mel_destroy", "adtfe_mel_frames", "adtfe_mel_fast_path", "adtfe_logmel", "adtfe_logmel_rows",
     "adtfe_render_logmel", "adtfe_frontend_host", "adtfe_plan_blob_layout",
+    "adtfe_resampler_create", "adtfe_resampler_destroy", "adtfe_resample_length", "adtfe_resample", "adtfe_downmix",
+    "adtfe_peak_normalise",
     "adtfe_trace_begin", "adtfe_trace_dump",
     "adtfe_planner_create", "adtfe_planner_destroy", "adtfe_planner_plan", "adtfe_planner_export",
 ]
@@ -60,6 +62,13 @@ def _declare(lib) -> None:
     lib.adtfe_render_logmel.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, vp, vp, sz, vp]
     lib.adtfe_frontend_host.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp, vp]
     lib.adtfe_plan_blob_layout.argtypes = [C.POINTER(Plan), C.POINTER(sz * 6), C.POINTER(sz)]
+    lib.adtfe_resampler_create.argtypes = [i32, i32, i32, vp, C.c_int, C.POINTER(vp)]
+    lib.adtfe_resampler_destroy.argtypes = [vp]
+    lib.adtfe_resample_length.argtypes = [vp, i64]
+    lib.adtfe_resample_length.restype = i64
+    lib.adtfe_resample.argtypes = [vp, vp, i32, i64, i64, vp, i64, vp, vp]
+    lib.adtfe_downmix.argtypes = [vp, i32, i64, i64, vp, vp]
+    lib.adtfe_peak_normalise.argtypes = [vp, i64, vp, i32, vp]
     lib.adtfe_trace_dump.argtypes = [C.c_char_p]
     lib.adtfe_planner_create.argtypes = [i32, C.c_double, C.c_double, C.c_double, i32, vp, vp, i32, vp, vp, vp, vp, vp,
                                          vp, C.POINTER(vp)]

@@ -18,6 +18,11 @@
  *   adtfe_render_logmel   both, back to back on one stream (train.py:52 H2D + model.py:248)
  *   adtfe_frontend_host   the same with HOST buffers: plan blob in, log-mel (and optionally
  *                         the waveform) out, copies included - the end-to-end entry
+ *   adtfe_resample* / adtfe_downmix / adtfe_peak_normalise
+ *                         the audio front of eval and inference: utils/audio_utils.py:17-23
+ *                         (resample = torchaudio.transforms.Resample, normalize = wav / max|wav|),
+ *                         the channel mean of utils/audio_utils.py:12 and inference.py:86-87; the
+ *                         chunking of inference.py:35-48 is then a view of the zero-padded signal
  *
  * Conventions: plain pointers and sizes; pointers named *_dev are device memory on the
  * bank's / mel's device, *_host are host memory (pinned for asynchronous copies).  All
@@ -185,6 +190,27 @@ int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel, const adtf
 /* Byte offsets of the six sections inside a plan blob (offsets[6]; *blob_bytes = offsets[5], where
  * tile_events starts - it runs to the end of the blob). */
 int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[6], size_t* blob_bytes);
+
+/* ---- long-form audio front (eval / inference) ------------------------------------------ */
+typedef struct adtfe_resampler adtfe_resampler;
+/* kernel_host: the (new_freq/gcd, 2*width + orig_freq/gcd) float32 filter bank torchaudio's Resample keeps in its
+ * `kernel` buffer (functional._get_sinc_resample_kernel), width its `width`.  Synchronous.  Rate pairs whose
+ * gcd is so small that the bank would not fit (taps > ~24k or > 16M coefficients) return ADTFE_ERR_UNSUPPORTED. */
+int adtfe_resampler_create(int32_t orig_freq, int32_t new_freq, int32_t width, const float* kernel_host, int device,
+                           adtfe_resampler** out);
+int adtfe_resampler_destroy(adtfe_resampler* resampler);
+/* ceil(new_freq * n_in / orig_freq): samples torchaudio returns for an n_in-long input; < 0 on a bad argument */
+int64_t adtfe_resample_length(const adtfe_resampler* resampler, int64_t n_in);
+/* x_dev: n_rows rows (channels / items) of n_in floats, pitch ld_in; y_dev: rows of adtfe_resample_length floats,
+ * pitch ld_out.  absmax_bits_dev: NULL, or one zero-initialised int32 that receives the float bits of max|y|
+ * over everything written (NaN if any output is NaN) - hand it to adtfe_peak_normalise with have_absmax = 1. */
+int adtfe_resample(const adtfe_resampler* resampler, const float* x_dev, int32_t n_rows, int64_t ld_in, int64_t n_in,
+                   float* y_dev, int64_t ld_out, int32_t* absmax_bits_dev, void* stream);
+/* out[i] = (x[0][i] + ... + x[n_rows-1][i]) / n_rows - torch.mean over the channel dimension */
+int adtfe_downmix(const float* x_dev, int32_t n_rows, int64_t ld, int64_t n, float* out_dev, void* stream);
+/* x / max|x| in place (IEEE division; an all-zero signal gives NaN like the reference's 0/0).  absmax_bits_dev:
+ * one int32 of scratch; have_absmax != 0 when it already holds the bits of max|x| (from adtfe_resample). */
+int adtfe_peak_normalise(float* x_dev, int64_t n, int32_t* absmax_bits_dev, int32_t have_absmax, void* stream);
 
 /* ---- diagnostics ----------------------------------------------------------------------- */
 /* Launch trace: after adtfe_trace_begin every kernel launched by adtfe_render / adtfe_render_logmel is bracketed

@@ -22,6 +22,7 @@ import warnings
 
 import numpy as np
 import torch
+import torchaudio
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -112,5 +113,61 @@ def main():
               f"mel {mel_err:.2e} (vs float64 {truth_err:.2e}), mel shape {ref_mel.shape}")
 
 
+def make_audio_front():
+    """tests/golden/audio_front.npz: the reference's own eval / inference audio front (utils/audio_utils.py:12-23,
+    inference.py:35-48,75-98) on seeded synthetic signals - inputs and outputs of the unmodified functions."""
+    from oracle import audio_oracle
+    au, inf = ref_harness.import_audio_front()
+    rng = np.random.default_rng(77)
+
+    def signal(ch, n, sr):  # decaying noise bursts + a low tone: broadband, non-stationary, |x| < 1
+        t = np.arange(n) / sr
+        env = np.exp(-8.0 * ((t * 3.0) % 1.0))
+        x = 0.4 * rng.standard_normal((ch, n)) * env + 0.3 * np.sin(2 * np.pi * 110.0 * t)[None]
+        return x.astype(np.float32)
+
+    out = {}
+    cases = [("stereo_44k1", 2, 44100, 24000, 115000), ("mono_48k", 1, 48000, 24000, 50001),
+             ("mono_22k05_16k", 1, 22050, 16000, 30000), ("stereo_24k", 2, 24000, 24000, 62001)]
+    mel24 = ref_harness.make_mel(24000, 2048, 0.01, 128)
+    mel16 = ref_harness.make_mel(16000, 2048, 0.01, 128)
+    names = []
+    for name, ch, sr, target, n in cases:
+        x = signal(ch, n, sr)
+        w = torch.from_numpy(x)
+        # inference.py:82-87: resample every channel, then the channel mean
+        y = torchaudio.transforms.Resample(sr, target)(w) if sr != target else w
+        res_per_channel = y.numpy().copy()
+        if y.shape[0] > 1:
+            y = y.mean(dim=0, keepdim=True)
+        chunk = int(round(2.56 * target))
+        chunks = inf._chunk_audio(y, chunk)
+        starts = np.array([s for s, _ in chunks], np.int64)
+        mat = torch.cat([c for _, c in chunks], 0)
+        mel = (mel24 if target == 24000 else mel16)(mat).numpy()
+        # utils/audio_utils.py:10-23: mean first, then resample, then normalize (load_and_resample / eval_dataset)
+        mono_first = au.resample(w.mean(0), sr, target) if sr != target else w.mean(0)
+        norm = au.normalize(mono_first).numpy()
+        ora = audio_oracle.long_form_chunks(x, sr, target, 2.56)
+        assert ora.shape == tuple(mat.shape) and float(np.abs(ora - mat.numpy()).max()) < 1e-6, name
+        if sr != target:
+            d = audio_oracle.resample_direct(x, sr, target, np.float64)
+            err = float(np.abs(d - res_per_channel).max())
+            assert err < 2e-6, (name, err)
+        if sr != target:
+            out[f"{name}/resampled"] = res_per_channel
+        out.update({f"{name}/x": x, f"{name}/sr": np.array([sr, target]),
+                    f"{name}/chunk_starts": starts, f"{name}/chunks": mat.numpy(), f"{name}/mel": mel,
+                    f"{name}/mono_first_normalized": norm})
+        names.append(name)
+        print(f"audio_front {name}: {x.shape} @ {sr} -> {res_per_channel.shape} @ {target}, {len(starts)} chunks, "
+              f"mel {mel.shape}")
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, "audio_front.npz"), **out)
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if "--audio-front-only" not in sys.argv:
+        main()
+    make_audio_front()

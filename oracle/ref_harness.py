@@ -119,3 +119,24 @@ def make_mel(sample_rate: int, win_length: int, time_res: float, n_mels: int):
     """The reference's ``ComputeMelSpectrogram`` (model.py:68-97)."""
     _, model = _import_reference()
     return model.ComputeMelSpectrogram(sample_rate, win_length, time_res, n_mels)
+
+
+def import_audio_front():
+    """The reference's ``utils.audio_utils`` (resample / normalize, :17-23) and ``inference`` (``_chunk_audio``,
+    :35-48) modules, unmodified.  ``inference.py`` imports packages that are not installed here (pretty_midi,
+    omegaconf ...); empty stand-in modules let the import through - none of them is touched by ``_chunk_audio``."""
+    import importlib
+    import importlib.machinery
+    _import_reference()  # transformers (via model.py) must be imported before the stand-ins exist
+    for name in ("pretty_midi", "omegaconf", "mir_eval", "soundfile", "librosa", "matplotlib", "accelerate"):
+        try:
+            importlib.import_module(name)
+        except Exception:
+            m = types.ModuleType(name)
+            m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+            sys.modules[name] = m
+    if not hasattr(sys.modules["omegaconf"], "OmegaConf"):
+        sys.modules["omegaconf"].OmegaConf = object
+    audio_utils = importlib.import_module("utils.audio_utils")
+    inference = importlib.import_module("inference")
+    return audio_utils, inference
