@@ -19,7 +19,7 @@ EXPORTS = [
     "adtfe_resampler_create", "adtfe_resampler_destroy", "adtfe_resample_length", "adtfe_resample", "adtfe_downmix",
     "adtfe_peak_normalise",
     "adtfe_trace_begin", "adtfe_trace_dump",
-    "adtfe_planner_create", "adtfe_planner_destroy", "adtfe_planner_plan", "adtfe_planner_export",
+    "adtfe_planner_create", "adtfe_planner_destroy", "adtfe_planner_plan", "adtfe_planner_export", "adtfe_planner_pack_batches",
 ]
 
 
@@ -75,6 +75,8 @@ def _declare(lib) -> None:
     lib.adtfe_planner_destroy.argtypes = [vp]
     lib.adtfe_planner_plan.argtypes = [vp, vp, vp, i32, vp, i64, vp, vp]
     lib.adtfe_planner_export.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.adtfe_planner_pack_batches.argtypes = [vp, vp, i32, i32, i32, i32, vp, sz, C.POINTER(Plan), vp, vp, vp,
+                                               C.POINTER(sz)]
 
 
 def load():

@@ -300,3 +300,95 @@ extern "C" int adtfe_planner_export(const adtfe_planner* P, adtfe_event* events,
     if (tile_events && !P->tile_events.empty()) memcpy(tile_events, P->tile_events.data(), P->tile_events.size() * 4);
     return ADTFE_OK;
 }
+
+// The last plan as `n_batches` collated batches laid end to end, written straight into a plan blob (the layout of
+// adtfe_plan_blob_layout) - what RenderPlan.set_batches + PlanBuffers.pack do in Python, without the interpreter:
+// every batch keeps its own width (its longest segment, train_dataset.py:53) and therefore its own frame count
+// max(0, 1 + width / hop - 2 * wpi - 1) (model.py:79,95-97); one render chunk per `chunk_batches` batches.
+extern "C" int adtfe_planner_pack_batches(const adtfe_planner* P, const int32_t* batch_sizes, int32_t n_batches,
+                                          int32_t chunk_batches, int32_t hop, int32_t wpi, void* blob_host,
+                                          size_t blob_capacity, adtfe_plan* shape_out, adtfe_chunk* chunks_out,
+                                          int64_t* batch_width_out, int64_t* batch_frames_out, size_t* blob_bytes_out) {
+    if (!P || !batch_sizes || n_batches <= 0 || hop <= 0 || wpi < 0 || !shape_out || !chunks_out || !blob_bytes_out) {
+        adtfe::set_error("adtfe_planner_pack_batches: bad argument");
+        return ADTFE_ERR_BAD_ARG;
+    }
+    const int32_t n_seg = (int32_t)P->segments.size();
+    int64_t total = 0;
+    for (int32_t b = 0; b < n_batches; ++b) {
+        if (batch_sizes[b] <= 0) {
+            adtfe::set_error("adtfe_planner_pack_batches: batch %d is empty", b);
+            return ADTFE_ERR_BAD_ARG;
+        }
+        total += batch_sizes[b];
+    }
+    if (total != n_seg) {
+        adtfe::set_error("adtfe_planner_pack_batches: batch sizes add up to %lld, the plan has %d segments",
+                         (long long)total, n_seg);
+        return ADTFE_ERR_BAD_ARG;
+    }
+    const int32_t step = std::max(1, chunk_batches);
+    std::vector<adtfe_mel_row> rows((size_t)n_seg);
+    int64_t row0 = 0;
+    int32_t s0 = 0, n_chunks = 0, max_count = 0;
+    // peak work items are ordered by first_event, so a chunk's first item is found by walking forward
+    size_t pw = 0;
+    for (int32_t b = 0; b < n_batches; ++b) {
+        const int32_t s1 = s0 + batch_sizes[b];
+        int64_t width = 0;
+        for (int32_t s = s0; s < s1; ++s) width = std::max<int64_t>(width, P->segments[s].len);
+        const int64_t frames = std::max<int64_t>(0, 1 + width / hop - 2 * (int64_t)wpi - 1);
+        for (int32_t s = s0; s < s1; ++s) {
+            rows[s].out_row = row0 + (int64_t)(s - s0) * frames;
+            rows[s].count = (int32_t)frames;
+            rows[s].reserved = 0;
+        }
+        if (batch_width_out) batch_width_out[b] = width;
+        if (batch_frames_out) batch_frames_out[b] = frames;
+        max_count = std::max<int32_t>(max_count, (int32_t)frames);
+        if (b % step == 0) {
+            const int32_t ev = P->segments[s0].first_event;
+            while (pw < P->peak_work.size() && P->peak_work[pw].first_event < ev) ++pw;
+            chunks_out[n_chunks].seg = s0;
+            chunks_out[n_chunks].event = ev;
+            chunks_out[n_chunks].peak_work = (int32_t)pw;
+            ++n_chunks;
+        }
+        row0 += (int64_t)batch_sizes[b] * frames;
+        s0 = s1;
+    }
+    chunks_out[n_chunks].seg = n_seg;
+    chunks_out[n_chunks].event = (int32_t)P->events.size();
+    chunks_out[n_chunks].peak_work = (int32_t)P->peak_work.size();
+
+    adtfe_plan shape;
+    memset(&shape, 0, sizeof(shape));
+    shape.n_events = (int32_t)P->events.size();
+    shape.n_seg = n_seg;
+    shape.tiles_per_seg = P->tiles_per_seg;
+    shape.n_peak_work = (int32_t)P->peak_work.size();
+    shape.ld_wav = P->ld_wav;
+    shape.mel_total_rows = row0;
+    shape.mel_max_count = max_count;
+    shape.n_chunks = n_chunks;
+    shape.chunks_host = chunks_out;
+    size_t off[6], fixed = 0;
+    int rc = adtfe_plan_blob_layout(&shape, off, &fixed);
+    if (rc != ADTFE_OK) return rc;
+    // mel_total_rows == 0 (every batch too short for a frame) drops the rows section: the ragged form needs rows
+    const size_t need = (fixed + 4 * P->tile_events.size() + 15) & ~(size_t)15;
+    *blob_bytes_out = need;
+    *shape_out = shape;
+    if (!blob_host || blob_capacity < need) {
+        adtfe::set_error("adtfe_planner_pack_batches: blob of %zu B needed, %zu B given", need, blob_capacity);
+        return ADTFE_ERR_WORKSPACE;
+    }
+    char* h = (char*)blob_host;
+    if (!P->events.empty()) memcpy(h + off[0], P->events.data(), P->events.size() * sizeof(adtfe_event));
+    if (n_seg) memcpy(h + off[1], P->segments.data(), (size_t)n_seg * sizeof(adtfe_segment));
+    memcpy(h + off[2], P->tile_ptr.data(), P->tile_ptr.size() * 4);
+    if (!P->peak_work.empty()) memcpy(h + off[3], P->peak_work.data(), P->peak_work.size() * sizeof(adtfe_peak_item));
+    if (row0 > 0) memcpy(h + off[4], rows.data(), rows.size() * sizeof(adtfe_mel_row));
+    if (!P->tile_events.empty()) memcpy(h + off[5], P->tile_events.data(), P->tile_events.size() * 4);
+    return ADTFE_OK;
+}

@@ -21,6 +21,17 @@ from .planner import EVENT_DTYPE, PEAK_ITEM_DTYPE, SEGMENT_DTYPE, RenderPlan, pl
 _ERRORS = {1: ValueError, 2: IndexError, 3: KeyError, 4: NotImplementedError}
 
 
+class PackedGroup:
+    """What the pipeline keeps of a group planned and packed natively (``NativePlanner.plan_group_into``): the
+    geometry ``FrontEnd.run_plan_host`` and ``GroupResult`` read - the records themselves are in the pinned blob."""
+    mel_rows = True   # ragged log-mel rows are part of the blob
+
+    def __init__(self, n_seg, ld_wav, mel_total_rows, wave_lengths, batch_ptr, batch_samples, batch_frames, n_events):
+        self.n_seg, self.ld_wav, self.mel_total_rows = n_seg, ld_wav, mel_total_rows
+        self.wave_lengths, self.batch_ptr = wave_lengths, batch_ptr
+        self.batch_samples, self.batch_frames, self.n_events = batch_samples, batch_frames, n_events
+
+
 class NativePlanner:
     def __init__(self, config: SynthDrumConfig, bank: OneShotBank):
         self.config, self.bank = config, bank
@@ -110,3 +121,71 @@ class NativePlanner:
                                                  peak_work.ctypes.data, tile_events.ctypes.data), "adtfe_planner_export")
         return RenderPlan(n_seg, ld, tps, segments, events, mix_len, group_ptr, tile_ptr, tile_events, peak_work,
                           segments["len"].astype(np.int64))
+
+    # ---- a whole group of batches planned and packed into a pinned blob without the interpreter in between
+    def plan_group(self, group: Sequence[Sequence], mt_state: np.ndarray) -> Optional[np.ndarray]:
+        """Plan all segments of ``group`` (batches of float32 (N, 4) note arrays) with the MT19937 state
+        ``mt_state`` (uint32[625], advanced in place - the caller's private stream).  The plan stays inside the
+        native planner until ``pack_group``.  Returns the counts of ``adtfe_planner_plan``, or None when the notes
+        are not plain float32 arrays (the caller then takes the general path; the state is untouched)."""
+        flat = [n for b in group for n in b]
+        for a in flat:
+            if type(a) is not np.ndarray or a.dtype != np.float32 or a.ndim != 2 or a.shape[1] != 4:
+                return None
+        n_seg = len(flat)
+        if n_seg == 0 or any(len(b) == 0 for b in group):
+            return None
+        counts = np.fromiter(map(len, flat), np.int32, n_seg)
+        notes = np.concatenate(flat) if n_seg > 1 else np.ascontiguousarray(flat[0])
+        out = np.zeros(8, np.int64)
+        info = np.zeros(2, np.int32)
+        rc = self.lib.adtfe_planner_plan(self.handle, notes.ctypes.data, counts.ctypes.data, n_seg,
+                                         mt_state.ctypes.data, 0, out.ctypes.data, info.ctypes.data)
+        if rc > 0:
+            seg, note = int(info[0]), int(info[1])
+            raise _ERRORS[rc](f"Invalid note: {flat[seg][note]}" if rc == 1 and note >= 0 else
+                              f"segment {seg} note {note} (planner status {rc})")
+        _lib.check(rc, "adtfe_planner_plan")
+        return out
+
+    def pack_group(self, sizes: Sequence[int], hop: int, wpi: int, chunk_batches: int, host_ptr: int, capacity: int):
+        """The plan of the last ``plan_group`` as ``len(sizes)`` collated batches, written into the blob at
+        ``host_ptr`` (``adtfe_planner_pack_batches``).  Returns ``(status, shape, bytes needed, chunks, width, frames)``;
+        status -3 = the blob is too small (nothing written)."""
+        sizes = np.ascontiguousarray(sizes, np.int32)
+        nb = len(sizes)
+        chunks = np.zeros((nb + 1) * 3, np.int32)
+        width, frames = np.zeros(nb, np.int64), np.zeros(nb, np.int64)
+        shape = _lib.Plan()
+        need = C.c_size_t()
+        rc = self.lib.adtfe_planner_pack_batches(self.handle, sizes.ctypes.data, nb, int(chunk_batches), int(hop),
+                                                 int(wpi), host_ptr, capacity, C.byref(shape), chunks.ctypes.data,
+                                                 width.ctypes.data, frames.ctypes.data, C.byref(need))
+        if rc not in (0, -3):
+            _lib.check(rc, "adtfe_planner_pack_batches")
+        return rc, shape, need.value, chunks, width, frames
+
+    def plan_group_into(self, group: Sequence[Sequence], mt_state: np.ndarray, acquire, hop: int, wpi: int,
+                        chunk_batches: int = 1) -> Optional[PackedGroup]:
+        """``plan_group``, then ``buf = acquire()`` (the ``PlanBuffers`` whose pinned blob receives the plan - the
+        caller may block there until a buffer set is free), then ``pack_group`` into it."""
+        out = self.plan_group(group, mt_state)
+        if out is None:
+            return None
+        buf = acquire()
+        sizes = np.fromiter(map(len, group), np.int32, len(group))
+        rc, shape, need, chunks, width, frames = self.pack_group(sizes, hop, wpi, chunk_batches, buf.host.data_ptr(),
+                                                                 buf.host.numel())
+        if rc == -3:   # ADTFE_ERR_WORKSPACE: grow the pinned blob and pack again
+            buf.reserve(need)
+            rc, shape, need, chunks, width, frames = self.pack_group(sizes, hop, wpi, chunk_batches,
+                                                                     buf.host.data_ptr(), buf.host.numel())
+        _lib.check(rc, "adtfe_planner_pack_batches")
+        buf.adopt(shape, need, chunks)
+        n_seg = int(out[2])
+        o = buf.offsets[1]
+        seg = np.frombuffer(buf.host.numpy()[o: o + SEGMENT_DTYPE.itemsize * n_seg].tobytes(), SEGMENT_DTYPE)
+        ptr = np.zeros(len(sizes) + 1, np.int64)
+        np.cumsum(sizes, out=ptr[1:])
+        return PackedGroup(n_seg, int(out[6]), int(shape.mel_total_rows), seg["len"].astype(np.int64), ptr, width,
+                           frames, int(out[0]))

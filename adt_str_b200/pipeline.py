@@ -95,19 +95,34 @@ class HostPipeline:
             with self._lock:
                 wid = self._next_worker
                 self._next_worker += 1
-            st = self._local.st = dict(rng=random.Random(self._seed * 1_000_003 + wid),
-                                       planner=NativePlanner(self.fe.synth.config, self.fe.synth.bank))
+            rng = random.Random(self._seed * 1_000_003 + wid)
+            st = self._local.st = dict(rng=rng, planner=NativePlanner(self.fe.synth.config, self.fe.synth.bank),
+                                       mt=np.array(rng.getstate()[1], np.uint32))   # the same stream, kept native
         return st
 
     def _plan(self, group: Sequence[Sequence], s: _Set):
         st = self._worker_state()
+
+        def acquire():
+            s.free.wait()          # the consumer released the set ...
+            s.free.clear()
+            s.done.synchronize()   # ... and the GPU has left it
+            return s.buf
+
+        # fast path: plan, wait for the buffer set, pack - two library calls, no interpreter work per note or record
+        spec = self.fe.mel.compute_spec
+        plan = st["planner"].plan_group_into(group, st["mt"], acquire, spec.hop_length, self.fe.mel.window_pad_idxs,
+                                             self.chunk_batches)
+        if plan is not None:
+            return plan, s.buf.shape
+        # general path (python lists, float64 notes ...): the worker's random.Random continues the native stream
+        version, _, gauss = st["rng"].getstate()
+        st["rng"].setstate((version, tuple(int(v) for v in st["mt"]), gauss))
         flat = [notes for b in group for notes in b]
         plan = st["planner"].plan_batch(flat, st["rng"]).set_batches([len(b) for b in group], self.fe.mel.n_frames,
                                                                      self.chunk_batches)
-        s.free.wait()          # the consumer released the set ...
-        s.free.clear()
-        s.done.synchronize()   # ... and the GPU has left it
-        shape = s.buf.pack(plan)
+        st["mt"][:] = np.array(st["rng"].getstate()[1], np.uint32)
+        shape = acquire().pack(plan)
         return plan, shape
 
     # ---- main thread: enqueue in order

@@ -86,6 +86,30 @@ class PlanBuffers:
         self.shape = shape
         return shape
 
+    def reserve(self, nbytes: int) -> None:
+        """Pinned and device blobs of at least ``nbytes`` (contents are not kept)."""
+        if self.host.numel() < nbytes:
+            cap = max(int(nbytes), 2 * self.host.numel(), 1 << 16)
+            self.host = torch.empty(cap, dtype=torch.uint8).pin_memory()
+            with torch.cuda.device(self.device):
+                self.dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
+
+    def adopt(self, shape: _lib.Plan, nbytes: int, chunks: np.ndarray) -> None:
+        """Take over a blob written in place by ``adtfe_planner_pack_batches`` (``shape`` as it returned it;
+        ``chunks``: the int32 array behind ``shape.chunks_host``, kept alive here)."""
+        lib = _lib.load()
+        self._chunks = chunks
+        off = (C.c_size_t * 6)()
+        fixed = C.c_size_t()
+        _lib.check(lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(fixed)), "adtfe_plan_blob_layout")
+        self.nbytes = int(nbytes)
+        need = lib.adtfe_render_workspace_bytes(shape.n_events, shape.n_seg, shape.tiles_per_seg)
+        if self.workspace.numel() < need:
+            with torch.cuda.device(self.device):
+                self.workspace = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=self.device)
+        self.offsets = [int(o) for o in off]
+        self.shape = shape
+
     def upload(self, shape: _lib.Plan) -> _lib.Plan:
         """H2D of the packed blob on the current stream; returns the plan with device pointers."""
         self.dev[: self.nbytes].copy_(self.host[: self.nbytes], non_blocking=True)

@@ -57,9 +57,11 @@ def parse_args():
     p.add_argument("--e2e-steps", type=int, default=2)
     p.add_argument("--cpu-segments", type=int, default=0, help="cpu_baseline sample size (0 = auto)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-long-form", action="store_true", help="skip the long-form inference front side measurement")
     p.add_argument("--e2e-group", type=int, default=8, help="batches per end-to-end plan")
     p.add_argument("--e2e-workers", type=int, default=0,
                    help="planner threads of the end-to-end pipeline (0 = host cores / ranks, at most 8)")
+    p.add_argument("--e2e-sets", type=int, default=6, help="rotating buffer sets of the end-to-end pipeline")
     p.add_argument("--chunk-batches", type=int, default=4, help="batches rendered together as one chunk")
     return p.parse_args()
 
@@ -205,6 +207,11 @@ def run_reference(args):
 # --------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     rank, world, local = dist_env()
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner under some
+    # NCCL_DEBUG settings) goes to stderr instead, the line itself to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     from adt_str_b200.config import SETTING_1, setting_1
     from adt_str_b200.synthetic import make_bank, make_segments
 
@@ -319,7 +326,7 @@ def run_b200(args):
     groups = [batches[i:i + group] for i in range(0, n_batches, group)]
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     args.e2e_workers = args.e2e_workers or max(1, min(8, cores // max(1, world)))
-    pipe = HostPipeline(fe, workers=args.e2e_workers, n_sets=4, seed=99 + rank, chunk_batches=args.chunk_batches)
+    pipe = HostPipeline(fe, workers=args.e2e_workers, n_sets=args.e2e_sets, seed=99 + rank, chunk_batches=args.chunk_batches)
     h2d = d2h = 0
     e2e_checksum = 0.0
 
@@ -347,6 +354,16 @@ def run_b200(args):
     e2e_ms = 1e3 * (time.perf_counter() - t0) / max(1, args.e2e_steps)
     clocks = sampler.stop() if sampler else None
     pipe.close()
+
+    # ---- BASELINE configs[4] beside the headline: the long-form inference front (tools/bench_longform.py)
+    long_form = None
+    if rank == 0 and world == 1 and not args.no_long_form:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_longform
+            long_form = bench_longform.measure(dev, 600.0, cpu_seconds=0.0 if args.no_cpu_baseline else 600.0)
+        except Exception as exc:  # never lose the headline line to the side measurement
+            long_form = {"error": repr(exc)}
 
     # ---- reduce over ranks: units add, time is the max
     from adt_str_b200.sharding import reduce_stats
@@ -383,7 +400,7 @@ def run_b200(args):
         "e2e": {"value": total_audio_e2e / (max_e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": max(1, args.e2e_steps),
                 "includes": f"host planning of note lists ({args.e2e_workers} planner threads), plan blob H2D, kernels, "
-                            f"log-mel D2H into pinned host memory; groups of {group} batches, 4 buffer sets"},
+                            f"log-mel D2H into pinned host memory; groups of {group} batches, {args.e2e_sets} buffer sets"},
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": "logmel6_kernel", "achieved": logmel_gbs, "peak": peak, "unit": "GB/s",
                      "frac": logmel_gbs / peak, "traffic": traffic,
@@ -395,8 +412,10 @@ def run_b200(args):
                      "path": {"bytes_alg_per_step": total_bytes / world, "achieved": path_gbs, "frac": path_gbs / peak,
                               "frac_of_nominal_8TBs": path_gbs / 8000.0}},
         "cpu_baseline": cpu,
+        "long_form": long_form,
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0

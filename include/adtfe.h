@@ -245,6 +245,19 @@ int adtfe_planner_plan(adtfe_planner* planner, const float* notes, const int32_t
 int adtfe_planner_export(const adtfe_planner* planner, adtfe_event* events, int32_t* mix_len, int32_t* group_ptr,
                          adtfe_segment* segments, int32_t* tile_ptr, adtfe_peak_item* peak_work, int32_t* tile_events);
 
+/* The last plan as n_batches collated batches laid end to end (batch_sizes[b] segments each), written straight into
+ * a plan blob for adtfe_frontend_host - RenderPlan.set_batches + PlanBuffers.pack of the Python host without the
+ * interpreter.  Every batch keeps its own width (its longest segment: collate_fn, train_dataset.py:53) and frame
+ * count max(0, 1 + width / hop - 2 * wpi - 1) (model.py:79,95-97); one render chunk per chunk_batches batches.
+ * shape_out: counts, ld_wav, mel_* and chunk fields filled (device pointers NULL; chunks_host = chunks_out, which
+ * must hold n_batches + 1 records and stay alive while the shape is used).  batch_width_out / batch_frames_out:
+ * n_batches values each (may be NULL).  *blob_bytes_out = bytes the blob takes; with blob_host NULL or
+ * blob_capacity too small nothing is written and ADTFE_ERR_WORKSPACE is returned (size query). */
+int adtfe_planner_pack_batches(const adtfe_planner* planner, const int32_t* batch_sizes, int32_t n_batches,
+                               int32_t chunk_batches, int32_t hop, int32_t wpi, void* blob_host, size_t blob_capacity,
+                               adtfe_plan* shape_out, adtfe_chunk* chunks_out, int64_t* batch_width_out,
+                               int64_t* batch_frames_out, size_t* blob_bytes_out);
+
 #ifdef __cplusplus
 }
 #endif

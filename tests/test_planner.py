@@ -276,3 +276,55 @@ def test_batches_in_one_plan_match_plans_one_by_one():
     assert tuple(big.chunks[-1]) == (14, big.n_events, len(big.peak_work)) and big.mel_total_rows == r0
     with pytest.raises(ValueError):
         big.set_batches([7, 6], mel.n_frames)
+
+
+def test_native_group_pack_equals_python_set_batches_and_pack():
+    """adtfe_planner_pack_batches (plan -> plan blob without the interpreter) writes byte for byte what
+    RenderPlan.set_batches + the blob layout give for the same RNG stream; the MT19937 state it advances in place is
+    the state random.Random ends in."""
+    import ctypes as C
+    import random
+    from adt_str_b200 import _lib
+    from adt_str_b200.config import setting_1
+    from adt_str_b200.mel import ComputeMelSpectrogram
+    from adt_str_b200.native_planner import NativePlanner
+    from adt_str_b200.planner import CHUNK_DTYPE
+    from adt_str_b200.synthetic import make_bank, make_segments
+    bank = make_bank(390, 24000, seed=31)
+    segs = make_segments(70, seed=32, empty_fraction=0.1)
+    cuts = [0, 9, 10, 26, 33, 41, 58, 70]
+    group = [segs[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    mel = ComputeMelSpectrogram(24000, 2048, 0.01, 128)
+    planner = NativePlanner(setting_1(), bank)
+    lib = _lib.load()
+    for chunk_batches in (1, 2, 3, 100):
+        rng = random.Random(555)
+        want = planner.plan_batch([n for b in group for n in b], rng).set_batches([len(b) for b in group], mel.n_frames,
+                                                                                 chunk_batches)
+        mt = np.array(random.Random(555).getstate()[1], np.uint32)
+        counts = planner.plan_group(group, mt)
+        assert tuple(mt.tolist()) == rng.getstate()[1]
+        assert int(counts[0]) == want.n_events and int(counts[6]) == want.ld_wav
+        rc, shape, need, chunks, width, frames = planner.pack_group([len(b) for b in group], 240, mel.window_pad_idxs,
+                                                                    chunk_batches, None, 0)
+        assert rc == -3 and need > 0                               # size query
+        blob = np.full(need + 64, 0xAB, np.uint8)
+        rc, shape, need2, chunks, width, frames = planner.pack_group([len(b) for b in group], 240,
+                                                                     mel.window_pad_idxs, chunk_batches,
+                                                                     blob.ctypes.data, blob.size)
+        assert rc == 0 and need2 == need
+        assert width.tolist() == want.batch_samples.tolist() and frames.tolist() == want.batch_frames.tolist()
+        assert shape.mel_total_rows == want.mel_total_rows and shape.mel_max_count == int(want.batch_frames.max())
+        assert shape.n_chunks == len(want.chunks) - 1
+        assert chunks.view(CHUNK_DTYPE)[: shape.n_chunks + 1].tolist() == want.chunks.tolist()
+        off = (C.c_size_t * 6)()
+        fixed = C.c_size_t()
+        assert lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(fixed)) == 0
+        for o, arr in zip(off, (want.events, want.segments, want.tile_ptr, want.peak_work, want.mel_rows,
+                                want.tile_events)):
+            raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+            assert np.array_equal(blob[o: o + raw.size], raw)
+        assert (blob[need:] == 0xAB).all()                         # nothing written past the blob
+    assert planner.plan_group([[np.zeros((1, 4), np.float64)]], mt) is None      # not float32: general path
+    with pytest.raises(ValueError):
+        planner.plan_group([[np.array([[0.5, 0.4, 36.0, 100.0]], np.float32)]], mt)   # offset < onset
