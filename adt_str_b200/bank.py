@@ -74,14 +74,14 @@ class OneShotBank:
         except ImportError as e:  # pragma: no cover - h5py absent here
             raise ImportError("h5py is required to convert an HDF5 one-shot bank") from e
         nested: Dict[str, Dict[str, Dict[str, np.ndarray]]] = {}
-        with h5py.File(path, "r") as f:  # pragma: no cover
+        with h5py.File(path, "r") as f:
             for pitch in f.keys():
                 if pitch == "index":
                     continue
                 for group in f[pitch].keys():
                     for name in f[pitch][group].keys():
                         nested.setdefault(pitch, {}).setdefault(group, {})[name] = f[pitch][group][name][...]
-        return cls.from_nested(nested)  # pragma: no cover
+        return cls.from_nested(nested)
 
     # ------------------------------------------------------------------- io
     def save(self, path: str) -> None:

@@ -32,8 +32,10 @@ namespace adtfe {
 constexpr int kPeakThreads = ADTFE_PEAK_THREADS;
 constexpr int kPeakChunk = 8;   // notes of one instrument handled per sweep over the one-shots
 constexpr int kPeakSpan = ADTFE_PEAK_SPAN;  // samples of the mixed one-shot per peak work item
-constexpr int kPeakIters = kPeakSpan / 4 / kPeakThreads;  // float4 per thread per one-shot
-static_assert(kPeakIters * kPeakThreads * 4 == kPeakSpan, "peak span must be a multiple of 4 * threads");
+constexpr int kPeakIters = 8;                                 // float4 per thread per one-shot
+constexpr int kPeakCtaSpan = kPeakIters * 4 * kPeakThreads;   // samples of the mixed one-shot scanned by one CTA
+constexpr int kPeakSplit = kPeakSpan / kPeakCtaSpan;          // CTAs per work item (1 at 128 threads, 2 at 64)
+static_assert(kPeakSplit >= 1 && kPeakSplit * kPeakCtaSpan == kPeakSpan, "peak span must be a multiple of 32 * threads");
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -91,7 +93,8 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
     ResolvedEvent* __restrict__ resolved, int* __restrict__ peak_bits) {
     __shared__ unsigned s_peak[kPeakChunk];
     __shared__ float s_ca[kPeakChunk], s_cb[kPeakChunk];
-    const adtfe_peak_item item = work[blockIdx.x];  // one fetch, then the data loads can start
+    const adtfe_peak_item item = work[blockIdx.x / kPeakSplit];  // one fetch, then the data loads can start
+    const int sub = blockIdx.x % kPeakSplit;                     // which part of the item's span this CTA scans
     const int chunk = item.chunk, tid = threadIdx.x;
     const int e0 = item.first_event, e1 = e0 + item.n_events;
     if (e0 >= e1) return;
@@ -99,14 +102,15 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
     const int la = item.la, lb = item.lb, n = item.mix_len;
     // every one-shot is padded to 4 floats, so whole float4s up to the padded length are readable
     const int la4 = (la + 3) >> 2, lb4 = (lb + 3) >> 2;
-    const int lo4 = chunk * (kPeakSpan / 4), hi4 = min((n + 3) >> 2, lo4 + kPeakSpan / 4);
+    const int lo4 = chunk * (kPeakSpan / 4) + sub * (kPeakCtaSpan / 4), hi4 = min((n + 3) >> 2, lo4 + kPeakCtaSpan / 4);
+    if (lo4 >= hi4 && !(chunk == 0 && sub == 0)) return;  // this part lies past the end of the mixed one-shot
     const float4* a4 = reinterpret_cast<const float4*>(pcm + a_off);
     const float4* b4 = reinterpret_cast<const float4*>(pcm + b_off);
 
     float4 va[kPeakIters], vb[kPeakIters];
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     // interior chunks (both one-shots reach past the chunk) need neither load predicates nor tail masks
-    const bool interior = lo4 + kPeakSpan / 4 <= (la >> 2) && lo4 + kPeakSpan / 4 <= (lb >> 2);
+    const bool interior = lo4 + kPeakCtaSpan / 4 <= (la >> 2) && lo4 + kPeakCtaSpan / 4 <= (lb >> 2);
     if (interior) {
 #pragma unroll
         for (int it = 0; it < kPeakIters; ++it) {
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
             vb[it] = (i4 < hi4 && i4 < lb4) ? __ldg(b4 + i4) : z;
         }
     }
-    if (chunk == 0) {  // resolve the bank lookups once per note for the tile mixer
+    if (chunk == 0 && sub == 0) {  // resolve the bank lookups once per note for the tile mixer
         for (int e = e0 + tid; e < e1; e += kPeakThreads) {
             const adtfe_event ev = events[e];
             ResolvedEvent r;
@@ -417,7 +421,10 @@ __global__ void __launch_bounds__(kMixThreads, kMixCtasPerSm) mix_kernel(const M
 // Row normalisation (wav / peak * max_volume, synthetiser.py:142-144,156): one CTA per tile; the
 // segment peak is the max of its tile maxima.  An all-zero mix gives NaN (the reference's 0/0),
 // samples beyond the segment's length stay exact zeros (collate_fn pads with 0.0).
-constexpr int kNormThreads = 256;
+#ifndef ADTFE_NORM_THREADS
+#define ADTFE_NORM_THREADS 256
+#endif
+constexpr int kNormThreads = ADTFE_NORM_THREADS;
 __global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_segment* __restrict__ segments,
                                                                  const float* __restrict__ tile_max, int tiles_per_seg,
                                                                  int64_t ld_wav, float* __restrict__ wav) {
@@ -535,7 +542,7 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
         const int pw0 = ch[c].peak_work, n_pw = ch[c + 1].peak_work - pw0;
         if (n_pw > 0) {
             trace_open("peak", c, st);
-            peak_kernel<<<n_pw, kPeakThreads, 0, st>>>(bank->pcm, plan->events_dev, plan->peak_work_dev + pw0, resolved,
+            peak_kernel<<<n_pw * kPeakSplit, kPeakThreads, 0, st>>>(bank->pcm, plan->events_dev, plan->peak_work_dev + pw0, resolved,
                                                       peak_bits);
             trace_close(st);
             ADTFE_CUDA(cudaGetLastError());

@@ -166,8 +166,44 @@ def make_audio_front():
     np.savez_compressed(os.path.join(OUT, "audio_front.npz"), **out)
 
 
+def make_tokens():
+    """tests/golden/tokens.npz: the reference's MidiTokenizer + collate_fn (token half) on seeded segments."""
+    tok, collate = ref_harness.import_tokenizer()
+    segs = make_segments(24, seed=91, empty_fraction=0.15)
+    out = {"notes": np.concatenate([s.reshape(-1, 4) for s in segs]).astype(np.float32),
+           "notes_count": np.array([len(s) for s in segs])}
+    for adtof in (False, True):
+        for vel in (False, True):
+            t = tok.MidiTokenizer(tok.MidiTokenizerConfig(adtof, 1, 2, 0, 3, vel))
+            toks = []
+            for s in segs:
+                if len(s) == 0:
+                    toks.append(t.empty_adt_tokens())
+                    continue
+                notes = t.map_notes_to_Gm_custom(torch.from_numpy(s.copy()))
+                toks.append(t.notes_to_adt_tokens(notes))
+            key = f"adtof{int(adtof)}_vel{int(vel)}"
+            out[f"{key}/tokens"] = torch.cat([x.double() for x in toks]).numpy()
+            out[f"{key}/count"] = np.array([len(x) for x in toks])
+            out[f"{key}/float"] = np.array([x.is_floating_point() for x in toks])
+            dec = [t.decode(x.numpy()) for x in toks]
+            out[f"{key}/decoded"] = np.concatenate([d.numpy().reshape(-1, 4) for d in dec]).astype(np.float64)
+            out[f"{key}/decoded_count"] = np.array([len(d) for d in dec])
+            if collate is not None:
+                c = collate([(torch.zeros(4), x.tolist()) for x in toks])
+                out[f"{key}/collated"] = c["tokens"].numpy()
+                out[f"{key}/collated_lengths"] = c["token_lengths"].numpy()
+    np.savez_compressed(os.path.join(OUT, "tokens.npz"), **out)
+    print("tokens: 24 segments x 4 tokenizer configurations")
+
+
 if __name__ == "__main__":
     import sys
-    if "--audio-front-only" not in sys.argv:
+    if "--audio-front-only" in sys.argv:
+        make_audio_front()
+    elif "--tokens-only" in sys.argv:
+        make_tokens()
+    else:
         main()
-    make_audio_front()
+        make_audio_front()
+        make_tokens()

@@ -140,3 +140,21 @@ def import_audio_front():
     audio_utils = importlib.import_module("utils.audio_utils")
     inference = importlib.import_module("inference")
     return audio_utils, inference
+
+
+def import_tokenizer():
+    """The reference's ``modules.midi_tokenizer`` module and ``data_modules.train_dataset.collate_fn``, unmodified
+    (``collate_fn`` is None when the dataset module cannot be imported here)."""
+    import importlib
+    _import_reference()
+    tok = importlib.import_module("modules.midi_tokenizer")
+    try:
+        import_audio_front()    # stand-ins for the uninstalled packages the dataset module pulls in
+        argv, sys.argv = sys.argv, ["train_dataset", "unused.yaml"]   # the module parses argv at import (:232-234)
+        try:
+            collate = importlib.import_module("data_modules.train_dataset").collate_fn
+        finally:
+            sys.argv = argv
+    except Exception:
+        collate = None
+    return tok, collate

@@ -328,3 +328,23 @@ def test_native_group_pack_equals_python_set_batches_and_pack():
     assert planner.plan_group([[np.zeros((1, 4), np.float64)]], mt) is None      # not float32: general path
     with pytest.raises(ValueError):
         planner.plan_group([[np.array([[0.5, 0.4, 36.0, 100.0]], np.float32)]], mt)   # offset < onset
+
+
+def test_bank_from_hdf5_walks_the_reference_layout():
+    """OneShotBank.from_hdf5 over the layout convert_augmented_to_hdf5.py:70-138 writes (<pitch>/<bin>/<name>
+    datasets plus a flat `index` group), through the dict-backed h5py stand-in of the oracle harness (h5py itself is
+    not installed in this image): the index group is skipped, names come out sorted like h5py's keys()."""
+    from oracle import ref_harness
+    ref_harness._install_shims()
+    rng = np.random.default_rng(3)
+    nested = {"36": {"gold": {"kick_b": rng.standard_normal(50).astype(np.float32),
+                              "kick_a": rng.standard_normal(33).astype(np.float32)},
+                     "100-90": {"k": rng.standard_normal(7).astype(np.float32)}},
+              "42": {"90-80": {"hat": rng.standard_normal(19).astype(np.float32)}}}
+    on_disk = dict(nested, index={"paths": np.zeros(4, np.float32), "labels": np.zeros(4, np.float32)})
+    ref_harness._BANKS["layout_test@24000.hdf5"] = on_disk
+    bank = OneShotBank.from_hdf5("layout_test@24000.hdf5")
+    want = OneShotBank.from_nested(nested)
+    assert bank.names == want.names == ["36/100-90/k", "36/gold/kick_a", "36/gold/kick_b", "42/90-80/hat"]
+    assert np.array_equal(bank.pcm, want.pcm) and bank.index == want.index
+    assert np.array_equal(bank.oneshot(1), nested["36"]["gold"]["kick_a"])
