@@ -11,9 +11,8 @@
 // torchaudio's algorithm (functional._apply_sinc_resample_kernel): with o = orig/gcd, n = new/gcd, K = 2*width + o,
 //   y[j*n + p] = sum_{k<K} xpad[j*o + k] * kernel[p][k],   xpad = `width` zeros, x, `width + o` zeros,
 // truncated to ceil(n * len / o) samples: a strided conv1d.  Here one CTA stages the input span of a tile of
-// groups j in shared memory; a thread owns one phase p and kResampleJ consecutive groups, so a kernel tap is
-// loaded once (table transposed to [k][p]: coalesced over p, L1-resident) for kResampleJ FMAs whose inputs are
-// warp-wide broadcasts from shared memory.  Taps are accumulated in ascending k in float32 FMAs.
+// groups j (and, when it fits, the filter bank) in shared memory; a thread owns a 4 x 4 register tile of groups x
+// phases.  Every output is one chain of float32 FMAs over ascending k.
 #include <algorithm>
 #include <vector>
 
@@ -25,59 +24,110 @@ struct adtfe_resampler {
     int32_t width = 0, taps = 0;
     float* table = nullptr;     // [taps][neu]: kernel[p][k] transposed
     int32_t groups_per_tile = 1;
+    int32_t phase_stride = 1;   // ceil(neu / kResampleP): a thread's phases are p0, p0 + stride, ...
+    bool table_in_smem = false;
     size_t smem_bytes = 0;
 };
 
 namespace adtfe {
 
 constexpr int kResampleThreads = 256;
-constexpr int kResampleJ = 4;           // groups per thread
-constexpr int kResampleTileOut = 4096;  // outputs per tile, about
-constexpr int kResampleSpanMax = 24576; // floats of input staged per tile (96 KB)
+constexpr int kResampleJ = 4;            // groups per thread
+constexpr int kResampleP = 4;            // phases per thread
+constexpr int kResampleSpanMax = 24576;  // floats of input staged per tile (96 KB)
+constexpr size_t kResampleSmemMax = 200 * 1024;
 
-// grid (tiles, rows).  absmax_bits (optional): atomicMax of the float bits of |y| - non-negative floats order like
-// integers and NaN's bits are above every number's, so a NaN wins, as in torch.max.
+// grid (tiles, rows).  A thread owns kResampleJ consecutive groups x kResampleP phases (p0, p0 + ps, p0 + 2 ps, ...):
+// per tap kResampleP table values (lanes hold consecutive phases: conflict-free rows of the [k][p] table) and
+// kResampleJ input samples (the same address across a warp: broadcasts) feed 16 FMAs, so the shared-memory pipe sees
+// 0.5-0.75 wavefronts per warp FMA instead of the 1.25 of one load pair per FMA.  kTableInSmem: the filter bank is
+// staged behind the input span (it fits for the usual rate pairs; 44.1 -> 16 kHz has 304 KB and stays in L1/L2).
+// absmax_bits (optional): atomicMax of the float bits of |y| - non-negative floats order like integers and NaN's
+// bits are above every number's, so a NaN wins, as in torch.max.
+template <bool kTableInSmem>
 __global__ void __launch_bounds__(kResampleThreads) resample_kernel(
     const float* __restrict__ x, int64_t ld_in, int64_t n_in, float* __restrict__ y, int64_t ld_out, int64_t n_out,
-    const float* __restrict__ table, int orig, int neu, int width, int taps, int groups_per_tile,
-    int* __restrict__ absmax_bits) {
+    const float* __restrict__ table, int orig, int neu, int width, int taps, int groups_per_tile, int phase_stride,
+    int64_t n_tiles, int* __restrict__ absmax_bits) {
     extern __shared__ __align__(16) float xs[];
     const int tid = threadIdx.x;
-    const int64_t j0 = (int64_t)blockIdx.x * groups_per_tile;
     const float* xr = x + (int64_t)blockIdx.y * ld_in;
     float* yr = y + (int64_t)blockIdx.y * ld_out;
     const int span = (groups_per_tile - 1) * orig + taps;
-    const int64_t first = j0 * orig - width;  // x index of xs[0]
-    for (int i = tid; i < span; i += kResampleThreads) {
-        const int64_t g = first + i;
-        xs[i] = (g >= 0 && g < n_in) ? __ldg(xr + g) : 0.0f;
+    const float* tbl = table;
+    if (kTableInSmem) {  // staged once: the CTA is persistent over its tiles
+        float* ts = xs + ((span + 3) & ~3);
+        for (int i = tid; i < taps * neu; i += kResampleThreads) ts[i] = __ldg(table + i);
+        tbl = ts;
     }
-    __syncthreads();
     const int quads = groups_per_tile / kResampleJ;
     float m = 0.0f;
     bool nan = false;
-    for (int w = tid; w < quads * neu; w += kResampleThreads) {
-        const int jq = w / neu, p = w - jq * neu;
-        const float* xa = xs + jq * kResampleJ * orig;
-        const float* tp = table + p;
-        float acc[kResampleJ];
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t j0 = tile * groups_per_tile;
+    const int64_t first = j0 * orig - width;  // x index of xs[0]
+    __syncthreads();                          // the previous tile's span is no longer read
+    for (int base = 0; base < span; base += 8 * kResampleThreads) {  // eight loads in flight per thread
+        float v[8];
 #pragma unroll
-        for (int r = 0; r < kResampleJ; ++r) acc[r] = 0.0f;
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * kResampleThreads + tid;
+            const int64_t g = first + i;
+            v[u] = (i < span && g >= 0 && g < n_in) ? __ldg(xr + g) : 0.0f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * kResampleThreads + tid;
+            if (i < span) xs[i] = v[u];
+        }
+    }
+    __syncthreads();
+    for (int w = tid; w < quads * phase_stride; w += kResampleThreads) {
+        const int jq = w / phase_stride, p0 = w - jq * phase_stride;
+        const float* xa = xs + jq * kResampleJ * orig;
+        int pi[kResampleP];   // phases past the last one read (and discard) phase p0
+#pragma unroll
+        for (int q = 0; q < kResampleP; ++q) pi[q] = p0 + q * phase_stride < neu ? p0 + q * phase_stride : p0;
+        float acc[kResampleJ][kResampleP];
+#pragma unroll
+        for (int r = 0; r < kResampleJ; ++r)
+#pragma unroll
+            for (int q = 0; q < kResampleP; ++q) acc[r][q] = 0.0f;
+        // one pointer per table column and per input row, bumped per tap: no index arithmetic in the loop
+        const float* tp[kResampleP];
+        const float* xp[kResampleJ];
+#pragma unroll
+        for (int q = 0; q < kResampleP; ++q) tp[q] = tbl + pi[q];
+#pragma unroll
+        for (int r = 0; r < kResampleJ; ++r) xp[r] = xa + r * orig;
 #pragma unroll 4
         for (int k = 0; k < taps; ++k) {
-            const float t = __ldg(tp + (size_t)k * neu);
+            float t[kResampleP], v[kResampleJ];
 #pragma unroll
-            for (int r = 0; r < kResampleJ; ++r) acc[r] = fmaf(xa[r * orig + k], t, acc[r]);
-        }
-#pragma unroll
-        for (int r = 0; r < kResampleJ; ++r) {
-            const int64_t o = (j0 + jq * kResampleJ + r) * neu + p;
-            if (o < n_out) {
-                yr[o] = acc[r];
-                nan |= acc[r] != acc[r];
-                m = fmaxf(m, fabsf(acc[r]));
+            for (int q = 0; q < kResampleP; ++q) {
+                t[q] = kTableInSmem ? *tp[q] : __ldg(tp[q]);
+                tp[q] += neu;
             }
+#pragma unroll
+            for (int r = 0; r < kResampleJ; ++r) v[r] = *xp[r]++;
+#pragma unroll
+            for (int r = 0; r < kResampleJ; ++r)
+#pragma unroll
+                for (int q = 0; q < kResampleP; ++q) acc[r][q] = fmaf(v[r], t[q], acc[r][q]);
         }
+#pragma unroll
+        for (int r = 0; r < kResampleJ; ++r)
+#pragma unroll
+            for (int q = 0; q < kResampleP; ++q) {
+                const int p = p0 + q * phase_stride;
+                const int64_t o = (j0 + jq * kResampleJ + r) * neu + p;
+                if (p < neu && o < n_out) {
+                    yr[o] = acc[r][q];
+                    nan |= acc[r][q] != acc[r][q];
+                    m = fmaxf(m, fabsf(acc[r][q]));
+                }
+            }
+    }
     }
     if (absmax_bits) {
         unsigned bits = nan ? 0x7fc00000u : __float_as_uint(m);
@@ -149,16 +199,22 @@ extern "C" int adtfe_resampler_create(int32_t orig_freq, int32_t new_freq, int32
         for (int64_t k = 0; k < taps; ++k) t[(size_t)k * n + p] = kernel_host[(size_t)p * taps + k];
     adtfe_resampler* r = new adtfe_resampler();
     r->device = device; r->orig = (int32_t)o; r->neu = (int32_t)n; r->width = width; r->taps = (int32_t)taps;
-    // groups per tile: about kResampleTileOut outputs, a multiple of kResampleJ, span within the staging limit
-    int64_t groups = std::max<int64_t>(1, kResampleTileOut / n);
+    // a tile: as many groups as give every thread of the CTA one (4 groups x 4 phases) item, a multiple of
+    // kResampleJ, with the input span within the staging limit
+    r->phase_stride = (int32_t)((n + kResampleP - 1) / kResampleP);
+    int64_t groups = (int64_t)kResampleJ * std::max<int64_t>(1, kResampleThreads / r->phase_stride);
     groups = std::min<int64_t>(groups, (kResampleSpanMax - taps) / o + 1);
     groups = std::max<int64_t>(kResampleJ, groups / kResampleJ * kResampleJ);
     r->groups_per_tile = (int32_t)groups;
-    r->smem_bytes = (size_t)((groups - 1) * o + taps) * 4;
+    const size_t span_bytes = (size_t)(((groups - 1) * o + taps + 3) & ~(int64_t)3) * 4;
+    r->table_in_smem = span_bytes + (size_t)taps * n * 4 <= kResampleSmemMax;
+    r->smem_bytes = span_bytes + (r->table_in_smem ? (size_t)taps * n * 4 : 0);
     if (cudaMalloc((void**)&r->table, t.size() * 4) != cudaSuccess ||
         cudaMemcpy(r->table, t.data(), t.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r->smem_bytes) !=
-            cudaSuccess) {
+        (r->table_in_smem ? cudaFuncSetAttribute(resample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)kResampleSmemMax)
+                          : cudaFuncSetAttribute(resample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)kResampleSmemMax)) != cudaSuccess) {
         set_error("adtfe_resampler_create: device set-up failed: %s", cudaGetErrorString(cudaGetLastError()));
         cudaFree(r->table);
         delete r;
@@ -195,9 +251,20 @@ extern "C" int adtfe_resample(const adtfe_resampler* r, const float* x_dev, int3
     const int64_t per_tile = (int64_t)r->groups_per_tile * r->neu;
     const int64_t tiles = (n_out + per_tile - 1) / per_tile;
     ADTFE_REQUIRE(tiles < (1ll << 31), ADTFE_ERR_UNSUPPORTED, "adtfe_resample: signal too long for one launch");
-    resample_kernel<<<dim3((unsigned)tiles, (unsigned)n_rows), kResampleThreads, r->smem_bytes, (cudaStream_t)stream>>>(
-        x_dev, ld_in, n_in, y_dev, ld_out, n_out, r->table, r->orig, r->neu, r->width, r->taps, r->groups_per_tile,
-        (int*)absmax_bits_dev);
+    // persistent CTAs: two per SM and row (shared-memory bound), each walks its tiles with the filter bank staged once
+    int device = 0, sms = 148;
+    ADTFE_CUDA(cudaGetDevice(&device));
+    sms = device_sm_count(device);
+    const int64_t per_row = std::max<int64_t>(1, (2 * (int64_t)sms + n_rows - 1) / n_rows);
+    const dim3 grid((unsigned)std::min<int64_t>(tiles, per_row), (unsigned)n_rows);
+    if (r->table_in_smem)
+        resample_kernel<true><<<grid, kResampleThreads, r->smem_bytes, (cudaStream_t)stream>>>(
+            x_dev, ld_in, n_in, y_dev, ld_out, n_out, r->table, r->orig, r->neu, r->width, r->taps, r->groups_per_tile,
+            r->phase_stride, tiles, (int*)absmax_bits_dev);
+    else
+        resample_kernel<false><<<grid, kResampleThreads, r->smem_bytes, (cudaStream_t)stream>>>(
+            x_dev, ld_in, n_in, y_dev, ld_out, n_out, r->table, r->orig, r->neu, r->width, r->taps, r->groups_per_tile,
+            r->phase_stride, tiles, (int*)absmax_bits_dev);
     ADTFE_CUDA(cudaGetLastError());
     return ADTFE_OK;
 }
