@@ -107,8 +107,28 @@ struct MelStage {
     float* out_dev;
     int group_chunks;
 };
+// Row scale of one segment (32 bytes), written by the tile mixer CTA that finishes the segment's last tile when the
+// normalisation is folded into the log-mel: peak = max of the tile maxima, r = 1/peak (rn), s2 = (vol/peak)^2.
+struct SegScale {
+    float peak, r, vol, s2;
+    int32_t len, flags, pad0, pad1;
+};
+static_assert(sizeof(SegScale) == 32, "SegScale layout");
+// Normalisation folded into the log-mel: what the kernel needs besides the raw mix.
+struct FoldStage {
+    const SegScale* seg_scale;
+};
+// raw mix -> normalised rows, out of place, from the row scales (runs beside the folded log-mel)
+int normalise_rows(const adtfe_bank* bank, const adtfe_plan* plan, const SegScale* seg_scale, const float* raw,
+                   float* wav_out, cudaStream_t stream);
+// raw_out != NULL: the tile mixer writes the raw mix there, the rows are NOT normalised and seg_scale_out[n_seg]
+// receives every row's scale (seg_ticket: n_seg zero-initialised... zeroed here); the caller folds the normalisation
+// into the log-mel.
 int render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
-                size_t workspace_bytes, void* stream, const MelStage* mel_stage);
+                size_t workspace_bytes, void* stream, const MelStage* mel_stage, float* raw_out = nullptr,
+                SegScale* seg_scale_out = nullptr, int* seg_ticket = nullptr);
+int logmel_fold(const adtfe_mel* mel, const float* raw_dev, int32_t n_seg, int64_t ld_wav, int64_t n_samples,
+                const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, const FoldStage* fold, void* stream);
 // Diagnostics (adtfe_trace_begin / adtfe_trace_dump): a pair of timing events around every kernel launch.
 void trace_open(const char* kernel, int index, cudaStream_t st);
 void trace_close(cudaStream_t st);

@@ -107,6 +107,8 @@ struct LogmelArgs {
     int64_t ld_wav;
     int32_t n_seg, first, count, hop, n_mels;
     int32_t rounds_per_seg, n_rounds;
+    // normalisation folded into the v6 kernel (adtfe_render_logmel): `wav` is then the RAW mix of the tile mixer
+    const SegScale* seg_scale = nullptr;      // per row: peak, 1/peak, max_volume, (max_volume/peak)^2, len, flags
 };
 
 // Round r = part q of segment seg: a segment's `count` frames are split evenly over rounds_per_seg rounds,
@@ -448,7 +450,7 @@ struct Logmel6Tables {
 };
 
 struct Unit6 {
-    int seg, j0, nf;
+    int seg, j0, nf, count;
     long long out_row;
 };
 template <int kUnitFrames>
@@ -464,6 +466,7 @@ __device__ __forceinline__ Unit6 unit6_geom(const LogmelArgs& p, int u, int unit
         count = row.z;
     }
     g.nf = max(0, min(kUnitFrames, count - g.j0));
+    g.count = count;
     g.out_row = base + g.j0;
     return g;
 }
@@ -482,7 +485,25 @@ __device__ __forceinline__ void issue_span6(const LogmelArgs& p, const Unit6& g,
 
 // `tma`: every unit's samples start on a 16-byte boundary (aligned base, row pitch a multiple of 4 floats); otherwise the
 // warp copies its span itself at the start of the unit (no prefetch) - same arithmetic, so results do not depend on it.
-template <int kWarps6, int kUnitFrames>
+// torch.max propagates NaN (the mixer's tile maxima do too)
+__device__ __forceinline__ float nan_max6(float a, float b) {
+    return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b);
+}
+
+// Row normalisation folded into the log-mel (kFold): the kernel reads the raw mix of the tile mixer and multiplies
+// its mel sums by the row's (max_volume / peak)^2 - the normalised rows themselves are written by
+// normalise_rows_kernel (mixer.cu) beside this kernel, off the critical path.  The row scale (written by the tile
+// mixer) is requested one unit ahead so that the loads are never waited for.
+__device__ __forceinline__ SegScale fold_prefetch6(const LogmelArgs& p, int seg) {
+    const int4* q = reinterpret_cast<const int4*>(p.seg_scale + seg);
+    const int4 a = __ldg(q), b = __ldg(q + 1);
+    SegScale f;
+    f.peak = __int_as_float(a.x); f.r = __int_as_float(a.y); f.vol = __int_as_float(a.z); f.s2 = __int_as_float(a.w);
+    f.len = b.x; f.flags = b.y; f.pad0 = 0; f.pad1 = 0;
+    return f;
+}
+
+template <int kWarps6, int kUnitFrames, bool kFold>
 __global__ void __launch_bounds__(kWarps6 * 32, 1) logmel6_kernel(const LogmelArgs p, const Logmel6Tables t6, int n_units,
                                                                 int units_per_seg, int tma) {
     constexpr int kThreads6 = kWarps6 * 32;
@@ -520,12 +541,15 @@ __global__ void __launch_bounds__(kWarps6 * 32, 1) logmel6_kernel(const LogmelAr
     if (kDirect6) tma = 0;
     if (tma && u < n_units) issue_span6(p, g, span, bar, lane);
     uint32_t parity = 0;
+    SegScale fp = {0.0f, 0.0f, 0.0f, 1.0f, 0, 0, 0, 0}, fpn = fp;
+    if (kFold && u < n_units) fp = fold_prefetch6(p, g.seg);
 
 #pragma unroll 1
     for (; u < n_units; u += gstride) {
         const bool more = u + gstride < n_units;
         Unit6 gn = g;
         if (more) gn = unit6_geom<kUnitFrames>(p, u + gstride, units_per_seg);
+        if (kFold && more) fpn = fold_prefetch6(p, gn.seg);
         if (tma) {
             mbar_wait(bar, parity);
             parity ^= 1u;
@@ -537,6 +561,12 @@ __global__ void __launch_bounds__(kWarps6 * 32, 1) logmel6_kernel(const LogmelAr
             __syncwarp();
         }
         const int n_pairs = (g.nf + 1) >> 1;
+        float s2 = 1.0f;   // (max_volume / peak)^2: the mel sums of the raw mix times this are those of the normalised row
+        int seg_len = 0;
+        if (kFold) {  // the rows are the RAW mix: its mel sums times (max_volume / peak)^2 are those of the normalised row
+            seg_len = fp.len;
+            s2 = fp.s2;
+        }
         if (tma && n_pairs == 0 && more) { __syncwarp(); issue_span6(p, gn, span, bar, lane); }
 #pragma unroll 1
         for (int pr = 0; pr < n_pairs; ++pr) {
@@ -666,9 +696,16 @@ __global__ void __launch_bounds__(kWarps6 * 32, 1) logmel6_kernel(const LogmelAr
                     const float2 m0 = mb[c[k].idx[0]], m1 = mb[c[k].idx[1]], m2 = mb[c[k].idx[2]];
                     v[k] = __fadd2_rn(__fadd2_rn(m0, m1), m2);
                 }
+                float s2a = s2, s2b = s2;
+                if (kFold) {  // a frame that lies entirely in the zero padding past the segment keeps log(1e-10)
+                    const long long fa = (long long)(p.first + g.j0 + f) * p.hop - 1024;
+                    if (fa >= seg_len) s2a = 1.0f;
+                    if (fa + hop_b >= seg_len) s2b = 1.0f;
+                }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int m = lane + 32 * k;
+                    if (kFold) { v[k].x *= s2a; v[k].y *= s2b; }
                     float a = __logf(v[k].x + 1e-10f), b = __logf(v[k].y + 1e-10f);
                     a = a != a ? a : fminf(fmaxf(a, -23.0f), 12.0f);    // torch.clamp keeps NaN
                     b = b != b ? b : fminf(fmaxf(b, -23.0f), 12.0f);
@@ -681,6 +718,7 @@ __global__ void __launch_bounds__(kWarps6 * 32, 1) logmel6_kernel(const LogmelAr
             __syncwarp();  // Q and M are rewritten by the next pair
         }
         g = gn;
+        if (kFold) fp = fpn;
     }
 }
 
@@ -714,7 +752,8 @@ static size_t logmel6_smem_bytes(int warps, int unit) {
 // `co`: the co-resident shape of the v6 kernel (kCoWarps warps, units of kCoUnit frames) - same arithmetic per frame
 // pair, so the results are bit-identical to the stand-alone shape.
 static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav, int32_t first,
-                         int32_t count, const adtfe_mel_row* rows_dev, float* out_dev, void* stream, bool co = false) {
+                         int32_t count, const adtfe_mel_row* rows_dev, float* out_dev, void* stream, bool co = false,
+                         const FoldStage* fold = nullptr) {
     // frames per round: as many as fit the span buffer, at most 32; a segment's frames are split evenly
     const int cap = std::min(kRound, (kSpanFloats - 2048) / mel->hop + 1);
     const int rounds_per_seg = (count + cap - 1) / cap;
@@ -736,15 +775,21 @@ static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_s
         t6.w = (const float2*)mel->w6; t6.lane = (const Lane6*)mel->lane6; t6.comb = (const Comb6*)mel->comb6;
         const long long ctas = (n_units + warps - 1) / warps;
         const int grid6 = (int)(ctas < mel->sm_count ? ctas : mel->sm_count);
-        if (co)
-            logmel6_kernel<kCoWarps, kCoUnit><<<grid6, kCoWarps * 32, mel->smem6co_bytes, (cudaStream_t)stream>>>(
+        if (fold) {
+            a.seg_scale = fold->seg_scale;
+            logmel6_kernel<kWarps6, kUnitFrames, true><<<grid6, kWarps6 * 32, mel->smem6_bytes, (cudaStream_t)stream>>>(
                 a, t6, (int)n_units, units_per_seg, tma);
-        else
-            logmel6_kernel<kWarps6, kUnitFrames><<<grid6, kWarps6 * 32, mel->smem6_bytes, (cudaStream_t)stream>>>(
+        } else if (co) {
+            logmel6_kernel<kCoWarps, kCoUnit, false><<<grid6, kCoWarps * 32, mel->smem6co_bytes, (cudaStream_t)stream>>>(
                 a, t6, (int)n_units, units_per_seg, tma);
+        } else {
+            logmel6_kernel<kWarps6, kUnitFrames, false><<<grid6, kWarps6 * 32, mel->smem6_bytes, (cudaStream_t)stream>>>(
+                a, t6, (int)n_units, units_per_seg, tma);
+        }
         ADTFE_CUDA(cudaGetLastError());
         return ADTFE_OK;
     }
+    ADTFE_REQUIRE(!fold, ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: the folded normalisation needs the v6 kernel");
     const int grid = (int)(n_rounds < mel->sm_count ? n_rounds : mel->sm_count);
     logmel_kernel<<<grid, kThreads, mel->smem_bytes, (cudaStream_t)stream>>>(a, mel->tables->t);
     ADTFE_CUDA(cudaGetLastError());
@@ -792,6 +837,20 @@ extern "C" int adtfe_logmel_rows(const adtfe_mel* mel, const float* wav_dev, int
 }
 
 namespace adtfe {
+// Log-mel of the RAW mix with the row scale folded in.  Returns ADTFE_ERR_UNSUPPORTED when the
+// v6 kernel or its TMA path cannot take the launch - the caller then normalises and featurises separately.
+int logmel_fold(const adtfe_mel* mel, const float* raw_dev, int32_t n_seg, int64_t ld_wav, int64_t n_samples,
+                const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, const FoldStage* fold, void* stream) {
+    if (!mel || !mel->v6_ok || getenv("ADTFE_LOGMEL_V5") || !fold || ((uintptr_t)raw_dev & 15) || ld_wav % 4 ||
+        n_seg <= 0)
+        return ADTFE_ERR_UNSUPPORTED;
+    int32_t first = mel->wpi, count = max_count;
+    if (!rows_dev) adtfe_mel_frames(mel, n_samples, &first, &count);
+    if ((int64_t)first * mel->hop < 1024 || (count > 0 && (int64_t)(first + count - 1) * mel->hop + 1024 > ld_wav))
+        return ADTFE_ERR_UNSUPPORTED;
+    if (count <= 0) return ADTFE_OK;   // no frames anywhere
+    return launch_logmel(mel, raw_dev, n_seg, ld_wav, first, std::max(count, 0), rows_dev, out_dev, stream, false, fold);
+}
 int logmel_rows_co(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
                    const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream) {
     return logmel_rows_checked(mel, wav_dev, n_seg, ld_wav, rows_dev, max_count, out_dev, stream,
@@ -1112,13 +1171,15 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
             MEL_UPLOAD(mel->comb6, comb6.data(), comb6.size() * sizeof(Comb6));
             mel->smem6_bytes = logmel6_smem_bytes(kWarps6, kUnitFrames);
             mel->smem6co_bytes = logmel6_smem_bytes(kCoWarps, kCoUnit);
-            if (cudaFuncSetAttribute(logmel6_kernel<kWarps6, kUnitFrames>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            if (cudaFuncSetAttribute(logmel6_kernel<kWarps6, kUnitFrames, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)mel->smem6_bytes) != cudaSuccess ||
+                cudaFuncSetAttribute(logmel6_kernel<kWarps6, kUnitFrames, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)mel->smem6_bytes) != cudaSuccess) {
                 cudaGetLastError();
                 mel->v6_ok = 0;
             }
             mel->v6co_ok = mel->v6_ok && (kCoUnit - 1) * hop + 2048 <= w6_span(kCoUnit) &&
-                           cudaFuncSetAttribute(logmel6_kernel<kCoWarps, kCoUnit>,
+                           cudaFuncSetAttribute(logmel6_kernel<kCoWarps, kCoUnit, false>,
                                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 (int)mel->smem6co_bytes) == cudaSuccess;
             cudaGetLastError();

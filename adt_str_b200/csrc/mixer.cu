@@ -237,6 +237,9 @@ struct MixArgs {
     int* tile_counter;
     int64_t ld_wav;
     int32_t tiles_per_seg, n_tiles;
+    // folded normalisation: the CTA that finishes a segment's last tile publishes the row scale
+    int* seg_ticket;
+    SegScale* seg_scale;
 };
 
 // Writes the finished (not yet normalised) tile and publishes its |max|.
@@ -260,6 +263,21 @@ __device__ __forceinline__ void finish_tile(const MixArgs& a, int tile_id, const
         float r = s_red[0];
         for (int i = 1; i < kMixConsumers; ++i) r = nan_max(r, s_red[i]);
         a.tile_max[tile_id] = r;
+        if (a.seg_scale) {
+            __threadfence();  // the tile maximum is visible before the ticket is taken
+            if (atomicAdd(a.seg_ticket + seg, 1) == a.tiles_per_seg - 1) {
+                __threadfence();
+                float pk = 0.0f;
+                for (int t = 0; t < a.tiles_per_seg; ++t) pk = nan_max(pk, __ldcg(a.tile_max + seg * a.tiles_per_seg + t));
+                const adtfe_segment sg = a.segments[seg];
+                SegScale sc;
+                sc.peak = pk; sc.r = __frcp_rn(pk); sc.vol = sg.max_volume;
+                const float q = __fdiv_rn(sg.max_volume, pk);
+                sc.s2 = sg.flags != 0 ? q * q : 1.0f;   // an empty segment is all zeros: nothing to scale
+                sc.len = sg.len; sc.flags = sg.flags; sc.pad0 = 0; sc.pad1 = 0;
+                a.seg_scale[seg] = sc;
+            }
+        }
     }
 }
 
@@ -458,6 +476,51 @@ __global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_seg
     for (int i = 4 * n4 + tid; i < n; i += kNormThreads) row[i] = norm(row[i]);
 }
 
+// The same out of place, from the row scales the mixer published (folded form: the log-mel reads the raw mix and this
+// kernel writes the normalised rows beside it).  Samples beyond the segment and empty segments are copied (zeros).
+// It runs in what the log-mel CTA leaves of an SM (about 16 k registers), so it is built small: 128-thread CTAs
+// that walk the tiles grid-stride, four float4 per thread in flight.
+constexpr int kNormRowsThreads = 128;
+__global__ void __launch_bounds__(kNormRowsThreads) normalise_rows_kernel(const SegScale* __restrict__ seg_scale,
+                                                                          const float* __restrict__ raw,
+                                                                          int tiles_per_seg, int64_t n_tiles,
+                                                                          int64_t ld_wav, float* __restrict__ wav) {
+    static_assert(ADTFE_TILE == 16 * kNormRowsThreads, "four float4 per thread and tile");
+    const int tid = threadIdx.x;
+    for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+        const int seg = (int)(tile_id / tiles_per_seg), lo = (int)(tile_id - (int64_t)seg * tiles_per_seg) * ADTFE_TILE;
+        if (lo >= ld_wav) continue;
+        const int4* q = reinterpret_cast<const int4*>(seg_scale + seg);
+        const int4 a = __ldg(q), b = __ldg(q + 1);
+        const float peak = __int_as_float(a.x), r = __int_as_float(a.y), vol = __int_as_float(a.z);
+        const int live_len = b.y != 0 ? b.x : 0;   // samples [0, live_len) are normalised
+        const float4* src = reinterpret_cast<const float4*>(raw + (int64_t)seg * ld_wav + lo);
+        float4* dst = reinterpret_cast<float4*>(wav + (int64_t)seg * ld_wav + lo);
+        const int n4 = (int)(min((int64_t)ADTFE_TILE, ld_wav - lo) >> 2);       // ld_wav is a multiple of 4
+        auto norm = [&](float v, int i) {
+            if (lo + i >= live_len) return v;
+            const float qv = __fmul_rn(v, r);
+            const float rem = __fmaf_rn(-qv, peak, v);
+            return __fmul_rn(__fmaf_rn(rem, r, qv), vol);
+        };
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + k * kNormRowsThreads;
+            v[k] = i < n4 ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + k * kNormRowsThreads;
+            if (i < n4) {
+                float4 o = v[k];
+                o.x = norm(o.x, 4 * i); o.y = norm(o.y, 4 * i + 1); o.z = norm(o.z, 4 * i + 2); o.w = norm(o.w, 4 * i + 3);
+                dst[i] = o;
+            }
+        }
+    }
+}
+
 static size_t mix_smem_bytes() { return mix_list_offset() + kListMax * sizeof(SliceMsg); }
 
 }  // namespace adtfe
@@ -472,13 +535,36 @@ extern "C" size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, 
            align256((size_t)n_seg * tiles_per_seg * 4) + 256;
 }
 
+int adtfe::normalise_rows(const adtfe_bank* bank, const adtfe_plan* plan, const SegScale* seg_scale, const float* raw,
+                          float* wav_out, cudaStream_t stream) {
+    const int64_t n_tiles = (int64_t)plan->n_seg * plan->tiles_per_seg;
+    ADTFE_REQUIRE(n_tiles < (1ll << 31), ADTFE_ERR_UNSUPPORTED, "adtfe_render_logmel: too many tiles for one launch");
+    trace_open("normalise", -2, stream);
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)bank->sm_count * 8);
+    normalise_rows_kernel<<<grid, kNormRowsThreads, 0, stream>>>(seg_scale, raw, plan->tiles_per_seg, n_tiles,
+                                                                plan->ld_wav, wav_out);
+    trace_close(stream);
+    ADTFE_CUDA(cudaGetLastError());
+    return ADTFE_OK;
+}
+
+extern "C" size_t adtfe_render_logmel_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg,
+                                                      int64_t ld_wav) {
+    const size_t base = adtfe_render_workspace_bytes(n_events, n_seg, tiles_per_seg);
+    if (base == 0 || ld_wav < 0) return 0;
+    // + the raw mix the log-mel normalises, the per-segment scales and the tickets that elect their writer
+    return base + align256((size_t)n_seg * (size_t)ld_wav * 4) + align256((size_t)n_seg * sizeof(SegScale)) +
+           align256((size_t)n_seg * 4) + 256;
+}
+
 extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
                             size_t workspace_bytes, void* stream) {
     return render_impl(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream, nullptr);
 }
 
 int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
-                       size_t workspace_bytes, void* stream, const MelStage* ms) {
+                       size_t workspace_bytes, void* stream, const MelStage* ms, float* raw_out,
+                       SegScale* seg_scale_out, int* seg_ticket) {
     ADTFE_REQUIRE(bank && plan, ADTFE_ERR_BAD_ARG, "adtfe_render: null bank or plan");
     ADTFE_REQUIRE(plan->n_seg >= 0 && plan->n_events >= 0 && plan->n_peak_work >= 0 && plan->tiles_per_seg >= 0,
                   ADTFE_ERR_BAD_ARG, "adtfe_render: negative count");
@@ -532,7 +618,11 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
         for (int k = 0; k < bank->n_streams && k < n_chunks; ++k)
             ADTFE_CUDA(cudaStreamWaitEvent(bank->streams[k], bank->fork_event, 0));
     }
-    const bool staged = ms && fork && plan->mel_rows_dev;  // log-mel of finished chunk groups beside the render
+    ADTFE_REQUIRE(!raw_out || (seg_scale_out && seg_ticket), ADTFE_ERR_BAD_ARG, "adtfe_render: fold buffers missing");
+    if (raw_out) ADTFE_CUDA(cudaMemsetAsync(seg_ticket, 0, (size_t)plan->n_seg * 4, user));
+    float* mix_out = raw_out ? raw_out : wav_out_dev;  // raw_out: the caller folds the normalisation into the log-mel
+    ADTFE_REQUIRE(!raw_out || ((uintptr_t)raw_out & 15) == 0, ADTFE_ERR_BAD_ARG, "adtfe_render: misaligned raw buffer");
+    const bool staged = ms && fork && plan->mel_rows_dev && !raw_out;  // log-mel of finished chunk groups beside the render
     if (staged) ADTFE_CUDA(cudaStreamWaitEvent(bank->mel_stream, bank->fork_event, 0));
     int group_first = 0;  // first chunk of the group being rendered
     const int tps = plan->tiles_per_seg;
@@ -550,18 +640,21 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
         MixArgs a;
         a.pcm = bank->pcm; a.resolved = resolved; a.peak_bits = peak_bits;
         a.tile_ptr = plan->tile_ptr_dev + (size_t)s0 * tps; a.tile_events = plan->tile_events_dev;
-        a.segments = plan->segments_dev + s0; a.wav = wav_out_dev + (size_t)s0 * plan->ld_wav;
+        a.segments = plan->segments_dev + s0; a.wav = mix_out + (size_t)s0 * plan->ld_wav;
         a.tile_max = tile_max + (size_t)s0 * tps; a.tile_counter = counters + c; a.ld_wav = plan->ld_wav;
         a.tiles_per_seg = tps; a.n_tiles = n_seg * tps;
+        a.seg_ticket = raw_out ? seg_ticket + s0 : nullptr; a.seg_scale = raw_out ? seg_scale_out + s0 : nullptr;
         const int grid = std::min(a.n_tiles, kMixCtasPerSm * bank->sm_count);
         trace_open("mix", c, st);
         mix_kernel<<<grid, kMixThreads, mix_smem_bytes(), st>>>(a);
         trace_close(st);
         ADTFE_CUDA(cudaGetLastError());
-        trace_open("normalise", c, st);
-        normalise_kernel<<<a.n_tiles, kNormThreads, 0, st>>>(a.segments, a.tile_max, tps, plan->ld_wav, a.wav);
-        trace_close(st);
-        ADTFE_CUDA(cudaGetLastError());
+        if (!raw_out) {
+            trace_open("normalise", c, st);
+            normalise_kernel<<<a.n_tiles, kNormThreads, 0, st>>>(a.segments, a.tile_max, tps, plan->ld_wav, a.wav);
+            trace_close(st);
+            ADTFE_CUDA(cudaGetLastError());
+        }
         if (staged && (c + 1 - group_first >= ms->group_chunks || c + 1 == n_chunks)) {
             // the group's chunks sit on the streams (group_first .. c) % n_streams: the mel stream waits for them
             const int used = std::min(c + 1 - group_first, bank->n_streams);

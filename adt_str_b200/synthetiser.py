@@ -79,12 +79,20 @@ class PlanBuffers:
             raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
             h[o: o + raw.size] = raw
         self.nbytes = total
-        need = lib.adtfe_render_workspace_bytes(plan.n_events, plan.n_seg, plan.tiles_per_seg)
+        need = self._workspace_bytes(lib, plan.n_events, plan.n_seg, plan.tiles_per_seg, plan.ld_wav)
         if self.workspace.numel() < need:
             self.workspace = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=self.device)
         self.offsets = [int(o) for o in off]
         self.shape = shape
         return shape
+
+    @staticmethod
+    def _workspace_bytes(lib, n_events, n_seg, tiles_per_seg, ld_wav) -> int:
+        """The render's scratch; with ADTFE_FOLD=1 (the opt-in folded form of adtfe_render_logmel) also room for
+        the raw mix."""
+        if os.environ.get("ADTFE_FOLD"):
+            return lib.adtfe_render_logmel_workspace_bytes(n_events, n_seg, tiles_per_seg, ld_wav)
+        return lib.adtfe_render_workspace_bytes(n_events, n_seg, tiles_per_seg)
 
     def reserve(self, nbytes: int) -> None:
         """Pinned and device blobs of at least ``nbytes`` (contents are not kept)."""
@@ -103,7 +111,7 @@ class PlanBuffers:
         fixed = C.c_size_t()
         _lib.check(lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(fixed)), "adtfe_plan_blob_layout")
         self.nbytes = int(nbytes)
-        need = lib.adtfe_render_workspace_bytes(shape.n_events, shape.n_seg, shape.tiles_per_seg)
+        need = self._workspace_bytes(lib, shape.n_events, shape.n_seg, shape.tiles_per_seg, shape.ld_wav)
         if self.workspace.numel() < need:
             with torch.cuda.device(self.device):
                 self.workspace = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=self.device)

@@ -172,6 +172,13 @@ int adtfe_logmel_rows(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg,
 int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel, const adtfe_plan* plan, int64_t n_samples,
                         float* wav_out_dev, float* mel_out_dev, void* workspace_dev, size_t workspace_bytes,
                         void* stream);
+/* Workspace for the fused call's folded form (opt-in: environment ADTFE_FOLD=1): adtfe_render_workspace_bytes plus
+ * room for the raw mix (n_seg * ld_wav floats) and the row scales.  With it the mixer leaves the raw mix in the
+ * workspace, the log-mel scales its mel sums by (max_volume / peak)^2 and the normalised rows are written beside
+ * it: same waveform bits as adtfe_render, log-mel within float32 rounding of adtfe_logmel on that waveform.  It
+ * measured slower than the default on B200, so the default - and any call with the smaller
+ * adtfe_render_workspace_bytes - normalises in place first, then runs the log-mel. */
+size_t adtfe_render_logmel_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg, int64_t ld_wav);
 
 /* ---- host-buffer entry (end to end) ------------------------------------------------ */
 /* Plan blob layout (host, 16-byte aligned sections in this order):

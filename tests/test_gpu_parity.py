@@ -252,6 +252,61 @@ def test_batches_in_one_plan_equal_batch_by_batch():
         assert torch.equal(w0, w1) and torch.equal(f0, f1)
 
 
+def test_folded_normalisation_equals_normalise_then_logmel(monkeypatch):
+    """adtfe_render_logmel's opt-in folded form (ADTFE_FOLD=1): the mixer writes the raw mix and publishes every row's
+    scale, the log-mel reads the raw mix and scales its mel sums by (max_volume / peak)^2, the normalised rows are
+    written out of place beside it.  Against the default (normalise in place, then log-mel): the waveforms are
+    bit-identical, the log-mel agrees to float32 rounding; empty segments, all-zero mixes (NaN rows, exact zeros in
+    the padding), ragged batches and rows too short for a frame included."""
+    import dataclasses
+    from adt_str_b200.config import setting_1
+    from adt_str_b200.synthetic import make_bank, make_segments
+    bank = make_bank(390, 24000, seed=18)
+    for input_sec in (2.56, 0.1):                          # 0.1 s: 11 STFT frames, none kept -> rows without frames
+        cfg = dataclasses.replace(setting_1(), input_sec=input_sec, similarity_threshold=1.0, mixup_range=0.0)
+        _, _, fe = _objects(cfg, bank)
+        # 0.1 s segments can only be empty ones (a note pushes the end past 0.2 s): every row is zeros, no frame is kept
+        segs = make_segments(37, seed=24, empty_fraction=0.15) if input_sec > 1 else [np.zeros((0, 4), np.float32)] * 37
+        batches = [segs[:9], segs[9:10], segs[10:26], segs[26:]]
+        out = {}
+        for fold in (True, False):
+            if fold:
+                monkeypatch.setenv("ADTFE_FOLD", "1")
+            else:
+                monkeypatch.delenv("ADTFE_FOLD", raising=False)
+            plan = fe.plan_batches(batches, random.Random(7), 2)
+            wav, feat = fe.run_plan(plan)
+            single = [fe(b, random.Random(11)) for b in batches[:2]]
+            torch.cuda.synchronize()
+            out[fold] = (wav.clone(), feat.clone(), [(w.clone(), f.clone()) for w, f in single])
+        monkeypatch.delenv("ADTFE_FOLD", raising=False)
+        (w1, f1, s1), (w0, f0, s0) = out[True], out[False]
+        assert torch.equal(w1, w0)
+        assert f1.shape == f0.shape and float((f1 - f0).abs().max() if f0.numel() else 0.0) <= 2e-6
+        for (wa, fa), (wb, fb) in zip(s1, s0):
+            assert torch.equal(wa, wb) and fa.shape == fb.shape
+            assert float((fa - fb).abs().max() if fb.numel() else 0.0) <= 2e-6
+    # an all-zero mix: the reference's 0/0 - NaN over the segment, exact zeros (and log(1e-10) -> 0.0) in the padding
+    cfg = dataclasses.replace(setting_1(), similarity_threshold=1.0, mixup_range=0.0)
+    silent = make_bank(78, 24000, seed=19)
+    silent.pcm[:] = 0.0
+    _, _, fe = _objects(cfg, silent)
+    long_seg = np.array([[0.1, 2.9, 36.0, 100.0]], np.float32)         # makes the batch wider than the silent segment
+    quiet = np.array([[0.2, 0.3, 38.0, 90.0]], np.float32)
+    for fold in (True, False):
+        if fold:
+            monkeypatch.setenv("ADTFE_FOLD", "1")
+        else:
+            monkeypatch.delenv("ADTFE_FOLD", raising=False)
+        wav, feat = fe([quiet, long_seg], random.Random(3))
+        torch.cuda.synchronize()
+        assert torch.isnan(wav[0, :61440]).all() and not wav[0, 61440:].any()
+        assert torch.isnan(feat[0, :240]).all()
+        t_pad = (61440 + 1024) // 240 + 1 - 5                            # first kept frame entirely inside the padding
+        assert feat.shape[1] > t_pad and not feat[0, t_pad:].any()
+    monkeypatch.delenv("ADTFE_FOLD", raising=False)
+
+
 def test_pipelined_front_end_equals_render_then_logmel(monkeypatch):
     """adtfe_render_logmel on a chunked plan featurises finished chunk groups (co-resident log-mel shape on the
     bank's mel stream) while later chunks render; whatever the group size, the waveforms and the log-mel are bit for
