@@ -436,3 +436,40 @@ def test_abi_status_codes_on_device():
     hm = C.c_void_p()
     assert lib.adtfe_mel_create(1024, 240, 128, w.data_ptr(), w.data_ptr(), 0, C.byref(hm)) == -2   # n_fft != 2048
     torch.cuda.synchronize()
+
+
+def test_logmel_band_limited_and_quiet_signals_against_reference_and_truth():
+    """Drum-like signals whose energy sits in a few bins (60 Hz kick, tonal snare body + noise burst, a full-scale
+    square wave, near-silence at 1e-6, tonal hats).  Where the float32 STFT resolves the cell (its mel power is within
+    six decades of the frame's loudest band) the north-star tolerance against the reference holds cell by cell.  In the quiet
+    bands beside a loud component float32 rounding noise decides the value - the reference is off its own truth by up
+    to 2e-2 there (the tolerance is ill-conditioned) - so no cell-by-cell comparison of two noise draws
+    means anything; there the kernel must be *as accurate as the reference*: mean, 99th percentile and maximum of
+    its error against the truth within 1.25x / 1.5x / 2x of the reference's (measured: 0.94x / 1.0x / 1.8x)."""
+    from adt_str_b200 import ComputeMelSpectrogram
+    for sr in (24000, 16000):
+        n = int(2.56 * sr)
+        t = np.arange(n) / sr
+        rng = np.random.default_rng(sr)
+        kick = np.sin(2 * np.pi * 60.0 * t * (1 + 0.5 * np.exp(-t * 30))) * np.exp(-t * 6.0)
+        snare = 0.6 * np.sin(2 * np.pi * 190.0 * t) * np.exp(-t * 18.0) + 0.3 * rng.standard_normal(n) * np.exp(-t * 25.0)
+        square = np.sign(np.sin(2 * np.pi * 440.0 * t))
+        hush = 1e-6 * rng.standard_normal(n)
+        hats = sum(np.sin(2 * np.pi * f * t) for f in (3000.0, 4500.0, 6100.0)) / 3 * np.exp(-((t * 8) % 1.0) * 12.0)
+        x = np.stack([kick, snare, square, hush, hats, kick + 0.01 * hats]).astype(np.float32)
+        mel = ComputeMelSpectrogram(sr, 2048, 0.01, 128)
+        got = mel(torch.from_numpy(x).cuda()).cpu().numpy().astype(np.float64)
+        ref = mel_oracle.logmel_torchaudio(x, sr, 2048, 0.01, 128).numpy().astype(np.float64)
+        truth = mel_oracle.logmel_direct(x, sr, 2048, 0.01, 128, np.float64)
+        assert got.shape == ref.shape and np.isfinite(got).all()
+        for i in range(len(x)):
+            e_got, e_ref = np.abs(got[i] - truth[i]), np.abs(ref[i] - truth[i])
+            resolved = truth[i] * 35.0 >= truth[i].max(axis=1, keepdims=True) * 35.0 - np.log(1e6)
+            assert resolved.mean() > 0.05
+            tol = 1e-4 * np.abs(ref[i]) + 2e-6
+            assert (np.abs(got[i] - ref[i])[resolved] <= tol[resolved]).all(), (i, np.abs(got[i] - ref[i])[resolved].max())
+            assert e_got.mean() <= 1.25 * e_ref.mean() + 1e-7, (i, e_got.mean(), e_ref.mean())
+            assert np.quantile(e_got, 0.99) <= 1.5 * np.quantile(e_ref, 0.99) + 2e-6, i
+            assert e_got.max() <= 2.0 * e_ref.max() + 2e-6, (i, e_got.max(), e_ref.max())
+            below = truth[i] == 0.0                       # the truth sits on the -23 clamp: noise may lift a cell off it
+            assert (got[i][below] > 0).sum() <= 1.5 * (ref[i][below] > 0).sum() + 16, i
