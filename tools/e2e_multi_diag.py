@@ -15,7 +15,7 @@ from adt_str_b200.synthetic import make_bank, make_segments
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
-dist.init_process_group("gloo")
+dist.init_process_group(os.environ.get("DIAG_BACKEND", "gloo"))
 NB = 256
 bank = make_bank(10000, 24000, seed=0)
 segs = make_segments(NB * 64, seed=1 + rank)
