@@ -124,7 +124,7 @@ __device__ __forceinline__ RoundGeom round_geom(const LogmelArgs& p, int r) {
     int count = p.count;
     long long base = (long long)g.seg * p.count;
     if (p.rows) {
-        const int4 row = __ldg(reinterpret_cast<const int4*>(p.rows + g.seg));  // {out_row lo, hi, count, -}
+        const int4 row = __ldg(reinterpret_cast<const int4*>(p.rows + g.seg));  // {out_row lo, hi, count, flags (a silent row is zeros anyway)}
         base = (long long)(((unsigned long long)(unsigned)row.y << 32) | (unsigned)row.x);
         count = row.z;
     }
@@ -451,6 +451,7 @@ struct Logmel6Tables {
 
 struct Unit6 {
     int seg, j0, nf, count;
+    bool silent;   // the row is all zeros (an empty segment): its frames are exact zeros, no transform needed
     long long out_row;
 };
 template <int kUnitFrames>
@@ -460,10 +461,12 @@ __device__ __forceinline__ Unit6 unit6_geom(const LogmelArgs& p, int u, int unit
     g.j0 = (u - g.seg * units_per_seg) * kUnitFrames;
     int count = p.count;
     long long base = (long long)g.seg * p.count;
+    g.silent = false;
     if (p.rows) {
-        const int4 row = __ldg(reinterpret_cast<const int4*>(p.rows + g.seg));  // {out_row lo, hi, count, -}
+        const int4 row = __ldg(reinterpret_cast<const int4*>(p.rows + g.seg));  // {out_row lo, hi, count, flags}
         base = (long long)(((unsigned long long)(unsigned)row.y << 32) | (unsigned)row.x);
         count = row.z;
+        g.silent = (row.w & ADTFE_MEL_ROW_SILENT) != 0;
     }
     g.nf = max(0, min(kUnitFrames, count - g.j0));
     g.count = count;
@@ -472,7 +475,7 @@ __device__ __forceinline__ Unit6 unit6_geom(const LogmelArgs& p, int u, int unit
 }
 __device__ __forceinline__ void issue_span6(const LogmelArgs& p, const Unit6& g, float* span, uint64_t* bar, int lane) {
     if (lane == 0) {
-        if (g.nf <= 0) {
+        if (g.nf <= 0 || g.silent) {
             mbar_arrive(bar);
         } else {
             const float* src = p.wav + (long long)g.seg * p.ld_wav + (long long)(p.first + g.j0) * p.hop - 1024;
@@ -553,14 +556,20 @@ __global__ void __launch_bounds__(kWarps6 * 32, 1) logmel6_kernel(const LogmelAr
         if (tma) {
             mbar_wait(bar, parity);
             parity ^= 1u;
-        } else if (!kDirect6 && g.nf > 0) {
+        } else if (!kDirect6 && g.nf > 0 && !g.silent) {
             const float* src = p.wav + (long long)g.seg * p.ld_wav + (long long)(p.first + g.j0) * p.hop - 1024;
             const int len = (g.nf - 1) * p.hop + 2048;
             __syncwarp();
             for (int i = lane; i < len; i += 32) span[i] = __ldg(src + i);
             __syncwarp();
         }
-        const int n_pairs = (g.nf + 1) >> 1;
+        const int n_pairs = g.silent ? 0 : (g.nf + 1) >> 1;
+        if (g.silent) {  // log(0 + 1e-10) = -23.03 -> clamp -23 -> exactly 0.0, like the reference on silence
+            for (int f = 0; f < g.nf; ++f) {
+                float* row = p.out + (g.out_row + f) * p.n_mels;
+                for (int m = lane; m < p.n_mels; m += 32) row[m] = 0.0f;
+            }
+        }
         float s2 = 1.0f;   // (max_volume / peak)^2: the mel sums of the raw mix times this are those of the normalised row
         int seg_len = 0;
         if (kFold) {  // the rows are the RAW mix: its mel sums times (max_volume / peak)^2 are those of the normalised row

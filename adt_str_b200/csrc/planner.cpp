@@ -341,7 +341,7 @@ extern "C" int adtfe_planner_pack_batches(const adtfe_planner* P, const int32_t*
         for (int32_t s = s0; s < s1; ++s) {
             rows[s].out_row = row0 + (int64_t)(s - s0) * frames;
             rows[s].count = (int32_t)frames;
-            rows[s].reserved = 0;
+            rows[s].flags = P->segments[s].flags == 0 ? ADTFE_MEL_ROW_SILENT : 0;  // an empty segment is all zeros
         }
         if (batch_width_out) batch_width_out[b] = width;
         if (batch_frames_out) batch_frames_out[b] = frames;

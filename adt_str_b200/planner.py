@@ -50,7 +50,8 @@ SEGMENT_DTYPE = np.dtype([("len", "<i4"), ("flags", "<i4"), ("max_volume", "<f4"
 PEAK_ITEM_DTYPE = np.dtype([("a_off", "<i8"), ("b_off", "<i8"), ("la", "<i4"), ("lb", "<i4"), ("mix_len", "<i4"),
                             ("first_event", "<i4"), ("n_events", "<i4"), ("chunk", "<i4")])
 #: numpy view of ``adtfe_mel_row`` (16 bytes)
-MEL_ROW_DTYPE = np.dtype([("out_row", "<i8"), ("count", "<i4"), ("reserved", "<i4")])
+MEL_ROW_DTYPE = np.dtype([("out_row", "<i8"), ("count", "<i4"), ("flags", "<i4")])
+MEL_ROW_SILENT = 1  # ADTFE_MEL_ROW_SILENT: the row is all zeros (an empty segment), its frames are exact zeros
 #: numpy view of ``adtfe_chunk`` (12 bytes)
 CHUNK_DTYPE = np.dtype([("seg", "<i4"), ("event", "<i4"), ("peak_work", "<i4")])
 SEG_EMPTY = 0      # no notes: all-zero waveform of int(input_sec*sr) samples, no normalisation
@@ -220,6 +221,7 @@ class RenderPlan:
         row0 = np.concatenate([[0], np.cumsum(sizes * frames)])
         batch_of = np.repeat(np.arange(len(sizes)), sizes)
         rows["count"] = frames[batch_of]
+        rows["flags"] = np.where(self.segments["flags"] == SEG_EMPTY, MEL_ROW_SILENT, 0)
         rows["out_row"] = row0[batch_of] + (np.arange(self.n_seg) - ptr[batch_of]) * frames[batch_of]
         cptr = np.unique(np.concatenate([ptr[::max(1, int(chunk_batches))], ptr[-1:]]))
         chunks = np.zeros(len(cptr), CHUNK_DTYPE)

@@ -93,8 +93,12 @@ typedef struct adtfe_peak_item {
 typedef struct adtfe_mel_row {
     int64_t out_row;
     int32_t count; /* >= 0; the frames must lie inside the row: (first+count-1)*hop + n_fft/2 <= ld_wav */
-    int32_t reserved;
+    int32_t flags; /* 0, or ADTFE_MEL_ROW_SILENT */
 } adtfe_mel_row;
+/* The caller knows the row is all zeros (an empty segment: synthetiser.py:257-258 returns zeros): its log-mel frames
+ * are exactly 0.0 (log(1e-10) clamped at -23) and are written without running the transform.  Purely a hint - a row
+ * of zeros without the flag gives the same output. */
+#define ADTFE_MEL_ROW_SILENT 1
 
 /* A chunk of a plan: segments, events and peak work items [x[c], x[c+1]) are rendered together, chunks
  * are independent and run on the library's internal streams (so that a chunk's one-shots are still in L2
