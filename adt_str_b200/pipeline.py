@@ -72,7 +72,7 @@ class GroupResult:
 
 
 class HostPipeline:
-    def __init__(self, frontend: FrontEnd, workers: int = 4, n_sets: int = 4, seed: int = 0, chunk_batches: int = 4):
+    def __init__(self, frontend: FrontEnd, workers: int = 4, n_sets: int = 4, seed: int = 0, chunk_batches: int = 8):
         self.fe = frontend
         self.workers = max(1, int(workers))
         self.n_sets = max(2, int(n_sets))
