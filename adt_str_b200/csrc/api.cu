@@ -184,8 +184,8 @@ extern "C" int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel,
                   "adtfe_render_logmel: n_samples exceeds the row pitch");
     // A chunked plan with ragged rows can be pipelined: the log-mel of a finished group of chunks runs beside the
     // render of the following ones (ADTFE_CO_GROUP chunks per group; 0 = render everything first, the default:
-    // on B200 the co-running kernels take as long as they do one after the other - the render saturates L2 and
-    // leaves the log-mel CTAs no room to keep their rate, see DESIGN.md "Pipelined front end").
+    // on B200 the co-running kernels take as long as they do one after the other - the render's latency-bound kernels need the
+    // occupancy the log-mel CTAs take, and both lose what the other gains, see DESIGN.md "Pipelined front end").
     const char* co_env = getenv("ADTFE_CO_GROUP");
     const int co_group = co_env ? atoi(co_env) : kCoGroupDefault;
     if (co_group > 0 && mel && mel->v6co_ok && plan->mel_rows_dev && plan->chunks_host && plan->n_chunks > co_group &&
@@ -196,7 +196,7 @@ extern "C" int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel,
     // With a workspace of adtfe_render_logmel_workspace_bytes the row normalisation leaves the critical path: the
     // mixer writes the raw mix into the workspace and publishes every row's scale, the log-mel reads the raw mix and
     // scales its mel sums by (max_volume / peak)^2, and the normalised rows are written by a kernel that runs BESIDE
-    // the log-mel (which leaves L2 idle) instead of between the L2-bound render kernels.
+    // the log-mel (which leaves L2 idle) instead of between the render kernels.
     // Measured on B200 (tools/_ab: 16.2 ms per step against 15.85 ms for normalise-in-place-then-log-mel): the render
     // does get shorter (7.8 -> 6.7 ms), but the out-of-place rows cost 8 GB more DRAM traffic per step (the in-place
     // pass works on an L2-resident chunk) and the log-mel loses more beside it than the render gains, so the form is
