@@ -200,7 +200,7 @@ constexpr int kPerThread = ADTFE_TILE / (kMixConsumers * 32);
 constexpr int kStages = ADTFE_MIX_STAGES;
 constexpr int kMixCtasPerSm = ADTFE_MIX_CTAS;
 constexpr int kStageFloats = 2080;                       // >= 2048 + 2*3 alignment slack, bytes a multiple of 128
-static_assert(kPerThread * kMixConsumers * 32 == ADTFE_TILE, "tile / consumer threads");
+static_assert(kPerThread * kMixConsumers * 32 == ADTFE_TILE && kPerThread < 32, "tile / consumer threads");
 
 struct __align__(16) StageDesc {   // written by the producer lane, read (broadcast) by every consumer
     int32_t kind;                  // 0: data, 1: a new tile begins (tile id in `tile`, < 0: no more work)
@@ -246,22 +246,24 @@ struct MixArgs {
 __device__ __forceinline__ void finish_tile(const MixArgs& a, int tile_id, const float (&acc)[kPerThread], int tid,
                                             float* s_red) {
     const int seg = tile_id / a.tiles_per_seg, lo = (tile_id - seg * a.tiles_per_seg) * ADTFE_TILE;
-    float m = 0.0f;
+    // |max| on the float bits: non-negative floats order like unsigned integers and a NaN's bits lie above infinity's,
+    // so the unsigned maximum propagates NaN like torch.max - one LOP3 + one integer max per sample, one REDUX per warp
+    unsigned mb = 0u;
     float* row = a.wav + (int64_t)seg * a.ld_wav;
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
         const int n = lo + tid + j * (kMixConsumers * 32);
         if (n < a.ld_wav) row[n] = acc[j];
-        m = nan_max(m, fabsf(acc[j]));
+        mb = max(mb, __float_as_uint(fabsf(acc[j])));
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = nan_max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    mb = __reduce_max_sync(0xffffffffu, mb);
     consumer_sync();  // s_red of the previous tile is no longer read
-    if ((tid & 31) == 0) s_red[tid >> 5] = m;
+    if ((tid & 31) == 0) s_red[tid >> 5] = __uint_as_float(mb);
     consumer_sync();
     if (tid == 0) {
-        float r = s_red[0];
-        for (int i = 1; i < kMixConsumers; ++i) r = nan_max(r, s_red[i]);
+        unsigned rb = __float_as_uint(s_red[0]);
+        for (int i = 1; i < kMixConsumers; ++i) rb = max(rb, __float_as_uint(s_red[i]));
+        const float r = __uint_as_float(rb);
         a.tile_max[tile_id] = r;
         if (a.seg_scale) {
             __threadfence();  // the tile maximum is visible before the ticket is taken
@@ -422,12 +424,15 @@ __global__ void __launch_bounds__(kMixThreads, kMixCtasPerSm) mix_kernel(const M
 #pragma unroll
             for (int j = 0; j < kPerThread; ++j) acc[j] = fmaf(src[j * (kMixConsumers * 32)], coef, acc[j]);
         } else {
+            // A note starts or ends inside the tile: this thread's samples tid + T*j lie inside [vlo, vhi) for
+            // jlo <= j < jhi.  One bit mask per slice instead of two compares per sample (the kernel is issue-bound);
+            // samples outside the note stay untouched even when coef is inf / NaN.
+            constexpr int T = kMixConsumers * 32;
+            const int jlo = (max(vlo - tid, 0) + T - 1) / T, jhi = min((max(vhi - tid, 0) + T - 1) / T, kPerThread);
+            const unsigned mask = jhi > jlo ? ((1u << jhi) - 1u) & ~((1u << jlo) - 1u) : 0u;
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j) {
-                const int i = tid + j * (kMixConsumers * 32);
-                // samples outside the note stay untouched even when coef is inf / NaN
-                if (i >= vlo && i < vhi) acc[j] = fmaf(src[j * (kMixConsumers * 32)], coef, acc[j]);
-            }
+            for (int j = 0; j < kPerThread; ++j)
+                if ((mask >> j) & 1u) acc[j] = fmaf(src[j * T], coef, acc[j]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty + stage);
