@@ -184,15 +184,18 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
 // atomic counter, so long and short tiles balance.  Measured on B200 (tools/gpu_variants.sh): the
 // kernel is bound by the latency chain of a tile (queue head -> tile_ptr -> events -> records -> TMA),
 // so many small CTAs (4 consumer warps x 16 samples per thread, a 2-slot ring, 8 CTAs per SM) beat
-// few large ones (8 x 8, 6 slots, 4 per SM) by 12 % on the whole render.
+// few large ones (8 x 8, 6 slots, 4 per SM) by 12 % on the whole render.  The kernel is issue-bound (ncu: 75 % issue
+// utilisation, a fifth of the instructions useful LDS + FFMA), so the per-slice hand-off is paid by as few warps as
+// possible: 2 consumer warps x 32 samples per thread, and as many CTAs as shared memory holds (10-11 per SM, launch
+// bound 12 = 55 registers) measured 15.04 ms per step against 15.26 ms for 4 x 16 / 8 CTAs.
 #ifndef ADTFE_MIX_CONSUMERS
-#define ADTFE_MIX_CONSUMERS 4
+#define ADTFE_MIX_CONSUMERS 2
 #endif
 #ifndef ADTFE_MIX_STAGES
 #define ADTFE_MIX_STAGES 2
 #endif
 #ifndef ADTFE_MIX_CTAS
-#define ADTFE_MIX_CTAS 8
+#define ADTFE_MIX_CTAS 12
 #endif
 constexpr int kMixConsumers = ADTFE_MIX_CONSUMERS;       // warps; each thread owns tile / (32 * warps) samples
 constexpr int kMixThreads = (kMixConsumers + 1) * 32;    // + the producer warp
@@ -200,7 +203,8 @@ constexpr int kPerThread = ADTFE_TILE / (kMixConsumers * 32);
 constexpr int kStages = ADTFE_MIX_STAGES;
 constexpr int kMixCtasPerSm = ADTFE_MIX_CTAS;
 constexpr int kStageFloats = 2080;                       // >= 2048 + 2*3 alignment slack, bytes a multiple of 128
-static_assert(kPerThread * kMixConsumers * 32 == ADTFE_TILE && kPerThread < 32, "tile / consumer threads");
+static_assert(kPerThread * kMixConsumers * 32 == ADTFE_TILE && kPerThread <= 32 && kPerThread % 2 == 0,
+              "tile / consumer threads");
 
 struct __align__(16) StageDesc {   // written by the producer lane, read (broadcast) by every consumer
     int32_t kind;                  // 0: data, 1: a new tile begins (tile id in `tile`, < 0: no more work)
@@ -243,7 +247,7 @@ struct MixArgs {
 };
 
 // Writes the finished (not yet normalised) tile and publishes its |max|.
-__device__ __forceinline__ void finish_tile(const MixArgs& a, int tile_id, const float (&acc)[kPerThread], int tid,
+__device__ __forceinline__ void finish_tile(const MixArgs& a, int tile_id, const float2 (&acc2)[kPerThread / 2], int tid,
                                             float* s_red) {
     const int seg = tile_id / a.tiles_per_seg, lo = (tile_id - seg * a.tiles_per_seg) * ADTFE_TILE;
     // |max| on the float bits: non-negative floats order like unsigned integers and a NaN's bits lie above infinity's,
@@ -253,8 +257,9 @@ __device__ __forceinline__ void finish_tile(const MixArgs& a, int tile_id, const
 #pragma unroll
     for (int j = 0; j < kPerThread; ++j) {
         const int n = lo + tid + j * (kMixConsumers * 32);
-        if (n < a.ld_wav) row[n] = acc[j];
-        mb = max(mb, __float_as_uint(fabsf(acc[j])));
+        const float v = (j & 1) ? acc2[j >> 1].y : acc2[j >> 1].x;
+        if (n < a.ld_wav) row[n] = v;
+        mb = max(mb, __float_as_uint(fabsf(v)));
     }
     mb = __reduce_max_sync(0xffffffffu, mb);
     consumer_sync();  // s_red of the previous tile is no longer read
@@ -398,9 +403,11 @@ __global__ void __launch_bounds__(kMixThreads, kMixCtasPerSm) mix_kernel(const M
     }
 
     // ================= consumer warps =================
-    float acc[kPerThread];
+    // sample j of the thread (tile index tid + T*j) is component j & 1 of acc2[j / 2]: a full slice costs one
+    // packed FFMA2 per two samples (the kernel is issue-bound)
+    float2 acc2[kPerThread / 2];
 #pragma unroll
-    for (int j = 0; j < kPerThread; ++j) acc[j] = 0.0f;
+    for (int k = 0; k < kPerThread / 2; ++k) acc2[k] = make_float2(0.0f, 0.0f);
     int tile = -1;
     for (;;) {
         mbar_wait_relaxed(s_full + stage, phase, 2000u);
@@ -409,11 +416,11 @@ __global__ void __launch_bounds__(kMixThreads, kMixCtasPerSm) mix_kernel(const M
             __syncwarp();
             if (lane == 0) mbar_arrive(s_empty + stage);
             if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            if (tile >= 0) finish_tile(a, tile, acc, tid, s_red);
+            if (tile >= 0) finish_tile(a, tile, acc2, tid, s_red);
             tile = d0.y;
             if (tile < 0) break;
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j) acc[j] = 0.0f;
+            for (int k = 0; k < kPerThread / 2; ++k) acc2[k] = make_float2(0.0f, 0.0f);
             continue;
         }
         const int4 d1 = *reinterpret_cast<const int4*>(reinterpret_cast<const char*>(s_desc + stage) + 16);
@@ -421,18 +428,27 @@ __global__ void __launch_bounds__(kMixThreads, kMixCtasPerSm) mix_kernel(const M
         const float coef = __int_as_float(d1.y);
         const float* src = s_buf + stage * kStageFloats + d0.z + tid;
         if (vlo == 0 && vhi == ADTFE_TILE) {
+            constexpr int T = kMixConsumers * 32;
+            const float2 c2 = make_float2(coef, coef);
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j) acc[j] = fmaf(src[j * (kMixConsumers * 32)], coef, acc[j]);
+            for (int k = 0; k < kPerThread / 2; ++k)
+                acc2[k] = __ffma2_rn(make_float2(src[(2 * k) * T], src[(2 * k + 1) * T]), c2, acc2[k]);
         } else {
             // A note starts or ends inside the tile: this thread's samples tid + T*j lie inside [vlo, vhi) for
             // jlo <= j < jhi.  One bit mask per slice instead of two compares per sample (the kernel is issue-bound);
             // samples outside the note stay untouched even when coef is inf / NaN.
             constexpr int T = kMixConsumers * 32;
             const int jlo = (max(vlo - tid, 0) + T - 1) / T, jhi = min((max(vhi - tid, 0) + T - 1) / T, kPerThread);
-            const unsigned mask = jhi > jlo ? ((1u << jhi) - 1u) & ~((1u << jlo) - 1u) : 0u;
+            const unsigned below_hi = jhi >= 32 ? 0xffffffffu : (1u << jhi) - 1u;
+            const unsigned below_lo = jlo >= 32 ? 0xffffffffu : (1u << jlo) - 1u;
+            const unsigned mask = below_hi & ~below_lo;   // empty when jhi <= jlo
 #pragma unroll
-            for (int j = 0; j < kPerThread; ++j)
-                if ((mask >> j) & 1u) acc[j] = fmaf(src[j * T], coef, acc[j]);
+            for (int j = 0; j < kPerThread; ++j) {
+                if ((mask >> j) & 1u) {
+                    if (j & 1) acc2[j >> 1].y = fmaf(src[j * T], coef, acc2[j >> 1].y);
+                    else acc2[j >> 1].x = fmaf(src[j * T], coef, acc2[j >> 1].x);
+                }
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(s_empty + stage);
