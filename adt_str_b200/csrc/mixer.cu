@@ -58,14 +58,17 @@ __device__ __forceinline__ float2 mix2(float ax, float ay, float bx, float by, f
 
 // max|ca*a + cb*b| over the float4s held in registers, for NC notes at once: per pair of samples two
 // packed fp32 instructions and one three-input FMNMX; the warp's maximum by one REDUX on the float bits
-// (non-negative floats order like unsigned integers), the CTA's through a shared-memory atomicMax.
+// (non-negative floats order like unsigned integers), published with one global atomicMax per warp and note
+// (no shared-memory staging, no CTA barrier: barriers were 12 % of the kernel's stalls).
 template <int NC>
 __device__ __forceinline__ void peak_chunk(const float4 (&va)[kPeakIters], const float4 (&vb)[kPeakIters],
-                                           const float* __restrict__ s_ca, const float* __restrict__ s_cb,
-                                           unsigned* s_peak, int tid) {
+                                           const adtfe_event* __restrict__ ev, int* __restrict__ peak_bits, int tid) {
     float ca[NC], cb[NC], m[NC];
 #pragma unroll
-    for (int i = 0; i < NC; ++i) { ca[i] = s_ca[i]; cb[i] = s_cb[i]; m[i] = 0.0f; }
+    for (int i = 0; i < NC; ++i) {   // the same address in every thread: broadcast loads that hit L1
+        const float2 c = __ldg(reinterpret_cast<const float2*>(&ev[i].ca));
+        ca[i] = c.x; cb[i] = c.y; m[i] = 0.0f;
+    }
 #pragma unroll
     for (int it = 0; it < kPeakIters; ++it) {
 #pragma unroll
@@ -77,9 +80,9 @@ __device__ __forceinline__ void peak_chunk(const float4 (&va)[kPeakIters], const
         }
     }
 #pragma unroll
-    for (int i = 0; i < NC; ++i) {
+    for (int i = 0; i < NC; ++i) {   // one REDUX per warp and note, then straight to the note's global maximum
         const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(m[i]));
-        if ((tid & 31) == 0 && w != 0u) atomicMax(s_peak + i, w);
+        if ((tid & 31) == 0 && w != 0u) atomicMax(peak_bits + i, (int)w);
     }
 }
 
@@ -91,8 +94,6 @@ __device__ __forceinline__ void peak_chunk(const float4 (&va)[kPeakIters], const
 __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
     const float* __restrict__ pcm, const adtfe_event* __restrict__ events, const adtfe_peak_item* __restrict__ work,
     ResolvedEvent* __restrict__ resolved, int* __restrict__ peak_bits) {
-    __shared__ unsigned s_peak[kPeakChunk];
-    __shared__ float s_ca[kPeakChunk], s_cb[kPeakChunk];
     const adtfe_peak_item item = work[blockIdx.x / kPeakSplit];  // one fetch, then the data loads can start
     const int sub = blockIdx.x % kPeakSplit;                     // which part of the item's span this CTA scans
     const int chunk = item.chunk, tid = threadIdx.x;
@@ -137,43 +138,35 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
         }
     }
     if (!interior) {
+        // the float4 that holds a one-shot's last sample: ignore whatever pads it (all later ones were not loaded)
+        const int qa = la >> 2, ra = la & 3, qb = lb >> 2, rb = lb & 3;
 #pragma unroll
-        for (int it = 0; it < kPeakIters; ++it) {  // last float4 of a one-shot: ignore whatever pads it
+        for (int it = 0; it < kPeakIters; ++it) {
             const int i4 = lo4 + tid + it * kPeakThreads;
-            if (4 * i4 + 3 >= la) {
-                if (4 * i4 + 1 >= la) va[it].y = 0.f;
-                if (4 * i4 + 2 >= la) va[it].z = 0.f;
+            if (i4 == qa && ra != 0) {
+                if (ra < 2) va[it].y = 0.f;
+                if (ra < 3) va[it].z = 0.f;
                 va[it].w = 0.f;
             }
-            if (4 * i4 + 3 >= lb) {
-                if (4 * i4 + 1 >= lb) vb[it].y = 0.f;
-                if (4 * i4 + 2 >= lb) vb[it].z = 0.f;
+            if (i4 == qb && rb != 0) {
+                if (rb < 2) vb[it].y = 0.f;
+                if (rb < 3) vb[it].z = 0.f;
                 vb[it].w = 0.f;
             }
         }
     }
     for (int c0 = e0; c0 < e1; c0 += kPeakChunk) {
         const int nc = min(kPeakChunk, e1 - c0);
-        __syncthreads();  // the previous sweep's peaks have been published
-        if (tid < kPeakChunk) {
-            const bool live = tid < nc;
-            s_ca[tid] = live ? events[c0 + tid].ca : 0.0f;
-            s_cb[tid] = live ? events[c0 + tid].cb : 0.0f;
-            s_peak[tid] = 0u;
-        }
-        __syncthreads();
         switch (nc) {
-            case 1: peak_chunk<1>(va, vb, s_ca, s_cb, s_peak, tid); break;
-            case 2: peak_chunk<2>(va, vb, s_ca, s_cb, s_peak, tid); break;
-            case 3: peak_chunk<3>(va, vb, s_ca, s_cb, s_peak, tid); break;
-            case 4: peak_chunk<4>(va, vb, s_ca, s_cb, s_peak, tid); break;
-            case 5: peak_chunk<5>(va, vb, s_ca, s_cb, s_peak, tid); break;
-            case 6: peak_chunk<6>(va, vb, s_ca, s_cb, s_peak, tid); break;
-            case 7: peak_chunk<7>(va, vb, s_ca, s_cb, s_peak, tid); break;
-            default: peak_chunk<8>(va, vb, s_ca, s_cb, s_peak, tid); break;
+            case 1: peak_chunk<1>(va, vb, events + c0, peak_bits + c0, tid); break;
+            case 2: peak_chunk<2>(va, vb, events + c0, peak_bits + c0, tid); break;
+            case 3: peak_chunk<3>(va, vb, events + c0, peak_bits + c0, tid); break;
+            case 4: peak_chunk<4>(va, vb, events + c0, peak_bits + c0, tid); break;
+            case 5: peak_chunk<5>(va, vb, events + c0, peak_bits + c0, tid); break;
+            case 6: peak_chunk<6>(va, vb, events + c0, peak_bits + c0, tid); break;
+            case 7: peak_chunk<7>(va, vb, events + c0, peak_bits + c0, tid); break;
+            default: peak_chunk<8>(va, vb, events + c0, peak_bits + c0, tid); break;
         }
-        __syncthreads();
-        if (tid < nc && s_peak[tid] != 0u) atomicMax(peak_bits + c0 + tid, (int)s_peak[tid]);
     }
 }
 
