@@ -62,7 +62,7 @@ def parse_args():
     p.add_argument("--e2e-workers", type=int, default=0,
                    help="planner threads of the end-to-end pipeline (0 = host cores / ranks, at most 8)")
     p.add_argument("--e2e-sets", type=int, default=4, help="rotating buffer sets of the end-to-end pipeline")
-    p.add_argument("--chunk-batches", type=int, default=16, help="batches rendered together as one chunk")
+    p.add_argument("--chunk-batches", type=int, default=64, help="batches rendered together as one chunk")
     return p.parse_args()
 
 
