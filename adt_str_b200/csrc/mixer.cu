@@ -6,19 +6,21 @@
 //   instrument_mixer 149-156: wav = sum_i track_i * gain_i ; wav / max|wav| * max_volume
 // and the zero padding of collate_fn (data_modules/train_dataset.py:53).
 //
-// The two data-dependent maxima make it two short kernels:
+// The two data-dependent maxima make it three short kernels per chunk of segments:
 //   1. peak_kernel      one CTA per (segment, instrument, 4096-sample chunk): both one-shots are
 //                       read once and max|ca*a + cb*b| is taken for every note of that
-//                       instrument at the same time (each note has its own mixup); chunks meet
-//                       in an atomicMax on the float bits (order-independent); chunk 0 also
+//                       instrument at the same time (each note has its own mixup); warps and chunks
+//                       meet in an atomicMax on the float bits (order-independent); chunk 0 also
 //                       resolves the bank lookups into ResolvedEvent records.
-//   2. mix_kernel       one CTA per 2048-sample output tile; events come from the host-built
-//                       CSR (tile -> events) and are added in array order into registers,
-//                       so the result is deterministic and needs no atomics; emits the
-//                       tile's |max|.
-//                       The last CTA of a segment to finish (atomic ticket) takes the max of the
-//                       tile maxima and normalises the row in place, wav / peak * max_volume
+//   2. mix_kernel       persistent CTAs take 2048-sample output tiles from a queue; a producer warp
+//                       streams the tile's one-shot slices through a shared-memory ring with TMA bulk
+//                       copies, consumer warps add them in event order (the host-built CSR
+//                       tile -> events) into registers, so the result is deterministic and needs no
+//                       atomics; writes the raw tile and its |max|.
+//   3. normalise_kernel row peak = max of the tile maxima; wav / peak * max_volume in place
 //                       (an all-zero mix gives NaN, like the reference's 0/0).
+// Opt-in (adtfe_render_logmel with ADTFE_FOLD=1): the mixer writes the raw mix elsewhere and publishes every
+// row's SegScale, normalise_rows_kernel writes the rows out of place beside the log-mel.
 #include <algorithm>
 #include <mutex>
 
@@ -27,7 +29,7 @@
 namespace adtfe {
 
 #ifndef ADTFE_PEAK_THREADS
-#define ADTFE_PEAK_THREADS 128   // 128 x 96 registers: 6 % faster render than 256 x 64 (more CTAs fit beside the mixer)
+#define ADTFE_PEAK_THREADS 128   // 128 x 94 registers: 6 % faster render than 256 x 64; 64 = two CTAs per work item
 #endif
 constexpr int kPeakThreads = ADTFE_PEAK_THREADS;
 constexpr int kPeakChunk = 8;   // notes of one instrument handled per sweep over the one-shots
