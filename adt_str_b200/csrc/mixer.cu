@@ -221,7 +221,7 @@ constexpr int kIssue = kStages / 2 > 0 ? kStages / 2 : 1;  // messages issued pe
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kMixConsumers * 32) : "memory"); }
 
 __host__ __device__ constexpr size_t mix_list_offset() {
-    return (((size_t)kStages * kStageFloats * 4 + kStages * 32 + 2 * kStages * 8 + kMixConsumers * 4) + 15) & ~(size_t)15;
+    return (((size_t)kStages * kStageFloats * 4 + kStages * 32 + 2 * kStages * 8 + (kMixConsumers + 2) * 4) + 15) & ~(size_t)15;
 }
 
 struct MixArgs {
@@ -236,9 +236,12 @@ struct MixArgs {
     int* tile_counter;
     int64_t ld_wav;
     int32_t tiles_per_seg, n_tiles;
-    // folded normalisation: the CTA that finishes a segment's last tile publishes the row scale
+    // seg_ticket: one counter per segment - the CTA that finishes a segment's last tile knows the row peak.  It then
+    // normalises the row in place (normalise_rows != 0: the default render) or publishes the row's scale for the
+    // opt-in folded form (seg_scale != NULL).
     int* seg_ticket;
     SegScale* seg_scale;
+    int normalise_rows;
 };
 
 // Writes the finished (not yet normalised) tile and publishes its |max|.
@@ -257,30 +260,67 @@ __device__ __forceinline__ void finish_tile(const MixArgs& a, int tile_id, const
         mb = max(mb, __float_as_uint(fabsf(v)));
     }
     mb = __reduce_max_sync(0xffffffffu, mb);
+    if (a.seg_ticket) __threadfence();  // this thread's samples are visible before the CTA takes the segment's ticket
     consumer_sync();  // s_red of the previous tile is no longer read
     if ((tid & 31) == 0) s_red[tid >> 5] = __uint_as_float(mb);
     consumer_sync();
+    float* s_last = s_red + kMixConsumers;  // {1.0 when this CTA finished the segment, the row peak}
     if (tid == 0) {
         unsigned rb = __float_as_uint(s_red[0]);
         for (int i = 1; i < kMixConsumers; ++i) rb = max(rb, __float_as_uint(s_red[i]));
         const float r = __uint_as_float(rb);
         a.tile_max[tile_id] = r;
-        if (a.seg_scale) {
+        float last = 0.0f, pk = 0.0f;
+        if (a.seg_ticket) {
             __threadfence();  // the tile maximum is visible before the ticket is taken
             if (atomicAdd(a.seg_ticket + seg, 1) == a.tiles_per_seg - 1) {
                 __threadfence();
-                float pk = 0.0f;
                 for (int t = 0; t < a.tiles_per_seg; ++t) pk = nan_max(pk, __ldcg(a.tile_max + seg * a.tiles_per_seg + t));
-                const adtfe_segment sg = a.segments[seg];
-                SegScale sc;
-                sc.peak = pk; sc.r = __frcp_rn(pk); sc.vol = sg.max_volume;
-                const float q = __fdiv_rn(sg.max_volume, pk);
-                sc.s2 = sg.flags != 0 ? q * q : 1.0f;   // an empty segment is all zeros: nothing to scale
-                sc.len = sg.len; sc.flags = sg.flags; sc.pad0 = 0; sc.pad1 = 0;
-                a.seg_scale[seg] = sc;
+                last = 1.0f;
+                if (a.seg_scale) {
+                    const adtfe_segment sg = a.segments[seg];
+                    SegScale sc;
+                    sc.peak = pk; sc.r = __frcp_rn(pk); sc.vol = sg.max_volume;
+                    const float q = __fdiv_rn(sg.max_volume, pk);
+                    sc.s2 = sg.flags != 0 ? q * q : 1.0f;   // an empty segment is all zeros: nothing to scale
+                    sc.len = sg.len; sc.flags = sg.flags; sc.pad0 = 0; sc.pad1 = 0;
+                    a.seg_scale[seg] = sc;
+                }
             }
         }
+        s_last[0] = last; s_last[1] = pk;
     }
+    if (!a.normalise_rows) return;
+    consumer_sync();
+    if (s_last[0] == 0.0f) return;
+    // This CTA finished the segment: every tile of the row is in L2 (each writer fenced before its ticket), so the row
+    // is normalised here and now - wav / peak * max_volume with normalise_kernel's arithmetic - instead of by a
+    // kernel that streams it from HBM again.  Samples beyond the segment's length stay as mixed (zeros).
+    const adtfe_segment sg = a.segments[seg];
+    if (sg.flags == 0) return;
+    const float peak = s_last[1], vol = sg.max_volume, r = __frcp_rn(peak);
+    auto norm = [&](float v) {
+        const float q = __fmul_rn(v, r);
+        const float rem = __fmaf_rn(-q, peak, v);
+        return __fmul_rn(__fmaf_rn(rem, r, q), vol);
+    };
+    constexpr int T = kMixConsumers * 32;
+    float4* row4 = reinterpret_cast<float4*>(row);
+    const int n4 = sg.len >> 2;
+    for (int base = 0; base < n4; base += 8 * T) {   // eight loads in flight per thread
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * T + tid;
+            v[u] = i < n4 ? __ldcg(row4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = base + u * T + tid;
+            if (i < n4) row4[i] = make_float4(norm(v[u].x), norm(v[u].y), norm(v[u].z), norm(v[u].w));
+        }
+    }
+    for (int i = 4 * n4 + tid; i < sg.len; i += T) row[i] = norm(__ldcg(row + i));
 }
 
 __global__ void __launch_bounds__(kMixThreads, kMixCtasPerSm) mix_kernel(const MixArgs a) {
@@ -547,7 +587,8 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg) {
     if (n_events < 0 || n_seg < 0 || tiles_per_seg < 0) return 0;
-    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_events * 4 + (size_t)n_seg * 4 + 4) +
+    // resolved events | peak bits, queue heads, segment tickets (one zeroed block) | tile maxima
+    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_events * 4 + (size_t)n_seg * 8 + 4) +
            align256((size_t)n_seg * tiles_per_seg * 4) + 256;
 }
 
@@ -618,14 +659,19 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
     ResolvedEvent* resolved = (ResolvedEvent*)ws;
     int* peak_bits = (int*)(ws + align256((size_t)plan->n_events * sizeof(ResolvedEvent)));
     int* counters = peak_bits + plan->n_events;  // one work-queue head per chunk (n_chunks <= n_seg)
-    float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4 + (size_t)plan->n_seg * 4 + 4));
+    int* tickets = counters + plan->n_seg + 1;   // one per segment: elects the CTA that finishes the row
+    float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4 + (size_t)plan->n_seg * 8 + 4));
+    // ADTFE_NORM_FUSED=1: the CTA that finishes a segment's last tile normalises the row inside the tile mixer (no
+    // normalise kernel, the row is still in L2).  Bit-identical, but measured slower on B200 (14.73 ms per step
+    // against 14.50 ms: the row pass stalls that CTA's ring), so the separate kernel stays the default.
+    const bool fused_norm = !raw_out && getenv("ADTFE_NORM_FUSED") != nullptr;
     static bool smem_set[64] = {};
     if (bank->device < 64 && !smem_set[bank->device]) {
         ADTFE_CUDA(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mix_smem_bytes()));
         smem_set[bank->device] = true;
     }
     // zero the peaks and the queue heads once, then fork the chunks over the bank's streams
-    ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, ((size_t)plan->n_events + plan->n_seg + 1) * 4, user));
+    ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, ((size_t)plan->n_events + 2 * (size_t)plan->n_seg + 1) * 4, user));
     const bool fork = n_chunks > 1 && bank->n_streams > 0;
     std::unique_lock<std::mutex> lock(bank->mu, std::defer_lock);
     if (fork) {
@@ -659,13 +705,15 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
         a.segments = plan->segments_dev + s0; a.wav = mix_out + (size_t)s0 * plan->ld_wav;
         a.tile_max = tile_max + (size_t)s0 * tps; a.tile_counter = counters + c; a.ld_wav = plan->ld_wav;
         a.tiles_per_seg = tps; a.n_tiles = n_seg * tps;
-        a.seg_ticket = raw_out ? seg_ticket + s0 : nullptr; a.seg_scale = raw_out ? seg_scale_out + s0 : nullptr;
+        a.seg_ticket = raw_out ? seg_ticket + s0 : (fused_norm ? tickets + s0 : nullptr);
+        a.seg_scale = raw_out ? seg_scale_out + s0 : nullptr;
+        a.normalise_rows = fused_norm ? 1 : 0;
         const int grid = std::min(a.n_tiles, kMixCtasPerSm * bank->sm_count);
         trace_open("mix", c, st);
         mix_kernel<<<grid, kMixThreads, mix_smem_bytes(), st>>>(a);
         trace_close(st);
         ADTFE_CUDA(cudaGetLastError());
-        if (!raw_out) {
+        if (!raw_out && !fused_norm) {
             trace_open("normalise", c, st);
             normalise_kernel<<<a.n_tiles, kNormThreads, 0, st>>>(a.segments, a.tile_max, tps, plan->ld_wav, a.wav);
             trace_close(st);

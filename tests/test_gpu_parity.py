@@ -307,6 +307,33 @@ def test_folded_normalisation_equals_normalise_then_logmel(monkeypatch):
     monkeypatch.delenv("ADTFE_FOLD", raising=False)
 
 
+def test_mixer_fused_normalisation_is_bit_identical(monkeypatch):
+    """ADTFE_NORM_FUSED=1: the tile mixer CTA that finishes a segment's last tile (atomic ticket) normalises the row
+    itself instead of the separate kernel - same arithmetic, so the same bits, including empty and all-zero rows."""
+    from adt_str_b200.config import setting_1
+    from adt_str_b200.synthetic import make_bank, make_segments
+    bank = make_bank(390, 24000, seed=20)
+    bank.pcm[bank.offsets[3]: bank.offsets[3] + bank.lengths[3]] = 0.0
+    _, _, fe = _objects(setting_1(), bank)
+    segs = make_segments(70, seed=25, empty_fraction=0.1)
+    batches = [segs[:9], segs[9:10], segs[10:40], segs[40:]]
+    out = {}
+    for fused in (False, True, False):
+        if fused:
+            monkeypatch.setenv("ADTFE_NORM_FUSED", "1")
+        else:
+            monkeypatch.delenv("ADTFE_NORM_FUSED", raising=False)
+        plan = fe.plan_batches(batches, random.Random(5), 2)
+        for _ in range(2):
+            wav, feat = fe.run_plan(plan)
+        torch.cuda.synchronize()
+        out.setdefault(fused, (wav.clone(), feat.clone()))
+    monkeypatch.delenv("ADTFE_NORM_FUSED", raising=False)
+    same = lambda a, b: torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
+    assert same(out[True][0], out[False][0]) and same(out[True][1], out[False][1])
+    assert float(out[False][0].abs().nan_to_num().max()) > 0.1
+
+
 def test_pipelined_front_end_equals_render_then_logmel(monkeypatch):
     """adtfe_render_logmel on a chunked plan featurises finished chunk groups (co-resident log-mel shape on the
     bank's mel stream) while later chunks render; whatever the group size, the waveforms and the log-mel are bit for
