@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define ADTFE_VERSION 2
+#define ADTFE_VERSION 3
 #define ADTFE_TILE 2048      /* output samples owned by one mixer CTA */
 #define ADTFE_PEAK_SPAN 4096 /* samples of a mixed one-shot scanned by one peak work item */
 
