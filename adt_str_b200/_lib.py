@@ -15,7 +15,7 @@ EXPORTS = [
     "adtfe_bank_create", "adtfe_bank_destroy", "adtfe_bank_bytes",
     "adtfe_render_workspace_bytes", "adtfe_render",
     "adtfe_mel_create", "adtfe_mel_destroy", "adtfe_mel_frames", "adtfe_mel_fast_path", "adtfe_logmel", "adtfe_logmel_rows",
-    "adtfe_render_logmel", "adtfe_render_logmel_workspace_bytes", "adtfe_frontend_host", "adtfe_plan_blob_layout",
+    "adtfe_render_logmel", "adtfe_mel_force_generic", "adtfe_frontend_host", "adtfe_plan_blob_layout",
     "adtfe_resampler_create", "adtfe_resampler_destroy", "adtfe_resample_length", "adtfe_resample", "adtfe_downmix",
     "adtfe_peak_normalise",
     "adtfe_trace_begin", "adtfe_trace_dump",
@@ -53,8 +53,7 @@ def _declare(lib) -> None:
     lib.adtfe_render_workspace_bytes.argtypes = [i32, i32, i32]
     lib.adtfe_render_workspace_bytes.restype = sz
     lib.adtfe_render.argtypes = [vp, C.POINTER(Plan), vp, vp, sz, vp]
-    lib.adtfe_render_logmel_workspace_bytes.argtypes = [i32, i32, i32, i64]
-    lib.adtfe_render_logmel_workspace_bytes.restype = sz
+    lib.adtfe_mel_force_generic.argtypes = [vp, i32]
     lib.adtfe_mel_create.argtypes = [i32, i32, i32, vp, vp, C.c_int, C.POINTER(vp)]
     lib.adtfe_mel_destroy.argtypes = [vp]
     lib.adtfe_mel_fast_path.argtypes = [vp]

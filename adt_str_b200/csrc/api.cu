@@ -51,11 +51,6 @@ int device_sm_count(int device) {
 
 using namespace adtfe;
 
-#ifndef ADTFE_CO_GROUP_DEFAULT
-#define ADTFE_CO_GROUP_DEFAULT 0
-#endif
-constexpr int kCoGroupDefault = ADTFE_CO_GROUP_DEFAULT;
-
 extern "C" int adtfe_version(void) { return ADTFE_VERSION; }
 extern "C" const char* adtfe_last_error(void) { return g_error; }
 
@@ -113,8 +108,6 @@ extern "C" int adtfe_bank_destroy(adtfe_bank* bank) {
         if (bank->join_events[k]) cudaEventDestroy(bank->join_events[k]);
     }
     if (bank->fork_event) cudaEventDestroy(bank->fork_event);
-    if (bank->mel_stream) cudaStreamDestroy(bank->mel_stream);
-    if (bank->mel_event) cudaEventDestroy(bank->mel_event);
     delete bank;
     return ADTFE_OK;
 }
@@ -156,17 +149,13 @@ extern "C" int adtfe_bank_create(const float* pcm_host, int64_t total_floats, co
         adtfe_bank_destroy(b);
         return ADTFE_ERR_CUDA;
     }
+    rc = mixer_prepare_device();
+    if (rc != ADTFE_OK) { adtfe_bank_destroy(b); return rc; }
     bool ok = cudaEventCreateWithFlags(&b->fork_event, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; ok && k < kBankStreams; ++k) {
         ok = cudaStreamCreateWithFlags(&b->streams[k], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&b->join_events[k], cudaEventDisableTiming) == cudaSuccess;
         if (ok) b->n_streams = k + 1;
-    }
-    if (ok) {
-        int least = 0, greatest = 0;
-        ok = cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess &&
-             cudaStreamCreateWithPriority(&b->mel_stream, cudaStreamNonBlocking, greatest) == cudaSuccess &&
-             cudaEventCreateWithFlags(&b->mel_event, cudaEventDisableTiming) == cudaSuccess;
     }
     if (!ok) {
         set_error("adtfe_bank_create: cannot create streams: %s", cudaGetErrorString(cudaGetLastError()));
@@ -182,69 +171,6 @@ extern "C" int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel,
                                    size_t workspace_bytes, void* stream) {
     ADTFE_REQUIRE(plan && (plan->mel_rows_dev || n_samples <= plan->ld_wav), ADTFE_ERR_BAD_ARG,
                   "adtfe_render_logmel: n_samples exceeds the row pitch");
-    // A chunked plan with ragged rows can be pipelined: the log-mel of a finished group of chunks runs beside the
-    // render of the following ones (ADTFE_CO_GROUP chunks per group; 0 = render everything first, the default:
-    // on B200 the co-running kernels take as long as they do one after the other - the render's latency-bound kernels need the
-    // occupancy the log-mel CTAs take, and both lose what the other gains, see DESIGN.md "Pipelined front end").
-    const char* co_env = getenv("ADTFE_CO_GROUP");
-    const int co_group = co_env ? atoi(co_env) : kCoGroupDefault;
-    if (co_group > 0 && mel && mel->v6co_ok && plan->mel_rows_dev && plan->chunks_host && plan->n_chunks > co_group &&
-        bank && bank->n_streams > 0 && mel_out_dev) {
-        const MelStage ms = {mel, mel_out_dev, co_group};
-        return render_impl(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream, &ms);
-    }
-    // With a workspace of adtfe_render_logmel_workspace_bytes the row normalisation leaves the critical path: the
-    // mixer writes the raw mix into the workspace and publishes every row's scale, the log-mel reads the raw mix and
-    // scales its mel sums by (max_volume / peak)^2, and the normalised rows are written by a kernel that runs BESIDE
-    // the log-mel (which leaves L2 idle) instead of between the render kernels.
-    // Measured on B200 (tools/_ab: 16.2 ms per step against 15.85 ms for normalise-in-place-then-log-mel): the render
-    // does get shorter (7.8 -> 6.7 ms), but the out-of-place rows cost 8 GB more DRAM traffic per step (the in-place
-    // pass works on an L2-resident chunk) and the log-mel loses more beside it than the render gains, so the form is
-    // opt-in: ADTFE_FOLD=1.  Default (or a smaller workspace): normalise in place, then log-mel.
-    if (mel && mel_out_dev && wav_out_dev && bank && bank->n_streams > 0 && plan->n_seg > 0 && plan->tiles_per_seg > 0 &&
-        plan->tiles_per_seg <= 64 &&
-        getenv("ADTFE_FOLD") && !getenv("ADTFE_NO_FOLD") &&
-        workspace_bytes >= adtfe_render_logmel_workspace_bytes(plan->n_events, plan->n_seg, plan->tiles_per_seg,
-                                                               plan->ld_wav)) {
-        const size_t base = adtfe_render_workspace_bytes(plan->n_events, plan->n_seg, plan->tiles_per_seg);
-        float* raw = (float*)(((uintptr_t)workspace_dev + base + 255) & ~(uintptr_t)255);
-        // can the v6 kernel take this launch?  (checked before anything is enqueued)
-        int32_t first = 0, count = 0;
-        if (!plan->mel_rows_dev) adtfe_mel_frames(mel, n_samples, &first, &count);
-        const bool geometry_ok = mel->v6_ok && !getenv("ADTFE_LOGMEL_V5") && ((uintptr_t)wav_out_dev & 15) == 0 &&
-                                 plan->ld_wav % 4 == 0 && (int64_t)mel->wpi * mel->hop >= 1024 &&
-                                 (plan->mel_rows_dev
-                                      ? (int64_t)(mel->wpi + plan->mel_max_count - 1) * mel->hop + 1024 <= plan->ld_wav
-                                      : (count == 0 || (int64_t)(first + count - 1) * mel->hop + 1024 <= n_samples));
-        if (geometry_ok) {
-            char* after_raw = (char*)raw + (((size_t)plan->n_seg * (size_t)plan->ld_wav * 4 + 255) & ~(size_t)255);
-            SegScale* seg_scale = (SegScale*)after_raw;
-            int* seg_ticket = (int*)(after_raw + (((size_t)plan->n_seg * sizeof(SegScale) + 255) & ~(size_t)255));
-            int rc = render_impl(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream, nullptr, raw, seg_scale,
-                                 seg_ticket);
-            if (rc != ADTFE_OK) return rc;
-            const FoldStage fold = {seg_scale};
-            // the log-mel first (its persistent CTAs take their slots), the row normalisation beside it on an
-            // internal stream: both only read the raw mix
-            cudaStream_t user = (cudaStream_t)stream, side = bank->streams[0];
-            {
-                std::lock_guard<std::mutex> lock(bank->mu);
-                ADTFE_CUDA(cudaEventRecord(bank->fork_event, user));
-                ADTFE_CUDA(cudaStreamWaitEvent(side, bank->fork_event, 0));
-            }
-            trace_open("logmel", -2, user);
-            rc = logmel_fold(mel, raw, plan->n_seg, plan->ld_wav, n_samples, plan->mel_rows_dev, plan->mel_max_count,
-                             mel_out_dev, &fold, stream);
-            trace_close(user);
-            if (rc != ADTFE_OK) return rc;
-            rc = normalise_rows(bank, plan, seg_scale, raw, wav_out_dev, side);
-            if (rc != ADTFE_OK) return rc;
-            std::lock_guard<std::mutex> lock(bank->mu);
-            ADTFE_CUDA(cudaEventRecord(bank->join_events[0], side));
-            ADTFE_CUDA(cudaStreamWaitEvent(user, bank->join_events[0], 0));
-            return ADTFE_OK;
-        }
-    }
     int rc = adtfe_render(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream);
     if (rc != ADTFE_OK) return rc;
     if (plan->mel_rows_dev) {

@@ -100,40 +100,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 struct adtfe_mel_tables;
 
 namespace adtfe {
-// Log-mel stage of the pipelined front end: after every `group_chunks` render chunks the finished rows are
-// featurised on the bank's mel stream while the following chunks render.
-struct MelStage {
-    const adtfe_mel* mel;
-    float* out_dev;
-    int group_chunks;
-};
-// Row scale of one segment (32 bytes), written by the tile mixer CTA that finishes the segment's last tile when the
-// normalisation is folded into the log-mel: peak = max of the tile maxima, r = 1/peak (rn), s2 = (vol/peak)^2.
-struct SegScale {
-    float peak, r, vol, s2;
-    int32_t len, flags, pad0, pad1;
-};
-static_assert(sizeof(SegScale) == 32, "SegScale layout");
-// Normalisation folded into the log-mel: what the kernel needs besides the raw mix.
-struct FoldStage {
-    const SegScale* seg_scale;
-};
-// raw mix -> normalised rows, out of place, from the row scales (runs beside the folded log-mel)
-int normalise_rows(const adtfe_bank* bank, const adtfe_plan* plan, const SegScale* seg_scale, const float* raw,
-                   float* wav_out, cudaStream_t stream);
-// raw_out != NULL: the tile mixer writes the raw mix there, the rows are NOT normalised and seg_scale_out[n_seg]
-// receives every row's scale (seg_ticket: n_seg zero-initialised... zeroed here); the caller folds the normalisation
-// into the log-mel.
+int mixer_prepare_device();
 int render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
-                size_t workspace_bytes, void* stream, const MelStage* mel_stage, float* raw_out = nullptr,
-                SegScale* seg_scale_out = nullptr, int* seg_ticket = nullptr);
-int logmel_fold(const adtfe_mel* mel, const float* raw_dev, int32_t n_seg, int64_t ld_wav, int64_t n_samples,
-                const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, const FoldStage* fold, void* stream);
+                size_t workspace_bytes, void* stream);
 // Diagnostics (adtfe_trace_begin / adtfe_trace_dump): a pair of timing events around every kernel launch.
 void trace_open(const char* kernel, int index, cudaStream_t st);
 void trace_close(cudaStream_t st);
-int logmel_rows_co(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
-                   const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream);
 }  // namespace adtfe
 
 #ifndef ADTFE_BANK_STREAMS
@@ -152,10 +124,6 @@ struct adtfe_bank {
     int n_streams = 0;
     cudaStream_t streams[kBankStreams] = {};
     cudaEvent_t fork_event = nullptr, join_events[kBankStreams] = {};
-    // pipelined front end: the log-mel of finished chunk groups runs here (highest priority, so that its
-    // CTAs are placed before the pending render CTAs of later chunks) beside the render of the next groups
-    cudaStream_t mel_stream = nullptr;
-    cudaEvent_t mel_event = nullptr;
     mutable std::mutex mu;
 };
 
@@ -173,8 +141,7 @@ struct adtfe_mel {
     int32_t v6_ok = 0;
     void *w6 = nullptr, *lane6 = nullptr, *comb6 = nullptr;
     size_t smem6_bytes = 0;
-    int32_t v6co_ok = 0;       // the co-resident shape of the v6 kernel can run (see adtfe_render_logmel)
-    size_t smem6co_bytes = 0;
+    int32_t force_generic = 0; // adtfe_mel_force_generic: take the generic kernel even where v6 applies (cross-checks)
     int32_t fast_path = 0;     // 1: the filterbank is triangular (<= 2 adjacent filters per bin)
     struct adtfe_mel_tables* tables = nullptr;  // mel-phase items + warp schedule, passed as a kernel parameter
     size_t smem_bytes = 0;

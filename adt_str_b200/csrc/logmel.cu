@@ -107,8 +107,6 @@ struct LogmelArgs {
     int64_t ld_wav;
     int32_t n_seg, first, count, hop, n_mels;
     int32_t rounds_per_seg, n_rounds;
-    // normalisation folded into the v6 kernel (adtfe_render_logmel): `wav` is then the RAW mix of the tile mixer
-    const SegScale* seg_scale = nullptr;      // per row: peak, 1/peak, max_volume, (max_volume/peak)^2, len, flags
 };
 
 // Round r = part q of segment seg: a segment's `count` frames are split evenly over rounds_per_seg rounds,
@@ -415,19 +413,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
 #ifndef ADTFE_LM6_UNIT
 #define ADTFE_LM6_UNIT 6      // frames per unit (even): the span of a unit is (UNIT-1)*hop + 2048 samples
 #endif
-// The co-resident shape: the same kernel with fewer warps and shorter units, so that its CTA leaves room on the SM
-// (shared memory and registers) for the render kernels of later chunks - see adtfe_render_logmel (mixer.cu).
-#ifndef ADTFE_CO_WARPS
-#define ADTFE_CO_WARPS 6
-#endif
-#ifndef ADTFE_CO_UNIT
-#define ADTFE_CO_UNIT 4
-#endif
 constexpr bool kDirect6 = ADTFE_LM6_DIRECT != 0;
 constexpr int kWarps6 = ADTFE_LM6_WARPS;
 constexpr int kUnitFrames = ADTFE_LM6_UNIT;
-constexpr int kCoWarps = ADTFE_CO_WARPS;
-constexpr int kCoUnit = ADTFE_CO_UNIT;
 // floats of a warp's span buffer for units of `unit` frames: hop <= 256
 __host__ __device__ constexpr int w6_span(int unit) { return kDirect6 ? 0 : (unit - 1) * 256 + 2048; }
 constexpr int kLaneBins = 33;                 // bins walked by one lane: 32 * 33 = 1056 >= n_bins
@@ -493,20 +481,7 @@ __device__ __forceinline__ float nan_max6(float a, float b) {
     return (a != a || b != b) ? __int_as_float(0x7fc00000) : fmaxf(a, b);
 }
 
-// Row normalisation folded into the log-mel (kFold): the kernel reads the raw mix of the tile mixer and multiplies
-// its mel sums by the row's (max_volume / peak)^2 - the normalised rows themselves are written by
-// normalise_rows_kernel (mixer.cu) beside this kernel, off the critical path.  The row scale (written by the tile
-// mixer) is requested one unit ahead so that the loads are never waited for.
-__device__ __forceinline__ SegScale fold_prefetch6(const LogmelArgs& p, int seg) {
-    const int4* q = reinterpret_cast<const int4*>(p.seg_scale + seg);
-    const int4 a = __ldg(q), b = __ldg(q + 1);
-    SegScale f;
-    f.peak = __int_as_float(a.x); f.r = __int_as_float(a.y); f.vol = __int_as_float(a.z); f.s2 = __int_as_float(a.w);
-    f.len = b.x; f.flags = b.y; f.pad0 = 0; f.pad1 = 0;
-    return f;
-}
-
-template <int kWarps6, int kUnitFrames, bool kFold>
+template <int kWarps6, int kUnitFrames>
 __global__ void __launch_bounds__(kWarps6 * 32, 1) logmel6_kernel(const LogmelArgs p, const Logmel6Tables t6, int n_units,
                                                                 int units_per_seg, int tma) {
     constexpr int kThreads6 = kWarps6 * 32;
@@ -544,15 +519,12 @@ __global__ void __launch_bounds__(kWarps6 * 32, 1) logmel6_kernel(const LogmelAr
     if (kDirect6) tma = 0;
     if (tma && u < n_units) issue_span6(p, g, span, bar, lane);
     uint32_t parity = 0;
-    SegScale fp = {0.0f, 0.0f, 0.0f, 1.0f, 0, 0, 0, 0}, fpn = fp;
-    if (kFold && u < n_units) fp = fold_prefetch6(p, g.seg);
 
 #pragma unroll 1
     for (; u < n_units; u += gstride) {
         const bool more = u + gstride < n_units;
         Unit6 gn = g;
         if (more) gn = unit6_geom<kUnitFrames>(p, u + gstride, units_per_seg);
-        if (kFold && more) fpn = fold_prefetch6(p, gn.seg);
         if (tma) {
             mbar_wait(bar, parity);
             parity ^= 1u;
@@ -569,12 +541,6 @@ __global__ void __launch_bounds__(kWarps6 * 32, 1) logmel6_kernel(const LogmelAr
                 float* row = p.out + (g.out_row + f) * p.n_mels;
                 for (int m = lane; m < p.n_mels; m += 32) row[m] = 0.0f;
             }
-        }
-        float s2 = 1.0f;   // (max_volume / peak)^2: the mel sums of the raw mix times this are those of the normalised row
-        int seg_len = 0;
-        if (kFold) {  // the rows are the RAW mix: its mel sums times (max_volume / peak)^2 are those of the normalised row
-            seg_len = fp.len;
-            s2 = fp.s2;
         }
         if (tma && n_pairs == 0 && more) { __syncwarp(); issue_span6(p, gn, span, bar, lane); }
 #pragma unroll 1
@@ -705,16 +671,9 @@ __global__ void __launch_bounds__(kWarps6 * 32, 1) logmel6_kernel(const LogmelAr
                     const float2 m0 = mb[c[k].idx[0]], m1 = mb[c[k].idx[1]], m2 = mb[c[k].idx[2]];
                     v[k] = __fadd2_rn(__fadd2_rn(m0, m1), m2);
                 }
-                float s2a = s2, s2b = s2;
-                if (kFold) {  // a frame that lies entirely in the zero padding past the segment keeps log(1e-10)
-                    const long long fa = (long long)(p.first + g.j0 + f) * p.hop - 1024;
-                    if (fa >= seg_len) s2a = 1.0f;
-                    if (fa + hop_b >= seg_len) s2b = 1.0f;
-                }
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int m = lane + 32 * k;
-                    if (kFold) { v[k].x *= s2a; v[k].y *= s2b; }
                     float a = __logf(v[k].x + 1e-10f), b = __logf(v[k].y + 1e-10f);
                     a = a != a ? a : fminf(fmaxf(a, -23.0f), 12.0f);    // torch.clamp keeps NaN
                     b = b != b ? b : fminf(fmaxf(b, -23.0f), 12.0f);
@@ -727,7 +686,6 @@ __global__ void __launch_bounds__(kWarps6 * 32, 1) logmel6_kernel(const LogmelAr
             __syncwarp();  // Q and M are rewritten by the next pair
         }
         g = gn;
-        if (kFold) fp = fpn;
     }
 }
 
@@ -758,11 +716,8 @@ static size_t logmel6_smem_bytes(int warps, int unit) {
            128 * sizeof(Comb6) + 128 + (size_t)warps * (w6_span(unit) + 2 * kQ2 + 2 * kMMax) * 4;
 }
 
-// `co`: the co-resident shape of the v6 kernel (kCoWarps warps, units of kCoUnit frames) - same arithmetic per frame
-// pair, so the results are bit-identical to the stand-alone shape.
 static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav, int32_t first,
-                         int32_t count, const adtfe_mel_row* rows_dev, float* out_dev, void* stream, bool co = false,
-                         const FoldStage* fold = nullptr) {
+                         int32_t count, const adtfe_mel_row* rows_dev, float* out_dev, void* stream) {
     // frames per round: as many as fit the span buffer, at most 32; a segment's frames are split evenly
     const int cap = std::min(kRound, (kSpanFloats - 2048) / mel->hop + 1);
     const int rounds_per_seg = (count + cap - 1) / cap;
@@ -773,10 +728,10 @@ static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_s
     a.weights = mel->weights; a.groups = (const MelGroup*)mel->groups; a.rows = rows_dev; a.ld_wav = ld_wav;
     a.n_seg = n_seg; a.first = first; a.count = count;
     a.hop = mel->hop; a.n_mels = mel->n_mels; a.rounds_per_seg = rounds_per_seg; a.n_rounds = (int32_t)n_rounds;
-    if (mel->v6_ok && !getenv("ADTFE_LOGMEL_V5")) {
+    if (mel->v6_ok && !mel->force_generic) {
         // TMA needs 16-byte aligned unit starts; other rows are copied by the warps (same results)
         const int tma = ((uintptr_t)wav_dev & 15) == 0 && ld_wav % 4 == 0;
-        const int unit = co ? kCoUnit : kUnitFrames, warps = co ? kCoWarps : kWarps6;
+        const int unit = kUnitFrames, warps = kWarps6;
         const int units_per_seg = (count + unit - 1) / unit;
         const long long n_units = (long long)n_seg * units_per_seg;
         ADTFE_REQUIRE(n_units < (1ll << 30), ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: too many frames for one launch");
@@ -784,21 +739,11 @@ static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_s
         t6.w = (const float2*)mel->w6; t6.lane = (const Lane6*)mel->lane6; t6.comb = (const Comb6*)mel->comb6;
         const long long ctas = (n_units + warps - 1) / warps;
         const int grid6 = (int)(ctas < mel->sm_count ? ctas : mel->sm_count);
-        if (fold) {
-            a.seg_scale = fold->seg_scale;
-            logmel6_kernel<kWarps6, kUnitFrames, true><<<grid6, kWarps6 * 32, mel->smem6_bytes, (cudaStream_t)stream>>>(
-                a, t6, (int)n_units, units_per_seg, tma);
-        } else if (co) {
-            logmel6_kernel<kCoWarps, kCoUnit, false><<<grid6, kCoWarps * 32, mel->smem6co_bytes, (cudaStream_t)stream>>>(
-                a, t6, (int)n_units, units_per_seg, tma);
-        } else {
-            logmel6_kernel<kWarps6, kUnitFrames, false><<<grid6, kWarps6 * 32, mel->smem6_bytes, (cudaStream_t)stream>>>(
-                a, t6, (int)n_units, units_per_seg, tma);
-        }
+        logmel6_kernel<kWarps6, kUnitFrames><<<grid6, kWarps6 * 32, mel->smem6_bytes, (cudaStream_t)stream>>>(
+            a, t6, (int)n_units, units_per_seg, tma);
         ADTFE_CUDA(cudaGetLastError());
         return ADTFE_OK;
     }
-    ADTFE_REQUIRE(!fold, ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: the folded normalisation needs the v6 kernel");
     const int grid = (int)(n_rounds < mel->sm_count ? n_rounds : mel->sm_count);
     logmel_kernel<<<grid, kThreads, mel->smem_bytes, (cudaStream_t)stream>>>(a, mel->tables->t);
     ADTFE_CUDA(cudaGetLastError());
@@ -822,8 +767,8 @@ extern "C" int adtfe_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t 
     return launch_logmel(mel, wav_dev, n_seg, ld_wav, first, count, nullptr, out_dev, stream);
 }
 
-static int logmel_rows_checked(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
-                               const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream, bool co) {
+extern "C" int adtfe_logmel_rows(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
+                                 const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream) {
     ADTFE_REQUIRE(mel && n_seg >= 0 && max_count >= 0 && ld_wav >= 0, ADTFE_ERR_BAD_ARG,
                   "adtfe_logmel_rows: bad argument (n_seg=%d ld_wav=%lld max_count=%d)", n_seg, (long long)ld_wav,
                   max_count);
@@ -835,37 +780,8 @@ static int logmel_rows_checked(const adtfe_mel* mel, const float* wav_dev, int32
     // the longest row must stay inside the pitch (the per-row counts live on the device: the caller's contract)
     ADTFE_REQUIRE((int64_t)first * mel->hop >= 1024 && (int64_t)(first + max_count - 1) * mel->hop + 1024 <= ld_wav,
                   ADTFE_ERR_UNSUPPORTED, "adtfe_logmel_rows: frame support leaves the row");
-    return launch_logmel(mel, wav_dev, n_seg, ld_wav, first, max_count, rows_dev, out_dev, stream, co);
+    return launch_logmel(mel, wav_dev, n_seg, ld_wav, first, max_count, rows_dev, out_dev, stream);
 }
-
-extern "C" int adtfe_logmel_rows(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
-                                 const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream) {
-    // ADTFE_LOGMEL_CO=1: the co-resident kernel shape on its own (tuning aid, same results)
-    const bool co = mel && mel->v6co_ok && getenv("ADTFE_LOGMEL_CO") != nullptr;
-    return logmel_rows_checked(mel, wav_dev, n_seg, ld_wav, rows_dev, max_count, out_dev, stream, co);
-}
-
-namespace adtfe {
-// Log-mel of the RAW mix with the row scale folded in.  Returns ADTFE_ERR_UNSUPPORTED when the
-// v6 kernel or its TMA path cannot take the launch - the caller then normalises and featurises separately.
-int logmel_fold(const adtfe_mel* mel, const float* raw_dev, int32_t n_seg, int64_t ld_wav, int64_t n_samples,
-                const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, const FoldStage* fold, void* stream) {
-    if (!mel || !mel->v6_ok || getenv("ADTFE_LOGMEL_V5") || !fold || ((uintptr_t)raw_dev & 15) || ld_wav % 4 ||
-        n_seg <= 0)
-        return ADTFE_ERR_UNSUPPORTED;
-    int32_t first = mel->wpi, count = max_count;
-    if (!rows_dev) adtfe_mel_frames(mel, n_samples, &first, &count);
-    if ((int64_t)first * mel->hop < 1024 || (count > 0 && (int64_t)(first + count - 1) * mel->hop + 1024 > ld_wav))
-        return ADTFE_ERR_UNSUPPORTED;
-    if (count <= 0) return ADTFE_OK;   // no frames anywhere
-    return launch_logmel(mel, raw_dev, n_seg, ld_wav, first, std::max(count, 0), rows_dev, out_dev, stream, false, fold);
-}
-int logmel_rows_co(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
-                   const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, void* stream) {
-    return logmel_rows_checked(mel, wav_dev, n_seg, ld_wav, rows_dev, max_count, out_dev, stream,
-                               mel && mel->v6co_ok);
-}
-}  // namespace adtfe
 
 extern "C" int adtfe_mel_destroy(adtfe_mel* mel) {
     if (!mel) return ADTFE_OK;
@@ -1179,19 +1095,11 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
             MEL_UPLOAD(mel->lane6, lane6.data(), lane6.size() * sizeof(Lane6));
             MEL_UPLOAD(mel->comb6, comb6.data(), comb6.size() * sizeof(Comb6));
             mel->smem6_bytes = logmel6_smem_bytes(kWarps6, kUnitFrames);
-            mel->smem6co_bytes = logmel6_smem_bytes(kCoWarps, kCoUnit);
-            if (cudaFuncSetAttribute(logmel6_kernel<kWarps6, kUnitFrames, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)mel->smem6_bytes) != cudaSuccess ||
-                cudaFuncSetAttribute(logmel6_kernel<kWarps6, kUnitFrames, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            if (cudaFuncSetAttribute(logmel6_kernel<kWarps6, kUnitFrames>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)mel->smem6_bytes) != cudaSuccess) {
                 cudaGetLastError();
                 mel->v6_ok = 0;
             }
-            mel->v6co_ok = mel->v6_ok && (kCoUnit - 1) * hop + 2048 <= w6_span(kCoUnit) &&
-                           cudaFuncSetAttribute(logmel6_kernel<kCoWarps, kCoUnit, false>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)mel->smem6co_bytes) == cudaSuccess;
-            cudaGetLastError();
         }
     }
 #undef MEL_UPLOAD
@@ -1206,3 +1114,9 @@ extern "C" int adtfe_mel_create(int32_t n_fft, int32_t hop, int32_t n_mels, cons
 }
 
 extern "C" int adtfe_mel_fast_path(const adtfe_mel* mel) { return mel ? mel->fast_path : -1; }
+
+extern "C" int adtfe_mel_force_generic(adtfe_mel* mel, int32_t on) {
+    ADTFE_REQUIRE(mel, ADTFE_ERR_BAD_ARG, "adtfe_mel_force_generic: null handle");
+    mel->force_generic = on != 0;
+    return ADTFE_OK;
+}

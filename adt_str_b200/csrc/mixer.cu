@@ -19,8 +19,6 @@
 //                       atomics; writes the raw tile and its |max|.
 //   3. normalise_kernel row peak = max of the tile maxima; wav / peak * max_volume in place
 //                       (an all-zero mix gives NaN, like the reference's 0/0).
-// Opt-in (adtfe_render_logmel with ADTFE_FOLD=1): the mixer writes the raw mix elsewhere and publishes every
-// row's SegScale, normalise_rows_kernel writes the rows out of place beside the log-mel.
 #include <algorithm>
 #include <mutex>
 
@@ -236,12 +234,6 @@ struct MixArgs {
     int* tile_counter;
     int64_t ld_wav;
     int32_t tiles_per_seg, n_tiles;
-    // seg_ticket: one counter per segment - the CTA that finishes a segment's last tile knows the row peak.  It then
-    // normalises the row in place (normalise_rows != 0: the default render) or publishes the row's scale for the
-    // opt-in folded form (seg_scale != NULL).
-    int* seg_ticket;
-    SegScale* seg_scale;
-    int normalise_rows;
 };
 
 // Writes the finished (not yet normalised) tile and publishes its |max|.
@@ -260,67 +252,14 @@ __device__ __forceinline__ void finish_tile(const MixArgs& a, int tile_id, const
         mb = max(mb, __float_as_uint(fabsf(v)));
     }
     mb = __reduce_max_sync(0xffffffffu, mb);
-    if (a.seg_ticket) __threadfence();  // this thread's samples are visible before the CTA takes the segment's ticket
     consumer_sync();  // s_red of the previous tile is no longer read
     if ((tid & 31) == 0) s_red[tid >> 5] = __uint_as_float(mb);
     consumer_sync();
-    float* s_last = s_red + kMixConsumers;  // {1.0 when this CTA finished the segment, the row peak}
     if (tid == 0) {
         unsigned rb = __float_as_uint(s_red[0]);
         for (int i = 1; i < kMixConsumers; ++i) rb = max(rb, __float_as_uint(s_red[i]));
-        const float r = __uint_as_float(rb);
-        a.tile_max[tile_id] = r;
-        float last = 0.0f, pk = 0.0f;
-        if (a.seg_ticket) {
-            __threadfence();  // the tile maximum is visible before the ticket is taken
-            if (atomicAdd(a.seg_ticket + seg, 1) == a.tiles_per_seg - 1) {
-                __threadfence();
-                for (int t = 0; t < a.tiles_per_seg; ++t) pk = nan_max(pk, __ldcg(a.tile_max + seg * a.tiles_per_seg + t));
-                last = 1.0f;
-                if (a.seg_scale) {
-                    const adtfe_segment sg = a.segments[seg];
-                    SegScale sc;
-                    sc.peak = pk; sc.r = __frcp_rn(pk); sc.vol = sg.max_volume;
-                    const float q = __fdiv_rn(sg.max_volume, pk);
-                    sc.s2 = sg.flags != 0 ? q * q : 1.0f;   // an empty segment is all zeros: nothing to scale
-                    sc.len = sg.len; sc.flags = sg.flags; sc.pad0 = 0; sc.pad1 = 0;
-                    a.seg_scale[seg] = sc;
-                }
-            }
-        }
-        s_last[0] = last; s_last[1] = pk;
+        a.tile_max[tile_id] = __uint_as_float(rb);
     }
-    if (!a.normalise_rows) return;
-    consumer_sync();
-    if (s_last[0] == 0.0f) return;
-    // This CTA finished the segment: every tile of the row is in L2 (each writer fenced before its ticket), so the row
-    // is normalised here and now - wav / peak * max_volume with normalise_kernel's arithmetic - instead of by a
-    // kernel that streams it from HBM again.  Samples beyond the segment's length stay as mixed (zeros).
-    const adtfe_segment sg = a.segments[seg];
-    if (sg.flags == 0) return;
-    const float peak = s_last[1], vol = sg.max_volume, r = __frcp_rn(peak);
-    auto norm = [&](float v) {
-        const float q = __fmul_rn(v, r);
-        const float rem = __fmaf_rn(-q, peak, v);
-        return __fmul_rn(__fmaf_rn(rem, r, q), vol);
-    };
-    constexpr int T = kMixConsumers * 32;
-    float4* row4 = reinterpret_cast<float4*>(row);
-    const int n4 = sg.len >> 2;
-    for (int base = 0; base < n4; base += 8 * T) {   // eight loads in flight per thread
-        float4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = base + u * T + tid;
-            v[u] = i < n4 ? __ldcg(row4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int i = base + u * T + tid;
-            if (i < n4) row4[i] = make_float4(norm(v[u].x), norm(v[u].y), norm(v[u].z), norm(v[u].w));
-        }
-    }
-    for (int i = 4 * n4 + tid; i < sg.len; i += T) row[i] = norm(__ldcg(row + i));
 }
 
 __global__ void __launch_bounds__(kMixThreads, kMixCtasPerSm) mix_kernel(const MixArgs a) {
@@ -532,51 +471,6 @@ __global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_seg
     for (int i = 4 * n4 + tid; i < n; i += kNormThreads) row[i] = norm(row[i]);
 }
 
-// The same out of place, from the row scales the mixer published (folded form: the log-mel reads the raw mix and this
-// kernel writes the normalised rows beside it).  Samples beyond the segment and empty segments are copied (zeros).
-// It runs in what the log-mel CTA leaves of an SM (about 16 k registers), so it is built small: 128-thread CTAs
-// that walk the tiles grid-stride, four float4 per thread in flight.
-constexpr int kNormRowsThreads = 128;
-__global__ void __launch_bounds__(kNormRowsThreads) normalise_rows_kernel(const SegScale* __restrict__ seg_scale,
-                                                                          const float* __restrict__ raw,
-                                                                          int tiles_per_seg, int64_t n_tiles,
-                                                                          int64_t ld_wav, float* __restrict__ wav) {
-    static_assert(ADTFE_TILE == 16 * kNormRowsThreads, "four float4 per thread and tile");
-    const int tid = threadIdx.x;
-    for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
-        const int seg = (int)(tile_id / tiles_per_seg), lo = (int)(tile_id - (int64_t)seg * tiles_per_seg) * ADTFE_TILE;
-        if (lo >= ld_wav) continue;
-        const int4* q = reinterpret_cast<const int4*>(seg_scale + seg);
-        const int4 a = __ldg(q), b = __ldg(q + 1);
-        const float peak = __int_as_float(a.x), r = __int_as_float(a.y), vol = __int_as_float(a.z);
-        const int live_len = b.y != 0 ? b.x : 0;   // samples [0, live_len) are normalised
-        const float4* src = reinterpret_cast<const float4*>(raw + (int64_t)seg * ld_wav + lo);
-        float4* dst = reinterpret_cast<float4*>(wav + (int64_t)seg * ld_wav + lo);
-        const int n4 = (int)(min((int64_t)ADTFE_TILE, ld_wav - lo) >> 2);       // ld_wav is a multiple of 4
-        auto norm = [&](float v, int i) {
-            if (lo + i >= live_len) return v;
-            const float qv = __fmul_rn(v, r);
-            const float rem = __fmaf_rn(-qv, peak, v);
-            return __fmul_rn(__fmaf_rn(rem, r, qv), vol);
-        };
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = tid + k * kNormRowsThreads;
-            v[k] = i < n4 ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int i = tid + k * kNormRowsThreads;
-            if (i < n4) {
-                float4 o = v[k];
-                o.x = norm(o.x, 4 * i); o.y = norm(o.y, 4 * i + 1); o.z = norm(o.z, 4 * i + 2); o.w = norm(o.w, 4 * i + 3);
-                dst[i] = o;
-            }
-        }
-    }
-}
-
 static size_t mix_smem_bytes() { return mix_list_offset() + kListMax * sizeof(SliceMsg); }
 
 }  // namespace adtfe
@@ -585,43 +479,27 @@ using namespace adtfe;
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-extern "C" size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg) {
-    if (n_events < 0 || n_seg < 0 || tiles_per_seg < 0) return 0;
-    // resolved events | peak bits, queue heads, segment tickets (one zeroed block) | tile maxima
-    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_events * 4 + (size_t)n_seg * 8 + 4) +
-           align256((size_t)n_seg * tiles_per_seg * 4) + 256;
-}
-
-int adtfe::normalise_rows(const adtfe_bank* bank, const adtfe_plan* plan, const SegScale* seg_scale, const float* raw,
-                          float* wav_out, cudaStream_t stream) {
-    const int64_t n_tiles = (int64_t)plan->n_seg * plan->tiles_per_seg;
-    ADTFE_REQUIRE(n_tiles < (1ll << 31), ADTFE_ERR_UNSUPPORTED, "adtfe_render_logmel: too many tiles for one launch");
-    trace_open("normalise", -2, stream);
-    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)bank->sm_count * 8);
-    normalise_rows_kernel<<<grid, kNormRowsThreads, 0, stream>>>(seg_scale, raw, plan->tiles_per_seg, n_tiles,
-                                                                plan->ld_wav, wav_out);
-    trace_close(stream);
-    ADTFE_CUDA(cudaGetLastError());
+// Called by adtfe_bank_create on the bank's device (cudaFuncSetAttribute is per device and idempotent): the kernels'
+// dynamic shared memory is opted in once per handle, not through process-wide state on the render path.
+int adtfe::mixer_prepare_device() {
+    ADTFE_CUDA(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mix_smem_bytes()));
     return ADTFE_OK;
 }
 
-extern "C" size_t adtfe_render_logmel_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg,
-                                                      int64_t ld_wav) {
-    const size_t base = adtfe_render_workspace_bytes(n_events, n_seg, tiles_per_seg);
-    if (base == 0 || ld_wav < 0) return 0;
-    // + the raw mix the log-mel normalises, the per-segment scales and the tickets that elect their writer
-    return base + align256((size_t)n_seg * (size_t)ld_wav * 4) + align256((size_t)n_seg * sizeof(SegScale)) +
-           align256((size_t)n_seg * 4) + 256;
+extern "C" size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg) {
+    if (n_events < 0 || n_seg < 0 || tiles_per_seg < 0) return 0;
+    // resolved events | peak bits, queue heads (one zeroed block) | tile maxima
+    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_events * 4 + (size_t)n_seg * 4 + 4) +
+           align256((size_t)n_seg * tiles_per_seg * 4) + 256;
 }
 
 extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
                             size_t workspace_bytes, void* stream) {
-    return render_impl(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream, nullptr);
+    return render_impl(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream);
 }
 
 int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
-                       size_t workspace_bytes, void* stream, const MelStage* ms, float* raw_out,
-                       SegScale* seg_scale_out, int* seg_ticket) {
+                       size_t workspace_bytes, void* stream) {
     ADTFE_REQUIRE(bank && plan, ADTFE_ERR_BAD_ARG, "adtfe_render: null bank or plan");
     ADTFE_REQUIRE(plan->n_seg >= 0 && plan->n_events >= 0 && plan->n_peak_work >= 0 && plan->tiles_per_seg >= 0,
                   ADTFE_ERR_BAD_ARG, "adtfe_render: negative count");
@@ -659,19 +537,9 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
     ResolvedEvent* resolved = (ResolvedEvent*)ws;
     int* peak_bits = (int*)(ws + align256((size_t)plan->n_events * sizeof(ResolvedEvent)));
     int* counters = peak_bits + plan->n_events;  // one work-queue head per chunk (n_chunks <= n_seg)
-    int* tickets = counters + plan->n_seg + 1;   // one per segment: elects the CTA that finishes the row
-    float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4 + (size_t)plan->n_seg * 8 + 4));
-    // ADTFE_NORM_FUSED=1: the CTA that finishes a segment's last tile normalises the row inside the tile mixer (no
-    // normalise kernel, the row is still in L2).  Bit-identical, but measured slower on B200 (14.73 ms per step
-    // against 14.50 ms: the row pass stalls that CTA's ring), so the separate kernel stays the default.
-    const bool fused_norm = !raw_out && getenv("ADTFE_NORM_FUSED") != nullptr;
-    static bool smem_set[64] = {};
-    if (bank->device < 64 && !smem_set[bank->device]) {
-        ADTFE_CUDA(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mix_smem_bytes()));
-        smem_set[bank->device] = true;
-    }
+    float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4 + (size_t)plan->n_seg * 4 + 4));
     // zero the peaks and the queue heads once, then fork the chunks over the bank's streams
-    ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, ((size_t)plan->n_events + 2 * (size_t)plan->n_seg + 1) * 4, user));
+    ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, ((size_t)plan->n_events + (size_t)plan->n_seg + 1) * 4, user));
     const bool fork = n_chunks > 1 && bank->n_streams > 0;
     std::unique_lock<std::mutex> lock(bank->mu, std::defer_lock);
     if (fork) {
@@ -680,13 +548,7 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
         for (int k = 0; k < bank->n_streams && k < n_chunks; ++k)
             ADTFE_CUDA(cudaStreamWaitEvent(bank->streams[k], bank->fork_event, 0));
     }
-    ADTFE_REQUIRE(!raw_out || (seg_scale_out && seg_ticket), ADTFE_ERR_BAD_ARG, "adtfe_render: fold buffers missing");
-    if (raw_out) ADTFE_CUDA(cudaMemsetAsync(seg_ticket, 0, (size_t)plan->n_seg * 4, user));
-    float* mix_out = raw_out ? raw_out : wav_out_dev;  // raw_out: the caller folds the normalisation into the log-mel
-    ADTFE_REQUIRE(!raw_out || ((uintptr_t)raw_out & 15) == 0, ADTFE_ERR_BAD_ARG, "adtfe_render: misaligned raw buffer");
-    const bool staged = ms && fork && plan->mel_rows_dev && !raw_out;  // log-mel of finished chunk groups beside the render
-    if (staged) ADTFE_CUDA(cudaStreamWaitEvent(bank->mel_stream, bank->fork_event, 0));
-    int group_first = 0;  // first chunk of the group being rendered
+    float* mix_out = wav_out_dev;
     const int tps = plan->tiles_per_seg;
     for (int c = 0; c < n_chunks; ++c) {
         cudaStream_t st = fork ? bank->streams[c % bank->n_streams] : user;
@@ -705,40 +567,15 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
         a.segments = plan->segments_dev + s0; a.wav = mix_out + (size_t)s0 * plan->ld_wav;
         a.tile_max = tile_max + (size_t)s0 * tps; a.tile_counter = counters + c; a.ld_wav = plan->ld_wav;
         a.tiles_per_seg = tps; a.n_tiles = n_seg * tps;
-        a.seg_ticket = raw_out ? seg_ticket + s0 : (fused_norm ? tickets + s0 : nullptr);
-        a.seg_scale = raw_out ? seg_scale_out + s0 : nullptr;
-        a.normalise_rows = fused_norm ? 1 : 0;
         const int grid = std::min(a.n_tiles, kMixCtasPerSm * bank->sm_count);
         trace_open("mix", c, st);
         mix_kernel<<<grid, kMixThreads, mix_smem_bytes(), st>>>(a);
         trace_close(st);
         ADTFE_CUDA(cudaGetLastError());
-        if (!raw_out && !fused_norm) {
-            trace_open("normalise", c, st);
-            normalise_kernel<<<a.n_tiles, kNormThreads, 0, st>>>(a.segments, a.tile_max, tps, plan->ld_wav, a.wav);
-            trace_close(st);
-            ADTFE_CUDA(cudaGetLastError());
-        }
-        if (staged && (c + 1 - group_first >= ms->group_chunks || c + 1 == n_chunks)) {
-            // the group's chunks sit on the streams (group_first .. c) % n_streams: the mel stream waits for them
-            const int used = std::min(c + 1 - group_first, bank->n_streams);
-            for (int j = 0; j < used; ++j) {
-                const int k = (c - j) % bank->n_streams;
-                ADTFE_CUDA(cudaEventRecord(bank->join_events[k], bank->streams[k]));
-                ADTFE_CUDA(cudaStreamWaitEvent(bank->mel_stream, bank->join_events[k], 0));
-            }
-            const int g0 = ch[group_first].seg, g1 = ch[c + 1].seg;
-            trace_open("logmel", group_first, bank->mel_stream);
-            const int rc = logmel_rows_co(ms->mel, wav_out_dev + (size_t)g0 * plan->ld_wav, g1 - g0, plan->ld_wav,
-                                          plan->mel_rows_dev + g0, plan->mel_max_count, ms->out_dev, bank->mel_stream);
-            trace_close(bank->mel_stream);
-            if (rc != ADTFE_OK) return rc;
-            group_first = c + 1;
-        }
-    }
-    if (staged) {
-        ADTFE_CUDA(cudaEventRecord(bank->mel_event, bank->mel_stream));
-        ADTFE_CUDA(cudaStreamWaitEvent(user, bank->mel_event, 0));
+        trace_open("normalise", c, st);
+        normalise_kernel<<<a.n_tiles, kNormThreads, 0, st>>>(a.segments, a.tile_max, tps, plan->ld_wav, a.wav);
+        trace_close(st);
+        ADTFE_CUDA(cudaGetLastError());
     }
     if (fork) {
         for (int k = 0; k < bank->n_streams && k < n_chunks; ++k) {

@@ -103,3 +103,5 @@ class FrontEnd:
                 mel_out_host.data_ptr(), wav_out_host.data_ptr() if wav_out_host is not None else None, stream,
                 copy_stream.cuda_stream if copy_stream is not None else None),
                 "adtfe_frontend_host")
+            buf._uploaded = torch.cuda.Event()   # the call's H2D copy reads the pinned blob: see PlanBuffers.fence
+            buf._uploaded.record()

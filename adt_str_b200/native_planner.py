@@ -79,8 +79,13 @@ class NativePlanner:
             return notes.reshape(-1, 4) if notes.size else notes.reshape(0, 4)
         if len(notes) == 0:
             return np.zeros((0, 4), np.float32)
-        if isinstance(notes, (list, tuple)) and all(isinstance(v, (int, float)) for r in notes for v in r):
-            return np.asarray(notes, np.float32).reshape(-1, 4)   # python numbers -> torch default float32
+        # torch.tensor(notes) is float32 only for plain python numbers with at least one float among them: numpy
+        # scalars (np.float64 is a float subclass) make it float64 and all-int rows int64, and the reference then
+        # does its index arithmetic in that type - those inputs take the general planner
+        if isinstance(notes, (list, tuple)):
+            kinds = {type(v) for r in notes for v in r}
+            if kinds <= {int, float} and float in kinds:
+                return np.asarray(notes, np.float32).reshape(-1, 4)
         return None
 
     def plan_batch(self, batch_notes: Sequence, rng=_random, ld_wav: Optional[int] = None) -> RenderPlan:

@@ -3,7 +3,8 @@
 The reference renders inside forked DataLoader workers, each with its own ``random``
 state (``train.py:235-237``, ``data_modules/train_dataset.py:213-229``).  Here the
 workers are *threads* that only plan - the C++ planner runs without the GIL - each with
-its own ``random.Random`` stream and planner handle; the main thread enqueues one
+its own planner handle; every group of batches gets its own ``random`` stream derived from
+(seed, rank, group index), so a seed reproduces the same draws whatever thread plans a group; the main thread enqueues one
 ``adtfe_frontend_host`` call per group of batches (plan blob H2D -> render -> log-mel on the
 current stream, the D2H on a copy stream so that it overlaps the next group's kernels).
 ``n_sets`` rotating buffer sets (pinned blob, device blob, workspace, device outputs, pinned
@@ -72,8 +73,14 @@ class GroupResult:
 
 
 class HostPipeline:
-    def __init__(self, frontend: FrontEnd, workers: int = 4, n_sets: int = 4, seed: int = 0, chunk_batches: int = 8):
+    def __init__(self, frontend: FrontEnd, workers: int = 4, n_sets: int = 4, seed: int = 0, chunk_batches: int = 8,
+                 rank: Optional[int] = None):
         self.fe = frontend
+        if rank is None:   # the process's rank under torch.distributed / torchrun, else 0
+            import os
+            import torch.distributed as dist
+            rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else int(os.environ.get("RANK", "0"))
+        self.rank = int(rank)
         self.workers = max(1, int(workers))
         self.n_sets = max(2, int(n_sets))
         self.chunk_batches = chunk_batches
@@ -82,8 +89,7 @@ class HostPipeline:
         self._sets = [_Set(self.device) for _ in range(self.n_sets)]
         self._local = threading.local()
         self._seed = seed
-        self._next_worker = 0
-        self._lock = threading.Lock()
+        self._groups_seen = 0   # group index across run() calls: part of every group's RNG seed
         self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="adtfe-plan")
         self._copy_stream = torch.cuda.Stream(self.device)   # D2H of group g overlaps the kernels of group g+1
 
@@ -92,16 +98,18 @@ class HostPipeline:
         st = getattr(self._local, "st", None)
         if st is None:
             from .native_planner import NativePlanner
-            with self._lock:
-                wid = self._next_worker
-                self._next_worker += 1
-            rng = random.Random(self._seed * 1_000_003 + wid)
-            st = self._local.st = dict(rng=rng, planner=NativePlanner(self.fe.synth.config, self.fe.synth.bank),
-                                       mt=np.array(rng.getstate()[1], np.uint32))   # the same stream, kept native
+            st = self._local.st = dict(rng=random.Random(0),
+                                       planner=NativePlanner(self.fe.synth.config, self.fe.synth.bank),
+                                       mt=np.zeros(625, np.uint32))
         return st
 
-    def _plan(self, group: Sequence[Sequence], s: _Set):
+    def _plan(self, group: Sequence[Sequence], s: _Set, index: int):
         st = self._worker_state()
+        # One RNG stream per GROUP, derived from (seed, rank, group index): which thread plans a group is up to the
+        # executor, the draws are not - a seed reproduces the same timbres and mixups run after run, and ranks that
+        # share a seed still render different augmentations (DataLoader workers: seed + worker id, per rank).
+        st["rng"].seed((self._seed * 1_000_003 + self.rank) * 1_000_003 + index)
+        st["mt"][:] = np.array(st["rng"].getstate()[1], np.uint32)   # the same stream, kept native
 
         def acquire():
             s.free.wait()          # the consumer released the set ...
@@ -141,7 +149,8 @@ class HostPipeline:
                     exhausted = True
                     break
                 s = self._sets[k % self.n_sets]
-                pending.append((self._pool.submit(self._plan, g, s), s))
+                pending.append((self._pool.submit(self._plan, g, s, self._groups_seen), s))
+                self._groups_seen += 1
                 k += 1
             if not pending:
                 return

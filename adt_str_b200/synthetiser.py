@@ -54,9 +54,18 @@ class PlanBuffers:
         self.dev = torch.empty(0, dtype=torch.uint8, device=device)
         self.workspace = torch.empty(0, dtype=torch.uint8, device=device)
         self.nbytes = 0
+        self._uploaded: Optional[torch.cuda.Event] = None   # recorded behind the last H2D copy of `host`
+
+    def fence(self) -> None:
+        """Block until the last ``upload`` has read the pinned blob: the copy is asynchronous, so the host must not
+        rewrite ``host`` (next ``pack`` / ``reserve`` / in-place native packing) while it is still in flight."""
+        if self._uploaded is not None:
+            self._uploaded.synchronize()
+            self._uploaded = None
 
     def pack(self, plan: RenderPlan) -> _lib.Plan:
         lib = _lib.load()
+        self.fence()
         batched = plan.mel_rows is not None
         self._chunks = np.ascontiguousarray(plan.chunks) if batched else None  # host memory the library reads
         shape = _lib.Plan(None, None, None, None, None, plan.n_events, plan.n_seg, plan.tiles_per_seg,
@@ -88,14 +97,11 @@ class PlanBuffers:
 
     @staticmethod
     def _workspace_bytes(lib, n_events, n_seg, tiles_per_seg, ld_wav) -> int:
-        """The render's scratch; with ADTFE_FOLD=1 (the opt-in folded form of adtfe_render_logmel) also room for
-        the raw mix."""
-        if os.environ.get("ADTFE_FOLD"):
-            return lib.adtfe_render_logmel_workspace_bytes(n_events, n_seg, tiles_per_seg, ld_wav)
         return lib.adtfe_render_workspace_bytes(n_events, n_seg, tiles_per_seg)
 
     def reserve(self, nbytes: int) -> None:
         """Pinned and device blobs of at least ``nbytes`` (contents are not kept)."""
+        self.fence()
         if self.host.numel() < nbytes:
             cap = max(int(nbytes), 2 * self.host.numel(), 1 << 16)
             self.host = torch.empty(cap, dtype=torch.uint8).pin_memory()
@@ -121,6 +127,9 @@ class PlanBuffers:
     def upload(self, shape: _lib.Plan) -> _lib.Plan:
         """H2D of the packed blob on the current stream; returns the plan with device pointers."""
         self.dev[: self.nbytes].copy_(self.host[: self.nbytes], non_blocking=True)
+        with torch.cuda.device(self.device):
+            self._uploaded = torch.cuda.Event()
+            self._uploaded.record()
         base = self.dev.data_ptr()
         o = self.offsets
         return _lib.Plan(base + o[0], base + o[1], base + o[2], base + o[5], base + o[3],

@@ -63,6 +63,10 @@ def parse_args():
                    help="planner threads of the end-to-end pipeline (0 = host cores / ranks, at most 8)")
     p.add_argument("--e2e-sets", type=int, default=4, help="rotating buffer sets of the end-to-end pipeline")
     p.add_argument("--chunk-batches", type=int, default=64, help="batches rendered together as one chunk")
+    p.add_argument("--no-library-baseline", action="store_true",
+                   help="skip the torchaudio (cuFFT + cuBLAS) log-mel on the same GPU, the comparator of BASELINE.md")
+    p.add_argument("--no-traffic", action="store_true", help="skip the in-run ncu measurement of roofline.traffic")
+    p.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     return p.parse_args()
 
 
@@ -204,6 +208,92 @@ def run_reference(args):
     return 0
 
 
+# --------------------------------------------------------------------------- GPU library comparator
+def library_logmel_module(dev):
+    """The reference's ComputeMelSpectrogram (model.py:68-97) as it runs on a GPU: torchaudio MelSpectrogram
+    (torch.stft -> cuFFT, |.|^2, MelScale matmul -> cuBLAS) and the reference's own log / clamp / affine / slice
+    lines, call for call.  Returns ``f(wave (B, L)) -> (B, T, n_mels)`` (a view, like the reference's)."""
+    import torch
+    import torchaudio.transforms as T
+    hop = int(0.01 * SR)
+    spec = T.MelSpectrogram(sample_rate=SR, n_fft=2048, hop_length=hop, n_mels=128, f_min=20.0, power=2).to(dev)
+    wpi = int((2048 / 2) // hop + 1)
+
+    def forward(wave):
+        with torch.no_grad(), torch.autocast(device_type="cuda", enabled=False):
+            x = spec(wave.float())
+            x = torch.log(x + 1e-10)
+            x = torch.clamp(x, -23, 12)
+            x = (x + 23) / (12 + 23)
+            return x.permute(0, 2, 1)[:, wpi: -(wpi + 1), :]
+    return forward
+
+
+def measure_traffic(timeout_s=240):
+    """roofline.traffic measured BY THIS RUN: a child process replays a resident plan under
+    ``ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`` and the log-mel launch's DRAM bytes per segment
+    come back.  None when ncu is missing, not permitted or too slow (the committed capture is then used)."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None
+    out = tempfile.mktemp(prefix="adtfe_traffic_", suffix=".csv")
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+           "regex:logmel", "-c", "1", "--csv", "--log-file", out, sys.executable, os.path.abspath(__file__),
+           "--traffic-child"]
+    try:
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=timeout_s, env=env)
+        n_seg = None
+        for line in res.stdout.decode(errors="replace").splitlines():
+            if line.startswith("TRAFFIC_CHILD_SEGMENTS"):
+                n_seg = int(line.split()[1])
+        total = 0.0
+        import csv
+        with open(out) as f:
+            rows = [r for r in csv.reader(f) if len(r) > 3]
+        head = next(i for i, r in enumerate(rows) if "Metric Name" in r)
+        col = {name: k for k, name in enumerate(rows[head])}
+        for r in rows[head + 1:]:
+            if r[col["Metric Name"]].startswith("dram__bytes_"):
+                v = float(r[col["Metric Value"]].replace(",", ""))
+                unit = r[col["Metric Unit"]].lower()
+                total += v * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+        if n_seg and total > 0:
+            return total / n_seg
+    except Exception:
+        pass
+    finally:
+        try:
+            os.unlink(out)
+        except OSError:
+            pass
+    return None
+
+
+def run_traffic_child(args):
+    """Under ncu (see measure_traffic): 32 training batches resident, rendered, then the log-mel launched twice (the
+    first launch is skipped by -c 1 only if it were first; both are identical) - waveform rows 0.5 GB >> L2."""
+    import torch
+    from adt_str_b200 import ComputeMelSpectrogram, FrontEnd, SynthDrum
+    from adt_str_b200.config import setting_1
+    from adt_str_b200.synthetic import make_bank, make_segments
+    from adt_str_b200.synthetiser import PlanBuffers
+    dev = torch.device("cuda", 0)
+    bank = make_bank(2000, SR, seed=0)
+    n_batches = 32
+    segs = make_segments(n_batches * BATCH, seed=1)
+    fe = FrontEnd(SynthDrum(setting_1(), bank=bank, device=dev), ComputeMelSpectrogram(SR, 2048, 0.01, 128))
+    plan = fe.plan_batches([segs[b * BATCH:(b + 1) * BATCH] for b in range(n_batches)], random.Random(1), 16)
+    buf = PlanBuffers(dev)
+    buf._dplan = buf.upload(buf.pack(plan)); buf._resident = plan
+    wav, feat = fe._outputs(plan, 0)
+    fe.run_plan(plan, buffers=buf, wav=wav, feat=feat, upload=False)
+    torch.cuda.synchronize(dev)
+    print("TRAFFIC_CHILD_SEGMENTS", plan.n_seg, flush=True)
+    return 0
+
+
 # --------------------------------------------------------------------------- B200 arm
 def run_b200(args):
     rank, world, local = dist_env()
@@ -318,6 +408,36 @@ def run_b200(args):
     one_w, one_f = fe._outputs(one_plan, int(one_plan.wave_lengths.max()))
     one = time_loop(lambda: fe.run_plan(one_plan, buffers=one_buf, wav=one_w, feat=one_f, upload=False), reps=20)
 
+    # ---- the GPU library comparator (the reference's own ComputeMelSpectrogram on the same B200):
+    # torchaudio MelSpectrogram + log / clamp / affine over the SAME resident waveform matrix, one call per collated
+    # batch of 64 as ADTModel.forward makes them (model.py:248), CUDA-event timed like logmel_ms above
+    library = None
+    if rank == 0 and not args.no_library_baseline:
+        try:
+            lib_forward = library_logmel_module(dev)
+            views = [wav[int(plan.batch_ptr[b]):int(plan.batch_ptr[b + 1]), :int(plan.batch_samples[b])]
+                     for b in range(n_batches)]
+            render_all(); torch.cuda.synchronize(dev)
+
+            def library_all():
+                for v in views:
+                    lib_forward(v)
+
+            lib_ms = time_loop(library_all, reps=2)
+            ours_one = mel(views[0]); theirs_one = lib_forward(views[0])
+            diff = float((ours_one - theirs_one).abs().max())
+            lib_one = time_loop(lambda: lib_forward(views[0]), reps=20)
+            ours_one_ms = time_loop(lambda: mel(views[0]), reps=20)
+            library = {"what": "torchaudio MelSpectrogram (cuFFT + cuBLAS) + log/clamp/affine on the same GPU over the same "
+                               "resident waveform rows, one call per batch of 64 (reference model.py:71-97)",
+                       "logmel_ms_per_step": lib_ms, "audio_s_per_s": audio_s_step / (lib_ms * 1e-3),
+                       "this_repo_logmel_ms_per_step": logmel_ms, "speedup_logmel": lib_ms / logmel_ms,
+                       "single_batch_ms": lib_one, "this_repo_single_batch_ms": ours_one_ms,
+                       "max_abs_diff_first_batch": diff,
+                       "dram_bytes": None, "dram_bytes_source": "profiles/r02_library_logmel.txt (ncu launch list + dram bytes of the library pipeline)"}
+        except Exception as exc:   # never lose the headline line to the comparator
+            library = {"error": repr(exc)}
+
     # ---- end to end: host notes -> plan -> pinned blob -> H2D -> kernels -> D2H log-mel (pinned), in groups of
     # batches through HostPipeline: planner threads (own RNG streams, like DataLoader workers), rotating buffer
     # sets, everything asynchronous on the current stream
@@ -381,12 +501,20 @@ def run_b200(args):
         return 0
 
     peak, peak_src = measured_peak()
-    traffic = None
-    try:  # DRAM bytes of the log-mel kernel per segment, from the committed ncu --set full capture
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            traffic = float(json.load(f)["dram_bytes_per_segment"]) * plan.n_seg
-    except Exception:
-        pass
+    traffic, traffic_src = None, None
+    if world == 1 and not args.no_traffic:
+        per_seg = measure_traffic()
+        if per_seg:
+            traffic = per_seg * plan.n_seg
+            traffic_src = ("measured by this run: ncu dram__bytes_read.sum + dram__bytes_write.sum of one log-mel launch "
+                           f"over 2048 resident segments in a child process ({per_seg:.0f} B per segment) x segments")
+    if traffic is None:
+        try:  # DRAM bytes of the log-mel kernel per segment, from the committed ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
+                traffic = float(json.load(f)["dram_bytes_per_segment"]) * plan.n_seg
+            traffic_src = "profiles/r02_traffic.json: dram bytes per segment of an ncu --set full capture x segments"
+        except Exception:
+            pass
     n_seg_step = n_batches * BATCH
     width_seg = np.repeat(plan.batch_samples, np.diff(plan.batch_ptr))
     logmel_bytes = 4 * int(width_seg.sum()) + 4 * 128 * int(n_frames_seg.sum())   # collated rows read + log-mel written
@@ -409,7 +537,7 @@ def run_b200(args):
         "gpu_launches": launches_per_step * args.steps,
         "roofline": {"bound": "hbm", "kernel": "logmel6_kernel", "achieved": logmel_gbs, "peak": peak, "unit": "GB/s",
                      "frac": logmel_gbs / peak, "traffic": traffic,
-                     "traffic_source": "profiles/r01_traffic.json: dram bytes per segment of an ncu --set full capture x segments",
+                     "traffic_source": traffic_src,
                      "peak_source": peak_src,
                      "bytes_per_launch": logmel_bytes, "avg_launch_ms": logmel_ms,
                      "share_of_step": logmel_ms / (max_ms / args.steps),
@@ -417,6 +545,7 @@ def run_b200(args):
                      "path": {"bytes_alg_per_step": total_bytes / world, "achieved": path_gbs, "frac": path_gbs / peak,
                               "frac_of_nominal_8TBs": path_gbs / 8000.0}},
         "cpu_baseline": cpu,
+        "gpu_library_baseline": library,
         "long_form": long_form,
     }
     sys.stdout.flush()
@@ -428,6 +557,8 @@ def run_b200(args):
 
 def main():
     args = parse_args()
+    if args.traffic_child:
+        return run_traffic_child(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define ADTFE_VERSION 3
+#define ADTFE_VERSION 4
 #define ADTFE_TILE 2048      /* output samples owned by one mixer CTA */
 #define ADTFE_PEAK_SPAN 4096 /* samples of a mixed one-shot scanned by one peak work item */
 
@@ -162,6 +162,10 @@ int adtfe_mel_frames(const adtfe_mel* mel, int64_t n_samples, int32_t* first, in
 /* 1 when the filterbank has the triangular structure (at most two adjacent filters per bin) the fast
  * mel phase needs, 0 when the per-filter path is used (any fb works), < 0 on a null handle. */
 int adtfe_mel_fast_path(const adtfe_mel* mel);
+/* on != 0: this handle runs the generic kernel (any hop, any filterbank) even where the warp-autonomous one applies -
+ * the two are cross-checked against each other in the tests.  Per handle; not meant to be flipped while launches of
+ * the handle are being enqueued from another thread. */
+int adtfe_mel_force_generic(adtfe_mel* mel, int32_t on);
 /* wav_dev: (n_seg, ld_wav) rows of n_samples valid floats; out_dev: (n_seg, count, n_mels). */
 int adtfe_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav, int64_t n_samples,
                  float* out_dev, void* stream);
@@ -176,14 +180,6 @@ int adtfe_logmel_rows(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg,
 int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel, const adtfe_plan* plan, int64_t n_samples,
                         float* wav_out_dev, float* mel_out_dev, void* workspace_dev, size_t workspace_bytes,
                         void* stream);
-/* Workspace for the fused call's folded form (opt-in: environment ADTFE_FOLD=1): adtfe_render_workspace_bytes plus
- * room for the raw mix (n_seg * ld_wav floats) and the row scales.  With it the mixer leaves the raw mix in the
- * workspace, the log-mel scales its mel sums by (max_volume / peak)^2 and the normalised rows are written beside
- * it: same waveform bits as adtfe_render, log-mel within float32 rounding of adtfe_logmel on that waveform.  It
- * measured slower than the default on B200, so the default - and any call with the smaller
- * adtfe_render_workspace_bytes - normalises in place first, then runs the log-mel. */
-size_t adtfe_render_logmel_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg, int64_t ld_wav);
-
 /* ---- host-buffer entry (end to end) ------------------------------------------------ */
 /* Plan blob layout (host, 16-byte aligned sections in this order):
  *   events | segments | tile_ptr | peak_work | mel_rows | tile_events

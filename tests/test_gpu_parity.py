@@ -252,118 +252,6 @@ def test_batches_in_one_plan_equal_batch_by_batch():
         assert torch.equal(w0, w1) and torch.equal(f0, f1)
 
 
-def test_folded_normalisation_equals_normalise_then_logmel(monkeypatch):
-    """adtfe_render_logmel's opt-in folded form (ADTFE_FOLD=1): the mixer writes the raw mix and publishes every row's
-    scale, the log-mel reads the raw mix and scales its mel sums by (max_volume / peak)^2, the normalised rows are
-    written out of place beside it.  Against the default (normalise in place, then log-mel): the waveforms are
-    bit-identical, the log-mel agrees to float32 rounding; empty segments, all-zero mixes (NaN rows, exact zeros in
-    the padding), ragged batches and rows too short for a frame included."""
-    import dataclasses
-    from adt_str_b200.config import setting_1
-    from adt_str_b200.synthetic import make_bank, make_segments
-    bank = make_bank(390, 24000, seed=18)
-    for input_sec in (2.56, 0.1):                          # 0.1 s: 11 STFT frames, none kept -> rows without frames
-        cfg = dataclasses.replace(setting_1(), input_sec=input_sec, similarity_threshold=1.0, mixup_range=0.0)
-        _, _, fe = _objects(cfg, bank)
-        # 0.1 s segments can only be empty ones (a note pushes the end past 0.2 s): every row is zeros, no frame is kept
-        segs = make_segments(37, seed=24, empty_fraction=0.15) if input_sec > 1 else [np.zeros((0, 4), np.float32)] * 37
-        batches = [segs[:9], segs[9:10], segs[10:26], segs[26:]]
-        out = {}
-        for fold in (True, False):
-            if fold:
-                monkeypatch.setenv("ADTFE_FOLD", "1")
-            else:
-                monkeypatch.delenv("ADTFE_FOLD", raising=False)
-            plan = fe.plan_batches(batches, random.Random(7), 2)
-            wav, feat = fe.run_plan(plan)
-            single = [fe(b, random.Random(11)) for b in batches[:2]]
-            torch.cuda.synchronize()
-            out[fold] = (wav.clone(), feat.clone(), [(w.clone(), f.clone()) for w, f in single])
-        monkeypatch.delenv("ADTFE_FOLD", raising=False)
-        (w1, f1, s1), (w0, f0, s0) = out[True], out[False]
-        assert torch.equal(w1, w0)
-        assert f1.shape == f0.shape and float((f1 - f0).abs().max() if f0.numel() else 0.0) <= 2e-6
-        for (wa, fa), (wb, fb) in zip(s1, s0):
-            assert torch.equal(wa, wb) and fa.shape == fb.shape
-            assert float((fa - fb).abs().max() if fb.numel() else 0.0) <= 2e-6
-    # an all-zero mix: the reference's 0/0 - NaN over the segment, exact zeros (and log(1e-10) -> 0.0) in the padding
-    cfg = dataclasses.replace(setting_1(), similarity_threshold=1.0, mixup_range=0.0)
-    silent = make_bank(78, 24000, seed=19)
-    silent.pcm[:] = 0.0
-    _, _, fe = _objects(cfg, silent)
-    long_seg = np.array([[0.1, 2.9, 36.0, 100.0]], np.float32)         # makes the batch wider than the silent segment
-    quiet = np.array([[0.2, 0.3, 38.0, 90.0]], np.float32)
-    for fold in (True, False):
-        if fold:
-            monkeypatch.setenv("ADTFE_FOLD", "1")
-        else:
-            monkeypatch.delenv("ADTFE_FOLD", raising=False)
-        wav, feat = fe([quiet, long_seg], random.Random(3))
-        torch.cuda.synchronize()
-        assert torch.isnan(wav[0, :61440]).all() and not wav[0, 61440:].any()
-        assert torch.isnan(feat[0, :240]).all()
-        t_pad = (61440 + 1024) // 240 + 1 - 5                            # first kept frame entirely inside the padding
-        assert feat.shape[1] > t_pad and not feat[0, t_pad:].any()
-    monkeypatch.delenv("ADTFE_FOLD", raising=False)
-
-
-def test_mixer_fused_normalisation_is_bit_identical(monkeypatch):
-    """ADTFE_NORM_FUSED=1: the tile mixer CTA that finishes a segment's last tile (atomic ticket) normalises the row
-    itself instead of the separate kernel - same arithmetic, so the same bits, including empty and all-zero rows."""
-    from adt_str_b200.config import setting_1
-    from adt_str_b200.synthetic import make_bank, make_segments
-    bank = make_bank(390, 24000, seed=20)
-    bank.pcm[bank.offsets[3]: bank.offsets[3] + bank.lengths[3]] = 0.0
-    _, _, fe = _objects(setting_1(), bank)
-    segs = make_segments(70, seed=25, empty_fraction=0.1)
-    batches = [segs[:9], segs[9:10], segs[10:40], segs[40:]]
-    out = {}
-    for fused in (False, True, False):
-        if fused:
-            monkeypatch.setenv("ADTFE_NORM_FUSED", "1")
-        else:
-            monkeypatch.delenv("ADTFE_NORM_FUSED", raising=False)
-        plan = fe.plan_batches(batches, random.Random(5), 2)
-        for _ in range(2):
-            wav, feat = fe.run_plan(plan)
-        torch.cuda.synchronize()
-        out.setdefault(fused, (wav.clone(), feat.clone()))
-    monkeypatch.delenv("ADTFE_NORM_FUSED", raising=False)
-    same = lambda a, b: torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))
-    assert same(out[True][0], out[False][0]) and same(out[True][1], out[False][1])
-    assert float(out[False][0].abs().nan_to_num().max()) > 0.1
-
-
-def test_pipelined_front_end_equals_render_then_logmel(monkeypatch):
-    """adtfe_render_logmel on a chunked plan featurises finished chunk groups (co-resident log-mel shape on the
-    bank's mel stream) while later chunks render; whatever the group size, the waveforms and the log-mel are bit for
-    bit those of render-everything-then-one-log-mel-launch (ADTFE_CO_GROUP=0)."""
-    from adt_str_b200.config import setting_1
-    from adt_str_b200.synthetic import make_bank, make_segments
-    bank = make_bank(390, 24000, seed=16)
-    _, _, fe = _objects(setting_1(), bank)
-    segs = make_segments(90, seed=23, empty_fraction=0.1)
-    cuts = [0, 7, 8, 20, 26, 33, 41, 42, 50, 57, 63, 70, 78, 84, 90]
-    batches = [segs[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
-    results = {}
-    for group, chunk_batches in (("0", 1), ("1", 1), ("3", 1), ("5", 2), (None, 1)):
-        if group is None:
-            monkeypatch.delenv("ADTFE_CO_GROUP", raising=False)
-        else:
-            monkeypatch.setenv("ADTFE_CO_GROUP", group)
-        plan = fe.plan_batches(batches, random.Random(99), chunk_batches)
-        for _ in range(2):     # twice: the second run overlaps the first one's tail on the internal streams
-            wav, feat = fe.run_plan(plan)
-        torch.cuda.synchronize()
-        results[(group, chunk_batches)] = (wav.clone(), feat.clone())
-    monkeypatch.delenv("ADTFE_CO_GROUP", raising=False)
-    w0, f0 = results[("0", 1)]
-    assert torch.isfinite(f0).all()
-    for key, (w, f) in results.items():
-        assert torch.equal(w, w0), key
-        assert torch.equal(f, f0), key
-
-
 def test_host_pipeline_equals_direct_calls():
     """HostPipeline (planner threads, rotating pinned buffer sets, host log-mel) returns what the direct
     device calls return for the same RNG stream; with several workers it stays self-consistent."""
@@ -375,41 +263,47 @@ def test_host_pipeline_equals_direct_calls():
     segs = make_segments(60, seed=22, empty_fraction=0.1)
     groups = [[segs[0:6], segs[6:10]], [segs[10:25]], [segs[25:31], segs[31:32], segs[32:40]], [segs[40:50], segs[50:60]],
               [segs[3:9]], [segs[20:44], segs[1:2]]]
-    pipe = HostPipeline(fe, workers=1, n_sets=2, seed=7)
-    rng = random.Random(7 * 1_000_003)
-    for res, group in zip(pipe.run(groups), groups):
+    pipe = HostPipeline(fe, workers=1, n_sets=2, seed=7, rank=0)
+    for k, (res, group) in enumerate(zip(pipe.run(groups), groups)):
         got = [(l.copy(), m.clone()) for l, m in res.wait().batches()]
         res.release()
-        want = fe.run_batches(group, rng)
+        want = fe.run_batches(group, random.Random((7 * 1_000_003 + 0) * 1_000_003 + k))   # one stream per group
         assert len(got) == len(want)
         for (lengths, mel_host), (wav, feat), b in zip(got, want, group):
             assert not mel_host.is_cuda and lengths.shape == (len(b),)
             assert torch.equal(mel_host, feat.cpu())
     pipe.close()
-    pipe = HostPipeline(fe, workers=3, n_sets=3, seed=7)
-    shapes = []
-    for res, group in zip(pipe.run(groups), groups):
-        shapes.append([tuple(m.shape) for _, m in res.wait().batches()])
-        for (_, m), b in zip(res.batches(), group):
-            assert m.shape[0] == len(b) and torch.isfinite(m).all() and float(m.max()) <= 1.0
-        res.release()
-    pipe.close()
-    assert len(shapes) == len(groups)
+    # several workers: which thread plans a group is up to the executor, the draws are not - the same seed gives the
+    # same log-mel bit for bit, another rank (same seed) different augmentations
+    runs = {}
+    for tag, workers, rank in (("a", 3, 0), ("b", 2, 0), ("other rank", 3, 1)):
+        pipe = HostPipeline(fe, workers=workers, n_sets=3, seed=7, rank=rank)
+        mels = []
+        for res, group in zip(pipe.run(groups), groups):
+            for (_, m), b in zip(res.wait().batches(), group):
+                assert m.shape[0] == len(b) and torch.isfinite(m).all() and float(m.max()) <= 1.0
+                mels.append(m.clone())
+            res.release()
+        pipe.close()
+        runs[tag] = mels
+    assert all(torch.equal(x, y) for x, y in zip(runs["a"], runs["b"]))
+    assert any(x.shape != y.shape or not torch.equal(x, y) for x, y in zip(runs["a"], runs["other rank"]))
 
 
-def test_logmel_warp_autonomous_kernel_agrees_with_the_round_kernel(monkeypatch):
+def test_logmel_warp_autonomous_kernel_agrees_with_the_round_kernel():
     """Both log-mel kernels (v6: warp-autonomous units, lane-walk mel; v5: CTA rounds, frame-lane mel) see the same
     spectra; they differ only in the order the mel sums are taken, i.e. by float32 rounding of the filter sums."""
-    from adt_str_b200 import ComputeMelSpectrogram
+    from adt_str_b200 import ComputeMelSpectrogram, _lib
     g = torch.Generator().manual_seed(11)
     for sr, n in ((24000, 63840), (16000, 40960), (24000, 61440 + 240 * 3)):
         mel = ComputeMelSpectrogram(sr, 2048, 0.01, 128)
         x = (torch.randn(5, n, generator=g) * torch.logspace(-3, 0, 5).unsqueeze(1)).cuda()
-        monkeypatch.delenv("ADTFE_LOGMEL_V5", raising=False)
         a = mel(x)
-        monkeypatch.setenv("ADTFE_LOGMEL_V5", "1")
+        native = mel._handle(x.device)
+        _lib.check(native.lib.adtfe_mel_force_generic(native.handle, 1))   # per handle, no process-wide switch
         b = mel(x)
-        monkeypatch.delenv("ADTFE_LOGMEL_V5", raising=False)
+        _lib.check(native.lib.adtfe_mel_force_generic(native.handle, 0))
+        assert torch.equal(mel(x), a)
         assert a.shape == b.shape and a.shape[1] == mel.n_frames(n)
         assert float((a - b).abs().max()) <= 2e-6
         want = mel_oracle.logmel_direct(x.cpu().numpy(), sr, 2048, 0.01, 128, np.float64)
