@@ -34,7 +34,7 @@ class Plan(C.Structure):
                 ("n_events", C.c_int32), ("n_seg", C.c_int32), ("tiles_per_seg", C.c_int32),
                 ("n_peak_work", C.c_int32), ("ld_wav", C.c_int64),
                 ("mel_rows_dev", C.c_void_p), ("mel_total_rows", C.c_int64), ("mel_max_count", C.c_int32),
-                ("n_chunks", C.c_int32), ("chunks_host", C.c_void_p)]
+                ("n_chunks", C.c_int32), ("chunks_host", C.c_void_p), ("n_tile_events", C.c_int32)]
 
 
 _lock = threading.Lock()
@@ -50,7 +50,7 @@ def _declare(lib) -> None:
     lib.adtfe_bank_destroy.argtypes = [vp]
     lib.adtfe_bank_bytes.argtypes = [vp]
     lib.adtfe_bank_bytes.restype = i64
-    lib.adtfe_render_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.adtfe_render_workspace_bytes.argtypes = [i32, i32, i32, i32]
     lib.adtfe_render_workspace_bytes.restype = sz
     lib.adtfe_render.argtypes = [vp, C.POINTER(Plan), vp, vp, sz, vp]
     lib.adtfe_mel_force_generic.argtypes = [vp, i32]

@@ -108,6 +108,9 @@ extern "C" int adtfe_bank_destroy(adtfe_bank* bank) {
         if (bank->join_events[k]) cudaEventDestroy(bank->join_events[k]);
     }
     if (bank->fork_event) cudaEventDestroy(bank->fork_event);
+    for (auto& stage : bank->stage_events)
+        for (cudaEvent_t e : stage)
+            if (e) cudaEventDestroy(e);
     delete bank;
     return ADTFE_OK;
 }
@@ -157,6 +160,8 @@ extern "C" int adtfe_bank_create(const float* pcm_host, int64_t total_floats, co
              cudaEventCreateWithFlags(&b->join_events[k], cudaEventDisableTiming) == cudaSuccess;
         if (ok) b->n_streams = k + 1;
     }
+    for (auto& stage : b->stage_events)
+        for (cudaEvent_t& e : stage) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         set_error("adtfe_bank_create: cannot create streams: %s", cudaGetErrorString(cudaGetLastError()));
         adtfe_bank_destroy(b);

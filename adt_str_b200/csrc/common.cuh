@@ -112,6 +112,7 @@ void trace_close(cudaStream_t st);
 #define ADTFE_BANK_STREAMS 4
 #endif
 constexpr int kBankStreams = ADTFE_BANK_STREAMS;
+constexpr int kStageEvents = 8;
 struct adtfe_bank {
     int device = 0;
     int sm_count = 148;
@@ -124,6 +125,9 @@ struct adtfe_bank {
     int n_streams = 0;
     cudaStream_t streams[kBankStreams] = {};
     cudaEvent_t fork_event = nullptr, join_events[kBankStreams] = {};
+    // pipeline of a chunked render: stage_events[k][c % kStageEvents] = chunk c left stage k (an event can be
+    // re-recorded as soon as the wait on its previous recording has been enqueued)
+    cudaEvent_t stage_events[2][kStageEvents] = {};
     mutable std::mutex mu;
 };
 

@@ -6,17 +6,18 @@
 //   instrument_mixer 149-156: wav = sum_i track_i * gain_i ; wav / max|wav| * max_volume
 // and the zero padding of collate_fn (data_modules/train_dataset.py:53).
 //
-// The two data-dependent maxima make it three short kernels per chunk of segments:
+// The two data-dependent maxima make it three kernels per chunk of segments:
 //   1. peak_kernel      one CTA per (segment, instrument, 4096-sample chunk): both one-shots are
 //                       read once and max|ca*a + cb*b| is taken for every note of that
 //                       instrument at the same time (each note has its own mixup); warps and chunks
 //                       meet in an atomicMax on the float bits (order-independent); chunk 0 also
 //                       resolves the bank lookups into ResolvedEvent records.
-//   2. mix_kernel       persistent CTAs take 2048-sample output tiles from a queue; a producer warp
-//                       streams the tile's one-shot slices through a shared-memory ring with TMA bulk
-//                       copies, consumer warps add them in event order (the host-built CSR
-//                       tile -> events) into registers, so the result is deterministic and needs no
-//                       atomics; writes the raw tile and its |max|.
+//   2. slice_kernel     per (tile, note) one 32-byte record with everything the mixer needs (copy source and
+//                       size, alignment, covered range, coefficients), in tile order.
+//      mix_kernel       persistent one-warp CTAs take 2048-sample output tiles from a queue; each warp streams
+//                       its tile's one-shot slices through its own shared-memory ring with TMA bulk copies
+//                       and adds them in event order (the host-built CSR tile -> events) into registers, so
+//                       the result is deterministic and needs no atomics; writes the raw tile and its |max|.
 //   3. normalise_kernel row peak = max of the tile maxima; wav / peak * max_volume in place
 //                       (an all-zero mix gives NaN, like the reference's 0/0).
 #include <algorithm>
@@ -171,64 +172,104 @@ __global__ void __launch_bounds__(kPeakThreads) peak_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tile mixer.  Persistent CTAs: one producer warp stages the one-shot slices a tile needs through a
-// ring of shared-memory buffers with TMA bulk copies (cp.async.bulk + mbarrier), the consumer
-// warps accumulate them in arrival (= event) order into registers.  Tiles are handed out by an
-// atomic counter, so long and short tiles balance.  Measured on B200 (tools/gpu_variants.sh): the
-// kernel is bound by the latency chain of a tile (queue head -> tile_ptr -> events -> records -> TMA),
-// so many small CTAs (4 consumer warps x 16 samples per thread, a 2-slot ring, 8 CTAs per SM) beat
-// few large ones (8 x 8, 6 slots, 4 per SM) by 12 % on the whole render.  The kernel is issue-bound (ncu: 75 % issue
-// utilisation, a fifth of the instructions useful LDS + FFMA), so the per-slice hand-off is paid by as few warps as
-// possible: 2 consumer warps x 32 samples per thread, and as many CTAs as shared memory holds (10-11 per SM, launch
-// bound 12 = 55 registers) measured 15.04 ms per step against 15.26 ms for 4 x 16 / 8 CTAs.
-#ifndef ADTFE_MIX_CONSUMERS
-#define ADTFE_MIX_CONSUMERS 2
-#endif
-#ifndef ADTFE_MIX_STAGES
-#define ADTFE_MIX_STAGES 2
+// Tile mixer, in two kernels.
+//
+// slice_kernel   one warp per output tile: lane i turns the tile's i-th note (host CSR tile -> events, the resolved
+//                bank lookups and the peak of the peak pass) into a 32-byte TileSlice record - which 16-byte
+//                granules of the two one-shots reach the tile, where they land relative to the tile, the covered
+//                sample range and the two coefficients c * gain / peak.  Records are stored in tile order, so the
+//                mixer fetches a tile's notes with ONE coalesced load instead of a three-deep dependent chain.
+// mix_kernel     persistent ONE-WARP CTAs, nothing shared between warps.  A warp owns a tile of 2048 output samples
+//                (64 per lane, sample lane + 32 j, in registers) and streams the tile's slices through its own ring
+//                of kDepth shared-memory slots with TMA bulk copies (cp.async.bulk + one mbarrier per slot).  There
+//                is no producer warp and no hand-off: the lane that owns a note issues that note's copies itself
+//                (it holds the record in registers), the warp waits on the slot's mbarrier, adds the slice
+//                `coef * x` into the accumulators - fixed event order, main then sub, no atomics - and the lane that
+//                owns stream position c + kDepth refills the freed slot.  The slice stream runs ACROSS tiles: the
+//                records of the next tile are fetched two tiles ahead (queue head -> tile_ptr -> records, one level
+//                per tile), so while a tile's last slices are consumed the next tile's first ones are already in
+//                flight and the ring never drains.
+// Round 1's mixer (a producer warp feeding consumer warps through full/empty mbarriers) spent 407 warp instructions
+// per slice, 96 of them the LDS + FFMA2 that do the work (ncu: 16 M of 91 M instructions mbarrier polling, 9 M
+// branches, the rest descriptor traffic); this one spends ~130.  TMA cannot realign: a tensor-map copy with an
+// element offset that is not a multiple of 16 bytes faults (tools/microbench/tma_shift.cu, profiles/r02_tma_shift.txt),
+// so a slice lands with its source alignment and the lanes read it with conflict-free scalar LDS (lane-contiguous).
+#ifndef ADTFE_MIX_DEPTH
+#define ADTFE_MIX_DEPTH 2
 #endif
 #ifndef ADTFE_MIX_CTAS
 #define ADTFE_MIX_CTAS 12
 #endif
-constexpr int kMixConsumers = ADTFE_MIX_CONSUMERS;       // warps; each thread owns tile / (32 * warps) samples
-constexpr int kMixThreads = (kMixConsumers + 1) * 32;    // + the producer warp
-constexpr int kPerThread = ADTFE_TILE / (kMixConsumers * 32);
-constexpr int kStages = ADTFE_MIX_STAGES;
-constexpr int kMixCtasPerSm = ADTFE_MIX_CTAS;
-constexpr int kStageFloats = 2080;                       // >= 2048 + 2*3 alignment slack, bytes a multiple of 128
-static_assert(kPerThread * kMixConsumers * 32 == ADTFE_TILE && kPerThread <= 32 && kPerThread % 2 == 0,
-              "tile / consumer threads");
+#ifndef ADTFE_MIX_WIDTH
+#define ADTFE_MIX_WIDTH 2048
+#endif
+constexpr int kDepth = ADTFE_MIX_DEPTH;                  // ring slots (slices in flight or being consumed) per warp
+constexpr int kMixCtasPerSm = ADTFE_MIX_CTAS;            // one-warp CTAs per SM (bounded by shared memory)
+constexpr int kWidth = ADTFE_MIX_WIDTH;                  // output samples a warp owns at a time: a host tile or a part of it
+constexpr int kSub = ADTFE_TILE / kWidth;                // warp tiles per host tile
+constexpr int kStageFloats = kWidth + 32;                // >= kWidth + 3 alignment slack, bytes a multiple of 128
+constexpr int kAcc = kWidth / 32;                        // samples per lane
+static_assert(kSub * kWidth == ADTFE_TILE && (kAcc == 64 || kAcc == 32 || kAcc == 16), "warp tile width");
 
-struct __align__(16) StageDesc {   // written by the producer lane, read (broadcast) by every consumer
-    int32_t kind;                  // 0: data, 1: a new tile begins (tile id in `tile`, < 0: no more work)
-    int32_t tile;
-    int32_t base;                  // sample i of the tile sits at buffer index i + base
-    int32_t vlo, vhi;              // samples vlo <= i < vhi of the tile are covered
-    float coef;
-    int32_t pad0, pad1;
+struct __align__(16) TileSlice {   // one (warp tile, note): 32 bytes
+    uint32_t a_g4, b_g4;           // first 16-byte granule to copy, as float offset / 4 into the bank
+    uint16_t na4, nb4;             // granules to copy (0: the source does not reach this tile)
+    int16_t base;                  // tile sample i sits at slot index i + base
+    uint16_t vlo;                  // tile samples vlo <= i < vhi_* are covered
+    uint16_t vhi_a, vhi_b;
+    uint32_t pad;
+    float coef_a, coef_b;          // ca * gain / peak, cb * gain / peak
 };
+static_assert(sizeof(TileSlice) == 32, "TileSlice layout");
 
-struct __align__(16) SliceMsg {    // producer-private list entry: the StageDesc words + what the TMA copy needs
-    int4 d0;                       // kind, tile, base, vlo
-    int4 d1;                       // vhi, coef bits, -, -
-    int4 d2;                       // source float offset (lo, hi), bytes (0: no copy, plain arrive), -
-};
-constexpr int kListMax = 65;       // a tile marker + two sources of 32 notes
-constexpr int kIssue = kStages / 2 > 0 ? kStages / 2 : 1;  // messages issued per producer pass
-
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kMixConsumers * 32) : "memory"); }
-
-__host__ __device__ constexpr size_t mix_list_offset() {
-    return (((size_t)kStages * kStageFloats * 4 + kStages * 32 + 2 * kStages * 8 + (kMixConsumers + 2) * 4) + 15) & ~(size_t)15;
+__global__ void __launch_bounds__(256) slice_kernel(const ResolvedEvent* __restrict__ resolved,
+                                                    const int* __restrict__ peak_bits,
+                                                    const int32_t* __restrict__ tile_ptr,
+                                                    const int32_t* __restrict__ tile_events,
+                                                    TileSlice* __restrict__ slices, int tiles_per_seg, int n_tiles) {
+    const int tile = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (tile >= n_tiles) return;
+    const int p0 = __ldg(tile_ptr + tile), p1 = __ldg(tile_ptr + tile + 1);
+    const int lo = (tile % tiles_per_seg) * ADTFE_TILE;
+    for (int p = p0 + lane; p < p1; p += 32) {
+        const int e = __ldg(tile_events + p);
+        const ResolvedEvent ev = resolved[e];
+        // an all-zero one-shot has peak 0: gain/0 = inf (or NaN), and 0 * inf = NaN over the whole note - the
+        // reference's o / 0 (synthetiser.py:225)
+        const float scale = ev.gain / __int_as_float(peak_bits[e]);
+        const int rel = lo - ev.start;                       // tile sample i is source sample i + rel
+        const int r_lo = max(0, rel);
+        const int r_hi_a = min(ev.la, rel + ADTFE_TILE), r_hi_b = min(ev.lb, rel + ADTFE_TILE);
+        const int g_lo = r_lo & ~3;                          // storage is padded to 4 floats
+        const int base = rel - g_lo, vlo = r_lo - rel;       // host tile: sample i sits at copy index i + base, i >= vlo
+        const int vhi_a = max(r_hi_a - rel, 0), vhi_b = max(r_hi_b - rel, 0);
+        const float coef_a = ev.ca * scale, coef_b = ev.cb * scale;
+#pragma unroll
+        for (int h = 0; h < kSub; ++h) {                     // the part of the note on warp tile h of the host tile
+            const int H = h * kWidth;
+            const int lo_h = max(vlo, H), hi_a = min(vhi_a, H + kWidth), hi_b = min(vhi_b, H + kWidth);
+            const int gs = max(lo_h + base, 0) >> 2;         // first granule of the copy that the part needs
+            TileSlice t;
+            t.a_g4 = (uint32_t)((ev.a_off + g_lo) >> 2) + (uint32_t)gs;
+            t.b_g4 = (uint32_t)((ev.b_off + g_lo) >> 2) + (uint32_t)gs;
+            t.na4 = hi_a > lo_h ? (uint16_t)(((hi_a + base + 3) >> 2) - gs) : 0;
+            t.nb4 = hi_b > lo_h ? (uint16_t)(((hi_b + base + 3) >> 2) - gs) : 0;
+            t.base = (int16_t)(H + base - 4 * gs);           // warp-tile sample i' = i - H sits at slot index i' + base'
+            t.vlo = (uint16_t)max(lo_h - H, 0);
+            t.vhi_a = (uint16_t)max(hi_a - H, 0);
+            t.vhi_b = (uint16_t)max(hi_b - H, 0);
+            t.pad = 0;
+            t.coef_a = coef_a;
+            t.coef_b = coef_b;
+            slices[(size_t)p * kSub + h] = t;
+        }
+    }
 }
 
 struct MixArgs {
     const float* pcm;
-    const ResolvedEvent* resolved;
-    const int* peak_bits;
+    const TileSlice* slices;
     const int32_t* tile_ptr;
-    const int32_t* tile_events;
-    const adtfe_segment* segments;
     float* wav;
     float* tile_max;
     int* tile_counter;
@@ -236,197 +277,226 @@ struct MixArgs {
     int32_t tiles_per_seg, n_tiles;
 };
 
-// Writes the finished (not yet normalised) tile and publishes its |max|.
-__device__ __forceinline__ void finish_tile(const MixArgs& a, int tile_id, const float2 (&acc2)[kPerThread / 2], int tid,
-                                            float* s_red) {
-    const int seg = tile_id / a.tiles_per_seg, lo = (tile_id - seg * a.tiles_per_seg) * ADTFE_TILE;
-    // |max| on the float bits: non-negative floats order like unsigned integers and a NaN's bits lie above infinity's,
-    // so the unsigned maximum propagates NaN like torch.max - one LOP3 + one integer max per sample, one REDUX per warp
-    unsigned mb = 0u;
-    float* row = a.wav + (int64_t)seg * a.ld_wav;
-#pragma unroll
-    for (int j = 0; j < kPerThread; ++j) {
-        const int n = lo + tid + j * (kMixConsumers * 32);
-        const float v = (j & 1) ? acc2[j >> 1].y : acc2[j >> 1].x;
-        if (n < a.ld_wav) row[n] = v;
-        mb = max(mb, __float_as_uint(fabsf(v)));
-    }
-    mb = __reduce_max_sync(0xffffffffu, mb);
-    consumer_sync();  // s_red of the previous tile is no longer read
-    if ((tid & 31) == 0) s_red[tid >> 5] = __uint_as_float(mb);
-    consumer_sync();
-    if (tid == 0) {
-        unsigned rb = __float_as_uint(s_red[0]);
-        for (int i = 1; i < kMixConsumers; ++i) rb = max(rb, __float_as_uint(s_red[i]));
-        a.tile_max[tile_id] = __uint_as_float(rb);
+// The notes of (up to 32 of) one tile, one per lane, as the mixer keeps them in registers.
+struct NoteRegs {
+    uint32_t a_g4, b_g4;
+    uint32_t n4;        // na4 | nb4 << 16
+    uint32_t base_vlo;  // (uint16)base | vlo << 16
+    uint32_t vhi;       // vhi_a | vhi_b << 16
+    float coef_a, coef_b;
+    int pos_a, pos_b;   // position of the lane's slices in the batch's stream (-1: not live)
+};
+struct Batch {
+    NoteRegs r;
+    unsigned m_a, m_b;  // lanes whose main / sub slice is live
+    int n;              // slices in the batch
+    int tile;           // < 0: no more work
+    int p_next, p_end;  // records of the tile not yet in a batch: [p_next, p_end)
+    int pre;            // slices of this batch already issued (behind the previous batch's)
+};
+
+__device__ __forceinline__ void load_records(const TileSlice* __restrict__ slices, int p0, int p1, int h, int lane,
+                                             uint4& q0, uint4& q1) {
+    q0 = make_uint4(0u, 0u, 0u, 0u);
+    q1 = make_uint4(0u, 0u, 0u, 0u);
+    if (p0 + lane < p1) {
+        const uint4* q = reinterpret_cast<const uint4*>(slices + (size_t)(p0 + lane) * kSub + h);
+        q0 = __ldg(q);
+        q1 = __ldg(q + 1);
     }
 }
 
-__global__ void __launch_bounds__(kMixThreads, kMixCtasPerSm) mix_kernel(const MixArgs a) {
+__device__ __forceinline__ void decode_batch(Batch& b, const uint4& q0, const uint4& q1, int lane) {
+    b.r.a_g4 = q0.x; b.r.b_g4 = q0.y; b.r.n4 = q0.z; b.r.base_vlo = q0.w;
+    b.r.vhi = q1.x; b.r.coef_a = __uint_as_float(q1.z); b.r.coef_b = __uint_as_float(q1.w);
+    const bool live_a = (q0.z & 0xffffu) != 0u, live_b = (q0.z >> 16) != 0u;
+    b.m_a = __ballot_sync(0xffffffffu, live_a);
+    b.m_b = __ballot_sync(0xffffffffu, live_b);
+    const unsigned below = (1u << lane) - 1u;
+    const int before = __popc(b.m_a & below) + __popc(b.m_b & below);
+    b.r.pos_a = live_a ? before : -1;
+    b.r.pos_b = live_b ? before + (live_a ? 1 : 0) : -1;
+    b.n = __popc(b.m_a) + __popc(b.m_b);
+    b.pre = 0;
+}
+
+// the lane that owns stream position `pos` of batch `b` (global sequence number seq) starts the copy into its slot
+__device__ __forceinline__ void issue_slice(const MixArgs& a, const NoteRegs& r, bool sub, unsigned seq, float* ring,
+                                            uint64_t* bars) {
+    const unsigned slot = seq % (unsigned)kDepth;
+    const uint32_t bytes = (sub ? (r.n4 >> 16) : (r.n4 & 0xffffu)) * 16u;
+    const float* src = a.pcm + (size_t)(sub ? r.b_g4 : r.a_g4) * 4u;
+    // The slot's previous contents were read by loads whose values have been consumed (the FMAs ran) before the
+    // __syncwarp that precedes this call, so the copy cannot overtake them; no proxy fence is needed for that
+    // read-then-overwrite order (it compiles to MEMBAR.ALL.CTA, which would also wait for the tile's global stores).
+    mbar_expect_tx(bars + slot, bytes);
+    bulk_g2s(ring + slot * kStageFloats, src, bytes, bars + slot);
+}
+
+// issue the stream positions [from, to) of batch b (b's position 0 has global sequence number seq0)
+__device__ __forceinline__ void issue_range(const MixArgs& a, const Batch& b, int from, int to, unsigned seq0, float* ring,
+                                            uint64_t* bars) {
+    if (b.r.pos_a >= from && b.r.pos_a < to) issue_slice(a, b.r, false, seq0 + (unsigned)b.r.pos_a, ring, bars);
+    if (b.r.pos_b >= from && b.r.pos_b < to) issue_slice(a, b.r, true, seq0 + (unsigned)b.r.pos_b, ring, bars);
+}
+
+__global__ void __launch_bounds__(32, kMixCtasPerSm) mix_kernel(const MixArgs a) {
     extern __shared__ __align__(128) unsigned char mix_smem[];
-    float* s_buf = reinterpret_cast<float*>(mix_smem);                               // kStages * kStageFloats
-    StageDesc* s_desc = reinterpret_cast<StageDesc*>(s_buf + kStages * kStageFloats);
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(s_desc + kStages);
-    uint64_t* s_empty = s_full + kStages;
-    float* s_red = reinterpret_cast<float*>(s_empty + kStages);
-    SliceMsg* s_list = reinterpret_cast<SliceMsg*>(mix_smem + mix_list_offset());
+    float* ring = reinterpret_cast<float*>(mix_smem);                                  // kDepth * kStageFloats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kDepth * kStageFloats);
+    const int lane = threadIdx.x;
+    if (lane < kDepth) mbar_init(bars + lane, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) { mbar_init(s_full + s, 1); mbar_init(s_empty + s, kMixConsumers); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    int stage = 0;
-    uint32_t phase = 0;
-
-    if (warp == kMixConsumers) {
-        // ================= producer warp =================
-        // Per tile: a marker message, then one message per live (note, source) slice in event order.  The
-        // messages of up to 32 notes are first laid out in a warp-private list (ballot + popcount give every
-        // lane its slots); then lane j takes the j-th next message: it waits for ring slot stage + j to drain,
-        // publishes the descriptor and starts the TMA copy - kStages slots are refilled per pass instead of one.
-        SliceMsg* list = s_list;
-        for (;;) {
-            int tile = 0;
-            if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
-            tile = __shfl_sync(0xffffffffu, tile, 0);
-            const bool done = tile >= a.n_tiles;
-            int p0 = 0, p1 = 0, lo = 0;
-            if (!done) {
-                const int seg = tile / a.tiles_per_seg;
-                lo = (tile - seg * a.tiles_per_seg) * ADTFE_TILE;
-                p0 = __ldg(a.tile_ptr + tile);
-                p1 = __ldg(a.tile_ptr + tile + 1);
+    // ---- metadata pipeline, one level per tile: queue head -> tile_ptr -> records -> decoded batch.  Every level's
+    // loads are issued one tile before their results are used, so none of the four round trips is ever waited for.
+    int ticket = 0;                         // lane 0: the queue head taken for the tile after id_c (not yet broadcast)
+    if (lane == 0) ticket = atomicAdd(a.tile_counter, 1);
+    int id_c = -1, pc0 = 0, pc1 = 0;        // tile whose tile_ptr entries are requested
+    int id_b = -1, pb0 = 0, pb1 = 0;        // tile whose records are requested
+    bool drained = false;                   // the queue is empty: no more tickets are taken
+    uint4 q0 = make_uint4(0u, 0u, 0u, 0u), q1 = q0;
+    Batch cur, nxt;
+    nxt.tile = -1; nxt.n = 0; nxt.pre = 0; nxt.p_next = nxt.p_end = 0; nxt.m_a = nxt.m_b = 0u;
+    nxt.r.pos_a = nxt.r.pos_b = -1;
+    // advance the pipeline by one tile: nxt <- decoded records of id_b; records of id_c requested; pointers of the
+    // tile behind the ticket requested; a new ticket taken
+    auto advance = [&]() {
+        nxt.tile = id_b;
+        nxt.p_next = min(pb0 + 32, pb1);
+        nxt.p_end = pb1;
+        decode_batch(nxt, q0, q1, lane);
+        id_b = id_c; pb0 = pc0; pb1 = pc1;
+        if (id_b >= 0) load_records(a.slices, pb0, min(pb0 + 32, pb1), id_b % kSub, lane, q0, q1);
+        else { q0 = make_uint4(0u, 0u, 0u, 0u); q1 = q0; }
+        id_c = -1;
+        if (!drained) {
+            const int t = __shfl_sync(0xffffffffu, ticket, 0);
+            if (t < a.n_tiles * kSub) {
+                id_c = t;                   // warp tile t: part t % kSub of host tile t / kSub
+                pc0 = __ldg(a.tile_ptr + t / kSub);
+                pc1 = __ldg(a.tile_ptr + t / kSub + 1);
+                if (lane == 0) ticket = atomicAdd(a.tile_counter, 1);
+            } else {
+                drained = true;
             }
-            bool first = true;
-            int base = p0;
-            do {
-                const int n = min(32, p1 - base);
-                // lane i owns event base + i: both of its sources, clipped to this tile
-                int64_t off[2] = {0, 0};
-                int r_lo = 0, r_hi[2] = {0, 0}, rel = 0;
-                float coef[2] = {0.0f, 0.0f};
-                if (lane < n) {
-                    const int e = __ldg(a.tile_events + base + lane);
-                    const ResolvedEvent ev = a.resolved[e];
-                    // an all-zero one-shot has peak 0: gain/0 = inf (or NaN), and 0 * inf = NaN over the
-                    // whole note - the reference's o / 0 (synthetiser.py:225)
-                    const float scale = ev.gain / __int_as_float(a.peak_bits[e]);
-                    rel = lo - ev.start;  // tile sample i is source sample i + rel
-                    off[0] = ev.a_off; off[1] = ev.b_off;
-                    coef[0] = ev.ca * scale; coef[1] = ev.cb * scale;
-                    r_lo = max(0, rel);
-                    r_hi[0] = min(ev.la, rel + ADTFE_TILE);
-                    r_hi[1] = min(ev.lb, rel + ADTFE_TILE);
-                }
-                const bool live0 = r_hi[0] > r_lo, live1 = r_hi[1] > r_lo;
-                const unsigned m0 = __ballot_sync(0xffffffffu, live0), m1 = __ballot_sync(0xffffffffu, live1);
-                const unsigned below = (1u << lane) - 1u;
-                int slot = (first ? 1 : 0) + __popc(m0 & below) + __popc(m1 & below);
-                const int total = (first ? 1 : 0) + __popc(m0) + __popc(m1);
-                if (first && lane == 0) {
-                    SliceMsg m;
-                    m.d0 = make_int4(1, done ? -1 : tile, 0, 0);
-                    m.d1 = make_int4(0, 0, 0, 0);
-                    m.d2 = make_int4(0, 0, 0, 0);
-                    list[0] = m;
-                }
+        }
+    };
+    advance();   // id_c <- first tile, its pointers requested
+    advance();   // id_b <- first tile, its records requested
+    advance();   // nxt  <- first tile
+    unsigned seq = 0;   // slices consumed so far by this warp: slot = seq % kDepth, parity = (seq / kDepth) & 1
+    if (nxt.tile >= 0) {
+        nxt.pre = min(nxt.n, kDepth);
+        issue_range(a, nxt, 0, nxt.pre, seq, ring, bars);
+    }
+
+    float2 acc2[kAcc / 2];
 #pragma unroll
-                for (int sidx = 0; sidx < 2; ++sidx) {
-                    if (sidx == 0 ? live0 : live1) {
-                        const int g_lo = r_lo & ~3, g_hi = (r_hi[sidx] + 3) & ~3;  // storage is padded to 4 floats
-                        const long long src = off[sidx] + g_lo;
-                        SliceMsg m;
-                        m.d0 = make_int4(0, tile, rel - g_lo, r_lo - rel);
-                        m.d1 = make_int4(r_hi[sidx] - rel, __float_as_int(coef[sidx]), 0, 0);
-                        m.d2 = make_int4((int)(unsigned)(src & 0xffffffffll), (int)(src >> 32), (g_hi - g_lo) * 4, 0);
-                        list[slot++] = m;
-                    }
-                }
-                __syncwarp();
-                for (int k0 = 0; k0 < total; k0 += kIssue) {
-                    const int k = k0 + lane;
-                    if (lane < kIssue && k < total) {
-                        int st = stage + lane;
-                        uint32_t ph = phase;
-                        if (st >= kStages) { st -= kStages; ph ^= 1u; }
-                        const SliceMsg m = list[k];
-                        mbar_wait_relaxed(s_empty + st, ph ^ 1u, 2000u);
-                        int4* d = reinterpret_cast<int4*>(s_desc + st);
-                        d[0] = m.d0;
-                        d[1] = m.d1;
-                        if (m.d2.z > 0) {
-                            const long long src = (long long)(((unsigned long long)(unsigned)m.d2.y << 32) | (unsigned)m.d2.x);
-                            mbar_expect_tx(s_full + st, (uint32_t)m.d2.z);
-                            bulk_g2s(s_buf + st * kStageFloats, a.pcm + src, (uint32_t)m.d2.z, s_full + st);
-                        } else {
-                            mbar_arrive(s_full + st);
+    for (int k = 0; k < kAcc / 2; ++k) acc2[k] = make_float2(0.0f, 0.0f);
+
+    for (;;) {
+        cur = nxt;
+        if (cur.tile < 0) break;
+        const bool last_batch = cur.p_next >= cur.p_end;   // the tile's notes fit this batch (<= 32: the usual case)
+        if (last_batch) {
+            advance();                                      // nxt: the next tile (its copies start behind cur's)
+        } else {                                            // more than 32 notes on the tile: the rest follows, fetched now
+            uint4 r0, r1;
+            load_records(a.slices, cur.p_next, min(cur.p_next + 32, cur.p_end), cur.tile % kSub, lane, r0, r1);
+            Batch more;
+            more.tile = cur.tile; more.p_next = min(cur.p_next + 32, cur.p_end); more.p_end = cur.p_end;
+            decode_batch(more, r0, r1, lane);
+            // the prefetched next tile keeps waiting in (id_b, q0, q1): park it by not advancing
+            nxt = more;
+        }
+        // stream: cur's slices 0 .. cur.n-1 (the first cur.pre already issued), then nxt's
+        const int n_x = cur.n, n_y = nxt.tile >= 0 ? nxt.n : 0;
+        const unsigned seq0 = seq;
+        {   // fill the ring: positions cur.pre .. kDepth-1 of the stream
+            issue_range(a, cur, cur.pre, min(n_x, kDepth), seq0, ring, bars);
+            if (n_x < kDepth) issue_range(a, nxt, 0, min(n_y, kDepth - n_x), seq0 + (unsigned)n_x, ring, bars);
+        }
+        int c = 0;   // stream position being consumed
+        unsigned todo = cur.m_a | cur.m_b;
+        while (todo) {
+            const int e = __ffs((int)todo) - 1;
+            todo &= todo - 1u;
+            const uint32_t base_vlo = __shfl_sync(0xffffffffu, cur.r.base_vlo, e);
+            const uint32_t vhi2 = __shfl_sync(0xffffffffu, cur.r.vhi, e);
+            const float coef_a = __shfl_sync(0xffffffffu, cur.r.coef_a, e);
+            const float coef_b = __shfl_sync(0xffffffffu, cur.r.coef_b, e);
+            const int base = (int)(int16_t)(base_vlo & 0xffffu), vlo = (int)(base_vlo >> 16);
+#pragma unroll 1
+            for (int sub = 0; sub < 2; ++sub) {
+                if (!(((sub ? cur.m_b : cur.m_a) >> e) & 1u)) continue;
+                const float coef = sub ? coef_b : coef_a;
+                const int vhi = (int)(sub ? (vhi2 >> 16) : (vhi2 & 0xffffu));
+                const unsigned slot = seq % (unsigned)kDepth;
+                mbar_wait(bars + slot, (seq / (unsigned)kDepth) & 1u);
+                const float* src = ring + slot * kStageFloats + base + lane;
+                if (vlo == 0 && vhi == kWidth) {
+                    const float2 c2 = make_float2(coef, coef);
+#pragma unroll
+                    for (int k = 0; k < kAcc / 2; ++k)
+                        acc2[k] = __ffma2_rn(make_float2(src[64 * k], src[64 * k + 32]), c2, acc2[k]);
+                } else {
+                    // A note starts or ends inside the tile: this lane's samples lane + 32 j lie inside [vlo, vhi) for
+                    // jlo <= j < jhi.  One bit mask per half instead of two compares per sample; samples outside the
+                    // note stay untouched even when coef is inf / NaN.
+                    const int jlo = (max(vlo - lane, 0) + 31) >> 5, jhi = min((max(vhi - lane, 0) + 31) >> 5, kAcc);
+                    auto below = [](int j) { return j >= 32 ? 0xffffffffu : (j <= 0 ? 0u : (1u << j) - 1u); };
+                    const unsigned mask_lo = below(jhi) & ~below(jlo);
+                    const unsigned mask_hi = below(jhi - 32) & ~below(jlo - 32);
+#pragma unroll
+                    for (int j = 0; j < kAcc; ++j) {
+                        if (((j < 32 ? mask_lo : mask_hi) >> (j & 31)) & 1u) {
+                            if (j & 1) acc2[j >> 1].y = fmaf(src[32 * j], coef, acc2[j >> 1].y);
+                            else acc2[j >> 1].x = fmaf(src[32 * j], coef, acc2[j >> 1].x);
                         }
                     }
-                    stage += min(kIssue, total - k0);
-                    if (stage >= kStages) { stage -= kStages; phase ^= 1u; }
                 }
-                __syncwarp();  // the list is rewritten by the next batch
-                first = false;
-                base += 32;
-            } while (base < p1);
-            if (done) break;
-        }
-        return;
-    }
-
-    // ================= consumer warps =================
-    // sample j of the thread (tile index tid + T*j) is component j & 1 of acc2[j / 2]: a full slice costs one
-    // packed FFMA2 per two samples (the kernel is issue-bound)
-    float2 acc2[kPerThread / 2];
-#pragma unroll
-    for (int k = 0; k < kPerThread / 2; ++k) acc2[k] = make_float2(0.0f, 0.0f);
-    int tile = -1;
-    for (;;) {
-        mbar_wait_relaxed(s_full + stage, phase, 2000u);
-        const int4 d0 = *reinterpret_cast<const int4*>(s_desc + stage);
-        if (d0.x != 0) {  // a new tile begins
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_empty + stage);
-            if (++stage == kStages) { stage = 0; phase ^= 1u; }
-            if (tile >= 0) finish_tile(a, tile, acc2, tid, s_red);
-            tile = d0.y;
-            if (tile < 0) break;
-#pragma unroll
-            for (int k = 0; k < kPerThread / 2; ++k) acc2[k] = make_float2(0.0f, 0.0f);
-            continue;
-        }
-        const int4 d1 = *reinterpret_cast<const int4*>(reinterpret_cast<const char*>(s_desc + stage) + 16);
-        const int vlo = d0.w, vhi = d1.x;
-        const float coef = __int_as_float(d1.y);
-        const float* src = s_buf + stage * kStageFloats + d0.z + tid;
-        if (vlo == 0 && vhi == ADTFE_TILE) {
-            constexpr int T = kMixConsumers * 32;
-            const float2 c2 = make_float2(coef, coef);
-#pragma unroll
-            for (int k = 0; k < kPerThread / 2; ++k)
-                acc2[k] = __ffma2_rn(make_float2(src[(2 * k) * T], src[(2 * k + 1) * T]), c2, acc2[k]);
-        } else {
-            // A note starts or ends inside the tile: this thread's samples tid + T*j lie inside [vlo, vhi) for
-            // jlo <= j < jhi.  One bit mask per slice instead of two compares per sample (the kernel is issue-bound);
-            // samples outside the note stay untouched even when coef is inf / NaN.
-            constexpr int T = kMixConsumers * 32;
-            const int jlo = (max(vlo - tid, 0) + T - 1) / T, jhi = min((max(vhi - tid, 0) + T - 1) / T, kPerThread);
-            const unsigned below_hi = jhi >= 32 ? 0xffffffffu : (1u << jhi) - 1u;
-            const unsigned below_lo = jlo >= 32 ? 0xffffffffu : (1u << jlo) - 1u;
-            const unsigned mask = below_hi & ~below_lo;   // empty when jhi <= jlo
-#pragma unroll
-            for (int j = 0; j < kPerThread; ++j) {
-                if ((mask >> j) & 1u) {
-                    if (j & 1) acc2[j >> 1].y = fmaf(src[j * T], coef, acc2[j >> 1].y);
-                    else acc2[j >> 1].x = fmaf(src[j * T], coef, acc2[j >> 1].x);
-                }
+                __syncwarp();   // every lane has read the slot: it can be refilled
+                const int t = c + kDepth;   // the stream position that takes the freed slot
+                if (t < n_x) issue_range(a, cur, t, t + 1, seq0, ring, bars);
+                else if (t - n_x < n_y) issue_range(a, nxt, t - n_x, t - n_x + 1, seq0 + (unsigned)n_x, ring, bars);
+                ++c;
+                ++seq;
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty + stage);
-        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+        nxt.pre = min(n_y, kDepth);
+        if (!last_batch) continue;   // the tile's remaining notes come with the next batch
+
+        // ---- the tile is complete: write it (not yet normalised) and publish its |max|
+        {
+            const int tile = cur.tile;   // warp tile: part tile % kSub of host tile tile / kSub
+            const int seg = tile / (a.tiles_per_seg * kSub), lo = (tile - seg * a.tiles_per_seg * kSub) * kWidth;
+            float* row = a.wav + (int64_t)seg * a.ld_wav + lo + lane;
+            // |max| on the float bits: non-negative floats order like unsigned integers and a NaN's bits lie above
+            // infinity's, so the unsigned maximum propagates NaN like torch.max; one REDUX per tile
+            unsigned mb = 0u;
+            if (lo + kWidth <= a.ld_wav) {
+#pragma unroll
+                for (int k = 0; k < kAcc / 2; ++k) {
+                    row[64 * k] = acc2[k].x;
+                    row[64 * k + 32] = acc2[k].y;
+                    mb = max(mb, max(__float_as_uint(fabsf(acc2[k].x)), __float_as_uint(fabsf(acc2[k].y))));
+                }
+            } else {
+                const int room = (int)(a.ld_wav - lo) - lane;   // samples of this lane's column that exist
+#pragma unroll
+                for (int k = 0; k < kAcc / 2; ++k) {
+                    if (64 * k < room) row[64 * k] = acc2[k].x;
+                    if (64 * k + 32 < room) row[64 * k + 32] = acc2[k].y;
+                    mb = max(mb, max(__float_as_uint(fabsf(acc2[k].x)), __float_as_uint(fabsf(acc2[k].y))));
+                }
+            }
+            mb = __reduce_max_sync(0xffffffffu, mb);
+            if (lane == 0) a.tile_max[tile] = __uint_as_float(mb);
+#pragma unroll
+            for (int k = 0; k < kAcc / 2; ++k) acc2[k] = make_float2(0.0f, 0.0f);
+        }
     }
 }
 
@@ -434,6 +504,10 @@ __global__ void __launch_bounds__(kMixThreads, kMixCtasPerSm) mix_kernel(const M
 // Row normalisation (wav / peak * max_volume, synthetiser.py:142-144,156): one CTA per tile; the
 // segment peak is the max of its tile maxima.  An all-zero mix gives NaN (the reference's 0/0),
 // samples beyond the segment's length stay exact zeros (collate_fn pads with 0.0).
+// Measured alternatives (both bit-identical, both slower on B200): the warp that completes a row (per-row ticket)
+// normalising it inside the tile mixer while it is still in L2 - 7.8 ms render against 7.0 ms, the row pass is a
+// latency-bound loop behind the mixer's own L2 traffic (~150 us per row and warp), and with small chunks the kernel
+// ends on a tail of single warps; round 1 measured the same for its CTA-wide form.
 #ifndef ADTFE_NORM_THREADS
 #define ADTFE_NORM_THREADS 256
 #endif
@@ -446,7 +520,9 @@ __global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_seg
     const adtfe_segment sg = segments[seg];
     if (sg.flags == 0 || lo >= sg.len) return;
     float peak = 0.0f;
-    for (int t = tid & 31; t < tiles_per_seg; t += 32) peak = nan_max(peak, __ldg(tile_max + seg * tiles_per_seg + t));
+    // one maximum per warp tile of the mixer (kSub per host tile)
+    for (int t = tid & 31; t < tiles_per_seg * kSub; t += 32)
+        peak = nan_max(peak, __ldg(tile_max + (size_t)seg * tiles_per_seg * kSub + t));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) peak = nan_max(peak, __shfl_xor_sync(0xffffffffu, peak, o));
     const float vol = sg.max_volume;
@@ -471,7 +547,7 @@ __global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_seg
     for (int i = 4 * n4 + tid; i < n; i += kNormThreads) row[i] = norm(row[i]);
 }
 
-static size_t mix_smem_bytes() { return mix_list_offset() + kListMax * sizeof(SliceMsg); }
+static size_t mix_smem_bytes() { return (size_t)kDepth * kStageFloats * 4 + kDepth * 8 + 64; }
 
 }  // namespace adtfe
 
@@ -486,11 +562,13 @@ int adtfe::mixer_prepare_device() {
     return ADTFE_OK;
 }
 
-extern "C" size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg) {
-    if (n_events < 0 || n_seg < 0 || tiles_per_seg < 0) return 0;
-    // resolved events | peak bits, queue heads (one zeroed block) | tile maxima
+extern "C" size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg,
+                                               int32_t n_tile_events) {
+    if (n_events < 0 || n_seg < 0 || tiles_per_seg < 0 || n_tile_events < 0) return 0;
+    // resolved events | peak bits, queue heads (one zeroed block) | tile maxima | per-tile slice records
     return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_events * 4 + (size_t)n_seg * 4 + 4) +
-           align256((size_t)n_seg * tiles_per_seg * 4) + 256;
+           align256((size_t)n_seg * tiles_per_seg * kSub * 4) +
+           align256((size_t)n_tile_events * kSub * sizeof(TileSlice)) + 256;
 }
 
 extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
@@ -501,7 +579,8 @@ extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, floa
 int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
                        size_t workspace_bytes, void* stream) {
     ADTFE_REQUIRE(bank && plan, ADTFE_ERR_BAD_ARG, "adtfe_render: null bank or plan");
-    ADTFE_REQUIRE(plan->n_seg >= 0 && plan->n_events >= 0 && plan->n_peak_work >= 0 && plan->tiles_per_seg >= 0,
+    ADTFE_REQUIRE(plan->n_seg >= 0 && plan->n_events >= 0 && plan->n_peak_work >= 0 && plan->tiles_per_seg >= 0 &&
+                      plan->n_tile_events >= 0,
                   ADTFE_ERR_BAD_ARG, "adtfe_render: negative count");
     if (plan->n_seg == 0 || plan->tiles_per_seg == 0) return ADTFE_OK;
     ADTFE_REQUIRE(plan->ld_wav > 0 && plan->ld_wav % 4 == 0 &&
@@ -513,7 +592,9 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
     ADTFE_REQUIRE(plan->n_events == 0 || (plan->events_dev && plan->tile_events_dev && plan->peak_work_dev &&
                                           bank->pcm && plan->n_peak_work > 0),
                   ADTFE_ERR_BAD_ARG, "adtfe_render: null event buffers");
-    const size_t need = adtfe_render_workspace_bytes(plan->n_events, plan->n_seg, plan->tiles_per_seg);
+    ADTFE_REQUIRE(bank->total / 4 < (1ll << 32), ADTFE_ERR_UNSUPPORTED, "adtfe_render: bank larger than 64 GB");
+    const size_t need = adtfe_render_workspace_bytes(plan->n_events, plan->n_seg, plan->tiles_per_seg,
+                                                     plan->n_tile_events);
     ADTFE_REQUIRE(workspace_dev && workspace_bytes >= need, ADTFE_ERR_WORKSPACE,
                   "adtfe_render: workspace %zu B < %zu B", workspace_bytes, need);
     // chunk boundaries: the plan's, or one chunk covering everything
@@ -538,50 +619,73 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
     int* peak_bits = (int*)(ws + align256((size_t)plan->n_events * sizeof(ResolvedEvent)));
     int* counters = peak_bits + plan->n_events;  // one work-queue head per chunk (n_chunks <= n_seg)
     float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4 + (size_t)plan->n_seg * 4 + 4));
+    TileSlice* slices = (TileSlice*)((char*)tile_max + align256((size_t)plan->n_seg * plan->tiles_per_seg * kSub * 4));
     // zero the peaks and the queue heads once, then fork the chunks over the bank's streams
     ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, ((size_t)plan->n_events + (size_t)plan->n_seg + 1) * 4, user));
-    const bool fork = n_chunks > 1 && bank->n_streams > 0;
+    const bool fork = n_chunks > 1 && bank->n_streams >= 3;
     std::unique_lock<std::mutex> lock(bank->mu, std::defer_lock);
+    // A chunked plan runs as a three-stage software pipeline over the bank's internal streams - stage 0: peaks and
+    // slice records, stage 1: tile mixer, stage 2: row normalisation - chunk c's stage k waiting (event) for its
+    // stage k-1, so that the peak pass of chunk c+2 (HBM reads), the mixer of chunk c+1 (L2 -> SM traffic) and the
+    // normalisation of chunk c (HBM read + write) can be on the GPU together.  Measured: the same 7.0 ms per step as
+    // whole chunks on four streams (round 1) - the kernels are bound by what an SM can keep in flight, and that
+    // they share - with one stream and two events fewer per chunk.
+    cudaStream_t s_peak = user, s_mix = user, s_norm = user;
     if (fork) {
         lock.lock();
+        s_peak = bank->streams[0]; s_mix = bank->streams[1]; s_norm = bank->streams[2];
         ADTFE_CUDA(cudaEventRecord(bank->fork_event, user));
-        for (int k = 0; k < bank->n_streams && k < n_chunks; ++k)
-            ADTFE_CUDA(cudaStreamWaitEvent(bank->streams[k], bank->fork_event, 0));
+        for (int k = 0; k < 3; ++k) ADTFE_CUDA(cudaStreamWaitEvent(bank->streams[k], bank->fork_event, 0));
     }
     float* mix_out = wav_out_dev;
     const int tps = plan->tiles_per_seg;
     for (int c = 0; c < n_chunks; ++c) {
-        cudaStream_t st = fork ? bank->streams[c % bank->n_streams] : user;
         const int s0 = ch[c].seg, n_seg = ch[c + 1].seg - s0;
         const int pw0 = ch[c].peak_work, n_pw = ch[c + 1].peak_work - pw0;
         if (n_pw > 0) {
-            trace_open("peak", c, st);
-            peak_kernel<<<n_pw * kPeakSplit, kPeakThreads, 0, st>>>(bank->pcm, plan->events_dev, plan->peak_work_dev + pw0, resolved,
-                                                      peak_bits);
-            trace_close(st);
+            trace_open("peak", c, s_peak);
+            peak_kernel<<<n_pw * kPeakSplit, kPeakThreads, 0, s_peak>>>(bank->pcm, plan->events_dev,
+                                                                        plan->peak_work_dev + pw0, resolved, peak_bits);
+            trace_close(s_peak);
             ADTFE_CUDA(cudaGetLastError());
         }
         MixArgs a;
-        a.pcm = bank->pcm; a.resolved = resolved; a.peak_bits = peak_bits;
-        a.tile_ptr = plan->tile_ptr_dev + (size_t)s0 * tps; a.tile_events = plan->tile_events_dev;
-        a.segments = plan->segments_dev + s0; a.wav = mix_out + (size_t)s0 * plan->ld_wav;
-        a.tile_max = tile_max + (size_t)s0 * tps; a.tile_counter = counters + c; a.ld_wav = plan->ld_wav;
+        a.pcm = bank->pcm; a.slices = slices;   // indexed like tile_events: the tile_ptr entries are global positions
+        a.tile_ptr = plan->tile_ptr_dev + (size_t)s0 * tps;
+        a.wav = mix_out + (size_t)s0 * plan->ld_wav;
+        a.tile_max = tile_max + (size_t)s0 * tps * kSub; a.tile_counter = counters + c; a.ld_wav = plan->ld_wav;
         a.tiles_per_seg = tps; a.n_tiles = n_seg * tps;
-        const int grid = std::min(a.n_tiles, kMixCtasPerSm * bank->sm_count);
-        trace_open("mix", c, st);
-        mix_kernel<<<grid, kMixThreads, mix_smem_bytes(), st>>>(a);
-        trace_close(st);
+        if (ch[c + 1].event > ch[c].event) {
+            trace_open("slice", c, s_peak);
+            slice_kernel<<<(a.n_tiles + 7) / 8, 256, 0, s_peak>>>(resolved, peak_bits, a.tile_ptr, plan->tile_events_dev,
+                                                                  slices, tps, a.n_tiles);
+            trace_close(s_peak);
+            ADTFE_CUDA(cudaGetLastError());
+        }
+        if (fork) {
+            cudaEvent_t e = bank->stage_events[0][c % kStageEvents];
+            ADTFE_CUDA(cudaEventRecord(e, s_peak));
+            ADTFE_CUDA(cudaStreamWaitEvent(s_mix, e, 0));
+        }
+        const int grid = std::min(a.n_tiles * kSub, kMixCtasPerSm * bank->sm_count);
+        trace_open("mix", c, s_mix);
+        mix_kernel<<<grid, 32, mix_smem_bytes(), s_mix>>>(a);
+        trace_close(s_mix);
         ADTFE_CUDA(cudaGetLastError());
-        trace_open("normalise", c, st);
-        normalise_kernel<<<a.n_tiles, kNormThreads, 0, st>>>(a.segments, a.tile_max, tps, plan->ld_wav, a.wav);
-        trace_close(st);
+        if (fork) {
+            cudaEvent_t e = bank->stage_events[1][c % kStageEvents];
+            ADTFE_CUDA(cudaEventRecord(e, s_mix));
+            ADTFE_CUDA(cudaStreamWaitEvent(s_norm, e, 0));
+        }
+        trace_open("normalise", c, s_norm);
+        normalise_kernel<<<a.n_tiles, kNormThreads, 0, s_norm>>>(plan->segments_dev + s0, a.tile_max, tps, plan->ld_wav,
+                                                                 a.wav);
+        trace_close(s_norm);
         ADTFE_CUDA(cudaGetLastError());
     }
-    if (fork) {
-        for (int k = 0; k < bank->n_streams && k < n_chunks; ++k) {
-            ADTFE_CUDA(cudaEventRecord(bank->join_events[k], bank->streams[k]));
-            ADTFE_CUDA(cudaStreamWaitEvent(user, bank->join_events[k], 0));
-        }
+    if (fork) {   // the last stage finishes last: one join
+        ADTFE_CUDA(cudaEventRecord(bank->join_events[2], s_norm));
+        ADTFE_CUDA(cudaStreamWaitEvent(user, bank->join_events[2], 0));
     }
     return ADTFE_OK;
 }

@@ -372,6 +372,7 @@ extern "C" int adtfe_planner_pack_batches(const adtfe_planner* P, const int32_t*
     shape.mel_max_count = max_count;
     shape.n_chunks = n_chunks;
     shape.chunks_host = chunks_out;
+    shape.n_tile_events = (int32_t)P->tile_events.size();
     size_t off[6], fixed = 0;
     int rc = adtfe_plan_blob_layout(&shape, off, &fixed);
     if (rc != ADTFE_OK) return rc;

@@ -73,7 +73,7 @@ class PlanBuffers:
                           plan.mel_total_rows if batched else 0,
                           int(plan.batch_frames.max()) if batched and len(plan.batch_frames) else 0,
                           len(self._chunks) - 1 if batched else 0,
-                          self._chunks.ctypes.data if batched else None)
+                          self._chunks.ctypes.data if batched else None, len(plan.tile_events))
         off = (C.c_size_t * 6)()
         fixed = C.c_size_t()
         _lib.check(lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(fixed)), "adtfe_plan_blob_layout")
@@ -88,16 +88,12 @@ class PlanBuffers:
             raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
             h[o: o + raw.size] = raw
         self.nbytes = total
-        need = self._workspace_bytes(lib, plan.n_events, plan.n_seg, plan.tiles_per_seg, plan.ld_wav)
+        need = lib.adtfe_render_workspace_bytes(plan.n_events, plan.n_seg, plan.tiles_per_seg, len(plan.tile_events))
         if self.workspace.numel() < need:
             self.workspace = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=self.device)
         self.offsets = [int(o) for o in off]
         self.shape = shape
         return shape
-
-    @staticmethod
-    def _workspace_bytes(lib, n_events, n_seg, tiles_per_seg, ld_wav) -> int:
-        return lib.adtfe_render_workspace_bytes(n_events, n_seg, tiles_per_seg)
 
     def reserve(self, nbytes: int) -> None:
         """Pinned and device blobs of at least ``nbytes`` (contents are not kept)."""
@@ -117,7 +113,7 @@ class PlanBuffers:
         fixed = C.c_size_t()
         _lib.check(lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(fixed)), "adtfe_plan_blob_layout")
         self.nbytes = int(nbytes)
-        need = self._workspace_bytes(lib, shape.n_events, shape.n_seg, shape.tiles_per_seg, shape.ld_wav)
+        need = lib.adtfe_render_workspace_bytes(shape.n_events, shape.n_seg, shape.tiles_per_seg, shape.n_tile_events)
         if self.workspace.numel() < need:
             with torch.cuda.device(self.device):
                 self.workspace = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=self.device)
@@ -135,7 +131,7 @@ class PlanBuffers:
         return _lib.Plan(base + o[0], base + o[1], base + o[2], base + o[5], base + o[3],
                          shape.n_events, shape.n_seg, shape.tiles_per_seg, shape.n_peak_work, shape.ld_wav,
                          base + o[4] if shape.mel_total_rows > 0 else None, shape.mel_total_rows,
-                         shape.mel_max_count, shape.n_chunks, shape.chunks_host)
+                         shape.mel_max_count, shape.n_chunks, shape.chunks_host, shape.n_tile_events)
 
 
 class SynthDrum:

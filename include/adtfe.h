@@ -125,6 +125,7 @@ typedef struct adtfe_plan {
     int32_t mel_max_count;               /* largest count in mel_rows_dev */
     int32_t n_chunks;                    /* boundaries in chunks_host: n_chunks + 1 records, first all-zero, */
     const adtfe_chunk* chunks_host;      /* last = {n_seg, n_events, n_peak_work}; HOST memory */
+    int32_t n_tile_events;               /* entries of tile_events_dev (= the last tile_ptr entry); required */
 } adtfe_plan;
 
 int adtfe_version(void);
@@ -141,10 +142,10 @@ int adtfe_bank_destroy(adtfe_bank* bank);
 int64_t adtfe_bank_bytes(const adtfe_bank* bank);
 
 /* ---- render ------------------------------------------------------------------------ */
-size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg);
+size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg, int32_t n_tile_events);
 /* Writes the (n_seg, ld_wav) float32 waveform matrix: every row normalised as the reference
- * does and zero-padded to ld_wav.  Three kernels per chunk: per-note peak of the mixed one-shot, the tile
- * mixer, the row normalisation.  A plan with chunks (plan->chunks_host) is rendered chunk by chunk on the
+ * does and zero-padded to ld_wav.  Four kernels per chunk: per-note peak of the mixed one-shot, the per-tile
+ * slice records, the tile mixer, the row normalisation.  A plan with chunks (plan->chunks_host) is rendered chunk by chunk on the
  * bank's internal streams, forked from and joined back into `stream`; calls on one bank handle must not
  * be made from several host threads at once. */
 int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,

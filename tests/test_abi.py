@@ -33,15 +33,15 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_sizes_match_numpy_views():
     from adt_str_b200.planner import EVENT_DTYPE, PEAK_ITEM_DTYPE, SEGMENT_DTYPE
     assert EVENT_DTYPE.itemsize == 32 and SEGMENT_DTYPE.itemsize == 16 and PEAK_ITEM_DTYPE.itemsize == 40
-    assert C.sizeof(_lib.Plan) == 5 * 8 + 4 * 4 + 8 + 8 + 8 + 4 + 4 + 8
+    assert C.sizeof(_lib.Plan) == 5 * 8 + 4 * 4 + 8 + 8 + 8 + 4 + 4 + 8 + 8   # n_tile_events + padding
     from adt_str_b200.planner import CHUNK_DTYPE, MEL_ROW_DTYPE
     assert MEL_ROW_DTYPE.itemsize == 16 and CHUNK_DTYPE.itemsize == 12
 
 
 def test_version_and_argument_errors_without_a_device(lib):
     assert lib.adtfe_version() == 4
-    assert lib.adtfe_render_workspace_bytes(10, 2, 30) >= 10 * 48 + 2 * 30 * 4
-    assert lib.adtfe_render_workspace_bytes(-1, 2, 30) == 0
+    assert lib.adtfe_render_workspace_bytes(10, 2, 30, 70) >= 10 * 48 + 2 * 30 * 4 + 70 * 32
+    assert lib.adtfe_render_workspace_bytes(-1, 2, 30, 70) == 0
     shape = _lib.Plan(None, None, None, None, None, 100, 4, 31, 9, 63488)
     off = (C.c_size_t * 6)()
     total = C.c_size_t()

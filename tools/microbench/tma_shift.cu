@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -85,7 +86,12 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int main() {
+// usage: tma_shift <variant>   (one process per variant: a faulting TMA poisons the context)
+//   0: 3-D overlapping {259, 64, N/256} strides {16, 1024}      1: the same with dim0 = 260      2: dim0 = 512
+//   3: 3-D overlapping, ALIGNED offsets only (multiples of 4)    4: 1-D map x 8 (strides pointer non-null)
+//   5: 1-D map x 8, aligned offsets only                         6: 2-D non-overlapping {256, N/256} box {256, 8}, aligned to 256
+int main(int argc, char** argv) {
+    const int variant = argc > 1 ? atoi(argv[1]) : 0;
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const size_t n_floats = 24u << 20;   // 96 MB: L2-resident
@@ -102,77 +108,86 @@ int main() {
         return 1;
     }
     CUtensorMap m3, m1;
-    {
-        const cuuint64_t dims[3] = {259, 64, n_floats / 256};
+    memset(&m3, 0, sizeof(m3)); memset(&m1, 0, sizeof(m1));
+    int mode = 1;
+    unsigned align_mask = ~0u;
+    CUresult r = CUDA_SUCCESS;
+    if (variant <= 3) {
+        const cuuint64_t d0 = variant == 1 ? 260 : variant == 2 ? 512 : 259;
+        const cuuint64_t dims[3] = {d0, 64, n_floats / 256};
         const cuuint64_t strides[2] = {16, 1024};
         const cuuint32_t box[3] = {256, 1, 8}, es[3] = {1, 1, 1};
-        const CUresult r = encode(&m3, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, buf, dims, strides, box, es,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        printf("encode 3-D overlapping map {259, 64, N/256} strides {16, 1024} box {256, 1, 8}: CUresult %d\n", (int)r);
-        if (r != CUDA_SUCCESS) memset(&m3, 0, sizeof(m3));
-    }
-    {
+        r = encode(&m3, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, buf, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (variant == 3) align_mask = ~3u;
+    } else if (variant <= 5) {
         const cuuint64_t dims[1] = {n_floats};
+        const cuuint64_t strides[1] = {0};
         const cuuint32_t box[1] = {256}, es[1] = {1};
-        const CUresult r = encode(&m1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, buf, dims, nullptr, box, es,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        printf("encode 1-D map box {256}: CUresult %d\n", (int)r);
+        r = encode(&m1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 1, buf, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        mode = 2;
+        if (variant == 5) align_mask = ~3u;
+    } else {
+        const cuuint64_t dims[3] = {256, 1, n_floats / 256};   // as a 3-D map so that the same kernel path serves
+        const cuuint64_t strides[2] = {1024, 1024};
+        const cuuint32_t box[3] = {256, 1, 8}, es[3] = {1, 1, 1};
+        r = encode(&m3, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, buf, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        align_mask = ~255u;
     }
+    printf("variant %d: encode CUresult %d\n", variant, (int)r);
+    if (r != CUDA_SUCCESS) return 0;
     const size_t smem = kStagesMax * kSlice * 4 + 128;
     cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     unsigned long long* bad;
     cudaMalloc(&bad, 8);
-
-    // ---- correctness: every shift 0..7 at a few bases, plus offsets near the end of the buffer
     {
         std::vector<unsigned> offs;
-        for (unsigned base : {0u, 4096u, 1000000u, 12345600u})
-            for (unsigned s = 0; s < 8; ++s) offs.push_back(base + s);
-        for (unsigned s = 0; s < 8; ++s) offs.push_back((unsigned)n_floats - kSlice - s);
+        for (unsigned base : {0u, 4096u, 1000000u - 64u, 12345600u})
+            for (unsigned s = 0; s < 8; ++s) offs.push_back((base + s) & align_mask);
+        for (unsigned s = 0; s < 8; ++s) offs.push_back(((unsigned)n_floats - kSlice - s) & align_mask);
         unsigned* d;
         cudaMalloc(&d, offs.size() * 4);
         cudaMemcpy(d, offs.data(), offs.size() * 4, cudaMemcpyHostToDevice);
-        for (int mode = 1; mode <= 2; ++mode) {
-            cudaMemset(bad, 0, 8);
-            probe<<<4, 32, smem>>>(buf, m3, m1, d, (int)offs.size(), 1, 4, mode, 1, bad);
-            const cudaError_t e = cudaDeviceSynchronize();
-            unsigned long long nb = 0;
-            cudaMemcpy(&nb, bad, 8, cudaMemcpyDeviceToHost);
-            printf("correctness mode %d (%s): %llu mismatching floats over %zu slices (%s)\n", mode,
-                   mode == 1 ? "3-D overlapping map" : "1-D map x 8", nb, offs.size(), cudaGetErrorString(e));
-        }
+        cudaMemset(bad, 0, 8);
+        probe<<<4, 32, smem>>>(buf, m3, m1, d, (int)offs.size(), 1, 4, mode, 1, bad);
+        const cudaError_t e = cudaDeviceSynchronize();
+        unsigned long long nb = 0;
+        cudaMemcpy(&nb, bad, 8, cudaMemcpyDeviceToHost);
+        printf("variant %d correctness: %llu mismatching floats over %zu slices (%s)\n", variant, nb, offs.size(),
+               cudaGetErrorString(e));
+        if (e != cudaSuccess) return 0;
         cudaFree(d);
     }
-    // ---- throughput on the mixer's pattern
+    // ---- throughput on the mixer's pattern, against the 16-byte aligned bulk copy
     const int n = 200000;
     std::vector<unsigned> offs(n);
     unsigned long long st = 88172645463325252ull;
     for (int i = 0; i < n; ++i) {
         st ^= st << 13; st ^= st >> 7; st ^= st << 17;
-        offs[i] = (unsigned)(st % (n_floats - kSlice));
+        offs[i] = (unsigned)(st % (n_floats - kSlice)) & align_mask;
     }
     unsigned* d;
     cudaMalloc(&d, n * 4);
     cudaMemcpy(d, offs.data(), n * 4, cudaMemcpyHostToDevice);
     const int configs[][2] = {{3, 8}, {3, 4}, {2, 8}, {1, 8}};
-    const char* names[3] = {"bulk 16B-aligned", "tensor 3-D any offset", "tensor 1-D x 8 any offset"};
-    for (int mode = 0; mode < 3; ++mode)
+    for (int md : {0, mode})
         for (auto& c : configs) {
             cudaEvent_t a, b;
             cudaEventCreate(&a); cudaEventCreate(&b);
             const int passes = 4;
             for (int rep = 0; rep < 2; ++rep) {
                 cudaEventRecord(a);
-                probe<<<sms * c[0], 32, smem>>>(buf, m3, m1, d, n, passes, c[1], mode, 0, bad);
+                probe<<<sms * c[0], 32, smem>>>(buf, m3, m1, d, n, passes, c[1], md, 0, bad);
                 cudaEventRecord(b);
                 cudaEventSynchronize(b);
             }
             float ms = 0.f;
             cudaEventElapsedTime(&ms, a, b);
-            printf("%-28s %d CTAs/SM x %d in flight: %8.3f ms  %8.1f GB/s  (%s)\n", names[mode], c[0], c[1], ms,
-                   (double)n * kSlice * 4 * passes / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+            printf("variant %d %-12s %d CTAs/SM x %d in flight: %8.3f ms  %8.1f GB/s  (%s)\n", variant,
+                   md == 0 ? "bulk aligned" : "tensor map", c[0], c[1], ms, (double)n * kSlice * 4 * passes / ms / 1e6,
+                   cudaGetErrorString(cudaGetLastError()));
         }
     return 0;
 }
