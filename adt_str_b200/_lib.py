@@ -20,6 +20,7 @@ EXPORTS = [
     "adtfe_peak_normalise",
     "adtfe_trace_begin", "adtfe_trace_dump",
     "adtfe_planner_create", "adtfe_planner_destroy", "adtfe_planner_plan", "adtfe_planner_export", "adtfe_planner_pack_batches",
+    "adtfe_planner_set_fx", "adtfe_planner_export_fx",
 ]
 
 
@@ -34,7 +35,8 @@ class Plan(C.Structure):
                 ("n_events", C.c_int32), ("n_seg", C.c_int32), ("tiles_per_seg", C.c_int32),
                 ("n_peak_work", C.c_int32), ("ld_wav", C.c_int64),
                 ("mel_rows_dev", C.c_void_p), ("mel_total_rows", C.c_int64), ("mel_max_count", C.c_int32),
-                ("n_chunks", C.c_int32), ("chunks_host", C.c_void_p), ("n_tile_events", C.c_int32)]
+                ("n_chunks", C.c_int32), ("chunks_host", C.c_void_p), ("n_tile_events", C.c_int32),
+                ("n_fx", C.c_int32), ("fx_dev", C.c_void_p), ("sample_rate", C.c_int32)]
 
 
 _lock = threading.Lock()
@@ -62,7 +64,7 @@ def _declare(lib) -> None:
     lib.adtfe_logmel_rows.argtypes = [vp, vp, i32, i64, vp, i32, vp, vp]
     lib.adtfe_render_logmel.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, vp, vp, sz, vp]
     lib.adtfe_frontend_host.argtypes = [vp, vp, C.POINTER(Plan), i64, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp, vp]
-    lib.adtfe_plan_blob_layout.argtypes = [C.POINTER(Plan), C.POINTER(sz * 6), C.POINTER(sz)]
+    lib.adtfe_plan_blob_layout.argtypes = [C.POINTER(Plan), C.POINTER(sz * 7), C.POINTER(sz)]
     lib.adtfe_resampler_create.argtypes = [i32, i32, i32, vp, C.c_int, C.POINTER(vp)]
     lib.adtfe_resampler_destroy.argtypes = [vp]
     lib.adtfe_resample_length.argtypes = [vp, i64]
@@ -77,7 +79,9 @@ def _declare(lib) -> None:
     lib.adtfe_planner_plan.argtypes = [vp, vp, vp, i32, vp, i64, vp, vp]
     lib.adtfe_planner_export.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.adtfe_planner_pack_batches.argtypes = [vp, vp, i32, i32, i32, i32, vp, sz, C.POINTER(Plan), vp, vp, vp,
-                                               C.POINTER(sz)]
+                                               C.POINTER(sz), C.POINTER(sz)]
+    lib.adtfe_planner_set_fx.argtypes = [vp, C.c_double, C.c_double, C.c_double]
+    lib.adtfe_planner_export_fx.argtypes = [vp, vp]
 
 
 def load():

@@ -40,8 +40,9 @@ class SynthDrumConfig(SharedConfig):
 
 
 #: the ``synthetiser:`` + ``shared:`` blocks of reference ``configs/train/setting-1.yaml:29-33,50-61``
-#: (use_fx_prob is 0.3 there; the FX chain is outside this path, SURVEY §8f, so the
-#: default here is 0.0 and a non-zero value raises at render time).
+#: with the FX chain off: the measured path of SURVEY §8d / BASELINE.json runs with ``use_fx_prob = 0`` (the yaml has
+#: 0.3; ``setting_1(use_fx_prob=0.3)`` or ``synth_config_from_sections`` on the yaml gives the training distribution -
+#: the FX chain runs on the GPU, csrc/fx.cu).
 SETTING_1 = dict(
     input_sec=2.56, time_res=0.01, win_length=2048, sample_rate=24000,
     oneshot_path="oneshot", similarity_threshold=0.8,

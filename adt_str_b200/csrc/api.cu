@@ -153,6 +153,7 @@ extern "C" int adtfe_bank_create(const float* pcm_host, int64_t total_floats, co
         return ADTFE_ERR_CUDA;
     }
     rc = mixer_prepare_device();
+    if (rc == ADTFE_OK) rc = fx_prepare_device();
     if (rc != ADTFE_OK) { adtfe_bank_destroy(b); return rc; }
     bool ok = cudaEventCreateWithFlags(&b->fork_event, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; ok && k < kBankStreams; ++k) {
@@ -190,9 +191,9 @@ extern "C" int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel,
 
 static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-extern "C" int adtfe_plan_blob_layout(const adtfe_plan* s, size_t offsets[6], size_t* blob_bytes) {
+extern "C" int adtfe_plan_blob_layout(const adtfe_plan* s, size_t offsets[7], size_t* blob_bytes) {
     ADTFE_REQUIRE(s && offsets && blob_bytes, ADTFE_ERR_BAD_ARG, "adtfe_plan_blob_layout: null pointer");
-    ADTFE_REQUIRE(s->n_events >= 0 && s->n_seg >= 0 && s->tiles_per_seg >= 0 && s->n_peak_work >= 0,
+    ADTFE_REQUIRE(s->n_events >= 0 && s->n_seg >= 0 && s->tiles_per_seg >= 0 && s->n_peak_work >= 0 && s->n_fx >= 0,
                   ADTFE_ERR_BAD_ARG, "adtfe_plan_blob_layout: negative count");
     size_t o = 0;
     offsets[0] = o; o = align16(o + (size_t)s->n_events * sizeof(adtfe_event));
@@ -200,7 +201,8 @@ extern "C" int adtfe_plan_blob_layout(const adtfe_plan* s, size_t offsets[6], si
     offsets[2] = o; o = align16(o + ((size_t)s->n_seg * s->tiles_per_seg + 1) * 4);
     offsets[3] = o; o = align16(o + (size_t)s->n_peak_work * sizeof(adtfe_peak_item));
     offsets[4] = o; o = align16(o + (s->mel_total_rows > 0 ? (size_t)s->n_seg * sizeof(adtfe_mel_row) : 0));
-    offsets[5] = o;  // tile_events runs to the end of the blob; its length is tile_ptr's last entry
+    offsets[5] = o; o = align16(o + (size_t)s->n_fx * sizeof(adtfe_fx));
+    offsets[6] = o;  // tile_events runs to the end of the blob; its length is tile_ptr's last entry
     *blob_bytes = o;
     return ADTFE_OK;
 }
@@ -211,7 +213,7 @@ extern "C" int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel,
                                    float* mel_out_host, float* wav_out_host, void* stream, void* copy_stream) {
     ADTFE_REQUIRE(bank && mel && shape && blob_host && blob_dev && mel_out_host, ADTFE_ERR_BAD_ARG,
                   "adtfe_frontend_host: null pointer");
-    size_t off[6], fixed = 0;
+    size_t off[7], fixed = 0;
     int rc = adtfe_plan_blob_layout(shape, off, &fixed);
     if (rc != ADTFE_OK) return rc;
     ADTFE_REQUIRE(blob_bytes >= fixed, ADTFE_ERR_BAD_ARG, "adtfe_frontend_host: plan blob %zu B < %zu B", blob_bytes,
@@ -225,7 +227,8 @@ extern "C" int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel,
     p.tile_ptr_dev = (const int32_t*)(d + off[2]);
     p.peak_work_dev = (const adtfe_peak_item*)(d + off[3]);
     p.mel_rows_dev = shape->mel_total_rows > 0 ? (const adtfe_mel_row*)(d + off[4]) : nullptr;
-    p.tile_events_dev = (const int32_t*)(d + off[5]);
+    p.fx_dev = shape->n_fx > 0 ? (const adtfe_fx*)(d + off[5]) : nullptr;
+    p.tile_events_dev = (const int32_t*)(d + off[6]);
     rc = adtfe_render_logmel(bank, mel, &p, n_samples, wav_dev, mel_dev, workspace_dev, workspace_bytes, stream);
     if (rc != ADTFE_OK) return rc;
     int32_t first = 0, count = 0;

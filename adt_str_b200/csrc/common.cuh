@@ -43,6 +43,7 @@ static_assert(sizeof(ResolvedEvent) == 48, "ResolvedEvent layout");
 static_assert(sizeof(adtfe_event) == 32, "adtfe_event layout");
 static_assert(sizeof(adtfe_segment) == 16, "adtfe_segment layout");
 static_assert(sizeof(adtfe_peak_item) == 40, "adtfe_peak_item layout");
+static_assert(sizeof(adtfe_fx) == 48 && sizeof(adtfe_chunk) == 16, "adtfe_fx / adtfe_chunk layout");
 
 int device_sm_count(int device);
 
@@ -101,6 +102,9 @@ struct adtfe_mel_tables;
 
 namespace adtfe {
 int mixer_prepare_device();
+int fx_prepare_device();
+// FX kernels over the rows fx_dev[r0 .. r0 + n_rows) of the plan, between the tile mixer and the normalisation
+int fx_launch(const adtfe_plan* plan, int r0, int n_rows, float* wav, float* tile_max, int max_per_seg, cudaStream_t st);
 int render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
                 size_t workspace_bytes, void* stream);
 // Diagnostics (adtfe_trace_begin / adtfe_trace_dump): a pair of timing events around every kernel launch.

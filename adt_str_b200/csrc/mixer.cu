@@ -580,8 +580,9 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
                        size_t workspace_bytes, void* stream) {
     ADTFE_REQUIRE(bank && plan, ADTFE_ERR_BAD_ARG, "adtfe_render: null bank or plan");
     ADTFE_REQUIRE(plan->n_seg >= 0 && plan->n_events >= 0 && plan->n_peak_work >= 0 && plan->tiles_per_seg >= 0 &&
-                      plan->n_tile_events >= 0,
+                      plan->n_tile_events >= 0 && plan->n_fx >= 0,
                   ADTFE_ERR_BAD_ARG, "adtfe_render: negative count");
+    ADTFE_REQUIRE(plan->n_fx == 0 || plan->fx_dev, ADTFE_ERR_BAD_ARG, "adtfe_render: n_fx > 0 without fx_dev");
     if (plan->n_seg == 0 || plan->tiles_per_seg == 0) return ADTFE_OK;
     ADTFE_REQUIRE(plan->ld_wav > 0 && plan->ld_wav % 4 == 0 &&
                       plan->ld_wav <= (int64_t)plan->tiles_per_seg * ADTFE_TILE,
@@ -598,19 +599,19 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
     ADTFE_REQUIRE(workspace_dev && workspace_bytes >= need, ADTFE_ERR_WORKSPACE,
                   "adtfe_render: workspace %zu B < %zu B", workspace_bytes, need);
     // chunk boundaries: the plan's, or one chunk covering everything
-    const adtfe_chunk whole[2] = {{0, 0, 0}, {plan->n_seg, plan->n_events, plan->n_peak_work}};
+    const adtfe_chunk whole[2] = {{0, 0, 0, 0}, {plan->n_seg, plan->n_events, plan->n_peak_work, plan->n_fx}};
     const adtfe_chunk* ch = whole;
     int n_chunks = 1;
     if (plan->chunks_host && plan->n_chunks > 0) {
         ch = plan->chunks_host;
         n_chunks = plan->n_chunks;
         ADTFE_REQUIRE(n_chunks <= plan->n_seg && ch[0].seg == 0 && ch[0].event == 0 && ch[0].peak_work == 0 &&
-                          ch[n_chunks].seg == plan->n_seg && ch[n_chunks].event == plan->n_events &&
-                          ch[n_chunks].peak_work == plan->n_peak_work,
+                          ch[0].fx_row == 0 && ch[n_chunks].seg == plan->n_seg && ch[n_chunks].event == plan->n_events &&
+                          ch[n_chunks].peak_work == plan->n_peak_work && ch[n_chunks].fx_row == plan->n_fx,
                       ADTFE_ERR_BAD_ARG, "adtfe_render: chunk boundaries do not cover the plan");
         for (int c = 0; c < n_chunks; ++c)
             ADTFE_REQUIRE(ch[c + 1].seg > ch[c].seg && ch[c + 1].event >= ch[c].event &&
-                              ch[c + 1].peak_work >= ch[c].peak_work,
+                              ch[c + 1].peak_work >= ch[c].peak_work && ch[c + 1].fx_row >= ch[c].fx_row,
                           ADTFE_ERR_BAD_ARG, "adtfe_render: chunk %d is empty or out of order", c);
     }
     cudaStream_t user = (cudaStream_t)stream;
@@ -676,6 +677,11 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
             cudaEvent_t e = bank->stage_events[1][c % kStageEvents];
             ADTFE_CUDA(cudaEventRecord(e, s_mix));
             ADTFE_CUDA(cudaStreamWaitEvent(s_norm, e, 0));
+        }
+        if (ch[c + 1].fx_row > ch[c].fx_row) {   // the chunk's FX rows: raw mix -> FX -> (new row peak) -> normalise
+            const int rc = fx_launch(plan, ch[c].fx_row, ch[c + 1].fx_row - ch[c].fx_row, mix_out, tile_max, tps * kSub,
+                                     s_norm);
+            if (rc != ADTFE_OK) return rc;
         }
         trace_open("normalise", c, s_norm);
         normalise_kernel<<<a.n_tiles, kNormThreads, 0, s_norm>>>(plan->segments_dev + s0, a.tile_max, tps, plan->ld_wav,

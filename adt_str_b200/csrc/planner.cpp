@@ -75,6 +75,7 @@ struct GroupRange {
 struct adtfe_planner {
     int32_t sample_rate = 24000;
     double input_sec = 2.56, mixup_range = 0.8, use_fx_prob = 0.0;
+    double use_reverb_prob = 0.0, use_compression_prob = 0.0, use_limiter_prob = 0.0;   // adtfe_planner_set_fx
     int adtof = 0;
     std::vector<int32_t> lengths;                 // one-shot lengths
     std::vector<int64_t> offsets;                 // one-shot starts in the bank (floats)
@@ -86,6 +87,7 @@ struct adtfe_planner {
     std::vector<int32_t> mix_len, group_ptr, tile_ptr, tile_events;
     std::vector<adtfe_peak_item> peak_work;
     std::vector<adtfe_segment> segments;
+    std::vector<adtfe_fx> fx;                     // one record per segment whose FX coin hit, ascending seg
     int64_t ld_wav = 0;
     int32_t tiles_per_seg = 0;
 };
@@ -120,6 +122,17 @@ extern "C" int adtfe_planner_destroy(adtfe_planner* p) {
     return ADTFE_OK;
 }
 
+extern "C" int adtfe_planner_set_fx(adtfe_planner* p, double use_reverb_prob, double use_compression_prob,
+                                    double use_limiter_prob) {
+    if (!p) {
+        adtfe::set_error("adtfe_planner_set_fx: null planner");
+        return ADTFE_ERR_BAD_ARG;
+    }
+    p->use_reverb_prob = use_reverb_prob; p->use_compression_prob = use_compression_prob;
+    p->use_limiter_prob = use_limiter_prob;
+    return ADTFE_OK;
+}
+
 static float vel_to_vol(float v) {  // synthetiser.py:204-212, float32 throughout
     if (v == 0.0f) return 0.0f;
     const float c = v < 0.0f ? 0.0f : (v > 127.0f ? 127.0f : v);
@@ -129,10 +142,10 @@ static float vel_to_vol(float v) {  // synthetiser.py:204-212, float32 throughou
     return 0.1f + t / 5.0f;
 }
 
-// status: 0 ok; 1 ValueError (invalid note); 2 IndexError (no admitted group); 3 KeyError; 4 FX hit;
+// status: 0 ok; 1 ValueError (invalid note); 2 IndexError (no admitted group); 3 KeyError;
 // info[0] = segment, info[1] = note index of the failure.
 extern "C" int adtfe_planner_plan(adtfe_planner* P, const float* notes, const int32_t* counts, int32_t n_seg,
-                                  uint32_t* mt_state /*625, updated*/, int64_t ld_wav_in, int64_t* out_counts /*8*/,
+                                  uint32_t* mt_state /*625, updated*/, int64_t ld_wav_in, int64_t* out_counts /*9*/,
                                   int32_t* info /*2*/) {
     if (!P || !counts || !mt_state || !out_counts || !info || n_seg < 0) {
         adtfe::set_error("adtfe_planner_plan: bad argument");
@@ -142,7 +155,7 @@ extern "C" int adtfe_planner_plan(adtfe_planner* P, const float* notes, const in
     memcpy(rng.s, mt_state, 624 * 4);
     rng.pos = (int)mt_state[624];
     const float sr_f = (float)P->sample_rate;
-    P->events.clear(); P->mix_len.clear(); P->segments.clear();
+    P->events.clear(); P->mix_len.clear(); P->segments.clear(); P->fx.clear();
     P->group_ptr.assign(1, 0);
     int status = 0;
     info[0] = info[1] = -1;
@@ -215,7 +228,31 @@ extern "C" int adtfe_planner_plan(adtfe_planner* P, const float* notes, const in
         for (int pi = 0; pi < 27; ++pi)  // gain lookup happens in instrument_mixer, after the loop
             if (rank[pi] >= 0 && P->gain[pi] < 0.0f) { status = 3; info[0] = s; info[1] = -1; }
         if (status) break;
-        if (rng.random() < P->use_fx_prob) { status = 4; info[0] = s; break; }  // synthetiser.py:154
+        if (rng.random() < P->use_fx_prob) {  // synthetiser.py:154 -> _add_fx -> BoardChain.get_board (:79-86)
+            const float nan = nanf("");
+            adtfe_fx f;
+            f.seg = s; f.flags = 0;
+            f.room_size = f.damping = f.wet_level = f.dry_level = f.width = 0.0f;
+            f.comp_threshold_db = f.comp_ratio = f.comp_attack_ms = f.comp_release_ms = f.lim_threshold_db = 0.0f;
+            if (rng.random() < P->use_reverb_prob) {  // _add_reverb (:44-61): four random.uniform(a, b) = a + (b - a) * random()
+                const double room = 0.2 + (0.8 - 0.2) * rng.random();
+                const double damping = 0.2 + (0.8 - 0.2) * rng.random();
+                const double wet = 0.1 + (0.4 - 0.1) * rng.random();
+                const double width = 0.6 + (1.0 - 0.6) * rng.random();
+                f.flags |= ADTFE_FX_REVERB;
+                f.room_size = (float)room; f.damping = (float)damping; f.wet_level = (float)wet;
+                f.dry_level = (float)(1.0 - wet); f.width = (float)width;
+            }
+            if (rng.random() < P->use_compression_prob) {  // _add_compression (:63-75): four draws from torch's generator
+                f.flags |= ADTFE_FX_COMPRESSOR;
+                f.comp_threshold_db = f.comp_ratio = f.comp_attack_ms = f.comp_release_ms = nan;
+            }
+            if (rng.random() < P->use_limiter_prob) {  // _add_limiter (:77-79): one draw from torch's generator
+                f.flags |= ADTFE_FX_LIMITER;
+                f.lim_threshold_db = nan;
+            }
+            P->fx.push_back(f);
+        }
         for (int32_t i = 0; i < n; ++i) ev[i].gain *= P->gain[(int)row[4 * i + 2] - 35];
         // track order: instrument by first appearance, then note order
         order.resize(n);
@@ -282,6 +319,7 @@ extern "C" int adtfe_planner_plan(adtfe_planner* P, const float* notes, const in
     out_counts[5] = (int64_t)P->tile_events.size();
     out_counts[6] = ld;
     out_counts[7] = max_len;
+    out_counts[8] = (int64_t)P->fx.size();
     return ADTFE_OK;
 }
 
@@ -301,6 +339,12 @@ extern "C" int adtfe_planner_export(const adtfe_planner* P, adtfe_event* events,
     return ADTFE_OK;
 }
 
+extern "C" int adtfe_planner_export_fx(const adtfe_planner* P, adtfe_fx* fx) {
+    if (!P) return ADTFE_ERR_BAD_ARG;
+    if (fx && !P->fx.empty()) memcpy(fx, P->fx.data(), P->fx.size() * sizeof(adtfe_fx));
+    return ADTFE_OK;
+}
+
 // The last plan as `n_batches` collated batches laid end to end, written straight into a plan blob (the layout of
 // adtfe_plan_blob_layout) - what RenderPlan.set_batches + PlanBuffers.pack do in Python, without the interpreter:
 // every batch keeps its own width (its longest segment, train_dataset.py:53) and therefore its own frame count
@@ -308,7 +352,8 @@ extern "C" int adtfe_planner_export(const adtfe_planner* P, adtfe_event* events,
 extern "C" int adtfe_planner_pack_batches(const adtfe_planner* P, const int32_t* batch_sizes, int32_t n_batches,
                                           int32_t chunk_batches, int32_t hop, int32_t wpi, void* blob_host,
                                           size_t blob_capacity, adtfe_plan* shape_out, adtfe_chunk* chunks_out,
-                                          int64_t* batch_width_out, int64_t* batch_frames_out, size_t* blob_bytes_out) {
+                                          int64_t* batch_width_out, int64_t* batch_frames_out, size_t* blob_bytes_out,
+                                          size_t* fx_offset_out) {
     if (!P || !batch_sizes || n_batches <= 0 || hop <= 0 || wpi < 0 || !shape_out || !chunks_out || !blob_bytes_out) {
         adtfe::set_error("adtfe_planner_pack_batches: bad argument");
         return ADTFE_ERR_BAD_ARG;
@@ -331,8 +376,8 @@ extern "C" int adtfe_planner_pack_batches(const adtfe_planner* P, const int32_t*
     std::vector<adtfe_mel_row> rows((size_t)n_seg);
     int64_t row0 = 0;
     int32_t s0 = 0, n_chunks = 0, max_count = 0;
-    // peak work items are ordered by first_event, so a chunk's first item is found by walking forward
-    size_t pw = 0;
+    // peak work items are ordered by first_event (FX records by seg), so a chunk's first one is found by walking forward
+    size_t pw = 0, fxr = 0;
     for (int32_t b = 0; b < n_batches; ++b) {
         const int32_t s1 = s0 + batch_sizes[b];
         int64_t width = 0;
@@ -349,9 +394,11 @@ extern "C" int adtfe_planner_pack_batches(const adtfe_planner* P, const int32_t*
         if (b % step == 0) {
             const int32_t ev = P->segments[s0].first_event;
             while (pw < P->peak_work.size() && P->peak_work[pw].first_event < ev) ++pw;
+            while (fxr < P->fx.size() && P->fx[fxr].seg < s0) ++fxr;
             chunks_out[n_chunks].seg = s0;
             chunks_out[n_chunks].event = ev;
             chunks_out[n_chunks].peak_work = (int32_t)pw;
+            chunks_out[n_chunks].fx_row = (int32_t)fxr;
             ++n_chunks;
         }
         row0 += (int64_t)batch_sizes[b] * frames;
@@ -360,6 +407,7 @@ extern "C" int adtfe_planner_pack_batches(const adtfe_planner* P, const int32_t*
     chunks_out[n_chunks].seg = n_seg;
     chunks_out[n_chunks].event = (int32_t)P->events.size();
     chunks_out[n_chunks].peak_work = (int32_t)P->peak_work.size();
+    chunks_out[n_chunks].fx_row = (int32_t)P->fx.size();
 
     adtfe_plan shape;
     memset(&shape, 0, sizeof(shape));
@@ -373,13 +421,16 @@ extern "C" int adtfe_planner_pack_batches(const adtfe_planner* P, const int32_t*
     shape.n_chunks = n_chunks;
     shape.chunks_host = chunks_out;
     shape.n_tile_events = (int32_t)P->tile_events.size();
-    size_t off[6], fixed = 0;
+    shape.n_fx = (int32_t)P->fx.size();
+    shape.sample_rate = P->sample_rate;
+    size_t off[7], fixed = 0;
     int rc = adtfe_plan_blob_layout(&shape, off, &fixed);
     if (rc != ADTFE_OK) return rc;
     // mel_total_rows == 0 (every batch too short for a frame) drops the rows section: the ragged form needs rows
     const size_t need = (fixed + 4 * P->tile_events.size() + 15) & ~(size_t)15;
     *blob_bytes_out = need;
     *shape_out = shape;
+    if (fx_offset_out) *fx_offset_out = off[5];
     if (!blob_host || blob_capacity < need) {
         adtfe::set_error("adtfe_planner_pack_batches: blob of %zu B needed, %zu B given", need, blob_capacity);
         return ADTFE_ERR_WORKSPACE;
@@ -390,6 +441,7 @@ extern "C" int adtfe_planner_pack_batches(const adtfe_planner* P, const int32_t*
     memcpy(h + off[2], P->tile_ptr.data(), P->tile_ptr.size() * 4);
     if (!P->peak_work.empty()) memcpy(h + off[3], P->peak_work.data(), P->peak_work.size() * sizeof(adtfe_peak_item));
     if (row0 > 0) memcpy(h + off[4], rows.data(), rows.size() * sizeof(adtfe_mel_row));
-    if (!P->tile_events.empty()) memcpy(h + off[5], P->tile_events.data(), P->tile_events.size() * 4);
+    if (!P->fx.empty()) memcpy(h + off[5], P->fx.data(), P->fx.size() * sizeof(adtfe_fx));
+    if (!P->tile_events.empty()) memcpy(h + off[6], P->tile_events.data(), P->tile_events.size() * 4);
     return ADTFE_OK;
 }

@@ -16,9 +16,10 @@ from . import _lib
 from .bank import OneShotBank
 from .config import SynthDrumConfig
 from .mapping import ADTOF_INVERSE, PITCH_MAX, PITCH_MIN, instrument_gain
-from .planner import EVENT_DTYPE, PEAK_ITEM_DTYPE, SEGMENT_DTYPE, RenderPlan, plan_batch, similarity_groups
+from .planner import (EVENT_DTYPE, FX_DTYPE, PEAK_ITEM_DTYPE, SEGMENT_DTYPE, RenderPlan, fill_fx_normals, plan_batch,
+                      similarity_groups)
 
-_ERRORS = {1: ValueError, 2: IndexError, 3: KeyError, 4: NotImplementedError}
+_ERRORS = {1: ValueError, 2: IndexError, 3: KeyError}
 
 
 class PackedGroup:
@@ -62,6 +63,8 @@ class NativePlanner:
                                             k[3].ctypes.data, k[4].ctypes.data, k[5].ctypes.data, k[6].ctypes.data,
                                             k[7].ctypes.data, C.byref(h)), "adtfe_planner_create")
         self.handle, self.lib = h, lib
+        _lib.check(lib.adtfe_planner_set_fx(h, float(config.use_reverb_prob), float(config.use_compression_prob),
+                                            float(config.use_limiter_prob)), "adtfe_planner_set_fx")
 
     def __del__(self):
         try:
@@ -88,10 +91,11 @@ class NativePlanner:
                 return np.asarray(notes, np.float32).reshape(-1, 4)
         return None
 
-    def plan_batch(self, batch_notes: Sequence, rng=_random, ld_wav: Optional[int] = None) -> RenderPlan:
+    def plan_batch(self, batch_notes: Sequence, rng=_random, ld_wav: Optional[int] = None, generator=None) -> RenderPlan:
+        """``generator``: torch generator of the FX chain's normal draws (None = the global one, like the reference)."""
         arrays = [self._as_f32(n) for n in batch_notes]
         if any(a is None for a in arrays) or not hasattr(rng, "getstate"):
-            return plan_batch(batch_notes, self.config, self.bank, rng, ld_wav)
+            return plan_batch(batch_notes, self.config, self.bank, rng, ld_wav, generator)
         for a in arrays:
             if a.ndim != 2 or a.shape[1] != 4:
                 raise ValueError(f"notes must have shape (N, 4), got {tuple(a.shape)}")
@@ -100,7 +104,7 @@ class NativePlanner:
         flat = np.ascontiguousarray(np.concatenate(arrays)) if n_seg else np.zeros((0, 4), np.float32)
         version, internal, gauss = rng.getstate()
         state = np.array(internal, np.uint32)
-        out = np.zeros(8, np.int64)
+        out = np.zeros(9, np.int64)
         info = np.zeros(2, np.int32)
         rc = self.lib.adtfe_planner_plan(self.handle, flat.ctypes.data, counts.ctypes.data, n_seg, state.ctypes.data,
                                          int(ld_wav or 0), out.ctypes.data, info.ctypes.data)
@@ -108,12 +112,11 @@ class NativePlanner:
         if rc > 0:
             seg, note = int(info[0]), int(info[1])
             what = f"Invalid note: {arrays[seg][note]}" if rc == 1 and note >= 0 else \
-                {2: "Cannot choose from an empty sequence", 3: f"segment {seg} note {note}",
-                 4: "the pedalboard FX chain (synthetiser.py:121-137) is outside the GPU path; set use_fx_prob=0"}[rc] \
+                {2: "Cannot choose from an empty sequence", 3: f"segment {seg} note {note}"}[rc] \
                 if rc != 1 else "Invalid note"
             raise _ERRORS[rc](what)
         _lib.check(rc, "adtfe_planner_plan")
-        n_ev, n_grp, _, tps, n_pw, n_te, ld, _ = (int(x) for x in out)
+        n_ev, n_grp, _, tps, n_pw, n_te, ld, _, n_fx = (int(x) for x in out)
         events = np.empty(n_ev, EVENT_DTYPE)
         mix_len = np.empty(n_ev, np.int32)
         group_ptr = np.empty(n_grp + 1, np.int32)
@@ -124,8 +127,14 @@ class NativePlanner:
         _lib.check(self.lib.adtfe_planner_export(self.handle, events.ctypes.data, mix_len.ctypes.data,
                                                  group_ptr.ctypes.data, segments.ctypes.data, tile_ptr.ctypes.data,
                                                  peak_work.ctypes.data, tile_events.ctypes.data), "adtfe_planner_export")
-        return RenderPlan(n_seg, ld, tps, segments, events, mix_len, group_ptr, tile_ptr, tile_events, peak_work,
+        plan = RenderPlan(n_seg, ld, tps, segments, events, mix_len, group_ptr, tile_ptr, tile_events, peak_work,
                           segments["len"].astype(np.int64))
+        plan.sample_rate = int(self.config.sample_rate)
+        if n_fx:   # the planner drew the coins and the reverb from `random`; the dynamics parameters are torch's
+            fx = np.empty(n_fx, FX_DTYPE)
+            _lib.check(self.lib.adtfe_planner_export_fx(self.handle, fx.ctypes.data), "adtfe_planner_export_fx")
+            plan.fx = fill_fx_normals(fx, generator)
+        return plan
 
     # ---- a whole group of batches planned and packed into a pinned blob without the interpreter in between
     def plan_group(self, group: Sequence[Sequence], mt_state: np.ndarray) -> Optional[np.ndarray]:
@@ -142,7 +151,7 @@ class NativePlanner:
             return None
         counts = np.fromiter(map(len, flat), np.int32, n_seg)
         notes = np.concatenate(flat) if n_seg > 1 else np.ascontiguousarray(flat[0])
-        out = np.zeros(8, np.int64)
+        out = np.zeros(9, np.int64)
         info = np.zeros(2, np.int32)
         rc = self.lib.adtfe_planner_plan(self.handle, notes.ctypes.data, counts.ctypes.data, n_seg,
                                          mt_state.ctypes.data, 0, out.ctypes.data, info.ctypes.data)
@@ -155,23 +164,23 @@ class NativePlanner:
 
     def pack_group(self, sizes: Sequence[int], hop: int, wpi: int, chunk_batches: int, host_ptr: int, capacity: int):
         """The plan of the last ``plan_group`` as ``len(sizes)`` collated batches, written into the blob at
-        ``host_ptr`` (``adtfe_planner_pack_batches``).  Returns ``(status, shape, bytes needed, chunks, width, frames)``;
-        status -3 = the blob is too small (nothing written)."""
+        ``host_ptr`` (``adtfe_planner_pack_batches``).  Returns ``(status, shape, bytes needed, chunks, width, frames,
+        fx offset)``; status -3 = the blob is too small (nothing written)."""
         sizes = np.ascontiguousarray(sizes, np.int32)
         nb = len(sizes)
-        chunks = np.zeros((nb + 1) * 3, np.int32)
+        chunks = np.zeros((nb + 1) * 4, np.int32)
         width, frames = np.zeros(nb, np.int64), np.zeros(nb, np.int64)
         shape = _lib.Plan()
-        need = C.c_size_t()
+        need, fx_off = C.c_size_t(), C.c_size_t()
         rc = self.lib.adtfe_planner_pack_batches(self.handle, sizes.ctypes.data, nb, int(chunk_batches), int(hop),
                                                  int(wpi), host_ptr, capacity, C.byref(shape), chunks.ctypes.data,
-                                                 width.ctypes.data, frames.ctypes.data, C.byref(need))
+                                                 width.ctypes.data, frames.ctypes.data, C.byref(need), C.byref(fx_off))
         if rc not in (0, -3):
             _lib.check(rc, "adtfe_planner_pack_batches")
-        return rc, shape, need.value, chunks, width, frames
+        return rc, shape, need.value, chunks, width, frames, fx_off.value
 
     def plan_group_into(self, group: Sequence[Sequence], mt_state: np.ndarray, acquire, hop: int, wpi: int,
-                        chunk_batches: int = 1) -> Optional[PackedGroup]:
+                        chunk_batches: int = 1, generator=None) -> Optional[PackedGroup]:
         """``plan_group``, then ``buf = acquire()`` (the ``PlanBuffers`` whose pinned blob receives the plan - the
         caller may block there until a buffer set is free), then ``pack_group`` into it."""
         out = self.plan_group(group, mt_state)
@@ -179,13 +188,16 @@ class NativePlanner:
             return None
         buf = acquire()
         sizes = np.fromiter(map(len, group), np.int32, len(group))
-        rc, shape, need, chunks, width, frames = self.pack_group(sizes, hop, wpi, chunk_batches, buf.host.data_ptr(),
-                                                                 buf.host.numel())
+        rc, shape, need, chunks, width, frames, fx_off = self.pack_group(sizes, hop, wpi, chunk_batches,
+                                                                         buf.host.data_ptr(), buf.host.numel())
         if rc == -3:   # ADTFE_ERR_WORKSPACE: grow the pinned blob and pack again
             buf.reserve(need)
-            rc, shape, need, chunks, width, frames = self.pack_group(sizes, hop, wpi, chunk_batches,
-                                                                     buf.host.data_ptr(), buf.host.numel())
+            rc, shape, need, chunks, width, frames, fx_off = self.pack_group(sizes, hop, wpi, chunk_batches,
+                                                                             buf.host.data_ptr(), buf.host.numel())
         _lib.check(rc, "adtfe_planner_pack_batches")
+        if shape.n_fx:   # the FX records sit in the blob with NaN dynamics parameters: fill them in place (torch's stream)
+            fx = buf.host.numpy()[fx_off: fx_off + FX_DTYPE.itemsize * shape.n_fx].view(FX_DTYPE)
+            fill_fx_normals(fx, generator)
         buf.adopt(shape, need, chunks)
         n_seg = int(out[2])
         o = buf.offsets[1]

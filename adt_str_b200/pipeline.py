@@ -108,8 +108,13 @@ class HostPipeline:
         # One RNG stream per GROUP, derived from (seed, rank, group index): which thread plans a group is up to the
         # executor, the draws are not - a seed reproduces the same timbres and mixups run after run, and ranks that
         # share a seed still render different augmentations (DataLoader workers: seed + worker id, per rank).
-        st["rng"].seed((self._seed * 1_000_003 + self.rank) * 1_000_003 + index)
+        group_seed = (self._seed * 1_000_003 + self.rank) * 1_000_003 + index
+        st["rng"].seed(group_seed)
         st["mt"][:] = np.array(st["rng"].getstate()[1], np.uint32)   # the same stream, kept native
+        gen = None
+        if self.fe.synth.config.use_fx_prob > 0:   # the FX chain's normal draws: torch's stream, one per group as well
+            gen = st.setdefault("gen", torch.Generator())
+            gen.manual_seed(group_seed % (1 << 63))
 
         def acquire():
             s.free.wait()          # the consumer released the set ...
@@ -120,15 +125,15 @@ class HostPipeline:
         # fast path: plan, wait for the buffer set, pack - two library calls, no interpreter work per note or record
         spec = self.fe.mel.compute_spec
         plan = st["planner"].plan_group_into(group, st["mt"], acquire, spec.hop_length, self.fe.mel.window_pad_idxs,
-                                             self.chunk_batches)
+                                             self.chunk_batches, gen)
         if plan is not None:
             return plan, s.buf.shape
         # general path (python lists, float64 notes ...): the worker's random.Random continues the native stream
         version, _, gauss = st["rng"].getstate()
         st["rng"].setstate((version, tuple(int(v) for v in st["mt"]), gauss))
         flat = [notes for b in group for notes in b]
-        plan = st["planner"].plan_batch(flat, st["rng"]).set_batches([len(b) for b in group], self.fe.mel.n_frames,
-                                                                     self.chunk_batches)
+        plan = st["planner"].plan_batch(flat, st["rng"], None, gen).set_batches([len(b) for b in group],
+                                                                                 self.fe.mel.n_frames, self.chunk_batches)
         st["mt"][:] = np.array(st["rng"].getstate()[1], np.uint32)
         shape = acquire().pack(plan)
         return plan, shape

@@ -52,8 +52,13 @@ PEAK_ITEM_DTYPE = np.dtype([("a_off", "<i8"), ("b_off", "<i8"), ("la", "<i4"), (
 #: numpy view of ``adtfe_mel_row`` (16 bytes)
 MEL_ROW_DTYPE = np.dtype([("out_row", "<i8"), ("count", "<i4"), ("flags", "<i4")])
 MEL_ROW_SILENT = 1  # ADTFE_MEL_ROW_SILENT: the row is all zeros (an empty segment), its frames are exact zeros
-#: numpy view of ``adtfe_chunk`` (12 bytes)
-CHUNK_DTYPE = np.dtype([("seg", "<i4"), ("event", "<i4"), ("peak_work", "<i4")])
+#: numpy view of ``adtfe_chunk`` (16 bytes)
+CHUNK_DTYPE = np.dtype([("seg", "<i4"), ("event", "<i4"), ("peak_work", "<i4"), ("fx_row", "<i4")])
+#: numpy view of ``adtfe_fx`` (48 bytes): the keyword arguments the reference hands to pedalboard
+FX_DTYPE = np.dtype([("seg", "<i4"), ("flags", "<i4"), ("room_size", "<f4"), ("damping", "<f4"), ("wet_level", "<f4"),
+                     ("dry_level", "<f4"), ("width", "<f4"), ("comp_threshold_db", "<f4"), ("comp_ratio", "<f4"),
+                     ("comp_attack_ms", "<f4"), ("comp_release_ms", "<f4"), ("lim_threshold_db", "<f4")])
+FX_REVERB, FX_COMPRESSOR, FX_LIMITER = 1, 2, 4   # ADTFE_FX_*
 SEG_EMPTY = 0      # no notes: all-zero waveform of int(input_sec*sr) samples, no normalisation
 SEG_NORMALISE = 1  # wav / max|wav| * max_volume (NaN when the mix is all zero, like the reference)
 
@@ -102,11 +107,61 @@ class SegmentPlan:
     events: np.ndarray            # EVENT_DTYPE, track order, seg field = 0
     mix_len: np.ndarray           # int32 per event: max(len_a, len_b) before truncation
     group_ptr: np.ndarray         # int32 (n_groups+1,): events of one instrument are contiguous
+    fx: np.ndarray = None         # FX_DTYPE (1,) when the FX coin hit (seg field = 0), else None
 
 
-def plan_segment(notes, config: SynthDrumConfig, bank: OneShotBank, rng=_random) -> SegmentPlan:
+def normal_draw(std: float, mean: float, high_bound: float, low_bound: float, generator=None) -> float:
+    """``draw_from_normal_distribution`` of the reference (``utils/utils.py:266-269``), the same torch calls - so the
+    same float32 arithmetic on the same draw of the same generator (``generator=None``: torch's global one, which is
+    what the reference uses)."""
+    z = torch.randn(1, generator=generator)
+    return torch.clamp(torch.clamp(z * std + mean, -1.0, 1.0).abs() * high_bound, low_bound, high_bound).item()
+
+
+def fill_fx_normals(fx: np.ndarray, generator=None) -> np.ndarray:
+    """The compressor and limiter parameters of FX records, drawn in the reference's order - record by record (one
+    ``SynthDrum.__call__`` each), ``_add_compression``'s four draws then ``_add_limiter``'s one
+    (``synthetiser.py:63-79,81-86``).  The native planner leaves them NaN: it owns the ``random`` stream, torch's
+    generator lives here."""
+    for r in range(len(fx)):
+        flags = int(fx["flags"][r])
+        if flags & FX_COMPRESSOR:
+            fx["comp_threshold_db"][r] = -normal_draw(0.15, 0.5, 10, 0, generator)
+            fx["comp_ratio"][r] = normal_draw(0.15, 0.5, 10, 1.0, generator)
+            fx["comp_attack_ms"][r] = normal_draw(0.05, 0.1, 1000, 0, generator)
+            fx["comp_release_ms"][r] = normal_draw(0.15, 0.2, 1000, 0, generator)
+        if flags & FX_LIMITER:
+            fx["lim_threshold_db"][r] = -normal_draw(0.2, 0.4, 3, 0, generator)
+    return fx
+
+
+def draw_fx(config: SynthDrumConfig, rng, generator=None) -> np.ndarray:
+    """``BoardChain.get_board`` (``synthetiser.py:81-87``): which plugins, with which parameters - the coins and the
+    reverb's uniforms from ``rng`` (the ``random`` stream), the dynamics parameters from torch's generator."""
+    fx = np.zeros(1, FX_DTYPE)
+    if rng.random() < config.use_reverb_prob:               # _add_reverb :44-61
+        room = rng.uniform(0.2, 0.8)
+        damping = rng.uniform(0.2, 0.8)
+        wet = rng.uniform(0.1, 0.4)
+        width = rng.uniform(0.6, 1.0)
+        fx["flags"] |= FX_REVERB
+        fx["room_size"], fx["damping"], fx["wet_level"], fx["dry_level"], fx["width"] = room, damping, wet, 1 - wet, width
+    if rng.random() < config.use_compression_prob:          # _add_compression :63-75
+        fx["flags"] |= FX_COMPRESSOR
+        fx["comp_threshold_db"] = -normal_draw(0.15, 0.5, 10, 0, generator)
+        fx["comp_ratio"] = normal_draw(0.15, 0.5, 10, 1.0, generator)
+        fx["comp_attack_ms"] = normal_draw(0.05, 0.1, 1000, 0, generator)
+        fx["comp_release_ms"] = normal_draw(0.15, 0.2, 1000, 0, generator)
+    if rng.random() < config.use_limiter_prob:              # _add_limiter :77-79
+        fx["flags"] |= FX_LIMITER
+        fx["lim_threshold_db"] = -normal_draw(0.2, 0.4, 3, 0, generator)
+    return fx
+
+
+def plan_segment(notes, config: SynthDrumConfig, bank: OneShotBank, rng=_random, generator=None) -> SegmentPlan:
     """Plan one ``SynthDrum.__call__``.  ``rng`` is the ``random`` module (default, so a
-    seeded reference run and a seeded run here draw the same numbers) or a ``random.Random``."""
+    seeded reference run and a seeded run here draw the same numbers) or a ``random.Random``;
+    ``generator``: the torch generator of the FX chain's normal draws (None = the global one, like the reference)."""
     sr = config.sample_rate
     if len(notes) == 0:  # synthetiser.py:257-258
         return SegmentPlan(int(config.input_sec * sr), SEG_EMPTY, 0.0,
@@ -157,9 +212,7 @@ def plan_segment(notes, config: SynthDrumConfig, bank: OneShotBank, rng=_random)
     for inst in rank:  # gain lookup happens in instrument_mixer, after the loop
         g = instrument_gain(inst, config.ADTOF_mapping)
         gains[pitch == inst] = g
-    if rng.random() < config.use_fx_prob:  # synthetiser.py:154
-        raise NotImplementedError(
-            "the pedalboard FX chain (synthetiser.py:121-137) is outside the GPU path; set use_fx_prob=0")
+    fx = draw_fx(config, rng, generator) if rng.random() < config.use_fx_prob else None  # synthetiser.py:154
 
     # ---- vectorised index rules
     vel = a[:, 3]
@@ -180,7 +233,7 @@ def plan_segment(notes, config: SynthDrumConfig, bank: OneShotBank, rng=_random)
     ev, mix_len = ev[perm], mix_len[perm].astype(np.int32)
     sorted_rank = order_rank[perm]
     group_ptr = np.concatenate([[0], np.flatnonzero(np.diff(sorted_rank)) + 1, [n]]).astype(np.int32)
-    return SegmentPlan(wave_length, SEG_NORMALISE, max_volume, ev, mix_len, group_ptr)
+    return SegmentPlan(wave_length, SEG_NORMALISE, max_volume, ev, mix_len, group_ptr, fx)
 
 
 @dataclass
@@ -204,6 +257,8 @@ class RenderPlan:
     mel_rows: np.ndarray = field(default=None)       # MEL_ROW_DTYPE (n_seg,)
     mel_total_rows: int = 0
     chunks: np.ndarray = field(default=None)         # CHUNK_DTYPE (n_chunks+1,)
+    fx: np.ndarray = field(default=None)             # FX_DTYPE (n_fx,), ascending seg: segments with an FX chain
+    sample_rate: int = 0                             # needed by the FX kernels (filter tunings)
 
     def set_batches(self, sizes: Sequence[int], n_frames, chunk_batches: int = 1) -> "RenderPlan":
         """Mark the plan as ``len(sizes)`` collated batches laid end to end (``sizes[b]`` segments
@@ -229,6 +284,8 @@ class RenderPlan:
         first_event = np.concatenate([self.segments["first_event"].astype(np.int64), [self.n_events]])
         chunks["event"] = first_event[cptr]
         chunks["peak_work"] = np.searchsorted(self.peak_work["first_event"], chunks["event"], side="left")
+        if self.fx is not None and len(self.fx):
+            chunks["fx_row"] = np.searchsorted(self.fx["seg"], chunks["seg"], side="left")
         self.batch_ptr, self.batch_samples, self.batch_frames = ptr, width.astype(np.int64), frames
         self.mel_rows, self.mel_total_rows, self.chunks = rows, int(row0[-1]), chunks
         return self
@@ -319,9 +376,17 @@ def assemble(plans: Sequence[SegmentPlan], bank: OneShotBank, ld_wav: int | None
     group_ptr = np.concatenate(gps).astype(np.int32)
     tile_ptr, tile_events = bucket_tiles(events["start"].astype(np.int64), events["len"].astype(np.int64),
                                          events["seg"], n_seg, tiles_per_seg)
-    return RenderPlan(n_seg, ld_wav, tiles_per_seg, segments, events, mix_len, group_ptr, tile_ptr,
+    fx_rows = []
+    for s, p in enumerate(plans):
+        if p.fx is not None:
+            r = p.fx.copy()
+            r["seg"] = s
+            fx_rows.append(r)
+    plan = RenderPlan(n_seg, ld_wav, tiles_per_seg, segments, events, mix_len, group_ptr, tile_ptr,
                       tile_events, peak_work_items(events, mix_len, group_ptr, bank),
                       np.array([p.wave_length for p in plans], np.int64))
+    plan.fx = np.concatenate(fx_rows) if fx_rows else None
+    return plan
 
 
 def peak_work_items(events: np.ndarray, mix_len: np.ndarray, group_ptr: np.ndarray, bank: OneShotBank) -> np.ndarray:
@@ -345,7 +410,9 @@ def peak_work_items(events: np.ndarray, mix_len: np.ndarray, group_ptr: np.ndarr
 
 
 def plan_batch(batch_notes: Sequence, config: SynthDrumConfig, bank: OneShotBank, rng=_random,
-               ld_wav: int | None = None) -> RenderPlan:
+               ld_wav: int | None = None, generator=None) -> RenderPlan:
     """Plan ``len(batch_notes)`` independent ``SynthDrum.__call__``s, in order (the RNG
-    stream advances exactly as that many reference calls would advance it)."""
-    return assemble([plan_segment(n, config, bank, rng) for n in batch_notes], bank, ld_wav)
+    streams advance exactly as that many reference calls would advance them)."""
+    plan = assemble([plan_segment(n, config, bank, rng, generator) for n in batch_notes], bank, ld_wav)
+    plan.sample_rate = int(config.sample_rate)
+    return plan

@@ -68,13 +68,15 @@ class PlanBuffers:
         self.fence()
         batched = plan.mel_rows is not None
         self._chunks = np.ascontiguousarray(plan.chunks) if batched else None  # host memory the library reads
+        n_fx = 0 if plan.fx is None else len(plan.fx)
         shape = _lib.Plan(None, None, None, None, None, plan.n_events, plan.n_seg, plan.tiles_per_seg,
                           len(plan.peak_work), plan.ld_wav, None,
                           plan.mel_total_rows if batched else 0,
                           int(plan.batch_frames.max()) if batched and len(plan.batch_frames) else 0,
                           len(self._chunks) - 1 if batched else 0,
-                          self._chunks.ctypes.data if batched else None, len(plan.tile_events))
-        off = (C.c_size_t * 6)()
+                          self._chunks.ctypes.data if batched else None, len(plan.tile_events),
+                          n_fx, None, int(plan.sample_rate))
+        off = (C.c_size_t * 7)()
         fixed = C.c_size_t()
         _lib.check(lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(fixed)), "adtfe_plan_blob_layout")
         total = (fixed.value + 4 * len(plan.tile_events) + 15) & ~15
@@ -84,7 +86,8 @@ class PlanBuffers:
             self.dev = torch.empty(cap, dtype=torch.uint8, device=self.device)
         h = self.host.numpy()
         rows = plan.mel_rows if batched else np.zeros(0, np.uint8)
-        for o, arr in zip(off, (plan.events, plan.segments, plan.tile_ptr, plan.peak_work, rows, plan.tile_events)):
+        fx = plan.fx if n_fx else np.zeros(0, np.uint8)
+        for o, arr in zip(off, (plan.events, plan.segments, plan.tile_ptr, plan.peak_work, rows, fx, plan.tile_events)):
             raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
             h[o: o + raw.size] = raw
         self.nbytes = total
@@ -109,7 +112,7 @@ class PlanBuffers:
         ``chunks``: the int32 array behind ``shape.chunks_host``, kept alive here)."""
         lib = _lib.load()
         self._chunks = chunks
-        off = (C.c_size_t * 6)()
+        off = (C.c_size_t * 7)()
         fixed = C.c_size_t()
         _lib.check(lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(fixed)), "adtfe_plan_blob_layout")
         self.nbytes = int(nbytes)
@@ -128,10 +131,11 @@ class PlanBuffers:
             self._uploaded.record()
         base = self.dev.data_ptr()
         o = self.offsets
-        return _lib.Plan(base + o[0], base + o[1], base + o[2], base + o[5], base + o[3],
+        return _lib.Plan(base + o[0], base + o[1], base + o[2], base + o[6], base + o[3],
                          shape.n_events, shape.n_seg, shape.tiles_per_seg, shape.n_peak_work, shape.ld_wav,
                          base + o[4] if shape.mel_total_rows > 0 else None, shape.mel_total_rows,
-                         shape.mel_max_count, shape.n_chunks, shape.chunks_host, shape.n_tile_events)
+                         shape.mel_max_count, shape.n_chunks, shape.chunks_host, shape.n_tile_events,
+                         shape.n_fx, base + o[5] if shape.n_fx > 0 else None, shape.sample_rate)
 
 
 class SynthDrum:
@@ -182,15 +186,17 @@ class SynthDrum:
         return self._buffers
 
     # ------------------------------------------------------------------ plan
-    def plan(self, batch_notes: Sequence, rng=_random, ld_wav: Optional[int] = None, native: bool = True) -> RenderPlan:
+    def plan(self, batch_notes: Sequence, rng=_random, ld_wav: Optional[int] = None, native: bool = True,
+             generator=None) -> RenderPlan:
         """Plan a batch on the host.  ``native`` uses the C++ planner (same RNG stream, same
-        indices); it falls back to ``planner.plan_batch`` by itself for float64 note arrays."""
+        indices); it falls back to ``planner.plan_batch`` by itself for float64 note arrays.
+        ``generator``: torch generator for the FX chain's normal draws (None: the global one, like the reference)."""
         if not native:
-            return plan_batch(batch_notes, self.config, self.bank, rng, ld_wav)
+            return plan_batch(batch_notes, self.config, self.bank, rng, ld_wav, generator)
         if self._native_planner is None:
             from .native_planner import NativePlanner
             self._native_planner = NativePlanner(self.config, self.bank)
-        return self._native_planner.plan_batch(batch_notes, rng, ld_wav)
+        return self._native_planner.plan_batch(batch_notes, rng, ld_wav, generator)
 
     def plan_batches(self, batches: Sequence[Sequence], n_frames, rng=_random, chunk_batches: int = 1) -> RenderPlan:
         """Plan several batches as ONE device plan (one H2D copy, one launch per kernel): the segments

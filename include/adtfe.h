@@ -100,12 +100,28 @@ typedef struct adtfe_mel_row {
  * of zeros without the flag gives the same output. */
 #define ADTFE_MEL_ROW_SILENT 1
 
-/* A chunk of a plan: segments, events and peak work items [x[c], x[c+1]) are rendered together, chunks
- * are independent and run on the library's internal streams (so that a chunk's one-shots are still in L2
- * when its tile mixer re-reads them, and small kernels of different chunks overlap). */
+/* A chunk of a plan: segments, events, peak work items and FX rows [x[c], x[c+1]) are rendered together;
+ * chunks are independent and go through the library's internal streams as a pipeline (so that a chunk's
+ * one-shots are still in L2 when its tile mixer re-reads them, and the kernels of different chunks overlap). */
 typedef struct adtfe_chunk {
-    int32_t seg, event, peak_work;
+    int32_t seg, event, peak_work, fx_row;
 } adtfe_chunk;
+
+/* FX chain of one segment (48 bytes): VolumeMixer._add_fx / BoardChain of the reference
+ * (modules/synthetiser.py:30-87,121-137), applied between the instrument sum and the global normalisation
+ * (:154).  The parameters are the keyword arguments the reference hands to pedalboard.Reverb / Compressor /
+ * Limiter; the host planner draws them from the reference's RNG streams in the reference's order.  Records are
+ * sorted by `seg`; segments without a record get no FX. */
+#define ADTFE_FX_REVERB 1
+#define ADTFE_FX_COMPRESSOR 2
+#define ADTFE_FX_LIMITER 4
+typedef struct adtfe_fx {
+    int32_t seg;
+    int32_t flags; /* ADTFE_FX_* (0: the FX coin hit but no plugin was drawn: the empty board) */
+    float room_size, damping, wet_level, dry_level, width;                 /* Reverb (freeze_mode 0) */
+    float comp_threshold_db, comp_ratio, comp_attack_ms, comp_release_ms; /* Compressor */
+    float lim_threshold_db;                                                /* Limiter (release_ms 100) */
+} adtfe_fx;
 
 typedef struct adtfe_bank adtfe_bank; /* one-shot bank resident in HBM */
 typedef struct adtfe_mel adtfe_mel;   /* window, mel filterbank (CSR) and twiddles on device */
@@ -126,6 +142,10 @@ typedef struct adtfe_plan {
     int32_t n_chunks;                    /* boundaries in chunks_host: n_chunks + 1 records, first all-zero, */
     const adtfe_chunk* chunks_host;      /* last = {n_seg, n_events, n_peak_work}; HOST memory */
     int32_t n_tile_events;               /* entries of tile_events_dev (= the last tile_ptr entry); required */
+    /* optional FX chain (NULL / 0 = no segment has FX) */
+    int32_t n_fx;                        /* records in fx_dev */
+    const adtfe_fx* fx_dev;              /* sorted by seg */
+    int32_t sample_rate;                 /* of the rendered audio; required when n_fx > 0 (filter tunings) */
 } adtfe_plan;
 
 int adtfe_version(void);
@@ -145,7 +165,8 @@ int64_t adtfe_bank_bytes(const adtfe_bank* bank);
 size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg, int32_t n_tile_events);
 /* Writes the (n_seg, ld_wav) float32 waveform matrix: every row normalised as the reference
  * does and zero-padded to ld_wav.  Four kernels per chunk: per-note peak of the mixed one-shot, the per-tile
- * slice records, the tile mixer, the row normalisation.  A plan with chunks (plan->chunks_host) is rendered chunk by chunk on the
+ * slice records, the tile mixer, the row normalisation; with plan->n_fx > 0 the FX kernels (reverb, dynamics) run
+ * on the chunk's FX rows between the mixer and the normalisation.  A plan with chunks (plan->chunks_host) is rendered chunk by chunk on the
  * bank's internal streams, forked from and joined back into `stream`; calls on one bank handle must not
  * be made from several host threads at once. */
 int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
@@ -183,9 +204,9 @@ int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel, const adtf
                         void* stream);
 /* ---- host-buffer entry (end to end) ------------------------------------------------ */
 /* Plan blob layout (host, 16-byte aligned sections in this order):
- *   events | segments | tile_ptr | peak_work | mel_rows | tile_events
+ *   events | segments | tile_ptr | peak_work | mel_rows | fx | tile_events
  * with the counts in `shape` (a plan whose device pointers are ignored; mel_rows is n_seg records when
- * shape->mel_total_rows > 0, else empty; shape->chunks_host is used as given).  The blob is copied to
+ * shape->mel_total_rows > 0, else empty; fx is shape->n_fx records; shape->chunks_host is used as given).  The blob is copied to
  * `blob_dev` (>= blob_bytes), the batch rendered and featurised, then the log-mel matrix
  * (and the waveform when wav_out_host != NULL) copied back.  Asynchronous on `stream`:
  * the host buffers must be pinned and stay alive until the stream is synchronised.
@@ -195,9 +216,9 @@ int adtfe_frontend_host(const adtfe_bank* bank, const adtfe_mel* mel, const adtf
                         const void* blob_host, size_t blob_bytes, void* blob_dev, float* wav_dev, float* mel_dev,
                         void* workspace_dev, size_t workspace_bytes, float* mel_out_host, float* wav_out_host,
                         void* stream, void* copy_stream);
-/* Byte offsets of the six sections inside a plan blob (offsets[6]; *blob_bytes = offsets[5], where
+/* Byte offsets of the seven sections inside a plan blob (offsets[7]; *blob_bytes = offsets[6], where
  * tile_events starts - it runs to the end of the blob). */
-int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[6], size_t* blob_bytes);
+int adtfe_plan_blob_layout(const adtfe_plan* shape, size_t offsets[7], size_t* blob_bytes);
 
 /* ---- long-form audio front (eval / inference) ------------------------------------------ */
 typedef struct adtfe_resampler adtfe_resampler;
@@ -242,29 +263,41 @@ int adtfe_planner_create(int32_t sample_rate, double input_sec, double mixup_ran
                          const int32_t* group_first, const int32_t* group_count, const float* gain,
                          const int32_t* inverse_ptr, const int32_t* inverse_pitch, adtfe_planner** out);
 int adtfe_planner_destroy(adtfe_planner* planner);
+/* Probabilities of the FX chain's three plugins (SynthDrumConfig.use_reverb_prob / use_compression_prob /
+ * use_limiter_prob; BoardChain.get_board, synthetiser.py:79-86).  Without this call an FX coin hit
+ * (use_fx_prob > 0) draws an empty board. */
+int adtfe_planner_set_fx(adtfe_planner* planner, double use_reverb_prob, double use_compression_prob,
+                         double use_limiter_prob);
 /* notes: float32 rows [onset, offset, pitch, velocity] of all segments back to back, counts[n_seg] rows
  * each.  mt_state[625]: random.getstate()[1], advanced in place.  ld_wav_in: 0 = derive.  Returns 0, a
- * negative adtfe_status, or 1 invalid note (ValueError) / 2 no admitted group (IndexError) / 3 KeyError /
- * 4 FX coin hit (NotImplementedError) with info = {segment, note}.
- * out_counts = {n_events, n_groups, n_seg, tiles_per_seg, n_peak_work, n_tile_events, ld_wav, max_len}.
+ * negative adtfe_status, or 1 invalid note (ValueError) / 2 no admitted group (IndexError) / 3 KeyError
+ * with info = {segment, note}.
+ * out_counts = {n_events, n_groups, n_seg, tiles_per_seg, n_peak_work, n_tile_events, ld_wav, max_len, n_fx}.
+ * FX: when the segment's FX coin hits (random() < use_fx_prob, synthetiser.py:154) the planner draws what
+ * BoardChain.get_board draws from `random` - the three plugin coins and the reverb's four uniforms - and
+ * leaves the compressor / limiter parameters, which the reference draws from torch's generator
+ * (utils/utils.py:266-269), as NaN for the caller to fill in record order (adtfe_planner_export_fx).
  * mix_len / group_ptr are exported for inspection only; the device plan does not need them. */
 int adtfe_planner_plan(adtfe_planner* planner, const float* notes, const int32_t* counts, int32_t n_seg,
                        uint32_t* mt_state, int64_t ld_wav_in, int64_t* out_counts, int32_t* info);
 int adtfe_planner_export(const adtfe_planner* planner, adtfe_event* events, int32_t* mix_len, int32_t* group_ptr,
                          adtfe_segment* segments, int32_t* tile_ptr, adtfe_peak_item* peak_work, int32_t* tile_events);
+/* The FX records of the last plan (out_counts[8] of them). */
+int adtfe_planner_export_fx(const adtfe_planner* planner, adtfe_fx* fx);
 
 /* The last plan as n_batches collated batches laid end to end (batch_sizes[b] segments each), written straight into
  * a plan blob for adtfe_frontend_host - RenderPlan.set_batches + PlanBuffers.pack of the Python host without the
  * interpreter.  Every batch keeps its own width (its longest segment: collate_fn, train_dataset.py:53) and frame
  * count max(0, 1 + width / hop - 2 * wpi - 1) (model.py:79,95-97); one render chunk per chunk_batches batches.
- * shape_out: counts, ld_wav, mel_* and chunk fields filled (device pointers NULL; chunks_host = chunks_out, which
- * must hold n_batches + 1 records and stay alive while the shape is used).  batch_width_out / batch_frames_out:
+ * shape_out: counts, ld_wav, mel_*, n_fx, sample_rate and chunk fields filled (device pointers NULL; chunks_host =
+ * chunks_out, which must hold n_batches + 1 records and stay alive while the shape is used).  fx_offset_out (may be
+ * NULL): byte offset of the blob's FX section, whose NaN fields the caller fills before the blob is uploaded.  batch_width_out / batch_frames_out:
  * n_batches values each (may be NULL).  *blob_bytes_out = bytes the blob takes; with blob_host NULL or
  * blob_capacity too small nothing is written and ADTFE_ERR_WORKSPACE is returned (size query). */
 int adtfe_planner_pack_batches(const adtfe_planner* planner, const int32_t* batch_sizes, int32_t n_batches,
                                int32_t chunk_batches, int32_t hop, int32_t wpi, void* blob_host, size_t blob_capacity,
                                adtfe_plan* shape_out, adtfe_chunk* chunks_out, int64_t* batch_width_out,
-                               int64_t* batch_frames_out, size_t* blob_bytes_out);
+                               int64_t* batch_frames_out, size_t* blob_bytes_out, size_t* fx_offset_out);
 
 #ifdef __cplusplus
 }

@@ -197,9 +197,80 @@ def make_tokens():
     print("tokens: 24 segments x 4 tokenizer configurations")
 
 
+FX_CASES = {
+    # name: (config overrides, bank kwargs, n_segments, events seed, python-random seed, torch seed)
+    "fx_24k": (dict(use_fx_prob=0.75, use_reverb_prob=0.6, use_compression_prob=0.6, use_limiter_prob=0.6),
+               dict(n_oneshots=156, max_len=9000, min_len=300, seed=20), 10, 21, 314, 2718),
+    "fx_16k_short": (dict(sample_rate=16000, input_sec=0.64, use_fx_prob=1.0, use_reverb_prob=1.0,
+                          use_compression_prob=1.0, use_limiter_prob=1.0),
+                     dict(n_oneshots=78, max_len=3000, min_len=200, seed=22, sample_rate=16000), 4, 23, 7, 11),
+}
+
+
+def make_fx():
+    """tests/golden/fx_*.npz: the UNMODIFIED reference rendering with the FX chain ON.  pedalboard is not installed, so
+    the reference's ``Pedalboard / Reverb / Compressor / Limiter`` names are pointed at the recording stand-in whose
+    DSP is ``oracle/fx_oracle.c`` (``ref_harness.enable_fx_stand_in``): which plugins are built, with which parameters,
+    from which draws, and where the chain sits are the reference's own; the DSP arithmetic is the restatement's
+    (parity with pedalboard itself: unpinned).  The oracle (same seeds) must agree before anything is written."""
+    fx = ref_harness.enable_fx_stand_in()
+    os.makedirs(OUT, exist_ok=True)
+    for name, (over, bank_kw, n, ev_seed, py_seed, torch_seed) in FX_CASES.items():
+        cfg = dict(SETTING_1, **over)
+        cfg["oneshot_path"] = f"golden_{name}"
+        bank = make_bank(**{"sample_rate": cfg["sample_rate"], **bank_kw})
+        nested = bank.to_nested()
+        segs = segments_for(cfg, n, ev_seed)
+        ref = ref_harness.make_synth(cfg, nested)
+        random.seed(py_seed)
+        torch.manual_seed(torch_seed)
+        ref_wavs, plugins = [], []
+        for s in segs:
+            fx.CALLS.clear()
+            ref_wavs.append(ref(s if len(s) else []).numpy())
+            plugins.append(sum({"Reverb": 1, "Compressor": 2, "Limiter": 4}[c[0]] for c in fx.CALLS))
+        random.seed(py_seed)
+        torch.manual_seed(torch_seed)
+        traces, ora_wavs, boards = [], [], []
+        for s in segs:
+            t = []
+            ora_wavs.append(synth_oracle.render(s, cfg, nested, trace=t, boards=boards) if len(s) else
+                            synth_oracle.render(s, cfg, nested))
+            if not len(s):
+                boards.append(None)
+            traces.append(t)
+        assert [len(w) for w in ref_wavs] == [len(w) for w in ora_wavs], name
+        wav_err = max(float(np.abs(a - b).max()) for a, b in zip(ref_wavs, ora_wavs))
+        assert wav_err < 1e-6, (name, wav_err)
+        flags = [0 if b is None else sum({"Reverb": 1, "Compressor": 2, "Limiter": 4}[p[0]] for p in b) for b in boards]
+        assert flags == plugins, (flags, plugins)
+        batch = synth_oracle.collate(ref_wavs)
+        mel_mod = ref_harness.make_mel(cfg["sample_rate"], cfg["win_length"], cfg["time_res"], 128)
+        ref_mel = mel_mod(torch.from_numpy(batch)).numpy()
+        name_to_id = {nm: i for i, nm in enumerate(bank.names)}
+        flat = [(si, t["start"], t["len"], name_to_id[t["main"]], name_to_id[t["sub"]], t["pitch"])
+                for si, tr in enumerate(traces) for t in tr]
+        np.savez_compressed(
+            os.path.join(OUT, f"{name}.npz"),
+            cfg_keys=np.array(sorted(k for k in cfg if k != "oneshot_path")),
+            cfg_vals=np.array([repr(cfg[k]) for k in sorted(cfg) if k != "oneshot_path"]),
+            py_seed=py_seed, torch_seed=torch_seed,
+            bank_pcm=bank.pcm, bank_offsets=bank.offsets, bank_lengths=bank.lengths, bank_names=np.array(bank.names),
+            notes=np.concatenate([s.reshape(-1, 4) for s in segs]).astype(np.float32),
+            notes_count=np.array([len(s) for s in segs]),
+            ref_wav=np.concatenate(ref_wavs), ref_len=np.array([len(w) for w in ref_wavs]),
+            trace=np.array(flat, np.int64).reshape(-1, 6),
+            trace_mixup=np.array([t["mixup"] for tr in traces for t in tr], np.float64),
+            ref_mel=ref_mel, fx_flags=np.array(plugins, np.int32),
+        )
+        print(f"{name}: {n} segments, plugins per segment {plugins}, oracle-vs-reference wav {wav_err:.2e}")
+
+
 if __name__ == "__main__":
     import sys
-    if "--audio-front-only" in sys.argv:
+    if "--fx-only" in sys.argv:
+        make_fx()
+    elif "--audio-front-only" in sys.argv:
         make_audio_front()
     elif "--tokens-only" in sys.argv:
         make_tokens()
@@ -207,3 +278,4 @@ if __name__ == "__main__":
         main()
         make_audio_front()
         make_tokens()
+        make_fx()

@@ -103,6 +103,18 @@ def _import_reference():
     return synth, model
 
 
+def enable_fx_stand_in():
+    """Let the UNMODIFIED reference run with ``use_fx_prob > 0``: the names ``modules.synthetiser`` imported from
+    ``pedalboard`` (``synthetiser.py:11``) are pointed at the recording stand-in of ``oracle/fx_oracle.py`` - plugin
+    classes that log their constructor arguments and, when the board is called, run the CPU restatement of the JUCE
+    DSP.  Nothing in the reference tree is touched; returns ``fx_oracle`` (its ``CALLS`` list is the log)."""
+    from . import fx_oracle
+    synth, _ = _import_reference()
+    for name in ("Pedalboard", "Reverb", "Compressor", "Limiter"):
+        setattr(synth, name, getattr(fx_oracle, name))
+    return fx_oracle
+
+
 def register_bank(oneshot_path: str, sample_rate: int, nested: dict) -> None:
     """Make ``f"{oneshot_path}@{sample_rate}.hdf5"`` resolve to ``nested`` (synthetiser.py:163)."""
     _BANKS[f"{oneshot_path}@{sample_rate}.hdf5"] = nested

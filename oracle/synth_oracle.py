@@ -1,4 +1,5 @@
-"""CPU restatement of the reference synthetiser (FX off) in NumPy float32.
+"""CPU restatement of the reference synthetiser in NumPy float32 (FX chain: the reference's draws and position, DSP from
+``oracle/fx_oracle.c`` - parity of that DSP with pedalboard is unpinned, see there).
 
 TEST INFRASTRUCTURE ONLY - see oracle/__init__.py.  Pinned against the running
 reference by tests/test_oracle_vs_reference.py (container) and against the
@@ -46,10 +47,54 @@ def vel_to_vol(v, dt):
     return dt(dt(0.1) + dt(dt(dt(0.9) * dt(dt(np.power(dt(6), x)) - dt(1))) / dt(5)))
 
 
-def render(notes, cfg: dict, bank: dict, rng=_random, trace: list | None = None) -> np.ndarray:
+def _normal(std, mean, high, low, generator=None):
+    """utils/utils.py:266-269 ``draw_from_normal_distribution``, the same torch calls."""
+    import torch
+    z = torch.randn(1, generator=generator)
+    return torch.clamp(torch.clamp(z * std + mean, -1.0, 1.0).abs() * high, low, high).item()
+
+
+def draw_board(cfg: dict, rng=_random, generator=None) -> list:
+    """``BoardChain.get_board`` (:81-87) -> ``[(plugin name, kwargs)]`` in board order; ``rng`` is the ``random``
+    stream (coins, reverb), ``generator`` torch's (compressor, limiter; None = the global one)."""
+    board = []
+    if rng.random() < cfg["use_reverb_prob"]:                                          # :44-61
+        room, damping, wet = rng.uniform(0.2, 0.8), rng.uniform(0.2, 0.8), rng.uniform(0.1, 0.4)
+        dry, width = 1 - wet, rng.uniform(0.6, 1.0)
+        board.append(("Reverb", dict(room_size=room, damping=damping, wet_level=wet, dry_level=dry, width=width)))
+    if rng.random() < cfg["use_compression_prob"]:                                     # :63-75
+        thr = -_normal(0.15, 0.5, 10, 0, generator)
+        ratio = _normal(0.15, 0.5, 10, 1.0, generator)
+        attack = _normal(0.05, 0.1, 1000, 0, generator)
+        release = _normal(0.15, 0.2, 1000, 0, generator)
+        board.append(("Compressor", dict(threshold_db=thr, ratio=ratio, attack_ms=attack, release_ms=release)))
+    if rng.random() < cfg["use_limiter_prob"]:                                         # :77-79
+        board.append(("Limiter", dict(threshold_db=-_normal(0.2, 0.4, 3, 0, generator))))
+    return board
+
+
+def apply_board(wav: np.ndarray, board: list, sample_rate: int) -> np.ndarray:
+    """``_add_fx`` (:121-137) with the FX oracle's DSP (``oracle/fx_oracle.c``; parity with pedalboard unpinned)."""
+    from . import fx_oracle
+    for name, kw in board:
+        kw = {k: float(np.float32(v)) for k, v in kw.items()}                          # pybind: python float -> C++ float
+        if name == "Reverb":
+            wav = fx_oracle.reverb(wav, sample_rate, kw["room_size"], kw["damping"], kw["wet_level"], kw["dry_level"],
+                                   kw["width"])
+        elif name == "Compressor":
+            wav = fx_oracle.compressor(wav, sample_rate, kw["threshold_db"], kw["ratio"], kw["attack_ms"], kw["release_ms"])
+        else:
+            wav = fx_oracle.limiter(wav, sample_rate, kw["threshold_db"])
+    return wav
+
+
+def render(notes, cfg: dict, bank: dict, rng=_random, trace: list | None = None, raw: bool = False, generator=None,
+           boards: list | None = None):
     """``SynthDrum(cfg)(notes)`` -> float32 waveform.  ``bank[pitch][group][name]`` is the
     HDF5 tree as nested dicts.  If ``trace`` is a list, one dict per note is appended
-    (start, copy length, chosen paths, mixup, volume) for the bit-exact index checks."""
+    (start, copy length, chosen paths, mixup, volume) for the bit-exact index checks.
+    ``raw``: stop before the FX coin and return ``(instrument sum, max_volume)``.  With ``use_fx_prob > 0`` a coin hit
+    draws the board like the reference and applies the FX oracle; ``boards`` (a list) receives the board or None."""
     sr = cfg["sample_rate"]
     if len(notes) == 0:
         return np.zeros(int(cfg["input_sec"] * sr), np.float32)                       # :257-258
@@ -101,8 +146,14 @@ def render(notes, cfg: dict, bank: dict, rng=_random, trace: list | None = None)
     for inst, trk in tracks.items():
         key = inst if cfg["ADTOF_mapping"] else _CLASS[inst]
         wav += trk * np.float32(_GAIN[_LABEL[key]])
-    if rng.random() < cfg["use_fx_prob"]:
-        raise NotImplementedError("pedalboard FX chain is outside the oracle (no pedalboard here)")
+    if raw:
+        return wav, np.float32(vel_to_vol(vmax, dt))
+    board = None
+    if rng.random() < cfg["use_fx_prob"]:                                              # :154
+        board = draw_board(cfg, rng, generator)
+        wav = apply_board(wav, board, sr)
+    if boards is not None:
+        boards.append(board)
     with np.errstate(invalid="ignore", divide="ignore"):
         return (wav / np.abs(wav).max() * np.float32(vel_to_vol(vmax, dt))).astype(np.float32)
 

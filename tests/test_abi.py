@@ -33,9 +33,10 @@ def test_every_declared_symbol_is_exported(lib):
 def test_struct_sizes_match_numpy_views():
     from adt_str_b200.planner import EVENT_DTYPE, PEAK_ITEM_DTYPE, SEGMENT_DTYPE
     assert EVENT_DTYPE.itemsize == 32 and SEGMENT_DTYPE.itemsize == 16 and PEAK_ITEM_DTYPE.itemsize == 40
-    assert C.sizeof(_lib.Plan) == 5 * 8 + 4 * 4 + 8 + 8 + 8 + 4 + 4 + 8 + 8   # n_tile_events + padding
-    from adt_str_b200.planner import CHUNK_DTYPE, MEL_ROW_DTYPE
-    assert MEL_ROW_DTYPE.itemsize == 16 and CHUNK_DTYPE.itemsize == 12
+    # ... + (n_tile_events, n_fx) + fx_dev + (sample_rate + padding)
+    assert C.sizeof(_lib.Plan) == 5 * 8 + 4 * 4 + 8 + 8 + 8 + 4 + 4 + 8 + 8 + 8 + 8
+    from adt_str_b200.planner import CHUNK_DTYPE, FX_DTYPE, MEL_ROW_DTYPE
+    assert MEL_ROW_DTYPE.itemsize == 16 and CHUNK_DTYPE.itemsize == 16 and FX_DTYPE.itemsize == 48
 
 
 def test_version_and_argument_errors_without_a_device(lib):
@@ -43,14 +44,16 @@ def test_version_and_argument_errors_without_a_device(lib):
     assert lib.adtfe_render_workspace_bytes(10, 2, 30, 70) >= 10 * 48 + 2 * 30 * 4 + 70 * 32
     assert lib.adtfe_render_workspace_bytes(-1, 2, 30, 70) == 0
     shape = _lib.Plan(None, None, None, None, None, 100, 4, 31, 9, 63488)
-    off = (C.c_size_t * 6)()
+    off = (C.c_size_t * 7)()
     total = C.c_size_t()
     assert lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(total)) == 0
-    assert list(off)[:3] == [0, 3200, 3264] and all(o % 16 == 0 for o in off) and total.value == off[5]
-    assert off[4] - off[3] == 368 and off[5] == off[4]          # no mel rows section without batches
+    assert list(off)[:3] == [0, 3200, 3264] and all(o % 16 == 0 for o in off) and total.value == off[6]
+    assert off[4] - off[3] == 368 and off[6] == off[5] == off[4]   # no mel rows / FX sections without batches / FX
     shape.mel_total_rows = 1000
+    shape.n_fx = 3
     assert lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(total)) == 0
     assert off[5] - off[4] == 4 * 16                            # one adtfe_mel_row per segment
+    assert off[6] - off[5] == 3 * 48                            # one adtfe_fx per segment with an FX chain
     assert lib.adtfe_plan_blob_layout(None, C.byref(off), C.byref(total)) == -1
     assert b"null" in lib.adtfe_last_error()
     # null handles are rejected before any CUDA call

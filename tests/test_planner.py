@@ -96,8 +96,8 @@ def test_invalid_notes_raise_like_the_reference():
         planner.plan_segment([[0.3, 0.2, 36, 100]], setting_1(), bank)      # offset < onset
     with pytest.raises(IndexError):                                         # pitch 61 has no one-shots: choice([])
         planner.plan_segment([[0.1, 0.2, 61, 100]], setting_1(), bank)
-    with pytest.raises(NotImplementedError):
-        planner.plan_segment([[0.1, 0.2, 36, 100]], setting_1(use_fx_prob=1.0), bank)
+    fx = planner.plan_segment([[0.1, 0.2, 36, 100]], setting_1(use_fx_prob=1.0, use_reverb_prob=1.0), bank).fx
+    assert fx is not None and int(fx["flags"][0]) & planner.FX_REVERB      # an FX coin hit is planned, not refused
     with pytest.raises(KeyError):                                           # ADTOF mode expects class pitches
         planner.plan_segment([[0.1, 0.2, 36, 100]], setting_1(ADTOF_mapping=True), bank)
 
@@ -227,8 +227,9 @@ def test_native_planner_errors_and_fallback():
         npl.plan_batch([np.array([[0.1, 0.2, 61, 100]], np.float32)])
     with pytest.raises(KeyError):
         NativePlanner(setting_1(ADTOF_mapping=True), bank).plan_batch([ok])
-    with pytest.raises(NotImplementedError):
-        NativePlanner(setting_1(use_fx_prob=1.0), bank).plan_batch([ok])
+    fx = NativePlanner(setting_1(use_fx_prob=1.0, use_limiter_prob=1.0), bank).plan_batch([ok, ok]).fx
+    assert len(fx) == 2 and fx["seg"].tolist() == [0, 1] and (fx["flags"] & planner.FX_LIMITER).all()
+    assert np.isfinite(fx["lim_threshold_db"]).all()          # the torch draws were filled in
     # float64 notes take the Python path (float64 index arithmetic, like torch.tensor(float64 array))
     random.seed(1)
     p64 = npl.plan_batch([np.array([[0.5, 2.5, 36.0, 100.0]], np.float64)])
@@ -269,11 +270,11 @@ def test_batches_in_one_plan_match_plans_one_by_one():
         rows = big.mel_rows[s0:s0 + p.n_seg]
         assert np.array_equal(rows["count"], np.full(p.n_seg, t))
         assert np.array_equal(rows["out_row"], r0 + t * np.arange(p.n_seg))
-        assert tuple(big.chunks[b]) == (s0, e0, pw0)
+        assert tuple(big.chunks[b]) == (s0, e0, pw0, 0)            # (seg, event, peak_work, fx_row): no FX here
         pw = big.peak_work[pw0:pw0 + len(p.peak_work)]
         assert np.array_equal(pw["first_event"], p.peak_work["first_event"] + e0)
         e0 += p.n_events; r0 += t * p.n_seg; pw0 += len(p.peak_work); s0 += p.n_seg
-    assert tuple(big.chunks[-1]) == (14, big.n_events, len(big.peak_work)) and big.mel_total_rows == r0
+    assert tuple(big.chunks[-1]) == (14, big.n_events, len(big.peak_work), 0) and big.mel_total_rows == r0
     with pytest.raises(ValueError):
         big.set_batches([7, 6], mel.n_frames)
 
@@ -295,32 +296,44 @@ def test_native_group_pack_equals_python_set_batches_and_pack():
     cuts = [0, 9, 10, 26, 33, 41, 58, 70]
     group = [segs[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
     mel = ComputeMelSpectrogram(24000, 2048, 0.01, 128)
-    planner = NativePlanner(setting_1(), bank)
+    import torch
+    from adt_str_b200.planner import FX_DTYPE, fill_fx_normals
     lib = _lib.load()
-    for chunk_batches in (1, 2, 3, 100):
+    for cfg, chunk_batches in [(setting_1(), 1), (setting_1(), 2), (setting_1(), 3), (setting_1(), 100),
+                               (setting_1(use_fx_prob=0.5), 2), (setting_1(use_fx_prob=1.0, use_reverb_prob=1.0), 3)]:
+        planner = NativePlanner(cfg, bank)
         rng = random.Random(555)
+        torch.manual_seed(9)
         want = planner.plan_batch([n for b in group for n in b], rng).set_batches([len(b) for b in group], mel.n_frames,
                                                                                  chunk_batches)
         mt = np.array(random.Random(555).getstate()[1], np.uint32)
         counts = planner.plan_group(group, mt)
         assert tuple(mt.tolist()) == rng.getstate()[1]
         assert int(counts[0]) == want.n_events and int(counts[6]) == want.ld_wav
-        rc, shape, need, chunks, width, frames = planner.pack_group([len(b) for b in group], 240, mel.window_pad_idxs,
-                                                                    chunk_batches, None, 0)
+        assert int(counts[8]) == (0 if want.fx is None else len(want.fx)) and (cfg.use_fx_prob == 0) == (want.fx is None)
+        rc, shape, need, chunks, width, frames, fx_off = planner.pack_group([len(b) for b in group], 240,
+                                                                            mel.window_pad_idxs, chunk_batches, None, 0)
         assert rc == -3 and need > 0                               # size query
         blob = np.full(need + 64, 0xAB, np.uint8)
-        rc, shape, need2, chunks, width, frames = planner.pack_group([len(b) for b in group], 240,
-                                                                     mel.window_pad_idxs, chunk_batches,
-                                                                     blob.ctypes.data, blob.size)
+        rc, shape, need2, chunks, width, frames, fx_off = planner.pack_group([len(b) for b in group], 240,
+                                                                             mel.window_pad_idxs, chunk_batches,
+                                                                             blob.ctypes.data, blob.size)
         assert rc == 0 and need2 == need
         assert width.tolist() == want.batch_samples.tolist() and frames.tolist() == want.batch_frames.tolist()
         assert shape.mel_total_rows == want.mel_total_rows and shape.mel_max_count == int(want.batch_frames.max())
-        assert shape.n_chunks == len(want.chunks) - 1
+        assert shape.n_chunks == len(want.chunks) - 1 and shape.sample_rate == 24000
+        assert shape.n_tile_events == len(want.tile_events)
         assert chunks.view(CHUNK_DTYPE)[: shape.n_chunks + 1].tolist() == want.chunks.tolist()
-        off = (C.c_size_t * 6)()
+        off = (C.c_size_t * 7)()
         fixed = C.c_size_t()
         assert lib.adtfe_plan_blob_layout(C.byref(shape), C.byref(off), C.byref(fixed)) == 0
-        for o, arr in zip(off, (want.events, want.segments, want.tile_ptr, want.peak_work, want.mel_rows,
+        fx = want.fx if want.fx is not None else np.zeros(0, FX_DTYPE)
+        if len(fx):   # the blob's FX records wait for the torch draws: the same generator state fills them identically
+            assert off[5] == fx_off
+            torch.manual_seed(9)
+            fill_fx_normals(blob[fx_off: fx_off + 48 * len(fx)].view(FX_DTYPE))
+            assert want.chunks["fx_row"][-1] == len(fx) and (np.diff(want.chunks["fx_row"]) >= 0).all()
+        for o, arr in zip(off, (want.events, want.segments, want.tile_ptr, want.peak_work, want.mel_rows, fx,
                                 want.tile_events)):
             raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
             assert np.array_equal(blob[o: o + raw.size], raw)
