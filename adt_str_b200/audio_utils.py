@@ -28,7 +28,11 @@ from . import _lib
 def sinc_resample_kernel(orig_freq: int, new_freq: int, lowpass_filter_width: int = 6, rolloff: float = 0.99,
                          resampling_method: str = "sinc_interp_hann", beta: Optional[float] = None
                          ) -> Tuple[torch.Tensor, int]:
-    """``(kernel (new/gcd, 1, 2*width + orig/gcd) float32, width)`` - what ``T.Resample`` caches."""
+    """``(kernel (new/gcd, 1, 2*width + orig/gcd) float32, width)`` - what ``T.Resample`` caches.
+
+    This restates ``torchaudio.functional.functional._get_sinc_resample_kernel`` operation for operation (the buffer has
+    to be bit-identical to the one in existing state dicts).  torchaudio is BSD 2-Clause licensed, Copyright (c) 2017
+    Facebook Inc. (Soumith Chintala); redistribution of this derived function keeps that notice."""
     if not (int(orig_freq) == orig_freq and int(new_freq) == new_freq):
         raise Exception("Frequencies must be of integer type to ensure quality resampling computation.")
     if resampling_method not in ("sinc_interp_hann", "sinc_interp_kaiser"):

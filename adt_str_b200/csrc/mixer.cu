@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_seg
     const int tile_id = blockIdx.x, tid = threadIdx.x;
     const int seg = tile_id / tiles_per_seg, lo = (tile_id - seg * tiles_per_seg) * ADTFE_TILE;
     const adtfe_segment sg = segments[seg];
-    if (sg.flags == 0 || lo >= sg.len) return;
+    if ((sg.flags & 1) == 0 || lo >= sg.len) return;   // 0: empty row; ADTFE_SEG_RAW: the caller wants the raw mix
     float peak = 0.0f;
     // one maximum per warp tile of the mixer (kSub per host tile)
     for (int t = tid & 31; t < tiles_per_seg * kSub; t += 32)

@@ -41,6 +41,14 @@ class FrontEnd:
         ``(wav (B, Lmax), mel (B, T, n_mels))`` on the device."""
         dev = self.synth.device
         n_samples = int(plan.wave_lengths.max()) if plan.n_seg else 0
+        if plan.fx is not None and len(plan.fx) and self.synth.fx_backend == "pedalboard":
+            # the FX chain runs on the host (the reference's own library): render, FX, then the log-mel per batch
+            full = self.synth.render_plan(plan)
+            if plan.mel_rows is None:
+                return full[:, :n_samples], self.mel(full[:, :n_samples])
+            parts = [self.mel(full[int(plan.batch_ptr[b]):int(plan.batch_ptr[b + 1]), :int(plan.batch_samples[b])])
+                     for b in range(len(plan.batch_frames))]
+            return full[:, :n_samples], torch.cat([p.reshape(-1, p.shape[-1]) for p in parts])
         with torch.cuda.device(dev):
             bank = self.synth.device_bank()
             native = self.mel._handle(dev)

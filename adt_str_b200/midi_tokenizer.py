@@ -10,7 +10,6 @@ with the literal 1 and shortens the longest lengths by one; all of that is kept.
 """
 from __future__ import annotations
 
-from collections import defaultdict
 from dataclasses import dataclass
 from typing import List, Sequence
 
@@ -128,34 +127,47 @@ class MidiTokenizer:
 
     # ---- midi_tokenizer.py:69-103
     def decode(self, tokens):
-        onsets = defaultdict(float)
-        pitches = defaultdict(float)
-        velocities = defaultdict(float)
-        notes = []
-        for i, token in enumerate(tokens):
-            if token in [self.BOS_token, self.EOS_token]:
-                continue
-            if token < PITCH_OFFSET and token >= TIME_OFFSET:
-                onsets[i] = (token - TIME_OFFSET) / 100
-            elif token >= PITCH_OFFSET and token < VELOCITY_OFFSET:
-                pitch = token - PITCH_OFFSET
-                if self.ADTOF_mapping:
-                    pitch = self.ADTOF_map[pitch]
-                if i - 1 not in onsets:
-                    continue
-                pitches[i - 1] = pitch
-            elif token >= VELOCITY_OFFSET:
-                velocity = token - VELOCITY_OFFSET
-                if i - 2 not in onsets:
-                    continue
-                velocities[i - 2] = velocity
-        if len(velocities.keys()) == 0:
-            velocities = defaultdict(float)
-            for i in range(len(onsets)):
-                velocities[i] = 100
-        for onset, pitch, velocity in zip(onsets.values(), pitches.values(), velocities.values()):
-            notes.append([onset, onset + 0.1, pitch, velocity])
-        return torch.tensor(notes)
+        """Token sequence -> ``(n, 4)`` rows ``[onset, onset + 0.1, pitch, velocity]``, as array operations.
+
+        What the reference's loop does, stated as masks: a token in ``[TIME_OFFSET, PITCH_OFFSET)`` at position ``i``
+        opens an onset; a pitch token counts only when position ``i - 1`` holds a time token, a velocity token only when
+        ``i - 2`` does; BOS / EOS never count.  The three accepted streams are then paired IN ORDER and cut to the
+        shortest (``zip`` over the dict values) - not matched by position - and without any accepted velocity every
+        note gets 100.  Result dtypes follow what ``torch.tensor`` makes of the reference's per-token arithmetic:
+        float tokens keep their dtype, integer tensors give float32, integer NumPy arrays float64, Python numbers
+        float32 (double arithmetic, rounded once)."""
+        if isinstance(tokens, torch.Tensor):
+            arr, kind = tokens.detach().cpu().numpy(), "torch"
+        elif isinstance(tokens, np.ndarray):
+            arr, kind = tokens, "numpy"
+        else:
+            arr, kind = np.asarray(list(tokens)), "python"
+        arr = arr.reshape(-1)
+        special = (arr == self.BOS_token) | (arr == self.EOS_token)
+        is_time = ~special & (arr >= TIME_OFFSET) & (arr < PITCH_OFFSET)
+        before = lambda k: np.concatenate([np.zeros(min(k, len(arr)), bool), is_time[: max(len(arr) - k, 0)]])  # noqa: E731
+        pitch_ok = ~special & (arr >= PITCH_OFFSET) & (arr < VELOCITY_OFFSET) & before(1)
+        vel_ok = ~special & (arr >= VELOCITY_OFFSET) & before(2)
+        if arr.dtype.kind == "f":
+            work = arr.dtype                                   # tensor / NumPy-scalar arithmetic stays in the tokens' dtype
+        elif kind == "torch":
+            work = np.dtype(np.float32)                        # integer tensor / 100 -> torch's default float
+        else:
+            work = np.dtype(np.float64)                        # np.int64 / 100 and python int / 100 are doubles
+        onset = (arr[is_time].astype(work) - work.type(TIME_OFFSET)) / work.type(100)
+        pitch = arr[pitch_ok].astype(work) - work.type(PITCH_OFFSET)
+        if self.ADTOF_mapping and len(pitch):
+            if kind == "torch":
+                raise KeyError(tokens[int(np.flatnonzero(pitch_ok)[0])] - PITCH_OFFSET)   # a tensor is not a key of the map
+            pitch = np.array([self.ADTOF_map[int(v)] if float(v).is_integer() else self.ADTOF_map[v] for v in pitch], work)
+        velocity = arr[vel_ok].astype(work) - work.type(VELOCITY_OFFSET) if vel_ok.any() else np.full(len(onset), 100, work)
+        n = min(len(onset), len(pitch), len(velocity))
+        if n == 0:
+            return torch.tensor([])
+        rows = np.stack([onset[:n], onset[:n] + work.type(0.1), pitch[:n], velocity[:n]], axis=1)
+        if kind == "python":
+            rows = rows.astype(np.float32)                     # torch.tensor(list of python floats)
+        return torch.from_numpy(np.ascontiguousarray(rows))
 
     def batch_decode(self, tokens):
         return [self.decode(token) for token in tokens]

@@ -151,6 +151,10 @@ class SynthDrum:
         self._device_bank: Optional[DeviceBank] = None
         self._buffers: Optional[PlanBuffers] = None
         self._native_planner = None
+        #: who runs the FX chain of segments whose FX coin hit (``use_fx_prob``): "gpu" - the kernels of csrc/fx.cu
+        #: (the published JUCE algorithms pedalboard wraps, everything stays on the device) - or "pedalboard": the
+        #: reference's own library on the host, for users who have it installed and want its exact DSP
+        self.fx_backend = "gpu"
 
     # ------------------------------------------------------------------ bank
     @property
@@ -207,8 +211,44 @@ class SynthDrum:
         return self.plan(flat, rng).set_batches([len(b) for b in batches], n_frames, chunk_batches)
 
     # ---------------------------------------------------------------- render
+    def _render_through_pedalboard(self, plan: RenderPlan, out: Optional[torch.Tensor]) -> torch.Tensor:
+        """``fx_backend = "pedalboard"``: the rows with an FX record are rendered RAW (ADTFE_SEG_RAW: no normalisation,
+        no GPU FX), brought to the host, sent through the plugins the reference builds (``_add_fx``,
+        synthetiser.py:121-137) with the parameters the plan drew, normalised like ``_normalize_audio(wav) * max_volume``
+        (:142-144, 156) and written back.  Slow (one round trip per batch) but it is the reference's own DSP."""
+        import copy
+        import pedalboard
+        raw = copy.copy(plan)
+        raw.segments = plan.segments.copy()
+        raw.segments["flags"][plan.fx["seg"]] = 2      # ADTFE_SEG_RAW
+        raw.fx = None
+        out = self.render_plan(raw, out)
+        sr = int(self.config.sample_rate)
+        for r in plan.fx:
+            seg, n = int(r["seg"]), int(plan.segments["len"][r["seg"]])
+            if plan.segments["flags"][seg] == 0:
+                continue
+            x = out[seg, :n].cpu().numpy()
+            board = pedalboard.Pedalboard([])
+            if r["flags"] & 1:
+                board.append(pedalboard.Reverb(room_size=float(r["room_size"]), damping=float(r["damping"]),
+                                               wet_level=float(r["wet_level"]), dry_level=float(r["dry_level"]),
+                                               width=float(r["width"]), freeze_mode=0.0))
+            if r["flags"] & 2:
+                board.append(pedalboard.Compressor(threshold_db=float(r["comp_threshold_db"]), ratio=float(r["comp_ratio"]),
+                                                   attack_ms=float(r["comp_attack_ms"]),
+                                                   release_ms=float(r["comp_release_ms"])))
+            if r["flags"] & 4:
+                board.append(pedalboard.Limiter(threshold_db=float(r["lim_threshold_db"])))
+            y = torch.from_numpy(np.asarray(board(x[None, :].T.astype(np.float32), sample_rate=sr)).T[0].copy())
+            y = y / y.abs().max() * float(plan.segments["max_volume"][seg])
+            out[seg, :n] = y.to(out.device)
+        return out
+
     def render_plan(self, plan: RenderPlan, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Enqueue one planned batch on the current stream -> (n_seg, ld_wav) float32 on the device."""
+        if plan.fx is not None and len(plan.fx) and self.fx_backend == "pedalboard":
+            return self._render_through_pedalboard(plan, out)
         dev = self.device
         bank = self.device_bank()
         with torch.cuda.device(dev):

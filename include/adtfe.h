@@ -71,10 +71,13 @@ typedef struct adtfe_event {
 /* One segment = one SynthDrum.__call__ (16 bytes). */
 typedef struct adtfe_segment {
     int32_t len;         /* wave_length in samples; the row is zero beyond it */
-    int32_t flags;       /* 0: no notes, all-zero row; 1: wav / max|wav| * max_volume */
+    int32_t flags;       /* 0: no notes, all-zero row; 1: wav / max|wav| * max_volume; ADTFE_SEG_RAW (2): the row keeps
+                          * the raw instrument sum (no normalisation) - for a caller that post-processes it itself */
     float max_volume;    /* vel_to_vol(max velocity) */
     int32_t first_event; /* index of the segment's first event */
 } adtfe_segment;
+
+#define ADTFE_SEG_RAW 2
 
 /* One work item of the peak pass (40 bytes): samples [chunk*ADTFE_PEAK_SPAN, (chunk+1)*ADTFE_PEAK_SPAN)
  * of the mixed one-shot shared by the notes first_event .. first_event+n_events-1 (one instrument of one

@@ -86,7 +86,7 @@ def test_fx_rows_in_batches_and_chunks_equal_single_calls():
         rows.append(synth.render_plan(p1)[0].clone())
     torch.cuda.synchronize()
     for s, row in enumerate(rows):
-        assert torch.equal(torch.nan_to_num(wav[s], nan=-7.0), torch.nan_to_num(row, nan=-7.0)), s
+        assert torch.equal(torch.nan_to_num(wav[s], nan=-7.0), torch.nan_to_num(row[: wav.shape[1]], nan=-7.0)), s
     # log-mel of the fused call = log-mel of the FX'd waveforms
     mel = fe.mel
     for (w_b, f_b) in plan.split(wav, feat):
@@ -135,3 +135,32 @@ def test_fx_kernels_against_the_oracle_on_this_box():
         want = synth_oracle.apply_board(raw, board, 24000)
         want = want / np.abs(want).max() * vol
         assert float(np.abs(got - want).max()) <= TOL, (b, float(np.abs(got - want).max()))
+
+
+def test_pedalboard_backend_routes_fx_rows_through_the_host_library():
+    """``SynthDrum.fx_backend = "pedalboard"``: raw rows (ADTFE_SEG_RAW) -> host -> the plugins the reference builds ->
+    normalise -> back.  With the stand-in pedalboard (same DSP as the fixtures) the result is the fixture's."""
+    import os
+    import sys
+    from conftest import GOLDEN_DIR
+    from oracle import fx_oracle
+    saved = sys.modules.get("pedalboard")
+    fx_oracle.install_pedalboard_stand_in()
+    try:
+        g = Golden("fx_24k")
+        z = np.load(os.path.join(GOLDEN_DIR, "fx_24k.npz"))
+        synth = _synth(g)
+        synth.fx_backend = "pedalboard"
+        random.seed(g.py_seed)
+        torch.manual_seed(int(z["torch_seed"]))
+        wav, lengths = synth.render_batch(g.segments)
+        wav = wav.cpu().numpy()
+        assert lengths.tolist() == g.ref_len.tolist()
+        for s, ref in enumerate(g.ref_wavs):
+            assert float(np.abs(wav[s, : len(ref)] - ref).max()) <= 1e-5, s   # rows without FX: the GPU mix; with FX: the same DSP
+            assert not wav[s, len(ref):].any()
+    finally:
+        if saved is None:
+            sys.modules.pop("pedalboard", None)
+        else:
+            sys.modules["pedalboard"] = saved
