@@ -5,7 +5,7 @@ from .config import SharedConfig, SynthDrumConfig, setting_1, config_default  # 
 from .bank import OneShotBank  # noqa: F401
 
 __all__ = ["SharedConfig", "SynthDrumConfig", "OneShotBank", "setting_1", "config_default",
-           "SynthDrum", "ComputeMelSpectrogram", "FrontEnd", "HostPipeline", "Resample", "LongFormFrontEnd", "MidiTokenizer", "MidiTokenizerConfig"]
+           "SynthDrum", "ComputeMelSpectrogram", "FrontEnd", "HostPipeline", "Resample", "LongFormFrontEnd", "MidiTokenizer", "MidiTokenizerConfig", "ProjectToMel"]
 
 
 def __getattr__(name):  # lazy: importing the package must not need the CUDA library
@@ -27,6 +27,9 @@ def __getattr__(name):  # lazy: importing the package must not need the CUDA lib
     if name == "LongFormFrontEnd":
         from .inference_front import LongFormFrontEnd
         return LongFormFrontEnd
+    if name == "ProjectToMel":
+        from .projection import ProjectToMel
+        return ProjectToMel
     if name in ("MidiTokenizer", "MidiTokenizerConfig"):
         from . import midi_tokenizer
         return getattr(midi_tokenizer, name)

@@ -21,6 +21,7 @@ EXPORTS = [
     "adtfe_trace_begin", "adtfe_trace_dump",
     "adtfe_planner_create", "adtfe_planner_destroy", "adtfe_planner_plan", "adtfe_planner_export", "adtfe_planner_pack_batches",
     "adtfe_planner_set_fx", "adtfe_planner_export_fx",
+    "adtfe_linear_create", "adtfe_linear_destroy", "adtfe_linear_forward",
 ]
 
 
@@ -82,6 +83,9 @@ def _declare(lib) -> None:
                                                C.POINTER(sz), C.POINTER(sz)]
     lib.adtfe_planner_set_fx.argtypes = [vp, C.c_double, C.c_double, C.c_double]
     lib.adtfe_planner_export_fx.argtypes = [vp, vp]
+    lib.adtfe_linear_create.argtypes = [i32, i32, vp, vp, C.c_int, C.POINTER(vp)]
+    lib.adtfe_linear_destroy.argtypes = [vp]
+    lib.adtfe_linear_forward.argtypes = [vp, vp, i64, vp, vp]
 
 
 def load():

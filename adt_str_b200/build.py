@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libadtfe.so")
-SOURCES = ["api.cu", "mixer.cu", "fx.cu", "logmel.cu", "resample.cu", "planner.cpp"]
+SOURCES = ["api.cu", "mixer.cu", "fx.cu", "logmel.cu", "project.cu", "resample.cu", "planner.cpp"]
 DEPS = SOURCES + ["common.cuh", "fft_gen.cuh", os.path.join("..", "..", "include", "adtfe.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false", "-Xcompiler", "-fPIC,-O2,-ffp-contract=off", "-shared"]

@@ -105,3 +105,11 @@ def install_mel(reference_model_module) -> None:
     existing checkpoints load strictly (``build_model.py:66``)."""
     from .mel import ComputeMelSpectrogram
     reference_model_module.ComputeMelSpectrogram = ComputeMelSpectrogram
+
+
+def install_projection(model) -> None:
+    """Swap ``model.project_to_mel`` (``nn.Linear(n_mels, d_query * nhead)``, ``model.py:224-226``) of a built
+    ``ADTModel`` for the tcgen05 ``ProjectToMel`` sharing the same parameters: state-dict keys, values and the
+    optimiser's parameter objects stay what they were."""
+    from .projection import ProjectToMel
+    model.project_to_mel = ProjectToMel.from_linear(model.project_to_mel)

@@ -18,6 +18,7 @@
  *   adtfe_render_logmel   both, back to back on one stream (train.py:52 H2D + model.py:248)
  *   adtfe_frontend_host   the same with HOST buffers: plan blob in, log-mel (and optionally
  *                         the waveform) out, copies included - the end-to-end entry
+ *   adtfe_linear_*        ADTModel.project_to_mel (model.py:224-226, 249): the bf16 Linear the log-mel feeds
  *   adtfe_resample* / adtfe_downmix / adtfe_peak_normalise
  *                         the audio front of eval and inference: utils/audio_utils.py:17-23
  *                         (resample = torchaudio.transforms.Resample, normalize = wav / max|wav|),
@@ -243,6 +244,20 @@ int adtfe_downmix(const float* x_dev, int32_t n_rows, int64_t ld, int64_t n, flo
 /* x / max|x| in place (IEEE division; an all-zero signal gives NaN like the reference's 0/0).  absmax_bits_dev:
  * one int32 of scratch; have_absmax != 0 when it already holds the bits of max|x| (from adtfe_resample). */
 int adtfe_peak_normalise(float* x_dev, int64_t n, int32_t* absmax_bits_dev, int32_t have_absmax, void* stream);
+
+/* ---- project_to_mel (the layer behind the log-mel) ------------------------------------- */
+/* nn.Linear(n_mels, d_query * nhead) of the reference model (model.py:224-226), applied to the log-mel at
+ * model.py:249 under bf16 autocast: out = bf16(bf16(x) @ bf16(W)^T + bf16(b)) with float32 accumulation - on the
+ * tcgen05 tensor cores, the cast of x fused in.  weight_host: (n_out, n_in) row-major float32 (nn.Linear.weight),
+ * bias_host: n_out floats or NULL.  n_in must be 128, n_out a multiple of 32 up to 768.  Synchronous. */
+typedef struct adtfe_linear adtfe_linear;
+int adtfe_linear_create(int32_t n_in, int32_t n_out, const float* weight_host, const float* bias_host, int device,
+                        adtfe_linear** out);
+int adtfe_linear_destroy(adtfe_linear* linear);
+/* x_dev: (n_rows, 128) float32, contiguous, 16-byte aligned - e.g. the (rows, n_mels) matrix adtfe_logmel writes;
+ * out_bf16_dev: (n_rows, n_out) bfloat16. */
+int adtfe_linear_forward(const adtfe_linear* linear, const float* x_dev, int64_t n_rows, void* out_bf16_dev,
+                         void* stream);
 
 /* ---- diagnostics ----------------------------------------------------------------------- */
 /* Launch trace: after adtfe_trace_begin every kernel launched by adtfe_render / adtfe_render_logmel is bracketed
