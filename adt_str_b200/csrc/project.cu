@@ -11,9 +11,11 @@
 // output row leaves through the epilogue once.
 //
 // One persistent CTA of 8 warps per SM.  Per tile of 128 rows:
-//   A      every thread converts half a row (64 floats, eight 16-byte groups) to bf16 and stores it into the K-major
-//          no-swizzle canonical layout: 8-row x 16-byte core matrices, rows of a k-group contiguous
-//          (offset(r, k) = (k / 8) * 2048 + r * 16 + (k % 8) * 2: LBO = 2048 B, SBO = 128 B)
+//   A      a warp instruction fetches one row (512 contiguous bytes), one tile AHEAD, behind the epilogue of the current
+//          one; each lane converts its four floats to bf16 and stores them into the K-major no-swizzle canonical
+//          layout: 8-row x 16-byte core matrices, rows of a k-group contiguous
+//          (offset(r, k) = (k / 8) * 2064 + r * 16 + (k % 8) * 2: LBO = 2064 B - 16 B of padding per k-group make the
+//          warp's stores conflict-free - SBO = 128 B)
 //   MMA    one thread issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = 256, K = 16) eight times per 256-column
 //          slab of the output, operands by shared-memory descriptors, D in tensor memory; three slabs for 768
 //          columns alternate between two 256-column TMEM stages; tcgen05.commit arrives on the stage's mbarrier
@@ -44,7 +46,9 @@ constexpr int kPM = 128;          // rows per tile = UMMA M
 constexpr int kPK = 128;          // n_mels
 constexpr int kPN = 256;          // columns per MMA slab = UMMA N (the last slab may be narrower)
 constexpr int kPThreads = 256;
-constexpr int kATileBytes = kPM * kPK * 2;   // 32 KB
+constexpr int kALbo = kPM * 16 + 16;         // bytes between the k-groups of the A tile: 2048 + 16, so that the 32 lanes of
+                                             // a warp (one row: 16 k-groups x 2 halves) store to 32 different banks
+constexpr int kATileBytes = 16 * kALbo;      // 32.25 KB
 
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     // cute::UMMA::SmemDescriptor: start address, leading / stride byte offsets (4 LSB dropped), version 1 (Blackwell),
@@ -84,8 +88,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&p);
@@ -97,9 +101,10 @@ __global__ void __launch_bounds__(kPThreads, 1) project_kernel(const float* __re
                                                                __nv_bfloat16* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* s_w = smem;                                     // n_out * 256 bytes
-    unsigned char* s_a = smem + (size_t)n_out * 256;               // 32 KB
+    unsigned char* s_a = smem + (size_t)n_out * 256;               // kATileBytes
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_a + kATileBytes);   // [0]: weight copy, [1], [2]: TMEM stages
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
+    __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(s_bar + 4);   // n_out bf16 (the bias is bf16 under autocast)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -108,6 +113,7 @@ __global__ void __launch_bounds__(kPThreads, 1) project_kernel(const float* __re
         mbar_init(s_bar + 2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    for (int i = tid; i < n_out; i += kPThreads) s_bias[i] = __float2bfloat16_rn(bias[i]);   // exact: rounded on the host
     if (warp == 0) {   // 512 columns of tensor memory: two stages of 256 float32 accumulator columns
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512)
                      : "memory");
@@ -139,36 +145,34 @@ __global__ void __launch_bounds__(kPThreads, 1) project_kernel(const float* __re
         const uint32_t d = tmem_base + (uint32_t)(j & 1) * kPN;
 #pragma unroll
         for (int ks = 0; ks < kPK / 16; ++ks) {
-            const uint64_t adesc = umma_desc(a_addr + (uint32_t)(2 * ks) * (kPM * 16), kPM * 16, 128);
+            const uint64_t adesc = umma_desc(a_addr + (uint32_t)(2 * ks) * kALbo, kALbo, 128);
             const uint64_t bdesc = umma_desc(w_addr + (uint32_t)(2 * ks) * w_lbo + (uint32_t)j * (kPN * 16), w_lbo, 128);
             umma_bf16(d, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
         }
         umma_commit(s_bar + 1 + (j & 1));
     };
 
+    // A tile in registers: iteration `it` of warp w is row it * 8 + w of the tile, lane l its float4 l - a whole row
+    // (512 contiguous bytes) per warp instruction.  Fetched one tile ahead, behind the epilogue of the current one.
+    float4 v[16];
+    auto fetch = [&](int64_t tile) {
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int64_t row = tile * kPM + it * 8 + warp;
+            v[it] = row < n_rows ? __ldg(reinterpret_cast<const float4*>(x + row * kPK) + lane)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    if ((int64_t)blockIdx.x < n_tiles) fetch(blockIdx.x);
+
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- A: 128 rows x 128 floats -> bf16, canonical layout.  Thread = (row, half of the k-groups).
-        {
-            const int r = tid & (kPM - 1), half = tid >> 7;
-            const int64_t row = tile * kPM + r;
-            const float4* src = reinterpret_cast<const float4*>(x + row * kPK) + half * 16;
-            float4 v[16];
-            if (row < n_rows) {
+        // ---- A: float32 -> bf16 into the canonical layout: k-group lane / 2, half lane % 2 of row it * 8 + warp
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = __ldg(src + i);
-            } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-                uint4 q;
-                q.x = pack_bf16(v[2 * g].x, v[2 * g].y);
-                q.y = pack_bf16(v[2 * g].z, v[2 * g].w);
-                q.z = pack_bf16(v[2 * g + 1].x, v[2 * g + 1].y);
-                q.w = pack_bf16(v[2 * g + 1].z, v[2 * g + 1].w);
-                *reinterpret_cast<uint4*>(s_a + (size_t)(half * 8 + g) * (kPM * 16) + r * 16) = q;
-            }
+        for (int it = 0; it < 16; ++it) {
+            uint2 q;
+            q.x = pack_bf16(v[it].x, v[it].y);
+            q.y = pack_bf16(v[it].z, v[it].w);
+            *reinterpret_cast<uint2*>(s_a + (size_t)(lane >> 1) * kALbo + (it * 8 + warp) * 16 + (lane & 1) * 8) = q;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to the tensor core
         __syncthreads();
@@ -181,6 +185,7 @@ __global__ void __launch_bounds__(kPThreads, 1) project_kernel(const float* __re
             issue_slab(0);
             if (n_slabs > 1) issue_slab(1);
         }
+        if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);   // the next tile's rows arrive behind the epilogue
         for (int j = 0; j < n_slabs; ++j) {
             const int stage = j & 1;
             mbar_wait(s_bar + 1 + stage, phase[stage]);
@@ -192,20 +197,33 @@ __global__ void __launch_bounds__(kPThreads, 1) project_kernel(const float* __re
                 const int q = warp & 3, chalf = warp >> 2;
                 const int64_t row = tile * kPM + q * 32 + lane;
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)stage * kPN;
-                for (int c0 = chalf * 128; c0 < min(cols, chalf * 128 + 128); c0 += 32) {
-                    uint32_t acc[32];
-                    tmem_ld32(taddr + (uint32_t)c0, acc);
+                // four chunks of 32 columns, software-pipelined: chunk k + 1 is on its way out of tensor memory while
+                // chunk k gets its bias, is rounded and stored
+                uint32_t acc[2][32];
+                const int c_lo = chalf * 128;
+                if (c_lo < cols) tmem_ld32(taddr + (uint32_t)c_lo, acc[0]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c0 = c_lo + 32 * k;
+                    if (c0 >= cols) break;                    // warp-uniform
+                    tmem_ld_wait();
+                    if (k < 3 && c0 + 32 < cols) tmem_ld32(taddr + (uint32_t)(c0 + 32), acc[(k + 1) & 1]);
+                    const uint32_t(&a)[32] = acc[k & 1];
                     if (row < n_rows) {
-                        const float4* b4 = reinterpret_cast<const float4*>(bias + j * kPN + c0);
+                        const uint4* b8 = reinterpret_cast<const uint4*>(s_bias + j * kPN + c0);   // 8 bf16 per load, broadcast
                         uint4* dst = reinterpret_cast<uint4*>(out + row * n_out + j * kPN + c0);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            const float4 ba = __ldg(b4 + 2 * i), bb = __ldg(b4 + 2 * i + 1);
+                            const uint4 b = b8[i];   // bf16 -> float32: the bits, shifted up
                             uint4 o;
-                            o.x = pack_bf16(__uint_as_float(acc[8 * i + 0]) + ba.x, __uint_as_float(acc[8 * i + 1]) + ba.y);
-                            o.y = pack_bf16(__uint_as_float(acc[8 * i + 2]) + ba.z, __uint_as_float(acc[8 * i + 3]) + ba.w);
-                            o.z = pack_bf16(__uint_as_float(acc[8 * i + 4]) + bb.x, __uint_as_float(acc[8 * i + 5]) + bb.y);
-                            o.w = pack_bf16(__uint_as_float(acc[8 * i + 6]) + bb.z, __uint_as_float(acc[8 * i + 7]) + bb.w);
+                            o.x = pack_bf16(__uint_as_float(a[8 * i + 0]) + __uint_as_float(b.x << 16),
+                                            __uint_as_float(a[8 * i + 1]) + __uint_as_float(b.x & 0xffff0000u));
+                            o.y = pack_bf16(__uint_as_float(a[8 * i + 2]) + __uint_as_float(b.y << 16),
+                                            __uint_as_float(a[8 * i + 3]) + __uint_as_float(b.y & 0xffff0000u));
+                            o.z = pack_bf16(__uint_as_float(a[8 * i + 4]) + __uint_as_float(b.z << 16),
+                                            __uint_as_float(a[8 * i + 5]) + __uint_as_float(b.z & 0xffff0000u));
+                            o.w = pack_bf16(__uint_as_float(a[8 * i + 6]) + __uint_as_float(b.w << 16),
+                                            __uint_as_float(a[8 * i + 7]) + __uint_as_float(b.w & 0xffff0000u));
                             dst[i] = o;
                         }
                     }
@@ -275,7 +293,7 @@ extern "C" int adtfe_linear_create(int32_t n_in, int32_t n_out, const float* wei
     }
     adtfe_linear* lin = new adtfe_linear();
     lin->device = device; lin->sm_count = device_sm_count(device); lin->n_in = n_in; lin->n_out = n_out;
-    lin->smem_bytes = (size_t)n_out * 256 + kATileBytes + 64;
+    lin->smem_bytes = (size_t)n_out * 256 + kATileBytes + 32 + (size_t)n_out * 2 + 32;
     if (cudaMalloc(&lin->w_image, image.size() * 2) != cudaSuccess ||
         cudaMemcpy(lin->w_image, image.data(), image.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMalloc((void**)&lin->bias, (size_t)n_out * 4) != cudaSuccess ||

@@ -39,3 +39,37 @@ def reduce_stats(units: float, elapsed_ms: float) -> Tuple[float, float]:
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(u.item()), float(t.item())
+
+
+def bind_to_local_cpus(device_index: int, rank: int = 0, world: int = 1):
+    """Pin this process to the CPUs that are local to its GPU (sysfs ``local_cpulist`` of the PCI device), and among
+    them to this rank's share when several ranks sit on the same node - BEFORE pinned host buffers are allocated, so
+    that first touch puts them on the GPU's NUMA node and the planner threads of different ranks do not compete for
+    cores.  Returns the CPU set chosen (None when sysfs gives nothing, e.g. in a container without the topology)."""
+    import os
+    import torch
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        text = open(f"/sys/bus/pci/devices/{bus}/local_cpulist").read().strip()
+    except Exception:
+        return None
+    cpus = set()
+    for part in text.split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif part.strip().isdigit():
+            cpus.add(int(part))
+    allowed = sorted(cpus & os.sched_getaffinity(0))
+    if not allowed:
+        return None
+    everything = len(allowed) == len(os.sched_getaffinity(0))
+    if world > 1 and everything and len(allowed) >= 2 * world:   # one node for all GPUs: an even share per rank
+        lo, hi = shard_range(len(allowed), rank, world)
+        allowed = allowed[lo:hi]
+    try:
+        os.sched_setaffinity(0, set(allowed))
+    except OSError:
+        return None
+    return allowed

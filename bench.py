@@ -330,9 +330,13 @@ def run_b200(args):
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_set = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
+        # each rank on the cores next to its GPU, before any pinned buffer exists (first touch = local memory)
+        from adt_str_b200.sharding import bind_to_local_cpus
+        cpu_set = bind_to_local_cpus(local, rank, world)
     synth = SynthDrum(setting_1(), bank=bank, device=dev)
     mel = ComputeMelSpectrogram(SR, 2048, 0.01, 128)
     fe = FrontEnd(synth, mel)
@@ -445,7 +449,7 @@ def run_b200(args):
     group = max(1, min(args.e2e_group, n_batches))
     groups = [batches[i:i + group] for i in range(0, n_batches, group)]
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    args.e2e_workers = args.e2e_workers or max(1, min(8, cores // max(1, world)))
+    args.e2e_workers = args.e2e_workers or max(1, min(8, cores if cpu_set else cores // max(1, world)))
     pipe = HostPipeline(fe, workers=args.e2e_workers, n_sets=args.e2e_sets, seed=99 + rank, chunk_batches=args.chunk_batches)
     h2d = d2h = 0
     e2e_checksum = 0.0
@@ -480,6 +484,20 @@ def run_b200(args):
     clocks = sampler.stop() if sampler else None
     pipe.close()
 
+    # ---- the copy ceiling of the end-to-end number: every rank moves one step's log-mel bytes device -> pinned host at
+    # the same time, nothing else running (no planning, no kernels) - what the host's links allow at this rank count
+    pin = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    srcb = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    n_copies = max(1, d2h // pin.numel())
+    pin.copy_(srcb, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_copies):
+        pin.copy_(srcb, non_blocking=True)
+    barrier()
+    d2h_ceiling_ms = 1e3 * (time.perf_counter() - t0) * (d2h / (n_copies * pin.numel()))
+    del pin, srcb
+
     # ---- BASELINE configs[4] beside the headline: the long-form inference front (tools/bench_longform.py)
     long_form = None
     if rank == 0 and world == 1 and not args.no_long_form:
@@ -494,6 +512,7 @@ def run_b200(args):
     from adt_str_b200.sharding import reduce_stats
     total_audio, max_ms = reduce_stats(audio_s_step * args.steps, elapsed_ms)
     total_audio_e2e, max_e2e_ms = reduce_stats(audio_s_step, e2e_ms)
+    _, max_ceiling_ms = reduce_stats(0.0, d2h_ceiling_ms)
     total_bytes, _ = reduce_stats(float(bytes_alg_step), 0.0)
     if rank != 0:
         if world > 1:
@@ -532,6 +551,12 @@ def run_b200(args):
         "clocks": clocks,
         "e2e": {"value": total_audio_e2e / (max_e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": max(1, args.e2e_steps),
+                "d2h_ceiling": {"value": total_audio_e2e / (max_ceiling_ms * 1e-3), "unit": UNIT,
+                                "ms_per_step": max_ceiling_ms, "gbs_per_rank": d2h / (max_ceiling_ms * 1e-3) / 1e9,
+                                "what": "the same log-mel bytes, device -> pinned host on every rank at once, nothing "
+                                        "else running: the host-link ceiling of e2e at this rank count"},
+                "frac_of_d2h_ceiling": max_ceiling_ms / max_e2e_ms,
+                "cpu_affinity": None if cpu_set is None else f"{len(cpu_set)} cores local to the GPU",
                 "includes": f"host planning of note lists ({args.e2e_workers} planner threads), plan blob H2D, kernels, "
                             f"log-mel D2H into pinned host memory; groups of {group} batches, {args.e2e_sets} buffer sets"},
         "gpu_launches": launches_per_step * args.steps,
