@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(32, kMixCtasPerSm) mix_kernel(const MixArgs a)
                 const float coef = sub ? coef_b : coef_a;
                 const int vhi = (int)(sub ? (vhi2 >> 16) : (vhi2 & 0xffffu));
                 const unsigned slot = seq % (unsigned)kDepth;
-                mbar_wait(bars + slot, (seq / (unsigned)kDepth) & 1u);
+                mbar_wait(bars + slot, (seq / (unsigned)kDepth) & 1u);   // (a suspend-time hint measures the same)
                 const float* src = ring + slot * kStageFloats + base + lane;
                 if (vlo == 0 && vhi == kWidth) {
                     const float2 c2 = make_float2(coef, coef);

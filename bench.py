@@ -508,6 +508,40 @@ def run_b200(args):
         except Exception as exc:  # never lose the headline line to the side measurement
             long_form = {"error": repr(exc)}
 
+    # ---- beside the headline: the stock training configuration has the FX chain ON (setting-1.yaml:58-61,
+    # use_fx_prob 0.3); the same render + log-mel with it, on 64 batches, next to the same 64 batches without
+    fx_side = None
+    proj_side = None
+    if rank == 0 and world == 1 and not args.no_long_form:
+        try:
+            nb = min(64, n_batches)
+            res = {}
+            for tag, prob in (("off", 0.0), ("on", 0.3)):
+                s2 = SynthDrum(setting_1(use_fx_prob=prob), bank=bank, device=dev)
+                s2._device_bank = synth.device_bank()                       # the same resident bank
+                fe2 = FrontEnd(s2, mel)
+                torch.manual_seed(7)
+                p2 = fe2.plan_batches(batches[:nb], random.Random(77), min(args.chunk_batches, 16))
+                b2 = PlanBuffers(dev)
+                b2._dplan = b2.upload(b2.pack(p2)); b2._resident = p2
+                w2, f2 = fe2._outputs(p2, 0)
+                res[tag] = time_loop(lambda: fe2.run_plan(p2, buffers=b2, wav=w2, feat=f2, upload=False), reps=3)
+                n_fx_rows = 0 if p2.fx is None else len(p2.fx)
+            fx_side = {"what": f"render + log-mel of {nb} batches with use_fx_prob = 0.3 (reverb / compressor / limiter kernels, "
+                               "csrc/fx.cu) against the same batches without FX",
+                       "ms_fx_off": res["off"], "ms_fx_on": res["on"], "segments_with_fx": n_fx_rows,
+                       "segments": nb * BATCH}
+        except Exception as exc:
+            fx_side = {"error": repr(exc)}
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_projection
+            proj_side = bench_projection.measure(dev, rows=int(n_frames_seg.sum()))
+            proj_side["single_batch"] = {k: v for k, v in bench_projection.measure(dev, rows=BATCH * 246, reps=20).items()
+                                         if k in ("rows", "ms", "library_ms", "speedup_vs_autocast_linear")}
+        except Exception as exc:
+            proj_side = {"error": repr(exc)}
+
     # ---- reduce over ranks: units add, time is the max
     from adt_str_b200.sharding import reduce_stats
     total_audio, max_ms = reduce_stats(audio_s_step * args.steps, elapsed_ms)
@@ -572,6 +606,8 @@ def run_b200(args):
         "cpu_baseline": cpu,
         "gpu_library_baseline": library,
         "long_form": long_form,
+        "fx_chain": fx_side,
+        "project_to_mel": proj_side,
     }
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
