@@ -18,9 +18,10 @@
 // fx_dynamics_kernel  lane = row (32 rows of the plan's FX list per warp).  An envelope follower
 //                     y = |x| + (|x| > y ? cAT : cRL)(y - |x|) has a data-dependent coefficient, so it cannot be
 //                     scanned: each lane walks its own row.  The three followers of the chain (compressor, limiter
-//                     stage 1, limiter stage 2) are SKEWED by one sample each - iteration n runs stage 1 on sample n,
-//                     stage 2 on sample n-1, stage 3 on sample n-2 - so the loop-carried dependency is one follower
-//                     (4 dependent instructions), not three followers and two pow() in series.  Disabled stages are
+//                     stage 1, limiter stage 2) are SKEWED by a block of four samples each - a trip runs stage 1 on
+//                     block b, stage 2 on block b-1, stage 3 on block b-2 - so the loop-carried dependency is one
+//                     follower (5 dependent instructions per sample), not three followers and two pow() in series, and
+//                     the pow() themselves are exp2(e * log2(x)) on the special-function unit.  Disabled stages are
 //                     the same code with an infinite threshold (gain 1), so rows with different chains share a warp.
 //                     The lane also tracks max|out| of its row: the row peak the normalisation needs.
 #include <math.h>
@@ -87,22 +88,31 @@ __global__ void __launch_bounds__(32) fx_reverb_kernel(const adtfe_segment* __re
         const float x = valid ? row[n0 + lane] : 0.0f;
         const float input = x * 0.015f;
         float out = 0.0f;
+        // the eight combs in lock step: their scans are independent chains of shuffles, interleaved they cost the
+        // latency of one
+        float* slot[8];
+        float y[8], v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             int idx = cpos[j] + lane;
             if (idx >= g.comb_size[j]) idx -= g.comb_size[j];
-            float* slot = s_delay + g.comb_off[j] + idx;
-            const float y = *slot;
-            // last[i] = y[i] (1 - damp) + damp last[i-1]: inclusive scan of v with ratio damp, then the carry
-            float v = y * one_minus_damp;
+            slot[j] = s_delay + g.comb_off[j] + idx;
+            y[j] = *slot[j];
+            v[j] = y[j] * one_minus_damp;   // last[i] = y[i] (1 - damp) + damp last[i-1]: inclusive scan with ratio damp
+        }
 #pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                const float t = __shfl_up_sync(0xffffffffu, v, 1 << k);
-                if (lane >= (1 << k)) v = fmaf(t, dpow[k], v);
+        for (int k = 0; k < 5; ++k) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = __shfl_up_sync(0xffffffffu, v[j], 1 << k);
+                if (lane >= (1 << k)) v[j] = fmaf(t, dpow[k], v[j]);
             }
-            float l = undenorm(fmaf(dcarry, last[j], v));
-            *slot = undenorm(__fadd_rn(input, __fmul_rn(l, feedback)));
-            out += y;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float l = undenorm(fmaf(dcarry, last[j], v[j]));   // + the carry of the previous step
+            *slot[j] = undenorm(__fadd_rn(input, __fmul_rn(l, feedback)));
+            out += y[j];
             last[j] = __shfl_sync(0xffffffffu, l, 31);
             cpos[j] += 32;
             if (cpos[j] >= g.comb_size[j]) cpos[j] -= g.comb_size[j];
@@ -139,14 +149,18 @@ __device__ __forceinline__ Follower make_follower(bool on, double exp_factor, fl
     return c;
 }
 
-// one sample through a stage: returns the stage's output, advances the follower
+// one sample through a stage: returns the stage's output, advances the follower.  The gain pow(env / thr, 1/ratio - 1)
+// is exp2(expo * log2(.)) on the special-function unit (relative error ~3e-7, far inside the waveform tolerance) and
+// branch-free, so that the three stages of the chain interleave: the loop-carried dependency is the follower alone.
 __device__ __forceinline__ float follower_step(Follower& c, float in) {
     const float rect = fabsf(in);
     const float cte = rect > c.y ? c.at : c.rl;
     const float env = __fadd_rn(rect, __fmul_rn(cte, c.y - rect));   // no contraction, like the x86 builds of JUCE
     c.y = env;
-    float gain = 1.0f;
-    if (!(env < c.thr)) gain = powf(env * c.thr_inv, c.expo);   // NaN envelopes take the pow branch, like the C++
+    float lg, p;   // the bare special-function instructions (no denormal / range fix-ups: the argument is a ratio >= 1)
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(env * c.thr_inv));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p) : "f"(c.expo * lg));
+    const float gain = env < c.thr ? 1.0f : p;                   // NaN envelopes take the pow value (NaN), like the C++
     return gain * in;
 }
 
@@ -173,22 +187,67 @@ __global__ void __launch_bounds__(32) fx_dynamics_kernel(const adtfe_segment* __
     }
     float* row = wav + (int64_t)seg * ld_wav;
     const int n = segments[seg].len;
-    float x2 = 0.0f, x3 = 0.0f;   // stage inputs handed from one iteration to the next (the skew)
     float peak = 0.0f;
-    for (int i = 0; i < n + 2; ++i) {
-        const float x1 = i < n ? row[i] : 0.0f;
-        const float y3 = follower_step(c3, x3);          // sample i - 2
-        const float n3 = follower_step(c2, x2);          // sample i - 1
-        const float n2 = follower_step(c1, x1);          // sample i
-        if (i >= 2) {
-            float v = y3 * out_gain;
-            v = v < -clip ? -clip : (v > clip ? clip : v);   // keeps NaN, like FloatVectorOperations::clip
-            if (lim_on || comp_on) row[i - 2] = v;
-            const float a = fabsf(v);
-            peak = (a != a || peak != peak) ? __int_as_float(0x7fc00000) : fmaxf(peak, a);   // torch.max keeps NaN
+    const bool rewrite = lim_on || comp_on;
+    // Four samples (one 16-byte load) per trip, the stages skewed by a whole trip: trip b runs stage 1 on block b,
+    // stage 2 on stage 1's output of block b - 1 and stage 3 on stage 2's output of block b - 2.  The three followers
+    // are then independent chains inside a trip (and the gains, off the chains, pipeline through the special-function
+    // unit); block b - 2 leaves as one aligned 16-byte store (the row starts on a 16-byte boundary: ld_wav % 4 == 0).
+    // The loads run a whole 128-byte line (eight trips) ahead: the in-place stores invalidate the line in L1, so
+    // every load is an L2 round trip - issued one line early it is never waited for.
+    float s1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, s2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const float4* row4 = reinterpret_cast<const float4*>(row);
+    const int n_blocks = (n + 3) / 4, pitch_blocks = (int)(ld_wav / 4);
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 cur[8], nxt[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) cur[t] = t < pitch_blocks ? row4[t] : zero4;
+    for (int line = 0; 8 * line < n_blocks + 2; ++line) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int blk = 8 * (line + 1) + t;
+            nxt[t] = blk < n_blocks && blk < pitch_blocks ? row4[blk] : zero4;
         }
-        x3 = n3;
-        x2 = n2;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const int b = 8 * line + t;
+            float xin[4] = {cur[t].x, cur[t].y, cur[t].z, cur[t].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (4 * b + k >= n) xin[k] = 0.0f;   // the row's padding is not part of the signal
+            float t1[4], t2[4], o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t1[k] = follower_step(c1, xin[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t2[k] = follower_step(c2, s1[k]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float v = follower_step(c3, s2[k]) * out_gain;
+                o[k] = v < -clip ? -clip : (v > clip ? clip : v);   // keeps NaN, like FloatVectorOperations::clip
+            }
+            if (b >= 2 && 4 * (b - 2) < n) {
+                const int s0 = 4 * (b - 2);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (s0 + k < n) {
+                        const float a = fabsf(o[k]);
+                        peak = (a != a || peak != peak) ? __int_as_float(0x7fc00000) : fmaxf(peak, a);   // torch.max keeps NaN
+                    }
+                }
+                if (rewrite) {
+                    if (s0 + 3 < n) reinterpret_cast<float4*>(row)[b - 2] = make_float4(o[0], o[1], o[2], o[3]);
+                    else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (s0 + k < n) row[s0 + k] = o[k];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { s1[k] = t1[k]; s2[k] = t2[k]; }
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) cur[t] = nxt[t];
     }
     // the normalisation takes the row peak from the tile maxima: this row's is now `peak`
     float* tm = tile_max + (size_t)seg * max_per_seg;
