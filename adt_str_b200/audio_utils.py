@@ -155,6 +155,20 @@ def resample(wav_seg: torch.Tensor, orig_sr: int, target_sr: int) -> torch.Tenso
     return Resample(orig_freq=orig_sr, new_freq=target_sr)(wav_seg)
 
 
+def load_and_resample(wav_file: str, target_sr: Optional[int], loader=None) -> torch.Tensor:
+    """utils/audio_utils.py:10-15: decode the file (``torchaudio.load``, on the host - or ``loader(path) -> (waveform
+    (channels, samples), sample_rate)``), channel mean, resample to ``target_sr`` (``None``: keep the rate).  Mean and
+    resampling run on the GPU; the result comes back where the decoded audio was (CPU), like the reference's."""
+    if loader is None:
+        import torchaudio
+        loader = torchaudio.load
+    wav_seg, orig_sr = loader(wav_file)
+    wav_seg = downmix(wav_seg)
+    if target_sr is None:
+        return wav_seg
+    return resample(wav_seg, int(orig_sr), int(target_sr))
+
+
 def normalize(wav_seg: torch.Tensor) -> torch.Tensor:
     """utils/audio_utils.py:22-23 - ``wav_seg / wav_seg.abs().max()`` (a new tensor; all-zero input gives NaN)."""
     src = wav_seg.device

@@ -120,3 +120,22 @@ class OneShotBank:
     @property
     def nbytes(self) -> int:
         return self.pcm.nbytes
+
+
+def _main(argv=None) -> int:
+    """``python -m adt_str_b200.bank <oneshot@SR.hdf5> <oneshot@SR.npz>``: the reference's HDF5 bank
+    (``data_modules/convert_augmented_to_hdf5.py:70-138``) -> the packed form ``SynthDrum`` loads.  Needs h5py (run it
+    where the bank was built)."""
+    import argparse
+    ap = argparse.ArgumentParser(prog="python -m adt_str_b200.bank", description=_main.__doc__)
+    ap.add_argument("hdf5")
+    ap.add_argument("npz")
+    args = ap.parse_args(argv)
+    bank = OneShotBank.from_hdf5(args.hdf5)
+    bank.save(args.npz)
+    print(f"{len(bank)} one-shots, {bank.nbytes / 1e6:.1f} MB of PCM, {len(bank.index)} (pitch, group) cells -> {args.npz}")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(_main())

@@ -419,6 +419,12 @@ def run_b200(args):
     if rank == 0 and not args.no_library_baseline:
         try:
             lib_forward = library_logmel_module(dev)
+            lib_dram = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "r02_library_traffic.json")) as f:
+                    lib_dram = float(json.load(f)["dram_bytes_per_segment"]) * plan.n_seg
+            except Exception:
+                pass
             views = [wav[int(plan.batch_ptr[b]):int(plan.batch_ptr[b + 1]), :int(plan.batch_samples[b])]
                      for b in range(n_batches)]
             render_all(); torch.cuda.synchronize(dev)
@@ -438,7 +444,8 @@ def run_b200(args):
                        "this_repo_logmel_ms_per_step": logmel_ms, "speedup_logmel": lib_ms / logmel_ms,
                        "single_batch_ms": lib_one, "this_repo_single_batch_ms": ours_one_ms,
                        "max_abs_diff_first_batch": diff,
-                       "dram_bytes": None, "dram_bytes_source": "profiles/r02_library_logmel.txt (ncu launch list + dram bytes of the library pipeline)"}
+                       "dram_bytes": lib_dram, "dram_bytes_source": "profiles/r02_library_traffic.json x segments (ncu launch list "
+                                                                    "of this leg with DRAM bytes: profiles/r02_launches.txt)"}
         except Exception as exc:   # never lose the headline line to the comparator
             library = {"error": repr(exc)}
 

@@ -361,3 +361,19 @@ def test_bank_from_hdf5_walks_the_reference_layout():
     assert bank.names == want.names == ["36/100-90/k", "36/gold/kick_a", "36/gold/kick_b", "42/90-80/hat"]
     assert np.array_equal(bank.pcm, want.pcm) and bank.index == want.index
     assert np.array_equal(bank.oneshot(1), nested["36"]["gold"]["kick_a"])
+
+
+def test_bank_converter_entry_point(tmp_path, capsys):
+    """``python -m adt_str_b200.bank in.hdf5 out.npz``: the converter a maintainer runs where the HDF5 bank lives."""
+    from adt_str_b200 import bank as bank_mod
+    from oracle import ref_harness
+    ref_harness._install_shims()
+    rng = np.random.default_rng(4)
+    ref_harness._BANKS["cli_test@24000.hdf5"] = {
+        "38": {"gold": {"s1": rng.standard_normal(41).astype(np.float32)}},
+        "index": {"paths": np.zeros(1, np.float32)}}
+    out = str(tmp_path / "cli_test@24000.npz")
+    assert bank_mod._main(["cli_test@24000.hdf5", out]) == 0
+    assert "1 one-shots" in capsys.readouterr().out
+    back = OneShotBank.load(out)
+    assert back.names == ["38/gold/s1"] and back.group_range(38, "gold") == (0, 1) and int(back.lengths[0]) == 41
