@@ -103,6 +103,8 @@ extern "C" int adtfe_bank_destroy(adtfe_bank* bank) {
     cudaFree(bank->pcm);
     cudaFree(bank->offsets);
     cudaFree(bank->lengths);
+    cudaFree(bank->blockmax);
+    cudaFree(bank->bm_off);
     for (int k = 0; k < bank->n_streams; ++k) {
         if (bank->streams[k]) cudaStreamDestroy(bank->streams[k]);
         if (bank->join_events[k]) cudaEventDestroy(bank->join_events[k]);
@@ -153,6 +155,7 @@ extern "C" int adtfe_bank_create(const float* pcm_host, int64_t total_floats, co
         return ADTFE_ERR_CUDA;
     }
     rc = mixer_prepare_device();
+    if (rc == ADTFE_OK) rc = bank_build_blockmax(b, lengths_host);
     if (rc == ADTFE_OK) rc = fx_prepare_device();
     if (rc != ADTFE_OK) { adtfe_bank_destroy(b); return rc; }
     bool ok = cudaEventCreateWithFlags(&b->fork_event, cudaEventDisableTiming) == cudaSuccess;

@@ -99,9 +99,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }  // namespace adtfe
 
 struct adtfe_mel_tables;
+struct adtfe_bank;
 
 namespace adtfe {
 int mixer_prepare_device();
+int bank_build_blockmax(struct ::adtfe_bank* b, const int32_t* lengths_host);
 int fx_prepare_device();
 // FX kernels over the rows fx_dev[r0 .. r0 + n_rows) of the plan, between the tile mixer and the normalisation
 int fx_launch(const adtfe_plan* plan, int r0, int n_rows, float* wav, float* tile_max, int max_per_seg, cudaStream_t st);
@@ -125,6 +127,10 @@ struct adtfe_bank {
     float* pcm = nullptr;
     int64_t* offsets = nullptr;
     int32_t* lengths = nullptr;
+    // max |x| of every ADTFE_PEAK_BLOCK-sample block of every one-shot (blocks of one-shot i start at bm_off[i]): the
+    // peak pass bounds the mixed one-shot's blocks with them and scans only the blocks that can hold the peak
+    float* blockmax = nullptr;
+    int32_t* bm_off = nullptr;
     // internal streams for chunked plans: forked from / joined into the caller's stream
     int n_streams = 0;
     cudaStream_t streams[kBankStreams] = {};

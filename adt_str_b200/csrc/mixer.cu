@@ -22,21 +22,15 @@
 //                       (an all-zero mix gives NaN, like the reference's 0/0).
 #include <algorithm>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
 namespace adtfe {
 
-#ifndef ADTFE_PEAK_THREADS
-#define ADTFE_PEAK_THREADS 128   // 128 x 94 registers: 6 % faster render than 256 x 64; 64 = two CTAs per work item
-#endif
-constexpr int kPeakThreads = ADTFE_PEAK_THREADS;
-constexpr int kPeakChunk = 8;   // notes of one instrument handled per sweep over the one-shots
-constexpr int kPeakSpan = ADTFE_PEAK_SPAN;  // samples of the mixed one-shot per peak work item
-constexpr int kPeakIters = 8;                                 // float4 per thread per one-shot
-constexpr int kPeakCtaSpan = kPeakIters * 4 * kPeakThreads;   // samples of the mixed one-shot scanned by one CTA
-constexpr int kPeakSplit = kPeakSpan / kPeakCtaSpan;          // CTAs per work item (1 at 128 threads, 2 at 64)
-static_assert(kPeakSplit >= 1 && kPeakSplit * kPeakCtaSpan == kPeakSpan, "peak span must be a multiple of 32 * threads");
+constexpr int kPeakWarps = 8;        // warps per CTA of the peak pass: one (segment, instrument) group per warp
+constexpr int kPeakNotes = 8;        // notes of one group bounded together (they share every block scan)
+constexpr int kBlock = ADTFE_PEAK_BLOCK;   // samples per block of the bank's block maxima
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -56,117 +50,158 @@ __device__ __forceinline__ float nan_max(float a, float b) {  // torch.max propa
 __device__ __forceinline__ float2 mix2(float ax, float ay, float bx, float by, float ca, float cb) {
     return __ffma2_rn(make_float2(bx, by), make_float2(cb, cb), __fmul2_rn(make_float2(ax, ay), make_float2(ca, ca)));
 }
+// the same arithmetic on the block maxima: fl(cb*B + fl(ca*A)) >= |fl(cb*b + fl(ca*a))| for every sample of the block,
+// because ca, cb >= 0, |a| <= A, |b| <= B and rounding to nearest is monotonic - a rigorous bound, no slack needed
+__device__ __forceinline__ float mix_bound(float A, float B, float ca, float cb) {
+    return __fmaf_rn(cb, B, __fmul_rn(ca, A));
+}
 
-// max|ca*a + cb*b| over the float4s held in registers, for NC notes at once: per pair of samples two
-// packed fp32 instructions and one three-input FMNMX; the warp's maximum by one REDUX on the float bits
-// (non-negative floats order like unsigned integers), published with one global atomicMax per warp and note
-// (no shared-memory staging, no CTA barrier: barriers were 12 % of the kernel's stalls).
-template <int NC>
-__device__ __forceinline__ void peak_chunk(const float4 (&va)[kPeakIters], const float4 (&vb)[kPeakIters],
-                                           const adtfe_event* __restrict__ ev, int* __restrict__ peak_bits, int tid) {
-    float ca[NC], cb[NC], m[NC];
-#pragma unroll
-    for (int i = 0; i < NC; ++i) {   // the same address in every thread: broadcast loads that hit L1
-        const float2 c = __ldg(reinterpret_cast<const float2*>(&ev[i].ca));
-        ca[i] = c.x; cb[i] = c.y; m[i] = 0.0f;
-    }
-#pragma unroll
-    for (int it = 0; it < kPeakIters; ++it) {
-#pragma unroll
-        for (int i = 0; i < NC; ++i) {
-            const float2 lo = mix2(va[it].x, va[it].y, vb[it].x, vb[it].y, ca[i], cb[i]);
-            const float2 hi = mix2(va[it].z, va[it].w, vb[it].z, vb[it].w, ca[i], cb[i]);
-            m[i] = fmaxf(fmaxf(m[i], fabsf(lo.x)), fabsf(lo.y));
-            m[i] = fmaxf(fmaxf(m[i], fabsf(hi.x)), fabsf(hi.y));
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < NC; ++i) {   // one REDUX per warp and note, then straight to the note's global maximum
-        const unsigned w = __reduce_max_sync(0xffffffffu, __float_as_uint(m[i]));
-        if ((tid & 31) == 0 && w != 0u) atomicMax(peak_bits + i, (int)w);
+// max |x| over every kBlock-sample block of every one-shot (bank creation, once): one CTA per one-shot, one warp per
+// block.  NaN samples are ignored, as fmaxf ignores them in the peak pass itself.
+__global__ void __launch_bounds__(256) blockmax_kernel(const float* __restrict__ pcm, const int64_t* __restrict__ offsets,
+                                                       const int32_t* __restrict__ lengths,
+                                                       const int32_t* __restrict__ bm_off, float* __restrict__ bm) {
+    const int id = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float* x = pcm + offsets[id];
+    const int len = lengths[id], nblk = (len + kBlock - 1) / kBlock;
+    for (int k = warp; k < nblk; k += 8) {
+        float m = 0.0f;
+        for (int i = k * kBlock + lane; i < min(len, (k + 1) * kBlock); i += 32) m = fmaxf(m, fabsf(x[i]));
+        m = warp_max(m);
+        if (lane == 0) bm[bm_off[id] + k] = m;
     }
 }
 
-// One CTA per (group, chunk) work item: a group is the notes of one instrument in one segment
-// (same two one-shots, one mixup each); a chunk is kPeakSpan samples of the mixed one-shot, read
-// once into registers (all loads in flight together) and reused for every note of the group.
-// Peaks are combined with atomicMax on the float bits (non-negative floats order like ints,
-// and max is order-independent, so the result is deterministic).
-__global__ void __launch_bounds__(kPeakThreads) peak_kernel(
-    const float* __restrict__ pcm, const adtfe_event* __restrict__ events, const adtfe_peak_item* __restrict__ work,
-    ResolvedEvent* __restrict__ resolved, int* __restrict__ peak_bits) {
-    const adtfe_peak_item item = work[blockIdx.x / kPeakSplit];  // one fetch, then the data loads can start
-    const int sub = blockIdx.x % kPeakSplit;                     // which part of the item's span this CTA scans
-    const int chunk = item.chunk, tid = threadIdx.x;
-    const int e0 = item.first_event, e1 = e0 + item.n_events;
-    if (e0 >= e1) return;
-    const int64_t a_off = item.a_off, b_off = item.b_off;
-    const int la = item.la, lb = item.lb, n = item.mix_len;
+// Exact max |ca*a + cb*b| over block k of the mixed one-shot for NC notes at once: 2 float4 per lane and one-shot, per
+// pair of samples two packed fp32 instructions and one three-input FMNMX per note; the warp's maximum by one REDUX on
+// the float bits (non-negative floats order like unsigned integers), returned to every lane.
+template <int NC>
+__device__ __forceinline__ void scan_block(const float4* __restrict__ a4, const float4* __restrict__ b4, int la, int lb,
+                                           int k, int lane, const float (&ca)[NC], const float (&cb)[NC], float (&best)[NC]) {
+    constexpr int kIters = kBlock / 128;
+    float4 va[kIters], vb[kIters];
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     // every one-shot is padded to 4 floats, so whole float4s up to the padded length are readable
     const int la4 = (la + 3) >> 2, lb4 = (lb + 3) >> 2;
-    const int lo4 = chunk * (kPeakSpan / 4) + sub * (kPeakCtaSpan / 4), hi4 = min((n + 3) >> 2, lo4 + kPeakCtaSpan / 4);
-    if (lo4 >= hi4 && !(chunk == 0 && sub == 0)) return;  // this part lies past the end of the mixed one-shot
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+        const int i4 = k * (kBlock / 4) + lane + 32 * it;
+        va[it] = i4 < la4 ? __ldg(a4 + i4) : z;
+        vb[it] = i4 < lb4 ? __ldg(b4 + i4) : z;
+        // the float4 that holds a one-shot's last sample: ignore whatever pads it
+        if (i4 == (la >> 2) && (la & 3)) {
+            if ((la & 3) < 2) va[it].y = 0.f;
+            if ((la & 3) < 3) va[it].z = 0.f;
+            va[it].w = 0.f;
+        }
+        if (i4 == (lb >> 2) && (lb & 3)) {
+            if ((lb & 3) < 2) vb[it].y = 0.f;
+            if ((lb & 3) < 3) vb[it].z = 0.f;
+            vb[it].w = 0.f;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        float m = 0.0f;
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+            const float2 lo = mix2(va[it].x, va[it].y, vb[it].x, vb[it].y, ca[i], cb[i]);
+            const float2 hi = mix2(va[it].z, va[it].w, vb[it].z, vb[it].w, ca[i], cb[i]);
+            m = fmaxf(fmaxf(m, fabsf(lo.x)), fabsf(lo.y));
+            m = fmaxf(fmaxf(m, fabsf(hi.x)), fabsf(hi.y));
+        }
+        best[i] = fmaxf(best[i], __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(m))));
+    }
+}
+
+// Peaks of NC notes of one group by branch and bound over the blocks of the mixed one-shot.  The bank holds max |x| of
+// every kBlock-sample block of every one-shot; the bound of block k for a note is mix_bound(A_k, B_k) - the note's own
+// arithmetic on the block maxima.  The block with the largest bound (of the first note) is scanned exactly, which
+// gives every note a lower bound of its peak; then only blocks whose bound still exceeds a note's lower bound are
+// scanned (in ascending order: a drum one-shot decays, so the survivors are the first few blocks).  The maximum found is
+// the maximum over all samples - bit-identical to a full scan - while a decaying one-shot costs a few KB of reads
+// instead of its whole length (measured on the bench workload: 7.7 GB -> 0.x GB of DRAM reads per step).
+template <int NC>
+__device__ __forceinline__ void peak_notes(const float4* __restrict__ a4, const float4* __restrict__ b4, int la, int lb,
+                                           const float* __restrict__ bma, const float* __restrict__ bmb,
+                                           const adtfe_event* __restrict__ ev, int* __restrict__ peak_bits, int lane) {
+    float ca[NC], cb[NC], best[NC];
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {   // the same address in every lane: broadcast loads
+        const float2 c = __ldg(reinterpret_cast<const float2*>(&ev[i].ca));
+        ca[i] = c.x; cb[i] = c.y; best[i] = 0.0f;
+    }
+    const int nba = (la + kBlock - 1) / kBlock, nbb = (lb + kBlock - 1) / kBlock, nblk = max(nba, nbb);
+    // the block with the largest bound for the first note
+    float top = -1.0f;
+    int top_k = 0;
+    for (int k = lane; k < nblk; k += 32) {
+        const float ub = mix_bound(k < nba ? __ldg(bma + k) : 0.0f, k < nbb ? __ldg(bmb + k) : 0.0f, ca[0], cb[0]);
+        if (ub > top) { top = ub; top_k = k; }
+    }
+    const unsigned top_bits = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(top, 0.0f)));
+    const unsigned holders = __ballot_sync(0xffffffffu, top >= 0.0f && __float_as_uint(top) == top_bits);
+    const int k0 = holders ? __shfl_sync(0xffffffffu, top_k, __ffs((int)holders) - 1) : 0;
+    if (nblk > 0) scan_block<NC>(a4, b4, la, lb, k0, lane, ca, cb, best);
+    for (int j0 = 0; j0 < nblk; j0 += 32) {
+        const int k = j0 + lane;
+        const float A = k < nba ? __ldg(bma + k) : 0.0f, B = k < nbb ? __ldg(bmb + k) : 0.0f;
+        bool cand = false;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) cand |= mix_bound(A, B, ca[i], cb[i]) > best[i];
+        unsigned todo = __ballot_sync(0xffffffffu, cand && k < nblk && k != k0);
+        while (todo) {
+            const int l = __ffs((int)todo) - 1;
+            todo &= todo - 1u;
+            const float Al = __shfl_sync(0xffffffffu, A, l), Bl = __shfl_sync(0xffffffffu, B, l);
+            bool still = false;   // the lower bounds have risen since the ballot
+#pragma unroll
+            for (int i = 0; i < NC; ++i) still |= mix_bound(Al, Bl, ca[i], cb[i]) > best[i];
+            if (still) scan_block<NC>(a4, b4, la, lb, j0 + l, lane, ca, cb, best);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NC; ++i)
+        if (lane == i) peak_bits[i] = (int)__float_as_uint(best[i]);   // an all-zero one-shot keeps 0: gain / 0 in the mixer
+}
+
+// One warp per group: the notes of one instrument in one segment (same two one-shots, one mixup each).  Work items with
+// chunk != 0 (the per-span items of ABI <= 4 planners) are skipped.  The warp also resolves the bank lookups of its
+// notes into ResolvedEvent records for the tile mixer.
+__global__ void __launch_bounds__(kPeakWarps * 32) peak_kernel(
+    const float* __restrict__ pcm, const float* __restrict__ bm, const int32_t* __restrict__ bm_off,
+    const adtfe_event* __restrict__ events, const adtfe_peak_item* __restrict__ work, int n_items,
+    ResolvedEvent* __restrict__ resolved, int* __restrict__ peak_bits) {
+    const int w = blockIdx.x * kPeakWarps + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (w >= n_items) return;
+    const adtfe_peak_item item = work[w];
+    const int e0 = item.first_event, e1 = e0 + item.n_events;
+    if (item.chunk != 0 || e0 >= e1) return;
+    const int64_t a_off = item.a_off, b_off = item.b_off;
+    const int la = item.la, lb = item.lb;
+    const int2 ids = __ldg(reinterpret_cast<const int2*>(&events[e0].main_id));
+    const float* bma = bm + __ldg(bm_off + ids.x);
+    const float* bmb = bm + __ldg(bm_off + ids.y);
+    for (int e = e0 + lane; e < e1; e += 32) {   // resolve the bank lookups once per note for the tile mixer
+        const adtfe_event ev = events[e];
+        ResolvedEvent r;
+        r.a_off = a_off; r.b_off = b_off;
+        r.la = min(la, ev.len); r.lb = min(lb, ev.len);
+        r.start = ev.start; r.len = ev.len; r.ca = ev.ca; r.cb = ev.cb; r.gain = ev.gain; r.pad = 0;
+        resolved[e] = r;
+    }
     const float4* a4 = reinterpret_cast<const float4*>(pcm + a_off);
     const float4* b4 = reinterpret_cast<const float4*>(pcm + b_off);
-
-    float4 va[kPeakIters], vb[kPeakIters];
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    // interior chunks (both one-shots reach past the chunk) need neither load predicates nor tail masks
-    const bool interior = lo4 + kPeakCtaSpan / 4 <= (la >> 2) && lo4 + kPeakCtaSpan / 4 <= (lb >> 2);
-    if (interior) {
-#pragma unroll
-        for (int it = 0; it < kPeakIters; ++it) {
-            const int i4 = lo4 + tid + it * kPeakThreads;
-            va[it] = __ldg(a4 + i4);
-            vb[it] = __ldg(b4 + i4);
-        }
-    } else {
-#pragma unroll
-        for (int it = 0; it < kPeakIters; ++it) {
-            const int i4 = lo4 + tid + it * kPeakThreads;
-            va[it] = (i4 < hi4 && i4 < la4) ? __ldg(a4 + i4) : z;
-            vb[it] = (i4 < hi4 && i4 < lb4) ? __ldg(b4 + i4) : z;
-        }
-    }
-    if (chunk == 0 && sub == 0) {  // resolve the bank lookups once per note for the tile mixer
-        for (int e = e0 + tid; e < e1; e += kPeakThreads) {
-            const adtfe_event ev = events[e];
-            ResolvedEvent r;
-            r.a_off = a_off; r.b_off = b_off;
-            r.la = min(la, ev.len); r.lb = min(lb, ev.len);
-            r.start = ev.start; r.len = ev.len; r.ca = ev.ca; r.cb = ev.cb; r.gain = ev.gain; r.pad = 0;
-            resolved[e] = r;
-        }
-    }
-    if (!interior) {
-        // the float4 that holds a one-shot's last sample: ignore whatever pads it (all later ones were not loaded)
-        const int qa = la >> 2, ra = la & 3, qb = lb >> 2, rb = lb & 3;
-#pragma unroll
-        for (int it = 0; it < kPeakIters; ++it) {
-            const int i4 = lo4 + tid + it * kPeakThreads;
-            if (i4 == qa && ra != 0) {
-                if (ra < 2) va[it].y = 0.f;
-                if (ra < 3) va[it].z = 0.f;
-                va[it].w = 0.f;
-            }
-            if (i4 == qb && rb != 0) {
-                if (rb < 2) vb[it].y = 0.f;
-                if (rb < 3) vb[it].z = 0.f;
-                vb[it].w = 0.f;
-            }
-        }
-    }
-    for (int c0 = e0; c0 < e1; c0 += kPeakChunk) {
-        const int nc = min(kPeakChunk, e1 - c0);
-        switch (nc) {
-            case 1: peak_chunk<1>(va, vb, events + c0, peak_bits + c0, tid); break;
-            case 2: peak_chunk<2>(va, vb, events + c0, peak_bits + c0, tid); break;
-            case 3: peak_chunk<3>(va, vb, events + c0, peak_bits + c0, tid); break;
-            case 4: peak_chunk<4>(va, vb, events + c0, peak_bits + c0, tid); break;
-            case 5: peak_chunk<5>(va, vb, events + c0, peak_bits + c0, tid); break;
-            case 6: peak_chunk<6>(va, vb, events + c0, peak_bits + c0, tid); break;
-            case 7: peak_chunk<7>(va, vb, events + c0, peak_bits + c0, tid); break;
-            default: peak_chunk<8>(va, vb, events + c0, peak_bits + c0, tid); break;
+    for (int c0 = e0; c0 < e1; c0 += kPeakNotes) {
+        switch (min(kPeakNotes, e1 - c0)) {
+            case 1: peak_notes<1>(a4, b4, la, lb, bma, bmb, events + c0, peak_bits + c0, lane); break;
+            case 2: peak_notes<2>(a4, b4, la, lb, bma, bmb, events + c0, peak_bits + c0, lane); break;
+            case 3: peak_notes<3>(a4, b4, la, lb, bma, bmb, events + c0, peak_bits + c0, lane); break;
+            case 4: peak_notes<4>(a4, b4, la, lb, bma, bmb, events + c0, peak_bits + c0, lane); break;
+            case 5: peak_notes<5>(a4, b4, la, lb, bma, bmb, events + c0, peak_bits + c0, lane); break;
+            case 6: peak_notes<6>(a4, b4, la, lb, bma, bmb, events + c0, peak_bits + c0, lane); break;
+            case 7: peak_notes<7>(a4, b4, la, lb, bma, bmb, events + c0, peak_bits + c0, lane); break;
+            default: peak_notes<8>(a4, b4, la, lb, bma, bmb, events + c0, peak_bits + c0, lane); break;
         }
     }
 }
@@ -557,6 +592,21 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Called by adtfe_bank_create on the bank's device (cudaFuncSetAttribute is per device and idempotent): the kernels'
 // dynamic shared memory is opted in once per handle, not through process-wide state on the render path.
+// Block maxima of the bank for the peak pass (called once by adtfe_bank_create, on the bank's device).
+int adtfe::bank_build_blockmax(adtfe_bank* b, const int32_t* lengths_host) {
+    std::vector<int32_t> off((size_t)b->n + 1, 0);
+    for (int32_t i = 0; i < b->n; ++i) off[i + 1] = off[i] + (lengths_host[i] + kBlock - 1) / kBlock;
+    ADTFE_CUDA(cudaMalloc((void**)&b->bm_off, off.size() * 4));
+    ADTFE_CUDA(cudaMemcpy(b->bm_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    ADTFE_CUDA(cudaMalloc((void**)&b->blockmax, (size_t)std::max(off.back(), 1) * 4));
+    if (b->n > 0) {
+        blockmax_kernel<<<b->n, 256>>>(b->pcm, b->offsets, b->lengths, b->bm_off, b->blockmax);
+        ADTFE_CUDA(cudaGetLastError());
+        ADTFE_CUDA(cudaDeviceSynchronize());
+    }
+    return ADTFE_OK;
+}
+
 int adtfe::mixer_prepare_device() {
     ADTFE_CUDA(cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mix_smem_bytes()));
     return ADTFE_OK;
@@ -645,8 +695,9 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
         const int pw0 = ch[c].peak_work, n_pw = ch[c + 1].peak_work - pw0;
         if (n_pw > 0) {
             trace_open("peak", c, s_peak);
-            peak_kernel<<<n_pw * kPeakSplit, kPeakThreads, 0, s_peak>>>(bank->pcm, plan->events_dev,
-                                                                        plan->peak_work_dev + pw0, resolved, peak_bits);
+            peak_kernel<<<(n_pw + kPeakWarps - 1) / kPeakWarps, kPeakWarps * 32, 0, s_peak>>>(
+                bank->pcm, bank->blockmax, bank->bm_off, plan->events_dev, plan->peak_work_dev + pw0, n_pw, resolved,
+                peak_bits);
             trace_close(s_peak);
             ADTFE_CUDA(cudaGetLastError());
         }

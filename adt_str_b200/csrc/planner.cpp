@@ -308,8 +308,8 @@ extern "C" int adtfe_planner_plan(adtfe_planner* P, const float* notes, const in
         it.la = P->lengths[head.main_id]; it.lb = P->lengths[head.sub_id];
         it.mix_len = P->mix_len[e0];
         it.first_event = e0; it.n_events = P->group_ptr[g + 1] - e0;
-        const int32_t chunks = std::max(1, (it.mix_len + ADTFE_PEAK_SPAN - 1) / ADTFE_PEAK_SPAN);
-        for (int32_t c = 0; c < chunks; ++c) { it.chunk = c; P->peak_work.push_back(it); }
+        it.chunk = 0;   // one item per group: the peak pass bounds and scans the blocks of the mixed one-shot itself
+        P->peak_work.push_back(it);
     }
     out_counts[0] = (int64_t)P->events.size();
     out_counts[1] = (int64_t)P->group_ptr.size() - 1;

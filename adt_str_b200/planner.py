@@ -39,7 +39,6 @@ from .mapping import (ADTOF_INVERSE, PITCH_MAX, PITCH_MIN, SIMILARITY_GROUPS,
                       instrument_gain)
 
 TILE = 2048       # output samples owned by one CTA of the tile mixer (ADTFE_TILE)
-PEAK_SPAN = 4096  # samples of a mixed one-shot scanned by one peak work item (ADTFE_PEAK_SPAN)
 
 #: numpy view of ``adtfe_event`` in include/adtfe.h (32 bytes)
 EVENT_DTYPE = np.dtype([("start", "<i4"), ("len", "<i4"), ("main_id", "<i4"), ("sub_id", "<i4"),
@@ -390,22 +389,18 @@ def assemble(plans: Sequence[SegmentPlan], bank: OneShotBank, ld_wav: int | None
 
 
 def peak_work_items(events: np.ndarray, mix_len: np.ndarray, group_ptr: np.ndarray, bank: OneShotBank) -> np.ndarray:
-    """One record per PEAK_SPAN-sample chunk of every group's mixed one-shot, bank lookups resolved."""
+    """One record per group (the notes of one instrument in one segment), bank lookups resolved; ``chunk`` stays 0."""
     n_groups = len(group_ptr) - 1
     if n_groups <= 0:
         return np.zeros(0, PEAK_ITEM_DTYPE)
-    first = group_ptr[:-1].astype(np.int64)
-    chunks = np.maximum(1, -(-mix_len[first].astype(np.int64) // PEAK_SPAN))
-    group = np.repeat(np.arange(n_groups, dtype=np.int64), chunks)
-    out = np.zeros(int(chunks.sum()), PEAK_ITEM_DTYPE)
-    e0 = first[group]
+    out = np.zeros(n_groups, PEAK_ITEM_DTYPE)
+    e0 = group_ptr[:-1].astype(np.int64)
     main, sub = events["main_id"][e0], events["sub_id"][e0]
     out["a_off"], out["b_off"] = bank.offsets[main], bank.offsets[sub]
     out["la"], out["lb"] = bank.lengths[main], bank.lengths[sub]
     out["mix_len"] = mix_len[e0]
     out["first_event"] = e0
-    out["n_events"] = np.diff(group_ptr)[group]
-    out["chunk"] = np.arange(len(out), dtype=np.int64) - np.repeat(np.cumsum(chunks) - chunks, chunks)
+    out["n_events"] = np.diff(group_ptr)
     return out
 
 

@@ -43,9 +43,9 @@
 extern "C" {
 #endif
 
-#define ADTFE_VERSION 4
+#define ADTFE_VERSION 5
 #define ADTFE_TILE 2048      /* output samples owned by one mixer CTA */
-#define ADTFE_PEAK_SPAN 4096 /* samples of a mixed one-shot scanned by one peak work item */
+#define ADTFE_PEAK_BLOCK 256 /* samples per block of the bank's block maxima (peak pass: branch and bound) */
 
 typedef enum adtfe_status {
     ADTFE_OK = 0,
@@ -80,10 +80,11 @@ typedef struct adtfe_segment {
 
 #define ADTFE_SEG_RAW 2
 
-/* One work item of the peak pass (40 bytes): samples [chunk*ADTFE_PEAK_SPAN, (chunk+1)*ADTFE_PEAK_SPAN)
- * of the mixed one-shot shared by the notes first_event .. first_event+n_events-1 (one instrument of one
- * segment).  Every group needs chunks 0 .. ceil(mix_len/ADTFE_PEAK_SPAN)-1.  Offsets and lengths are the
- * bank's, resolved on the host so the kernel starts its loads after a single record fetch. */
+/* One work item of the peak pass (40 bytes): the mixed one-shot shared by the notes first_event ..
+ * first_event+n_events-1 (one instrument of one segment).  One item per group, chunk = 0 (ABI <= 4 split a group
+ * into per-span items chunk = 0, 1, ...: items with chunk != 0 are ignored).  Offsets and lengths are the bank's,
+ * resolved on the host so the kernel starts its loads after a single record fetch; events[first_event].main_id /
+ * sub_id name the two one-shots (block maxima lookup). */
 typedef struct adtfe_peak_item {
     int64_t a_off, b_off; /* float offsets of the main / sub one-shot in the bank */
     int32_t la, lb;       /* their lengths */
