@@ -106,7 +106,9 @@ int mixer_prepare_device();
 int bank_build_blockmax(struct ::adtfe_bank* b, const int32_t* lengths_host);
 int fx_prepare_device();
 // FX kernels over the rows fx_dev[r0 .. r0 + n_rows) of the plan, between the tile mixer and the normalisation
-int fx_launch(const adtfe_plan* plan, int r0, int n_rows, float* wav, float* tile_max, int max_per_seg, cudaStream_t st);
+int fx_reverb_launch(const adtfe_plan* plan, int r0, int n_rows, float* wav, cudaStream_t st);
+int fx_dynamics_launch(const adtfe_plan* plan, int r0, int n_rows, float* wav, float* tile_max, int max_per_seg,
+                       cudaStream_t st);
 int render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
                 size_t workspace_bytes, void* stream);
 // Diagnostics (adtfe_trace_begin / adtfe_trace_dump): a pair of timing events around every kernel launch.
@@ -115,7 +117,7 @@ void trace_close(cudaStream_t st);
 }  // namespace adtfe
 
 #ifndef ADTFE_BANK_STREAMS
-#define ADTFE_BANK_STREAMS 4
+#define ADTFE_BANK_STREAMS 7
 #endif
 constexpr int kBankStreams = ADTFE_BANK_STREAMS;
 constexpr int kStageEvents = 8;

@@ -15,15 +15,16 @@
 //                     last[n] = y[n] (1 - damp) + damp last[n-1]: a first-order linear recurrence with a constant
 //                     coefficient, solved across the lanes by a 5-step shuffle scan.  The 8 combs and then the 4
 //                     series allpasses (each parallel over the step) run from 27 KB of delay lines in shared memory.
-// fx_dynamics_kernel  lane = row (32 rows of the plan's FX list per warp).  An envelope follower
+// fx_dynamics_kernel  lane = (row, stage): 8 rows of the plan's FX list per warp, 4 lanes each.  An envelope follower
 //                     y = |x| + (|x| > y ? cAT : cRL)(y - |x|) has a data-dependent coefficient, so it cannot be
-//                     scanned: each lane walks its own row.  The three followers of the chain (compressor, limiter
-//                     stage 1, limiter stage 2) are SKEWED by a block of four samples each - a trip runs stage 1 on
-//                     block b, stage 2 on block b-1, stage 3 on block b-2 - so the loop-carried dependency is one
-//                     follower (5 dependent instructions per sample), not three followers and two pow() in series, and
-//                     the pow() themselves are exp2(e * log2(x)) on the special-function unit.  Disabled stages are
-//                     the same code with an infinite threshold (gain 1), so rows with different chains share a warp.
-//                     The lane also tracks max|out| of its row: the row peak the normalisation needs.
+//                     scanned: a row is walked sample by sample.  The three followers of the chain (compressor, limiter
+//                     stage 1, limiter stage 2) and the output step sit in four neighbouring lanes, SKEWED by a block of
+//                     four samples each - in a trip stage 0 works on block b, stage 1 on block b-1, ... - and pass their
+//                     blocks on with shuffles, so the sequential cost of a sample is one follower (5 dependent
+//                     instructions; its pow() is exp2(e * log2(x)) on the special-function unit), not three followers
+//                     and two pow() in series.  Disabled stages are the same code with an infinite threshold (gain 1),
+//                     so rows with different chains share a warp.  The output lane also tracks max|out| of its row: the
+//                     row peak the normalisation needs.
 #include <math.h>
 
 #include <algorithm>
@@ -164,21 +165,37 @@ __device__ __forceinline__ float follower_step(Follower& c, float in) {
     return gain * in;
 }
 
+// Four lanes per row: lane 4 j + s is stage s of the warp's row j - 0: compressor, 1 and 2: the limiter's two stages,
+// 3: output (gain, clip, row peak, store).  A trip is a block of four samples (one 16-byte load / store); the stages are
+// skewed by a trip, so that in trip t stage s works on block t - s and hands its four outputs to stage s + 1 with one
+// shuffle each.  Every lane runs ONE follower, all of a row's followers advance in the same instructions, and the
+// sequential cost of a sample is one follower (with its two special-function instructions) instead of three: 0.8 ms
+// for a row of 61 442 samples against 4.3 ms with lane = row (whatever the number of rows, up to the machine's warps).
+// The arithmetic per stage and sample is unchanged.
+// Sixteen zero bytes: where the prefetch of a row reads once it is past the row's end.  The choice is made on the
+// ADDRESS, so that the load itself is unconditional and lands in its ring register - a predicated load (or a select
+// behind it) makes ptxas load into a temporary and move, and the move waits for the load right away.
+__device__ const float4 g_zero_block = {0.0f, 0.0f, 0.0f, 0.0f};
+
 __global__ void __launch_bounds__(32) fx_dynamics_kernel(const adtfe_segment* __restrict__ segments,
                                                          const adtfe_fx* __restrict__ fx, int n_fx, float* __restrict__ wav,
                                                          int64_t ld_wav, float* __restrict__ tile_max, int max_per_seg,
                                                          int sample_rate) {
-    const int r = blockIdx.x * 32 + threadIdx.x;   // lane = one row of the FX list
-    if (r >= n_fx) return;                          // no warp-wide operation below
-    const adtfe_fx f = fx[r];
+    const int lane = threadIdx.x, stage = lane & 3;
+    const int r = blockIdx.x * 8 + (lane >> 2);
+    adtfe_fx f;
+    f.flags = 0; f.seg = 0;
+    if (r < n_fx) f = fx[r];
     const int seg = f.seg;
-    if (f.flags == 0 || segments[seg].flags == 0) return;
+    const bool live = r < n_fx && f.flags != 0 && segments[seg].flags != 0;
+    if (!__any_sync(0xffffffffu, live)) return;
     const double exp_factor = -2.0 * 3.14159265358979323846 * 1000.0 / (double)sample_rate;
-    const bool comp_on = (f.flags & ADTFE_FX_COMPRESSOR) != 0, lim_on = (f.flags & ADTFE_FX_LIMITER) != 0;
-    Follower c1 = make_follower(comp_on, exp_factor, f.comp_threshold_db, f.comp_ratio, f.comp_attack_ms,
-                                f.comp_release_ms);
-    Follower c2 = make_follower(lim_on, exp_factor, -10.0f, 4.0f, 2.0f, 200.0f);
-    Follower c3 = make_follower(lim_on, exp_factor, f.lim_threshold_db, 1000.0f, 0.001f, 100.0f);
+    const bool comp_on = live && (f.flags & ADTFE_FX_COMPRESSOR) != 0, lim_on = live && (f.flags & ADTFE_FX_LIMITER) != 0;
+    // this lane's follower; the output lane (and every stage that is off) runs one with an infinite threshold: gain 1
+    Follower c = make_follower(false, exp_factor, 0.0f, 1.0f, 1.0f, 1.0f);
+    if (stage == 0) c = make_follower(comp_on, exp_factor, f.comp_threshold_db, f.comp_ratio, f.comp_attack_ms, f.comp_release_ms);
+    if (stage == 1) c = make_follower(lim_on, exp_factor, -10.0f, 4.0f, 2.0f, 200.0f);
+    if (stage == 2) c = make_follower(lim_on, exp_factor, f.lim_threshold_db, 1000.0f, 0.001f, 100.0f);
     float out_gain = 1.0f, clip = __int_as_float(0x7f800000);
     if (lim_on) {
         out_gain = (float)pow(10.0, 10.0 * (1.0 - (double)0.25f) / 40.0);
@@ -186,73 +203,61 @@ __global__ void __launch_bounds__(32) fx_dynamics_kernel(const adtfe_segment* __
         clip = 1.0f;
     }
     float* row = wav + (int64_t)seg * ld_wav;
-    const int n = segments[seg].len;
-    float peak = 0.0f;
-    const bool rewrite = lim_on || comp_on;
-    // Four samples (one 16-byte load) per trip, the stages skewed by a whole trip: trip b runs stage 1 on block b,
-    // stage 2 on stage 1's output of block b - 1 and stage 3 on stage 2's output of block b - 2.  The three followers
-    // are then independent chains inside a trip (and the gains, off the chains, pipeline through the special-function
-    // unit); block b - 2 leaves as one aligned 16-byte store (the row starts on a 16-byte boundary: ld_wav % 4 == 0).
-    // The loads run a whole 128-byte line (eight trips) ahead: the in-place stores invalidate the line in L1, so
-    // every load is an L2 round trip - issued one line early it is never waited for.
-    float s1[4] = {0.0f, 0.0f, 0.0f, 0.0f}, s2[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const int n = live ? segments[seg].len : 0;
+    const bool first = stage == 0, last = stage == 3, rewrite = last && (lim_on || comp_on);
+    // |max| on the float bits: non-negative floats order like unsigned integers and a NaN's bits lie above infinity's,
+    // so the unsigned maximum propagates NaN like torch.max.  Blocks outside the row (pipeline fill, trips of a longer
+    // row in the same warp) carry zeros through the chain and do not move it.
+    unsigned peak_bits = 0u;
     const float4* row4 = reinterpret_cast<const float4*>(row);
-    const int n_blocks = (n + 3) / 4, pitch_blocks = (int)(ld_wav / 4);
-    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    float4 cur[8], nxt[8];
+    const int n_blocks = (n + 3) / 4;
+    int trips = n_blocks + 3;   // the last block leaves the output lane three trips after it entered stage 0
 #pragma unroll
-    for (int t = 0; t < 8; ++t) cur[t] = t < pitch_blocks ? row4[t] : zero4;
-    for (int line = 0; 8 * line < n_blocks + 2; ++line) {
+    for (int o = 16; o >= 4; o >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, o));   // the warp's longest row
+    // The loads run kAhead trips (a line and a half) ahead through a ring of registers indexed by the unrolled trip
+    // number: a trip is ~100 clocks and a row's samples come from HBM (the raw mix of a chunk is larger than L2), so a
+    // load issued eight trips early was still waited for (ncu: 58 % of the stalls on the first use of the loaded block).  (The four lanes of a row load the same address: one request.)  The trip has no
+    // branch: the samples of the row's last block that lie beyond its length are zeros in memory (the waveform matrix
+    // is zero beyond every segment's length), travel through the chain as zeros and are stored back with the block; the
+    // output lane clears them again after the loop, so that they stay exact zeros even in a row that went NaN.
+    constexpr int kRing = 16, kAhead = 12;
+    float4 buf[kRing];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int blk = 8 * (line + 1) + t;
-            nxt[t] = blk < n_blocks && blk < pitch_blocks ? row4[blk] : zero4;
-        }
+    for (int t = 0; t < kAhead; ++t) buf[t] = *(t < n_blocks ? row4 + t : &g_zero_block);
+    float in[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // what the previous stage handed over in the last trip
+    for (int base = 0; base < trips; base += kRing) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-            const int b = 8 * line + t;
-            float xin[4] = {cur[t].x, cur[t].y, cur[t].z, cur[t].w};
+        for (int t = 0; t < kRing; ++t) {
+            const int b = base + t;   // the trip: stage s works on block b - s
+            buf[(t + kAhead) % kRing] = *(b + kAhead < n_blocks ? row4 + b + kAhead : &g_zero_block);
+            in[0] = first ? buf[t].x : in[0];
+            in[1] = first ? buf[t].y : in[1];
+            in[2] = first ? buf[t].z : in[2];
+            in[3] = first ? buf[t].w : in[3];
+            float out[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (4 * b + k >= n) xin[k] = 0.0f;   // the row's padding is not part of the signal
-            float t1[4], t2[4], o[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) t1[k] = follower_step(c1, xin[k]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) t2[k] = follower_step(c2, s1[k]);
+            for (int k = 0; k < 4; ++k) out[k] = follower_step(c, in[k]);
+            // the output step on what stage 2 handed over (block b - 3); the other lanes' results are not used
+            float o[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                float v = follower_step(c3, s2[k]) * out_gain;
+                const float v = in[k] * out_gain;
                 o[k] = v < -clip ? -clip : (v > clip ? clip : v);   // keeps NaN, like FloatVectorOperations::clip
+                peak_bits = max(peak_bits, __float_as_uint(fabsf(o[k])));
             }
-            if (b >= 2 && 4 * (b - 2) < n) {
-                const int s0 = 4 * (b - 2);
+            if (rewrite && b >= 3 && b - 3 < n_blocks) reinterpret_cast<float4*>(row)[b - 3] = make_float4(o[0], o[1], o[2], o[3]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (s0 + k < n) {
-                        const float a = fabsf(o[k]);
-                        peak = (a != a || peak != peak) ? __int_as_float(0x7fc00000) : fmaxf(peak, a);   // torch.max keeps NaN
-                    }
-                }
-                if (rewrite) {
-                    if (s0 + 3 < n) reinterpret_cast<float4*>(row)[b - 2] = make_float4(o[0], o[1], o[2], o[3]);
-                    else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (s0 + k < n) row[s0 + k] = o[k];
-                    }
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) { s1[k] = t1[k]; s2[k] = t2[k]; }
+            for (int k = 0; k < 4; ++k) in[k] = __shfl_up_sync(0xffffffffu, out[k], 1, 4);   // stage s -> stage s + 1
         }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) cur[t] = nxt[t];
     }
-    // the normalisation takes the row peak from the tile maxima: this row's is now `peak`
-    float* tm = tile_max + (size_t)seg * max_per_seg;
-    tm[0] = peak;
-    for (int t = 1; t < max_per_seg; ++t) tm[t] = 0.0f;
+    if (rewrite)
+        for (int i = n; i < 4 * n_blocks; ++i) row[i] = 0.0f;
+    // the normalisation takes the row peak from the tile maxima: this row's is now the output lane's maximum
+    if (live && last) {
+        float* tm = tile_max + (size_t)seg * max_per_seg;
+        tm[0] = __uint_as_float(peak_bits);
+        for (int t = 1; t < max_per_seg; ++t) tm[t] = 0.0f;
+    }
 }
 
 int fx_prepare_device() {
@@ -261,8 +266,12 @@ int fx_prepare_device() {
     return ADTFE_OK;
 }
 
-// FX of the rows fx_dev[r0 .. r0 + n_rows) (their `seg` fields index segments / wav / tile_max of the whole plan)
-int fx_launch(const adtfe_plan* plan, int r0, int n_rows, float* wav, float* tile_max, int max_per_seg, cudaStream_t st) {
+// FX of the rows fx_dev[r0 .. r0 + n_rows) (their `seg` fields index segments / wav / tile_max of the whole plan), in
+// the chain's order: the reverb first, then compressor and limiter.  The two halves are launched separately because
+// they scale differently: the reverb is one warp per row (throughput: rows per wave of warps), the dynamics kernel takes
+// the same ~4 ms whatever the number of rows (32 rows per warp, a recursion over the row's samples) - so a chunked render
+// runs the reverb chunk by chunk behind the tile mixer and the dynamics ONCE for all the plan's FX rows.
+int fx_reverb_launch(const adtfe_plan* plan, int r0, int n_rows, float* wav, cudaStream_t st) {
     if (n_rows <= 0) return ADTFE_OK;
     const int sr = plan->sample_rate;
     ADTFE_REQUIRE(sr >= 8000 && sr <= 96000, ADTFE_ERR_UNSUPPORTED,
@@ -274,9 +283,15 @@ int fx_launch(const adtfe_plan* plan, int r0, int n_rows, float* wav, float* til
     fx_reverb_kernel<<<n_rows, 32, (size_t)g.total * 4, st>>>(plan->segments_dev, plan->fx_dev + r0, wav, plan->ld_wav, g);
     trace_close(st);
     ADTFE_CUDA(cudaGetLastError());
+    return ADTFE_OK;
+}
+
+int fx_dynamics_launch(const adtfe_plan* plan, int r0, int n_rows, float* wav, float* tile_max, int max_per_seg,
+                       cudaStream_t st) {
+    if (n_rows <= 0) return ADTFE_OK;
     trace_open("fx_dynamics", r0, st);
-    fx_dynamics_kernel<<<(n_rows + 31) / 32, 32, 0, st>>>(plan->segments_dev, plan->fx_dev + r0, n_rows, wav, plan->ld_wav,
-                                                         tile_max, max_per_seg, sr);
+    fx_dynamics_kernel<<<(n_rows + 7) / 8, 32, 0, st>>>(plan->segments_dev, plan->fx_dev + r0, n_rows, wav, plan->ld_wav,
+                                                         tile_max, max_per_seg, plan->sample_rate);
     trace_close(st);
     ADTFE_CUDA(cudaGetLastError());
     return ADTFE_OK;

@@ -547,11 +547,23 @@ __global__ void __launch_bounds__(32, kMixCtasPerSm) mix_kernel(const MixArgs a)
 #define ADTFE_NORM_THREADS 256
 #endif
 constexpr int kNormThreads = ADTFE_NORM_THREADS;
+// `segments`, `tile_max` and `wav` cover the whole plan.  Per chunk (fx_rows == nullptr) the rows are seg0 + blockIdx.x /
+// tiles_per_seg, minus the rows marked in seg_fx: those still have the FX chain ahead of them and are normalised at
+// the end of the render, by a launch over the plan's FX records (fx_rows != nullptr).
+__global__ void fx_mark_kernel(const adtfe_fx* __restrict__ fx_rows, int n_rows, int* __restrict__ seg_fx) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rows) seg_fx[fx_rows[r].seg] = 1;
+}
+
 __global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_segment* __restrict__ segments,
                                                                  const float* __restrict__ tile_max, int tiles_per_seg,
-                                                                 int64_t ld_wav, float* __restrict__ wav) {
-    const int tile_id = blockIdx.x, tid = threadIdx.x;
-    const int seg = tile_id / tiles_per_seg, lo = (tile_id - seg * tiles_per_seg) * ADTFE_TILE;
+                                                                 int64_t ld_wav, float* __restrict__ wav, int seg0,
+                                                                 const int* __restrict__ seg_fx,
+                                                                 const adtfe_fx* __restrict__ fx_rows) {
+    const int tid = threadIdx.x;
+    const int row_id = blockIdx.x / tiles_per_seg, lo = (blockIdx.x - row_id * tiles_per_seg) * ADTFE_TILE;
+    const int seg = fx_rows ? fx_rows[row_id].seg : seg0 + row_id;
+    if (!fx_rows && seg_fx[seg]) return;
     const adtfe_segment sg = segments[seg];
     if ((sg.flags & 1) == 0 || lo >= sg.len) return;   // 0: empty row; ADTFE_SEG_RAW: the caller wants the raw mix
     float peak = 0.0f;
@@ -581,6 +593,9 @@ __global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_seg
     }
     for (int i = 4 * n4 + tid; i < n; i += kNormThreads) row[i] = norm(row[i]);
 }
+
+constexpr int kFxStreams = 4;   // streams the chunks' reverb launches rotate over (bank streams 3 .. 6)
+static_assert(kBankStreams >= 3 + kFxStreams, "bank streams");
 
 static size_t mix_smem_bytes() { return (size_t)kDepth * kStageFloats * 4 + kDepth * 8 + 64; }
 
@@ -615,8 +630,8 @@ int adtfe::mixer_prepare_device() {
 extern "C" size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg,
                                                int32_t n_tile_events) {
     if (n_events < 0 || n_seg < 0 || tiles_per_seg < 0 || n_tile_events < 0) return 0;
-    // resolved events | peak bits, queue heads (one zeroed block) | tile maxima | per-tile slice records
-    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_events * 4 + (size_t)n_seg * 4 + 4) +
+    // resolved events | peak bits, queue heads, FX row marks (one zeroed block) | tile maxima | per-tile slice records
+    return align256((size_t)n_events * sizeof(ResolvedEvent)) + align256((size_t)n_events * 4 + (size_t)n_seg * 8 + 4) +
            align256((size_t)n_seg * tiles_per_seg * kSub * 4) +
            align256((size_t)n_tile_events * kSub * sizeof(TileSlice)) + 256;
 }
@@ -669,11 +684,16 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
     ResolvedEvent* resolved = (ResolvedEvent*)ws;
     int* peak_bits = (int*)(ws + align256((size_t)plan->n_events * sizeof(ResolvedEvent)));
     int* counters = peak_bits + plan->n_events;  // one work-queue head per chunk (n_chunks <= n_seg)
-    float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4 + (size_t)plan->n_seg * 4 + 4));
+    int* seg_fx = counters + plan->n_seg + 1;    // 1: the row has an FX record (normalised after the FX chain)
+    float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4 + (size_t)plan->n_seg * 8 + 4));
     TileSlice* slices = (TileSlice*)((char*)tile_max + align256((size_t)plan->n_seg * plan->tiles_per_seg * kSub * 4));
     // zero the peaks and the queue heads once, then fork the chunks over the bank's streams
-    ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, ((size_t)plan->n_events + (size_t)plan->n_seg + 1) * 4, user));
-    const bool fork = n_chunks > 1 && bank->n_streams >= 3;
+    ADTFE_CUDA(cudaMemsetAsync(peak_bits, 0, ((size_t)plan->n_events + 2 * (size_t)plan->n_seg + 1) * 4, user));
+    if (plan->n_fx > 0) {
+        fx_mark_kernel<<<(plan->n_fx + 127) / 128, 128, 0, user>>>(plan->fx_dev, plan->n_fx, seg_fx);
+        ADTFE_CUDA(cudaGetLastError());
+    }
+    const bool fork = n_chunks > 1 && bank->n_streams >= 3 + kFxStreams;
     std::unique_lock<std::mutex> lock(bank->mu, std::defer_lock);
     // A chunked plan runs as a three-stage software pipeline over the bank's internal streams - stage 0: peaks and
     // slice records, stage 1: tile mixer, stage 2: row normalisation - chunk c's stage k waiting (event) for its
@@ -681,12 +701,21 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
     // normalisation of chunk c (HBM read + write) can be on the GPU together.  Measured: the same 7.0 ms per step as
     // whole chunks on four streams (round 1) - the kernels are bound by what an SM can keep in flight, and that
     // they share - with one stream and two events fewer per chunk.
-    cudaStream_t s_peak = user, s_mix = user, s_norm = user;
+    // FX rows take further streams.  Both FX kernels are recursions over a row's samples: a launch takes about the same
+    // time whatever its number of rows (reverb 1.3 ms up to 8 rows per SM, dynamics 0.8 ms), so the FX launches of the
+    // chunks must not queue behind each other (one stream for all of them cost 25.7 ms instead of 3.3 ms for 64 batches
+    // of the stock FX configuration): the reverb of a chunk's FX rows goes behind the chunk's mixer on one of kFxStreams
+    // streams in turn, and - once the last chunk's reverb is enqueued - ONE dynamics launch and one normalisation cover
+    // all the plan's FX rows.
+    cudaStream_t s_peak = user, s_mix = user, s_norm = user, s_fx[kFxStreams];
+    for (cudaStream_t& st : s_fx) st = user;
     if (fork) {
         lock.lock();
         s_peak = bank->streams[0]; s_mix = bank->streams[1]; s_norm = bank->streams[2];
+        for (int k = 0; k < kFxStreams; ++k) s_fx[k] = bank->streams[3 + k];
         ADTFE_CUDA(cudaEventRecord(bank->fork_event, user));
-        for (int k = 0; k < 3; ++k) ADTFE_CUDA(cudaStreamWaitEvent(bank->streams[k], bank->fork_event, 0));
+        for (int k = 0; k < 3 + (plan->n_fx > 0 ? kFxStreams : 0); ++k)
+            ADTFE_CUDA(cudaStreamWaitEvent(bank->streams[k], bank->fork_event, 0));
     }
     float* mix_out = wav_out_dev;
     const int tps = plan->tiles_per_seg;
@@ -724,25 +753,45 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
         mix_kernel<<<grid, 32, mix_smem_bytes(), s_mix>>>(a);
         trace_close(s_mix);
         ADTFE_CUDA(cudaGetLastError());
+        const int fx0 = ch[c].fx_row, n_fx = ch[c + 1].fx_row - fx0;
         if (fork) {
             cudaEvent_t e = bank->stage_events[1][c % kStageEvents];
             ADTFE_CUDA(cudaEventRecord(e, s_mix));
             ADTFE_CUDA(cudaStreamWaitEvent(s_norm, e, 0));
-        }
-        if (ch[c + 1].fx_row > ch[c].fx_row) {   // the chunk's FX rows: raw mix -> FX -> (new row peak) -> normalise
-            const int rc = fx_launch(plan, ch[c].fx_row, ch[c + 1].fx_row - ch[c].fx_row, mix_out, tile_max, tps * kSub,
-                                     s_norm);
-            if (rc != ADTFE_OK) return rc;
+            if (n_fx > 0) ADTFE_CUDA(cudaStreamWaitEvent(s_fx[c % kFxStreams], e, 0));
         }
         trace_open("normalise", c, s_norm);
-        normalise_kernel<<<a.n_tiles, kNormThreads, 0, s_norm>>>(plan->segments_dev + s0, a.tile_max, tps, plan->ld_wav,
-                                                                 a.wav);
+        normalise_kernel<<<a.n_tiles, kNormThreads, 0, s_norm>>>(plan->segments_dev, tile_max, tps, plan->ld_wav, mix_out,
+                                                                 s0, seg_fx, nullptr);
         trace_close(s_norm);
         ADTFE_CUDA(cudaGetLastError());
+        if (n_fx > 0) {   // the chunk's FX rows: raw mix -> reverb now; dynamics, the new row peak and normalise below
+            const int rc = fx_reverb_launch(plan, fx0, n_fx, mix_out, s_fx[c % kFxStreams]);
+            if (rc != ADTFE_OK) return rc;
+        }
     }
-    if (fork) {   // the last stage finishes last: one join
+    if (plan->n_fx > 0) {
+        if (fork) {   // every reverb before the dynamics
+            for (int k = 1; k < kFxStreams; ++k) {
+                ADTFE_CUDA(cudaEventRecord(bank->join_events[3 + k], s_fx[k]));
+                ADTFE_CUDA(cudaStreamWaitEvent(s_fx[0], bank->join_events[3 + k], 0));
+            }
+        }
+        const int rc = fx_dynamics_launch(plan, 0, plan->n_fx, mix_out, tile_max, tps * kSub, s_fx[0]);
+        if (rc != ADTFE_OK) return rc;
+        trace_open("normalise_fx", 0, s_fx[0]);
+        normalise_kernel<<<plan->n_fx * tps, kNormThreads, 0, s_fx[0]>>>(plan->segments_dev, tile_max, tps, plan->ld_wav,
+                                                                         mix_out, 0, seg_fx, plan->fx_dev);
+        trace_close(s_fx[0]);
+        ADTFE_CUDA(cudaGetLastError());
+    }
+    if (fork) {   // the last stage and the FX chain finish last: two joins
         ADTFE_CUDA(cudaEventRecord(bank->join_events[2], s_norm));
         ADTFE_CUDA(cudaStreamWaitEvent(user, bank->join_events[2], 0));
+        if (plan->n_fx > 0) {
+            ADTFE_CUDA(cudaEventRecord(bank->join_events[3], s_fx[0]));
+            ADTFE_CUDA(cudaStreamWaitEvent(user, bank->join_events[3], 0));
+        }
     }
     return ADTFE_OK;
 }

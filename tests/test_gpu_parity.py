@@ -147,6 +147,57 @@ def test_long_form_render_chunk_and_featurise():
 
 
 # ------------------------------------------------------------------ edge cases
+def test_peak_pass_on_banks_that_defeat_its_pruning():
+    """The peak pass bounds the blocks of a mixed one-shot with per-block maxima and scans only the blocks that can
+    hold the peak.  One-shots built against that: flat envelopes (every block is a candidate), the peak in the very
+    last sample / last block, lengths around the block size and the float4 granule (1, 3, 255, 256, 257, 513 ...),
+    two one-shots whose mix cancels almost everywhere (the bound is loose), an all-zero one-shot, and more notes of
+    one instrument than the kernel bounds together (8).  The waveform must still equal the oracle's."""
+    from adt_str_b200.bank import OneShotBank
+    from adt_str_b200.config import SETTING_1, setting_1
+    rng = np.random.default_rng(91)
+    shots = []
+    for n in (1, 3, 255, 256, 257, 513, 1024, 3000, 7777):
+        shots.append(rng.standard_normal(n).astype(np.float32))                       # flat envelope
+    late = (0.1 * rng.standard_normal(5000)).astype(np.float32); late[-1] = 3.0     # the peak is the last sample
+    ramp = (rng.standard_normal(4100) * np.linspace(0.01, 1.0, 4100)).astype(np.float32)   # loudest block last
+    base = rng.standard_normal(6000).astype(np.float32)
+    anti = (-base + 1e-3 * rng.standard_normal(6000)).astype(np.float32)             # cancels `base` when mixed
+    shots += [late, ramp, base, anti, np.zeros(700, np.float32)]
+    nested = {}
+    for pitch in (36, 38, 42):                                                        # every pitch draws from all of them
+        nested[str(pitch)] = {"gold": {f"s{i:02d}": (x / max(np.abs(x).max(), 1e-30)).astype(np.float32) if x.any() else x
+                                       for i, x in enumerate(shots)}}
+    nested["44"] = {"gold": {"z0": np.zeros(700, np.float32), "z1": np.zeros(300, np.float32)}}   # main = sub = silence
+    bank = OneShotBank.from_nested(nested)
+    synth, _, _ = _objects(setting_1(), bank)
+    segs = []
+    for k in range(48):
+        e = int(rng.integers(1, 40))                                                  # up to ~13 notes per instrument
+        onset = np.sort(rng.uniform(0.0, 2.4, e)).astype(np.float32)
+        notes = np.stack([onset, onset + np.float32(0.1), rng.choice([36, 38, 42], e).astype(np.float32),
+                          rng.integers(1, 127, e).astype(np.float32)], 1)
+        if k % 6 == 5:
+            notes[e // 2, 2] = 44.0                                                   # 0 / 0 over that note's samples
+        segs.append(notes)
+    random.seed(1234)
+    wav, lengths = synth.render_batch(segs)
+    wav = wav.cpu().numpy()
+    random.seed(1234)
+    c = dict(SETTING_1)
+    nan_rows = 0
+    for i, notes in enumerate(segs):
+        ref = synth_oracle.render(notes, c, nested)
+        assert int(lengths[i]) == len(ref)
+        got = wav[i, : len(ref)]
+        if np.isnan(ref).any():                                                       # a note whose mixed one-shot is silence: 0 / 0
+            assert np.array_equal(np.isnan(got), np.isnan(ref))
+            nan_rows += 1
+        else:
+            assert np.abs(got - ref).max() <= WAV_TOL, i
+    assert 0 < nan_rows < len(segs)
+
+
 def test_silent_mix_is_nan_like_the_reference_and_neighbours_are_untouched():
     from adt_str_b200.config import SETTING_1, setting_1
     from adt_str_b200.synthetic import make_bank
