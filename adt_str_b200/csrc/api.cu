@@ -175,11 +175,60 @@ extern "C" int adtfe_bank_create(const float* pcm_host, int64_t total_floats, co
     return ADTFE_OK;
 }
 
+// The log-mel of a render chunk is launched as soon as the chunk is normalised, on the caller's stream, and runs while
+// the next chunks are rendered: the log-mel kernel is bound by instruction issue and shared memory and uses a tenth of
+// the HBM bandwidth, the normalisation is bound by HBM and uses neither - under one log-mel launch at the end of the
+// render the two ran one after the other.  (Peaks and the tile mixer need the shared memory the log-mel CTAs hold, so
+// they take turns with them.)  Rows with an FX record are left out of the per-chunk launches and featurised by one more
+// launch when the FX chain is through.
+namespace {
+struct MelPerChunk {
+    const adtfe_bank* bank;
+    const adtfe_mel* mel;
+    const adtfe_plan* plan;
+    const float* wav;
+    float* out;
+    cudaStream_t user;
+    bool fx;
+};
+int mel_chunk_hook(void* ctx, int chunk, int seg0, int n_seg, const int* seg_fx, cudaStream_t done) {
+    const MelPerChunk* m = (const MelPerChunk*)ctx;
+    if (done != m->user) {
+        cudaEvent_t e = m->bank->stage_events[2][chunk % kStageEvents];
+        ADTFE_CUDA(cudaEventRecord(e, done));
+        ADTFE_CUDA(cudaStreamWaitEvent(m->user, e, 0));
+    }
+    trace_open("logmel", chunk, m->user);
+    const int rc = logmel_rows_filtered(m->mel, m->wav + (size_t)seg0 * m->plan->ld_wav, n_seg, m->plan->ld_wav,
+                                        m->plan->mel_rows_dev + seg0, m->plan->mel_max_count, m->out,
+                                        m->fx ? seg_fx + seg0 : nullptr, 0, m->user);
+    trace_close(m->user);
+    return rc;
+}
+}  // namespace
+
 extern "C" int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel, const adtfe_plan* plan,
                                    int64_t n_samples, float* wav_out_dev, float* mel_out_dev, void* workspace_dev,
                                    size_t workspace_bytes, void* stream) {
     ADTFE_REQUIRE(plan && (plan->mel_rows_dev || n_samples <= plan->ld_wav), ADTFE_ERR_BAD_ARG,
                   "adtfe_render_logmel: n_samples exceeds the row pitch");
+    if (plan->mel_rows_dev && plan->n_chunks > 1 && plan->chunks_host && mel && logmel_has_row_filter(mel) &&
+        mel_out_dev && plan->mel_max_count > 0) {
+        ADTFE_REQUIRE(((uintptr_t)plan->mel_rows_dev & 15) == 0 &&
+                          (int64_t)mel->wpi * mel->hop >= 1024 &&
+                          (int64_t)(mel->wpi + plan->mel_max_count - 1) * mel->hop + 1024 <= plan->ld_wav,
+                      ADTFE_ERR_UNSUPPORTED, "adtfe_render_logmel: frame support leaves the row");
+        MelPerChunk m{bank, mel, plan, wav_out_dev, mel_out_dev, (cudaStream_t)stream, plan->n_fx > 0};
+        const ChunkHook hook{mel_chunk_hook, &m};
+        const int* seg_fx = nullptr;
+        int rc = render_impl(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream, &hook, &seg_fx);
+        if (rc != ADTFE_OK || plan->n_fx == 0) return rc;
+        trace_open("logmel_fx", -1, (cudaStream_t)stream);   // the FX rows: the render has joined its FX stream into `stream`
+        rc = logmel_rows_filtered(mel, wav_out_dev, plan->n_seg, plan->ld_wav, plan->mel_rows_dev, plan->mel_max_count,
+                                  mel_out_dev, seg_fx, 1, stream);
+        trace_close((cudaStream_t)stream);
+        return rc;
+    }
     int rc = adtfe_render(bank, plan, wav_out_dev, workspace_dev, workspace_bytes, stream);
     if (rc != ADTFE_OK) return rc;
     if (plan->mel_rows_dev) {

@@ -100,6 +100,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 struct adtfe_mel_tables;
 struct adtfe_bank;
+struct adtfe_mel;
 
 namespace adtfe {
 int mixer_prepare_device();
@@ -109,8 +110,18 @@ int fx_prepare_device();
 int fx_reverb_launch(const adtfe_plan* plan, int r0, int n_rows, float* wav, cudaStream_t st);
 int fx_dynamics_launch(const adtfe_plan* plan, int r0, int n_rows, float* wav, float* tile_max, int max_per_seg,
                        cudaStream_t st);
+// Called by render_impl behind the normalisation of every chunk (rows [seg0, seg0 + n_seg) are final except those
+// marked in seg_fx, which wait for the FX chain): `done` is on the stream that ran the normalisation.
+struct ChunkHook {
+    int (*fn)(void* ctx, int chunk, int seg0, int n_seg, const int* seg_fx, cudaStream_t done);
+    void* ctx;
+};
 int render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
-                size_t workspace_bytes, void* stream);
+                size_t workspace_bytes, void* stream, const ChunkHook* hook = nullptr, const int** seg_fx_out = nullptr);
+bool logmel_has_row_filter(const struct ::adtfe_mel* mel);
+int logmel_rows_filtered(const struct ::adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
+                         const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, const int* seg_mark,
+                         int mark_want, void* stream);
 // Diagnostics (adtfe_trace_begin / adtfe_trace_dump): a pair of timing events around every kernel launch.
 void trace_open(const char* kernel, int index, cudaStream_t st);
 void trace_close(cudaStream_t st);
@@ -139,7 +150,7 @@ struct adtfe_bank {
     cudaEvent_t fork_event = nullptr, join_events[kBankStreams] = {};
     // pipeline of a chunked render: stage_events[k][c % kStageEvents] = chunk c left stage k (an event can be
     // re-recorded as soon as the wait on its previous recording has been enqueued)
-    cudaEvent_t stage_events[2][kStageEvents] = {};
+    cudaEvent_t stage_events[3][kStageEvents] = {};   // [2]: chunk c is normalised (the log-mel of the chunk waits for it)
     mutable std::mutex mu;
 };
 

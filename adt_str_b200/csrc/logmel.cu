@@ -104,6 +104,8 @@ struct LogmelArgs {
     const float* weights;
     const MelGroup* groups;
     const adtfe_mel_row* rows;  // ragged form: per-segment frame count and first output row (else NULL)
+    const int* seg_mark;        // row filter of the warp-autonomous kernel (else NULL): rows with (seg_mark[seg] != 0) !=
+    int32_t mark_want;          // (mark_want != 0) are left out of this launch (the render's FX rows come later)
     int64_t ld_wav;
     int32_t n_seg, first, count, hop, n_mels;
     int32_t rounds_per_seg, n_rounds;
@@ -456,6 +458,7 @@ __device__ __forceinline__ Unit6 unit6_geom(const LogmelArgs& p, int u, int unit
         count = row.z;
         g.silent = (row.w & ADTFE_MEL_ROW_SILENT) != 0;
     }
+    if (p.seg_mark && (__ldg(p.seg_mark + g.seg) != 0) != (p.mark_want != 0)) count = 0;
     g.nf = max(0, min(kUnitFrames, count - g.j0));
     g.count = count;
     g.out_row = base + g.j0;
@@ -717,7 +720,8 @@ static size_t logmel6_smem_bytes(int warps, int unit) {
 }
 
 static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav, int32_t first,
-                         int32_t count, const adtfe_mel_row* rows_dev, float* out_dev, void* stream) {
+                         int32_t count, const adtfe_mel_row* rows_dev, float* out_dev, void* stream,
+                         const int* seg_mark = nullptr, int mark_want = 0) {
     // frames per round: as many as fit the span buffer, at most 32; a segment's frames are split evenly
     const int cap = std::min(kRound, (kSpanFloats - 2048) / mel->hop + 1);
     const int rounds_per_seg = (count + cap - 1) / cap;
@@ -726,6 +730,7 @@ static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_s
     LogmelArgs a;
     a.wav = wav_dev; a.out = out_dev; a.window = mel->window; a.twiddle = mel->twiddle; a.lane_tw = mel->lane_tw;
     a.weights = mel->weights; a.groups = (const MelGroup*)mel->groups; a.rows = rows_dev; a.ld_wav = ld_wav;
+    a.seg_mark = seg_mark; a.mark_want = mark_want;
     a.n_seg = n_seg; a.first = first; a.count = count;
     a.hop = mel->hop; a.n_mels = mel->n_mels; a.rounds_per_seg = rounds_per_seg; a.n_rounds = (int32_t)n_rounds;
     if (mel->v6_ok && !mel->force_generic) {
@@ -744,6 +749,7 @@ static int launch_logmel(const adtfe_mel* mel, const float* wav_dev, int32_t n_s
         ADTFE_CUDA(cudaGetLastError());
         return ADTFE_OK;
     }
+    ADTFE_REQUIRE(!seg_mark, ADTFE_ERR_UNSUPPORTED, "adtfe_logmel: the row filter needs the warp-autonomous kernel");
     const int grid = (int)(n_rounds < mel->sm_count ? n_rounds : mel->sm_count);
     logmel_kernel<<<grid, kThreads, mel->smem_bytes, (cudaStream_t)stream>>>(a, mel->tables->t);
     ADTFE_CUDA(cudaGetLastError());
@@ -781,6 +787,16 @@ extern "C" int adtfe_logmel_rows(const adtfe_mel* mel, const float* wav_dev, int
     ADTFE_REQUIRE((int64_t)first * mel->hop >= 1024 && (int64_t)(first + max_count - 1) * mel->hop + 1024 <= ld_wav,
                   ADTFE_ERR_UNSUPPORTED, "adtfe_logmel_rows: frame support leaves the row");
     return launch_logmel(mel, wav_dev, n_seg, ld_wav, first, max_count, rows_dev, out_dev, stream);
+}
+
+// The ragged form over a range of a plan's rows with a row filter (api.cu: the log-mel of a render chunk runs while
+// later chunks are still being rendered; rows with an FX record follow when the FX chain is through).
+bool adtfe::logmel_has_row_filter(const adtfe_mel* mel) { return mel && mel->v6_ok && !mel->force_generic; }
+int adtfe::logmel_rows_filtered(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg, int64_t ld_wav,
+                                const adtfe_mel_row* rows_dev, int32_t max_count, float* out_dev, const int* seg_mark,
+                                int mark_want, void* stream) {
+    if (n_seg == 0 || max_count == 0) return ADTFE_OK;
+    return launch_logmel(mel, wav_dev, n_seg, ld_wav, mel->wpi, max_count, rows_dev, out_dev, stream, seg_mark, mark_want);
 }
 
 extern "C" int adtfe_mel_destroy(adtfe_mel* mel) {

@@ -642,7 +642,7 @@ extern "C" int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, floa
 }
 
 int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
-                       size_t workspace_bytes, void* stream) {
+                       size_t workspace_bytes, void* stream, const ChunkHook* hook, const int** seg_fx_out) {
     ADTFE_REQUIRE(bank && plan, ADTFE_ERR_BAD_ARG, "adtfe_render: null bank or plan");
     ADTFE_REQUIRE(plan->n_seg >= 0 && plan->n_events >= 0 && plan->n_peak_work >= 0 && plan->tiles_per_seg >= 0 &&
                       plan->n_tile_events >= 0 && plan->n_fx >= 0,
@@ -685,6 +685,7 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
     int* peak_bits = (int*)(ws + align256((size_t)plan->n_events * sizeof(ResolvedEvent)));
     int* counters = peak_bits + plan->n_events;  // one work-queue head per chunk (n_chunks <= n_seg)
     int* seg_fx = counters + plan->n_seg + 1;    // 1: the row has an FX record (normalised after the FX chain)
+    if (seg_fx_out) *seg_fx_out = seg_fx;
     float* tile_max = (float*)((char*)peak_bits + align256((size_t)plan->n_events * 4 + (size_t)plan->n_seg * 8 + 4));
     TileSlice* slices = (TileSlice*)((char*)tile_max + align256((size_t)plan->n_seg * plan->tiles_per_seg * kSub * 4));
     // zero the peaks and the queue heads once, then fork the chunks over the bank's streams
@@ -765,6 +766,10 @@ int adtfe::render_impl(const adtfe_bank* bank, const adtfe_plan* plan, float* wa
                                                                  s0, seg_fx, nullptr);
         trace_close(s_norm);
         ADTFE_CUDA(cudaGetLastError());
+        if (hook) {
+            const int rc = hook->fn(hook->ctx, c, s0, n_seg, seg_fx, s_norm);
+            if (rc != ADTFE_OK) return rc;
+        }
         if (n_fx > 0) {   // the chunk's FX rows: raw mix -> reverb now; dynamics, the new row peak and normalise below
             const int rc = fx_reverb_launch(plan, fx0, n_fx, mix_out, s_fx[c % kFxStreams]);
             if (rc != ADTFE_OK) return rc;
