@@ -169,11 +169,13 @@ int64_t adtfe_bank_bytes(const adtfe_bank* bank);
 /* ---- render ------------------------------------------------------------------------ */
 size_t adtfe_render_workspace_bytes(int32_t n_events, int32_t n_seg, int32_t tiles_per_seg, int32_t n_tile_events);
 /* Writes the (n_seg, ld_wav) float32 waveform matrix: every row normalised as the reference
- * does and zero-padded to ld_wav.  Four kernels per chunk: per-note peak of the mixed one-shot, the per-tile
- * slice records, the tile mixer, the row normalisation; with plan->n_fx > 0 the FX kernels (reverb, dynamics) run
- * on the chunk's FX rows between the mixer and the normalisation.  A plan with chunks (plan->chunks_host) is rendered chunk by chunk on the
- * bank's internal streams, forked from and joined back into `stream`; calls on one bank handle must not
- * be made from several host threads at once. */
+ * does and zero-padded to ld_wav.  Four kernels per chunk: per-note peak of the mixed one-shot (branch and bound
+ * over the bank's block maxima), the per-tile slice records, the tile mixer, the row normalisation.  With
+ * plan->n_fx > 0 the rows with an FX record are left out of the per-chunk normalisation: their reverb runs behind
+ * the chunk's mixer, then one dynamics launch and one normalisation cover all the plan's FX rows.  A plan with chunks
+ * (plan->chunks_host) is rendered chunk by chunk on the bank's internal streams, forked from and joined back into
+ * `stream`; calls on one bank handle must not be made from several host threads at once.  The waveform matrix must
+ * not be read between the chunks: rows are final when the call's work on `stream` is. */
 int adtfe_render(const adtfe_bank* bank, const adtfe_plan* plan, float* wav_out_dev, void* workspace_dev,
                  size_t workspace_bytes, void* stream);
 
@@ -203,7 +205,9 @@ int adtfe_logmel_rows(const adtfe_mel* mel, const float* wav_dev, int32_t n_seg,
 /* ---- fused call -------------------------------------------------------------------- */
 /* adtfe_render then adtfe_logmel over the first n_samples (<= plan->ld_wav) floats of every
  * row: n_samples is the collated batch width (longest segment), which sets the frame count.
- * With plan->mel_rows_dev the ragged form is used instead and n_samples is ignored. */
+ * With plan->mel_rows_dev the ragged form is used instead and n_samples is ignored; a plan with chunks then gets
+ * the log-mel of every chunk launched behind the chunk's normalisation (on `stream`, while later chunks are being
+ * rendered) and the rows with an FX record featurised by one more launch at the end - same results. */
 int adtfe_render_logmel(const adtfe_bank* bank, const adtfe_mel* mel, const adtfe_plan* plan, int64_t n_samples,
                         float* wav_out_dev, float* mel_out_dev, void* workspace_dev, size_t workspace_bytes,
                         void* stream);
