@@ -10,22 +10,22 @@
 // another 768 B per row), the whole weight matrix stays in shared memory for the life of a CTA, and the 768-wide
 // output row leaves through the epilogue once.
 //
-// One persistent CTA of 8 warps per SM; the output columns are split over a PAIR of CTAs (n_out > 384: 384 columns
-// each), so that half the weight per CTA leaves 70 KB of shared memory for a staged epilogue.  Per tile of 128 rows:
-//   A      a warp instruction fetches one row (512 contiguous bytes), one tile AHEAD, behind the epilogue of the current
-//          one; each lane converts its four floats to bf16 and stores them into the K-major no-swizzle canonical
-//          layout: 8-row x 16-byte core matrices, rows of a k-group contiguous
+// Persistent CTAs of 8 warps, TWO per SM; the output columns are split over the CTAs of a tile of 128 rows in parts of at
+// most 192 columns (768 -> 4 x 192), so that a CTA's weight part (48 KB), its bf16 copy of the tile (32 KB) and the
+// epilogue staging (20 KB) fit twice into an SM - the second CTA is what overlaps the phases of a tile.  Per tile:
+//   A      a warp instruction fetches one row (512 contiguous bytes), sixteen in flight per warp; each lane converts
+//          its four floats to bf16 and stores them into the K-major no-swizzle canonical layout: 8-row x 16-byte core
+//          matrices, rows of a k-group contiguous
 //          (offset(r, k) = (k / 8) * 2064 + r * 16 + (k % 8) * 2: LBO = 2064 B - 16 B of padding per k-group make the
 //          warp's stores conflict-free - SBO = 128 B)
-//   MMA    one thread issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = 256, K = 16) eight times per 256-column
-//          slab of the output, operands by shared-memory descriptors, D in tensor memory; three slabs for 768
-//          columns alternate between two 256-column TMEM stages; tcgen05.commit arrives on the stage's mbarrier
-//   D      all eight warps drain a stage: warp w reads the TMEM lanes of its quarter (w % 4) and its half of the
-//          columns (w / 4) with tcgen05.ld.32x32b.x32 - one output row per thread, 32 columns per instruction - adds
-//          the bias, rounds to bf16 and parks the row in the warp's staging rows; the warp then writes the rows out
-//          together, consecutive lanes consecutive 16-byte pieces: whole 128-byte lines per store instruction (a thread
-//          storing its own row touches 32 different lines per instruction: 4x the L1 store transactions, measured
-//          3.3 ms against the library's 1.7 ms on 4 M rows).  The next slab's MMAs run meanwhile.
+//   MMA    one thread issues tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = the part's columns, K = 16) eight times,
+//          operands by shared-memory descriptors, D in tensor memory (256 columns per CTA); tcgen05.commit arrives on
+//          the accumulator's mbarrier
+//   D      all eight warps drain: warp w reads the TMEM lanes of its quarter (w % 4) and its half of the part's
+//          32-column units (w / 4) with tcgen05.ld.32x32b.x32 - one output row per thread - adds the bias, rounds to
+//          bf16 and parks the 32 x 32 block in the warp's staging rows; the warp then writes the block out together,
+//          consecutive lanes consecutive 16-byte pieces: whole sectors, 64 contiguous bytes per row (a thread storing
+//          its own row touches 32 different lines per instruction: 4x the L1 store transactions).
 #include <cuda_bf16.h>
 
 #include <string.h>
@@ -39,8 +39,8 @@ struct adtfe_linear {
     int device = 0;
     int sm_count = 148;
     int32_t n_in = 128, n_out = 768;
-    int32_t n_halves = 1;      // CTAs that share a tile of rows, each with its own range of output columns
-    void* w_image = nullptr;   // bf16, canonical K-major layout per column half, halves back to back: n_out * 256 bytes
+    int32_t n_parts = 1;       // CTAs that share a tile of rows, each with its own range of output columns
+    void* w_image = nullptr;   // bf16, canonical K-major layout per column part, parts back to back: n_out * 256 bytes
     float* bias = nullptr;     // n_out floats, already rounded to bf16 (autocast casts the bias too)
     size_t smem_bytes = 0;
 };
@@ -49,7 +49,6 @@ namespace adtfe {
 
 constexpr int kPM = 128;          // rows per tile = UMMA M
 constexpr int kPK = 128;          // n_mels
-constexpr int kPN = 256;          // columns per MMA slab = UMMA N (the last slab may be narrower)
 constexpr int kPThreads = 256;
 constexpr int kALbo = kPM * 16 + 16;         // bytes between the k-groups of the A tile: 2048 + 16, so that the 32 lanes of
                                              // a warp (one row: 16 k-groups x 2 halves) store to 32 different banks
@@ -100,42 +99,51 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&p);
 }
 
-constexpr int kStagePitch = 256 + 16;         // bytes per staged row: 128 bf16 columns + 16 B so that the rows' 16-byte stores spread over the banks
-constexpr int kStageBytes = 32 * kStagePitch; // per warp: its 32 rows x its (up to) 128 columns of a slab
+constexpr int kPartCols = 192;                // output columns per CTA at most: 48 KB of weight, 192 of 256 TMEM columns
+constexpr int kStagePitch = 64;               // bytes per staged row: 32 bf16 columns; the 16-byte pieces of row r sit at
+                                              // piece ^ ((r >> 1) & 3), which keeps both the row-wise stores (lane = row) and
+                                              // the piece-wise loads (lane = quarter row) free of bank conflicts
+constexpr int kStageBytes = 32 * kStagePitch; // per warp: its 32 rows x 32 columns
 
-// Column split: output columns [col0, col0 + nh) belong to CTA half `half` of a CTA pair (n_halves = 2 when n_out > 384:
-// half the weight per CTA leaves shared memory for a staged, coalesced epilogue; both CTAs of a pair convert the same
-// 128 rows - the second read of the tile comes from L2).
-__host__ __device__ inline int half_cols(int n_out, int n_halves, int half) {
-    if (n_halves == 1) return n_out;
-    const int first = ((n_out / 2 + 31) / 32) * 32;
-    return half == 0 ? first : n_out - first;
+// Column split: the n_out columns go to n_parts = ceil(n_out / 192) CTAs per tile of rows, in multiples of 32 columns
+// (768 -> 4 x 192, 512 -> 192 + 160 + 160, 256 -> 2 x 128).  A part's weight (<= 48 KB), its bf16 copy of the tile
+// (32 KB) and the epilogue staging (20 KB) leave room for TWO CTAs per SM, which is what overlaps the phases of a tile
+// - load and convert, MMA, drain and store - without any hand-off code: while one CTA drains, the other loads.  The
+// CTAs of a tile convert the same 128 rows (the re-reads come from L2).
+__host__ __device__ inline int n_parts_of(int n_out) { return (n_out + kPartCols - 1) / kPartCols; }
+__host__ __device__ inline int part_cols(int n_out, int part) {
+    const int u = n_out / 32, np = n_parts_of(n_out);
+    return 32 * (u / np + (part < u % np ? 1 : 0));
+}
+__host__ __device__ inline int part_col0(int n_out, int part) {
+    int c = 0;
+    for (int p = 0; p < part; ++p) c += part_cols(n_out, p);
+    return c;
 }
 
-__global__ void __launch_bounds__(kPThreads, 1) project_kernel(const float* __restrict__ x, int64_t n_rows,
+__global__ void __launch_bounds__(kPThreads, 2) project_kernel(const float* __restrict__ x, int64_t n_rows,
                                                                const void* __restrict__ w_image,
-                                                               const float* __restrict__ bias, int n_out, int n_halves,
+                                                               const float* __restrict__ bias, int n_out, int n_parts,
                                                                __nv_bfloat16* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int half = (int)blockIdx.x % n_halves;
-    const int nh = half_cols(n_out, n_halves, half), col0 = half == 0 ? 0 : half_cols(n_out, n_halves, 0);
-    unsigned char* s_w = smem;                                     // this half's weight image: nh * 256 bytes
-    unsigned char* s_a = smem + (size_t)half_cols(n_out, n_halves, 0) * 256;   // kATileBytes (same offset in both halves)
+    const int part = (int)blockIdx.x % n_parts;
+    const int nh = part_cols(n_out, part), col0 = part_col0(n_out, part);
+    unsigned char* s_w = smem;                                     // this part's weight image: nh * 256 bytes
+    unsigned char* s_a = smem + (size_t)part_cols(n_out, 0) * 256; // kATileBytes (part 0 is the widest)
     unsigned char* s_stage = s_a + kATileBytes;                    // 8 warps x kStageBytes
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + 8 * kStageBytes);   // [0]: weight copy, [1], [2]: TMEM stages
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 3);
-    __nv_bfloat16* s_bias = reinterpret_cast<__nv_bfloat16*>(s_bar + 4);   // nh bf16 (the bias is bf16 under autocast)
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_stage + 8 * kStageBytes);   // [0]: weight copy, [1]: accumulator
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+    float* s_bias = reinterpret_cast<float*>(s_bar + 4);   // nh floats holding bf16 values (the bias is bf16 under autocast)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         mbar_init(s_bar + 0, 1);
         mbar_init(s_bar + 1, 1);
-        mbar_init(s_bar + 2, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < nh; i += kPThreads) s_bias[i] = __float2bfloat16_rn(bias[col0 + i]);   // exact: rounded on the host
-    if (warp == 0) {   // 512 columns of tensor memory: two stages of 256 float32 accumulator columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512)
+    for (int i = tid; i < nh; i += kPThreads) s_bias[i] = bias[col0 + i];   // rounded to bf16 on the host
+    if (warp == 0) {   // 256 columns of tensor memory (two CTAs per SM share the 512)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -144,36 +152,27 @@ __global__ void __launch_bounds__(kPThreads, 1) project_kernel(const float* __re
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *s_tmem;
 
-    if (tid == 0) {   // this half's weight image, once per CTA: one k-group (nh rows x 16 bytes) per bulk copy
+    if (tid == 0) {   // this part's weight image, once per CTA: one k-group (nh rows x 16 bytes) per bulk copy
         const uint32_t group_bytes = (uint32_t)nh * 16u;
-        const unsigned char* src = (const unsigned char*)w_image + (size_t)col0 * 256;   // the halves lie back to back
+        const unsigned char* src = (const unsigned char*)w_image + (size_t)col0 * 256;   // the parts lie back to back
         mbar_expect_tx(s_bar + 0, group_bytes * 16u);
         for (int g = 0; g < 16; ++g) bulk_g2s(s_w + (size_t)g * group_bytes, src + (size_t)g * group_bytes, group_bytes, s_bar + 0);
     }
 
-    const int n_slabs = (nh + kPN - 1) / kPN;
     const uint32_t a_addr = smem_u32(s_a), w_addr = smem_u32(s_w);
     const uint32_t w_lbo = (uint32_t)nh * 16u;
-    uint32_t phase[2] = {0u, 0u};
+    const uint32_t idesc = umma_idesc_bf16(kPM, nh);
+    uint32_t phase = 0u;
     bool w_ready = false;
     const int64_t n_tiles = (n_rows + kPM - 1) / kPM;
-    const int64_t tile0 = (int64_t)blockIdx.x / n_halves, tile_step = (int64_t)gridDim.x / n_halves;
-
-    auto issue_slab = [&](int j) {   // one thread: the eight K = 16 steps of this half's columns [256 j, 256 j + cols)
-        const int cols = min(kPN, nh - j * kPN);
-        const uint32_t idesc = umma_idesc_bf16(kPM, cols);
-        const uint32_t d = tmem_base + (uint32_t)(j & 1) * kPN;
-#pragma unroll
-        for (int ks = 0; ks < kPK / 16; ++ks) {
-            const uint64_t adesc = umma_desc(a_addr + (uint32_t)(2 * ks) * kALbo, kALbo, 128);
-            const uint64_t bdesc = umma_desc(w_addr + (uint32_t)(2 * ks) * w_lbo + (uint32_t)j * (kPN * 16), w_lbo, 128);
-            umma_bf16(d, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
-        }
-        umma_commit(s_bar + 1 + (j & 1));
-    };
+    const int64_t tile0 = (int64_t)blockIdx.x / n_parts, tile_step = (int64_t)gridDim.x / n_parts;
+    // the epilogue's share of this warp: TMEM lanes of quarter q, the 32-column units [u_lo, u_hi) of the part
+    const int q = warp & 3, units = nh / 32;
+    const int u_lo = (warp >> 2) == 0 ? 0 : (units + 1) / 2, u_hi = (warp >> 2) == 0 ? (units + 1) / 2 : units;
+    unsigned char* mine = s_stage + warp * kStageBytes;
 
     // A tile in registers: iteration `it` of warp w is row it * 8 + w of the tile, lane l its float4 l - a whole row
-    // (512 contiguous bytes) per warp instruction.  Fetched one tile ahead, behind the epilogue of the current one.
+    // (512 contiguous bytes) per warp instruction.  Fetched one tile AHEAD, behind the epilogue of the current one.
     float4 v[16];
     auto fetch = [&](int64_t tile) {
 #pragma unroll
@@ -189,10 +188,10 @@ __global__ void __launch_bounds__(kPThreads, 1) project_kernel(const float* __re
         // ---- A: float32 -> bf16 into the canonical layout: k-group lane / 2, half lane % 2 of row it * 8 + warp
 #pragma unroll
         for (int it = 0; it < 16; ++it) {
-            uint2 q;
-            q.x = pack_bf16(v[it].x, v[it].y);
-            q.y = pack_bf16(v[it].z, v[it].w);
-            *reinterpret_cast<uint2*>(s_a + (size_t)(lane >> 1) * kALbo + (it * 8 + warp) * 16 + (lane & 1) * 8) = q;
+            uint2 qv;
+            qv.x = pack_bf16(v[it].x, v[it].y);
+            qv.y = pack_bf16(v[it].z, v[it].w);
+            *reinterpret_cast<uint2*>(s_a + (size_t)(lane >> 1) * kALbo + (it * 8 + warp) * 16 + (lane & 1) * 8) = qv;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> visible to the tensor core
         __syncthreads();
@@ -200,86 +199,65 @@ __global__ void __launch_bounds__(kPThreads, 1) project_kernel(const float* __re
             mbar_wait(s_bar + 0, 0u);
             w_ready = true;
         }
-        if (tid == 0) {
+        if (tid == 0) {   // one thread: the eight K = 16 steps of this part's columns
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            issue_slab(0);
-            if (n_slabs > 1) issue_slab(1);
+#pragma unroll
+            for (int ks = 0; ks < kPK / 16; ++ks) {
+                const uint64_t adesc = umma_desc(a_addr + (uint32_t)(2 * ks) * kALbo, kALbo, 128);
+                const uint64_t bdesc = umma_desc(w_addr + (uint32_t)(2 * ks) * w_lbo, w_lbo, 128);
+                umma_bf16(tmem_base, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(s_bar + 1);
         }
         if (tile + tile_step < n_tiles) fetch(tile + tile_step);   // the next tile's rows arrive behind the epilogue
-        for (int j = 0; j < n_slabs; ++j) {
-            const int stage = j & 1;
-            mbar_wait(s_bar + 1 + stage, phase[stage]);
-            phase[stage] ^= 1u;
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // ---- D: warp w drains the TMEM lanes of its quarter (w % 4) and its half (w / 4) of the slab's columns into
-            // its staging rows (one output row per thread, 32 columns per tcgen05.ld), then the warp writes the rows
-            // out together: consecutive lanes consecutive 16-byte pieces of a row - whole 128-byte lines per instruction
-            {
-                const int cols = min(kPN, nh - j * kPN);
-                const int q = warp & 3, chalf = warp >> 2;
-                const bool split = (cols & 63) == 0;                  // both warp groups take half of the slab's columns
-                const int wcols = split ? cols / 2 : (chalf == 0 ? cols : 0);
-                const int c_lo = split ? chalf * wcols : 0;
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)stage * kPN;
-                unsigned char* mine = s_stage + warp * kStageBytes;
-                uint32_t acc[2][32];
-                if (wcols > 0) tmem_ld32(taddr + (uint32_t)c_lo, acc[0]);
+        mbar_wait(s_bar + 1, phase);
+        phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- D: the warp drains its TMEM lanes, 32 columns per tcgen05.ld (one output row per thread), adds the bias,
+        // rounds to bf16 and parks the 32 x 32 block in its staging rows; the warp then writes the block out together,
+        // consecutive lanes consecutive 16-byte pieces of a row: whole 32-byte sectors, four pieces (64 contiguous
+        // bytes) per row and eight rows per store instruction (a thread storing its own row touches 32 different lines
+        // per instruction: 4x the L1 store transactions, 3.3 ms against the library's 1.7 ms on 4 M rows)
+        {
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+            const int64_t row_base = tile * kPM + q * 32;
+            for (int u = u_lo; u < u_hi; ++u) {   // warp-uniform: at most three units (192 columns over two warp groups)
+                uint32_t a[32];
+                tmem_ld32(taddr + (uint32_t)(32 * u), a);
+                tmem_ld_wait();
+                const float4* b4 = reinterpret_cast<const float4*>(s_bias + 32 * u);   // broadcast loads
+                const int swz = (lane >> 1) & 3;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int c0 = c_lo + 32 * k;
-                    if (32 * k >= wcols) break;                       // warp-uniform
-                    tmem_ld_wait();
-                    if (k < 3 && 32 * (k + 1) < wcols) tmem_ld32(taddr + (uint32_t)(c0 + 32), acc[(k + 1) & 1]);
-                    const uint32_t(&a)[32] = acc[k & 1];
-                    const uint4* b8 = reinterpret_cast<const uint4*>(s_bias + j * kPN + c0);   // 8 bf16 per load, broadcast
-                    uint4* dst = reinterpret_cast<uint4*>(mine + lane * kStagePitch + k * 64);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const uint4 b = b8[i];   // bf16 -> float32: the bits, shifted up
-                        uint4 o;
-                        o.x = pack_bf16(__uint_as_float(a[8 * i + 0]) + __uint_as_float(b.x << 16),
-                                        __uint_as_float(a[8 * i + 1]) + __uint_as_float(b.x & 0xffff0000u));
-                        o.y = pack_bf16(__uint_as_float(a[8 * i + 2]) + __uint_as_float(b.y << 16),
-                                        __uint_as_float(a[8 * i + 3]) + __uint_as_float(b.y & 0xffff0000u));
-                        o.z = pack_bf16(__uint_as_float(a[8 * i + 4]) + __uint_as_float(b.z << 16),
-                                        __uint_as_float(a[8 * i + 5]) + __uint_as_float(b.z & 0xffff0000u));
-                        o.w = pack_bf16(__uint_as_float(a[8 * i + 6]) + __uint_as_float(b.w << 16),
-                                        __uint_as_float(a[8 * i + 7]) + __uint_as_float(b.w & 0xffff0000u));
-                        dst[i] = o;
-                    }
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b0 = b4[2 * i], b1 = b4[2 * i + 1];
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(a[8 * i + 0]) + b0.x, __uint_as_float(a[8 * i + 1]) + b0.y);
+                    o.y = pack_bf16(__uint_as_float(a[8 * i + 2]) + b0.z, __uint_as_float(a[8 * i + 3]) + b0.w);
+                    o.z = pack_bf16(__uint_as_float(a[8 * i + 4]) + b1.x, __uint_as_float(a[8 * i + 5]) + b1.y);
+                    o.w = pack_bf16(__uint_as_float(a[8 * i + 6]) + b1.z, __uint_as_float(a[8 * i + 7]) + b1.w);
+                    *reinterpret_cast<uint4*>(mine + lane * kStagePitch + ((i ^ swz) << 4)) = o;
                 }
                 __syncwarp();
-                if (wcols > 0) {
-                    const int pieces = wcols / 8;                     // 16-byte pieces per row: 4, 8 or 16 (wcols 32 .. 128)
-                    const int rows_per_pass = 32 / pieces;
-                    const int64_t row_base = tile * kPM + q * 32;
-                    __nv_bfloat16* obase = out + (size_t)col0 + (size_t)j * kPN + c_lo;
-                    for (int r0 = 0; r0 < 32; r0 += rows_per_pass) {
-                        const int r = r0 + lane / pieces, piece = lane % pieces;
-                        const uint4 val = *reinterpret_cast<const uint4*>(mine + r * kStagePitch + piece * 16);
-                        if (row_base + r < n_rows)
-                            *reinterpret_cast<uint4*>(obase + (row_base + r) * n_out + piece * 8) = val;
-                    }
+                __nv_bfloat16* obase = out + (size_t)col0 + 32 * u;
+#pragma unroll
+                for (int r0 = 0; r0 < 32; r0 += 8) {
+                    const int r = r0 + (lane >> 2), piece = lane & 3;
+                    const uint4 val = *reinterpret_cast<const uint4*>(mine + r * kStagePitch + ((piece ^ ((r >> 1) & 3)) << 4));
+                    if (row_base + r < n_rows) *reinterpret_cast<uint4*>(obase + (row_base + r) * n_out + piece * 8) = val;
                 }
-                __syncwarp();   // the staging rows are rewritten by the next slab
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (j + 2 < n_slabs) {   // the stage just drained takes slab j + 2
-                __syncthreads();
-                if (tid == 0) {
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    issue_slab(j + 2);
-                }
+                __syncwarp();   // the staging rows are rewritten by the next unit
             }
         }
-        __syncthreads();   // every MMA of the tile has completed (their commits were waited for): A and TMEM are free
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();   // the MMAs of the tile have completed (their commit was waited for) and the accumulator is
+                           // drained: A and TMEM are free
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0) {
         if (!w_ready) mbar_wait(s_bar + 0, 0u);   // a CTA without tiles still has the weight copy in flight
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
     }
 }
 
@@ -312,26 +290,19 @@ extern "C" int adtfe_linear_create(int32_t n_in, int32_t n_out, const float* wei
     ADTFE_REQUIRE(n_out >= 32 && n_out <= 768 && n_out % 32 == 0, ADTFE_ERR_UNSUPPORTED,
                   "adtfe_linear_create: n_out %d unsupported (a multiple of 32 up to 768: the weight stays in shared memory)",
                   n_out);
-    for (int h = 0, nhv = n_out > 384 ? 2 : 1; h < nhv; ++h) {   // the epilogue handles slab widths 256, 128, 64 and 32
-        const int rest = half_cols(n_out, nhv, h) % kPN;
-        ADTFE_REQUIRE(rest == 0 || rest == 128 || rest == 64 || rest == 32, ADTFE_ERR_UNSUPPORTED,
-                      "adtfe_linear_create: n_out %d unsupported (per half of the columns, the part beyond whole 256-column "
-                      "slabs must be 32, 64 or 128 wide; 768, 640, 512, 384, 256, 128 ... are fine)", n_out);
-    }
     int rc = adtfe_device_ok(device);
     if (rc != ADTFE_OK) return rc;
     ADTFE_CUDA(cudaSetDevice(device));
-    // canonical K-major image per column half (nh columns from col0 on):
+    // canonical K-major image per column part (nh columns from col0 on):
     // offset(n, k) = col0 * 256 + (k / 8) * (nh * 16) + (n - col0) * 16 + (k % 8) * 2 bytes
-    const int n_halves = n_out > 384 ? 2 : 1;
+    const int n_parts = n_parts_of(n_out);
     std::vector<uint16_t> image((size_t)n_out * kPK);
-    for (int h = 0, col0 = 0; h < n_halves; ++h) {
-        const int nh = half_cols(n_out, n_halves, h);
+    for (int h = 0; h < n_parts; ++h) {
+        const int nh = part_cols(n_out, h), col0 = part_col0(n_out, h);
         for (int n = 0; n < nh; ++n)
             for (int k = 0; k < kPK; ++k)
                 image[(size_t)col0 * kPK + ((size_t)(k / 8) * nh + n) * 8 + (k % 8)] =
                     bf16_bits(weight_host[(size_t)(col0 + n) * kPK + k]);
-        col0 += nh;
     }
     std::vector<float> bias(n_out, 0.0f);
     for (int n = 0; bias_host && n < n_out; ++n) {
@@ -340,9 +311,9 @@ extern "C" int adtfe_linear_create(int32_t n_in, int32_t n_out, const float* wei
     }
     adtfe_linear* lin = new adtfe_linear();
     lin->device = device; lin->sm_count = device_sm_count(device); lin->n_in = n_in; lin->n_out = n_out;
-    lin->n_halves = n_halves;
-    lin->smem_bytes = (size_t)half_cols(n_out, n_halves, 0) * 256 + kATileBytes + 8 * kStageBytes + 32 +
-                      (size_t)half_cols(n_out, n_halves, 0) * 2 + 32;
+    lin->n_parts = n_parts;
+    lin->smem_bytes = (size_t)part_cols(n_out, 0) * 256 + kATileBytes + 8 * kStageBytes + 32 +
+                      (size_t)part_cols(n_out, 0) * 4 + 32;
     if (cudaMalloc(&lin->w_image, image.size() * 2) != cudaSuccess ||
         cudaMemcpy(lin->w_image, image.data(), image.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMalloc((void**)&lin->bias, (size_t)n_out * 4) != cudaSuccess ||
@@ -363,9 +334,10 @@ extern "C" int adtfe_linear_forward(const adtfe_linear* lin, const float* x_dev,
     ADTFE_REQUIRE(x_dev && out_bf16_dev && ((uintptr_t)x_dev & 15) == 0 && ((uintptr_t)out_bf16_dev & 15) == 0,
                   ADTFE_ERR_BAD_ARG, "adtfe_linear_forward: null or misaligned buffer (16 bytes)");
     const int64_t n_tiles = (n_rows + kPM - 1) / kPM;
-    const int grid = lin->n_halves * (int)std::min<int64_t>(n_tiles, lin->sm_count / lin->n_halves);
+    // two CTAs per SM: n_parts CTAs per tile of rows
+    const int grid = lin->n_parts * (int)std::min<int64_t>(n_tiles, std::max(1, 2 * lin->sm_count / lin->n_parts));
     project_kernel<<<grid, kPThreads, lin->smem_bytes, (cudaStream_t)stream>>>(x_dev, n_rows, lin->w_image, lin->bias,
-                                                                              lin->n_out, lin->n_halves,
+                                                                              lin->n_out, lin->n_parts,
                                                                               (__nv_bfloat16*)out_bf16_dev);
     ADTFE_CUDA(cudaGetLastError());
     return ADTFE_OK;
