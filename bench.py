@@ -284,7 +284,8 @@ def run_traffic_child(args):
     n_batches = 32
     segs = make_segments(n_batches * BATCH, seed=1)
     fe = FrontEnd(SynthDrum(setting_1(), bank=bank, device=dev), ComputeMelSpectrogram(SR, 2048, 0.01, 128))
-    plan = fe.plan_batches([segs[b * BATCH:(b + 1) * BATCH] for b in range(n_batches)], random.Random(1), 16)
+    # one render chunk: the log-mel is then ONE launch over all the plan's rows (a chunked plan gets one launch per chunk)
+    plan = fe.plan_batches([segs[b * BATCH:(b + 1) * BATCH] for b in range(n_batches)], random.Random(1), n_batches)
     buf = PlanBuffers(dev)
     buf._dplan = buf.upload(buf.pack(plan)); buf._resident = plan
     wav, feat = fe._outputs(plan, 0)
