@@ -104,6 +104,24 @@ def test_training_shape_batch_vs_oracle(sr, n_seg):
     assert_logmel_close(feat.cpu().numpy(), want, truth=_truth(ref, cfg))
 
 
+def test_bench_workload_batch_vs_oracle():
+    """The benchmark's own workload at its own sizes - the 10 000 one-shot bank (one-shots up to 48 000 samples) and
+    the first training batch of bench.py's event streams - against the oracle: waveform, lengths and log-mel."""
+    from adt_str_b200.config import SETTING_1, setting_1
+    from adt_str_b200.synthetic import make_bank, make_segments
+    bank = make_bank(10_000, 24000, seed=0)
+    segs = make_segments(64, seed=1)
+    nested = bank.to_nested()
+    random.seed(99)
+    ref = synth_oracle.collate([synth_oracle.render(s, dict(SETTING_1), nested) for s in segs])
+    _, _, fe = _objects(setting_1(), bank)
+    random.seed(99)
+    wav, feat = fe(segs)
+    assert wav.shape == ref.shape and np.abs(wav.cpu().numpy() - ref).max() <= WAV_TOL
+    want = mel_oracle.logmel_torchaudio(ref, 24000, 2048, 0.01, 128).numpy()
+    assert_logmel_close(feat.cpu().numpy(), want, truth=_truth(ref, SETTING_1))
+
+
 def test_dense_polyphony_deterministic_and_correct():
     from adt_str_b200.config import SETTING_1, setting_1
     from adt_str_b200.planner import TILE
