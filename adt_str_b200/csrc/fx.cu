@@ -84,9 +84,16 @@ __global__ void __launch_bounds__(32) fx_reverb_kernel(const adtfe_segment* __re
     for (int j = 0; j < 4; ++j) apos[j] = 0;
     float* row = wav + (int64_t)seg * ld_wav;
     const int n = sg.len;
+    // the row's samples are fetched four steps (512 bytes) ahead: a step is ~600 clocks of dependent work, a load from
+    // HBM at the top of the step would be waited for in full
+    float xq[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) xq[a] = 32 * a + lane < n ? row[32 * a + lane] : 0.0f;
     for (int n0 = 0; n0 < n; n0 += 32) {
         const bool valid = n0 + lane < n;
-        const float x = valid ? row[n0 + lane] : 0.0f;
+        const float x = xq[0];
+        xq[0] = xq[1]; xq[1] = xq[2]; xq[2] = xq[3];
+        xq[3] = n0 + 128 + lane < n ? row[n0 + 128 + lane] : 0.0f;
         const float input = x * 0.015f;
         float out = 0.0f;
         // the eight combs in lock step: their scans are independent chains of shuffles, interleaved they cost the
@@ -166,23 +173,35 @@ __device__ __forceinline__ float follower_step(Follower& c, float in) {
 }
 
 // Four lanes per row: lane 4 j + s is stage s of the warp's row j - 0: compressor, 1 and 2: the limiter's two stages,
-// 3: output (gain, clip, row peak, store).  A trip is a block of four samples (one 16-byte load / store); the stages are
-// skewed by a trip, so that in trip t stage s works on block t - s and hands its four outputs to stage s + 1 with one
-// shuffle each.  Every lane runs ONE follower, all of a row's followers advance in the same instructions, and the
-// sequential cost of a sample is one follower (with its two special-function instructions) instead of three: 0.8 ms
-// for a row of 61 442 samples against 4.3 ms with lane = row (whatever the number of rows, up to the machine's warps).
-// The arithmetic per stage and sample is unchanged.
-// Sixteen zero bytes: where the prefetch of a row reads once it is past the row's end.  The choice is made on the
-// ADDRESS, so that the load itself is unconditional and lands in its ring register - a predicated load (or a select
-// behind it) makes ptxas load into a temporary and move, and the move waits for the load right away.
-__device__ const float4 g_zero_block = {0.0f, 0.0f, 0.0f, 0.0f};
+// 3: output (gain, clip, row peak, store).  A trip is a block of four samples; the stages are skewed by a trip, so
+// that in trip t stage s works on block t - s and hands its four outputs to stage s + 1 with one shuffle each.  Every
+// lane runs ONE follower, all of a row's followers advance in the same instructions, and the sequential cost of a
+// sample is one follower (with its two special-function instructions) instead of three.  The arithmetic per stage and
+// sample is unchanged.
+//
+// The rows move through shared memory in chunks of kDynChunk samples: the whole warp fetches the next chunk of its
+// eight rows with coalesced 512-byte row reads a chunk ahead (the loads stay in registers for the 32 trips of the
+// current chunk - never waited for), stage 0 takes its block from shared memory, the output lane parks its block
+// there, and a finished chunk leaves with coalesced 512-byte row writes.  The loop body is four trips long: a single
+// warp per scheduler runs as fast as its instructions arrive, and the register ring this replaces needed 16-32 unrolled
+// trips (30-60 KB of code: 22 % of the stalls were instruction fetch, 21 % the loads of a row that eight lanes read
+// 16 bytes at a time).
+constexpr int kDynChunk = 128;                       // samples of a row per chunk: 32 trips
+constexpr int kDynTrips = kDynChunk / 4;
+constexpr int kDynPitch = kDynChunk + 4;             // floats between the rows of a buffer: 528 B, so that the eight rows'
+                                                     // 16-byte blocks of one trip lie in different banks
+constexpr int kDynBuf = 8 * kDynPitch;               // floats per buffer (eight rows)
+__host__ __device__ constexpr size_t dyn_smem_bytes() { return (size_t)4 * kDynBuf * 4 + 32 * 16; }   // in[2] | out[2] | scratch
 
 __global__ void __launch_bounds__(32) fx_dynamics_kernel(const adtfe_segment* __restrict__ segments,
                                                          const adtfe_fx* __restrict__ fx, int n_fx, float* __restrict__ wav,
                                                          int64_t ld_wav, float* __restrict__ tile_max, int max_per_seg,
                                                          int sample_rate) {
-    const int lane = threadIdx.x, stage = lane & 3;
-    const int r = blockIdx.x * 8 + (lane >> 2);
+    extern __shared__ __align__(16) float s_dyn[];
+    float* s_in = s_dyn;                  // [2][8][kDynPitch]
+    float* s_out = s_dyn + 2 * kDynBuf;   // [2][8][kDynPitch]
+    const int lane = threadIdx.x, stage = lane & 3, j = lane >> 2;
+    const int r = blockIdx.x * 8 + j;
     adtfe_fx f;
     f.flags = 0; f.seg = 0;
     if (r < n_fx) f = fx[r];
@@ -204,53 +223,103 @@ __global__ void __launch_bounds__(32) fx_dynamics_kernel(const adtfe_segment* __
     }
     float* row = wav + (int64_t)seg * ld_wav;
     const int n = live ? segments[seg].len : 0;
-    const bool first = stage == 0, last = stage == 3, rewrite = last && (lim_on || comp_on);
+    const bool first = stage == 0, last = stage == 3, rewrite = lim_on || comp_on;
+    const int n_blocks = (n + 3) / 4;
+    // the eight rows of the warp, for the chunk copies: lane l moves block l of every row's chunk
+    const float4* rows4[8];
+    int rows_blocks[8];
+    unsigned rewrite_mask = __ballot_sync(0xffffffffu, rewrite && last);   // bit 4 j + 3: row j is written back
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const unsigned long long p = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)row, 4 * k);
+        rows4[k] = reinterpret_cast<const float4*>((uintptr_t)p);
+        rows_blocks[k] = __shfl_sync(0xffffffffu, n_blocks, 4 * k);
+    }
+    int max_blocks = n_blocks;
+#pragma unroll
+    for (int o = 16; o >= 4; o >>= 1) max_blocks = max(max_blocks, __shfl_xor_sync(0xffffffffu, max_blocks, o));
+    // chunks to run: the last block leaves the output lane three trips after it entered stage 0, and a chunk is written
+    // back at the end of the iteration after its own
+    const int n_iter = (max_blocks + 3 + kDynTrips - 1) / kDynTrips + 1;
+    const float4 zero4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    float4 ld[8];
+    auto fetch = [&](int chunk) {   // the chunk's block `lane` of every row, zeros past the row's end
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int blk = chunk * kDynTrips + lane;
+            ld[k] = blk < rows_blocks[k] ? rows4[k][blk] : zero4;
+        }
+    };
+    auto park = [&](int chunk) {    // ... into the input buffer of that chunk
+        float* dst = s_in + (chunk & 1) * kDynBuf + 4 * lane;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) *reinterpret_cast<float4*>(dst + k * kDynPitch) = ld[k];
+    };
+    fetch(0);
+    park(0);
+    fetch(1);
+    __syncwarp();
     // |max| on the float bits: non-negative floats order like unsigned integers and a NaN's bits lie above infinity's,
     // so the unsigned maximum propagates NaN like torch.max.  Blocks outside the row (pipeline fill, trips of a longer
     // row in the same warp) carry zeros through the chain and do not move it.
     unsigned peak_bits = 0u;
-    const float4* row4 = reinterpret_cast<const float4*>(row);
-    const int n_blocks = (n + 3) / 4;
-    int trips = n_blocks + 3;   // the last block leaves the output lane three trips after it entered stage 0
-#pragma unroll
-    for (int o = 16; o >= 4; o >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, o));   // the warp's longest row
-    // The loads run kAhead trips (a line and a half) ahead through a ring of registers indexed by the unrolled trip
-    // number: a trip is ~100 clocks and a row's samples come from HBM (the raw mix of a chunk is larger than L2), so a
-    // load issued eight trips early was still waited for (ncu: 58 % of the stalls on the first use of the loaded block).  (The four lanes of a row load the same address: one request.)  The trip has no
-    // branch: the samples of the row's last block that lie beyond its length are zeros in memory (the waveform matrix
-    // is zero beyond every segment's length), travel through the chain as zeros and are stored back with the block; the
-    // output lane clears them again after the loop, so that they stay exact zeros even in a row that went NaN.
-    constexpr int kRing = 16, kAhead = 12;
-    float4 buf[kRing];
-#pragma unroll
-    for (int t = 0; t < kAhead; ++t) buf[t] = *(t < n_blocks ? row4 + t : &g_zero_block);
     float in[4] = {0.0f, 0.0f, 0.0f, 0.0f};   // what the previous stage handed over in the last trip
-    for (int base = 0; base < trips; base += kRing) {
-#pragma unroll
-        for (int t = 0; t < kRing; ++t) {
-            const int b = base + t;   // the trip: stage s works on block b - s
-            buf[(t + kAhead) % kRing] = *(b + kAhead < n_blocks ? row4 + b + kAhead : &g_zero_block);
-            in[0] = first ? buf[t].x : in[0];
-            in[1] = first ? buf[t].y : in[1];
-            in[2] = first ? buf[t].z : in[2];
-            in[3] = first ? buf[t].w : in[3];
-            float out[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) out[k] = follower_step(c, in[k]);
-            // the output step on what stage 2 handed over (block b - 3); the other lanes' results are not used
-            float o[4];
+    // where a lane parks its output blocks: the output lane in the row's output buffers, the other lanes (whose output
+    // step is not used) in a scratch block of their own - the store is then unconditional and the trip has no branch
+    float* const scratch = s_dyn + 4 * kDynBuf + 4 * lane;
+    for (int it = 0; it < n_iter; ++it) {
+        const float* src = s_in + (it & 1) * kDynBuf + j * kDynPitch;
+        // block b - 3 goes to the buffer of its chunk: the first three trips of an iteration finish the previous chunk
+        float* const cur = last ? s_out + (it & 1) * kDynBuf + j * kDynPitch : scratch;
+        float* const prev = last ? s_out + ((it + 1) & 1) * kDynBuf + j * kDynPitch + 4 * (kDynTrips - 3) : scratch;
+        float4 x = *reinterpret_cast<const float4*>(src);   // the four lanes of a row: one address
+        for (int t4 = 0; t4 < kDynTrips; t4 += 4) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const float v = in[k] * out_gain;
-                o[k] = v < -clip ? -clip : (v > clip ? clip : v);   // keeps NaN, like FloatVectorOperations::clip
-                peak_bits = max(peak_bits, __float_as_uint(fabsf(o[k])));
-            }
-            if (rewrite && b >= 3 && b - 3 < n_blocks) reinterpret_cast<float4*>(row)[b - 3] = make_float4(o[0], o[1], o[2], o[3]);
+                const int t = t4 + k;               // the trip: stage s works on block it * kDynTrips + t - s
+                in[0] = first ? x.x : in[0];
+                in[1] = first ? x.y : in[1];
+                in[2] = first ? x.z : in[2];
+                in[3] = first ? x.w : in[3];
+                // the next trip's block, a trip ahead (the last trip of the chunk reads the row's padding block)
+                x = *reinterpret_cast<const float4*>(src + 4 * (t + 1));
+                float out[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) in[k] = __shfl_up_sync(0xffffffffu, out[k], 1, 4);   // stage s -> stage s + 1
+                for (int m = 0; m < 4; ++m) out[m] = follower_step(c, in[m]);
+                // the output step on what stage 2 handed over (block b - 3); the other lanes' results are not used
+                float4 o;
+                {
+                    float v;
+                    v = in[0] * out_gain; o.x = v < -clip ? -clip : (v > clip ? clip : v);   // keeps NaN, like FloatVectorOperations::clip
+                    v = in[1] * out_gain; o.y = v < -clip ? -clip : (v > clip ? clip : v);
+                    v = in[2] * out_gain; o.z = v < -clip ? -clip : (v > clip ? clip : v);
+                    v = in[3] * out_gain; o.w = v < -clip ? -clip : (v > clip ? clip : v);
+                }
+                peak_bits = max(max(peak_bits, __float_as_uint(fabsf(o.x))), __float_as_uint(fabsf(o.y)));
+                peak_bits = max(max(peak_bits, __float_as_uint(fabsf(o.z))), __float_as_uint(fabsf(o.w)));
+                float* dst = (t4 == 0 && k < 3) ? prev + (last ? 4 * k : 0) : cur + (last ? 4 * (t - 3) : 0);
+                *reinterpret_cast<float4*>(dst) = o;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) in[m] = __shfl_up_sync(0xffffffffu, out[m], 1, 4);   // stage s -> stage s + 1
+            }
         }
+        __syncwarp();
+        // chunk it - 1 is complete in its output buffer: write the rows that the chain rewrites, whole 512-byte pieces
+        if (it >= 1) {
+            const float* done = s_out + ((it - 1) & 1) * kDynBuf + 4 * lane;
+            const int blk = (it - 1) * kDynTrips + lane;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (((rewrite_mask >> (4 * k + 3)) & 1u) && blk < rows_blocks[k])
+                    const_cast<float4*>(rows4[k])[blk] = *reinterpret_cast<const float4*>(done + k * kDynPitch);
+        }
+        park(it + 1);     // the chunk fetched during this iteration becomes the next input
+        fetch(it + 2);
+        __syncwarp();
     }
-    if (rewrite)
+    // the last block was stored whole: what lies beyond the row's length in it goes back to exact zeros (it carried
+    // zeros through the chain, but a row that went NaN would leave NaN there)
+    if (live && last && rewrite)
         for (int i = n; i < 4 * n_blocks; ++i) row[i] = 0.0f;
     // the normalisation takes the row peak from the tile maxima: this row's is now the output lane's maximum
     if (live && last) {
@@ -290,7 +359,7 @@ int fx_dynamics_launch(const adtfe_plan* plan, int r0, int n_rows, float* wav, f
                        cudaStream_t st) {
     if (n_rows <= 0) return ADTFE_OK;
     trace_open("fx_dynamics", r0, st);
-    fx_dynamics_kernel<<<(n_rows + 7) / 8, 32, 0, st>>>(plan->segments_dev, plan->fx_dev + r0, n_rows, wav, plan->ld_wav,
+    fx_dynamics_kernel<<<(n_rows + 7) / 8, 32, dyn_smem_bytes(), st>>>(plan->segments_dev, plan->fx_dev + r0, n_rows, wav, plan->ld_wav,
                                                          tile_max, max_per_seg, plan->sample_rate);
     trace_close(st);
     ADTFE_CUDA(cudaGetLastError());
