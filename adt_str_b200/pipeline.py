@@ -74,7 +74,12 @@ class GroupResult:
 
 class HostPipeline:
     def __init__(self, frontend: FrontEnd, workers: int = 4, n_sets: int = 4, seed: int = 0, chunk_batches: int = 8,
-                 rank: Optional[int] = None):
+                 rank: Optional[int] = None, compute_streams: Optional[int] = None):
+        """``compute_streams``: streams the groups' kernels rotate over.  1 = the stream that is current when ``run``
+        enqueues (the default without FX).  With the FX chain on (``use_fx_prob > 0``) the default is one per buffer
+        set: a group's FX rows are recursions over the row's samples that finish ~2.5 ms after its last mixer launch
+        whatever the group's size (a warp or two per SM), and on one stream every group would wait for the previous
+        group's chain; on several, the chains of the groups in flight run beside each other and under the next renders."""
         self.fe = frontend
         if rank is None:   # the process's rank under torch.distributed / torchrun, else 0
             import os
@@ -92,6 +97,10 @@ class HostPipeline:
         self._groups_seen = 0   # group index across run() calls: part of every group's RNG seed
         self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="adtfe-plan")
         self._copy_stream = torch.cuda.Stream(self.device)   # D2H of group g overlaps the kernels of group g+1
+        if compute_streams is None:
+            compute_streams = self.n_sets if frontend.synth.config.use_fx_prob > 0 else 1
+        self._compute = [torch.cuda.Stream(self.device) for _ in range(compute_streams)] if compute_streams > 1 else []
+        self._enqueued = 0
 
     # ---- worker side: plan + pack into the set's pinned blob (no CUDA calls besides the event wait)
     def _worker_state(self):
@@ -173,8 +182,16 @@ class HostPipeline:
             s.feat = torch.empty((rows, self.n_mels), dtype=torch.float32, device=dev)
             s.host = torch.empty((rows, self.n_mels), dtype=torch.float32).pin_memory()
         wav = s.wav[: plan.n_seg * plan.ld_wav].view(plan.n_seg, plan.ld_wav)
-        self.fe.run_plan_host(plan, s.host, None, buffers=s.buf, wav=wav, feat=s.feat, packed=True,
-                              copy_stream=self._copy_stream)
+        if self._compute:   # the set's buffers are free (the worker waited for its `done`): any stream may take them
+            st = self._compute[self._enqueued % len(self._compute)]
+            st.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(st):
+                self.fe.run_plan_host(plan, s.host, None, buffers=s.buf, wav=wav, feat=s.feat, packed=True,
+                                      copy_stream=self._copy_stream)
+        else:
+            self.fe.run_plan_host(plan, s.host, None, buffers=s.buf, wav=wav, feat=s.feat, packed=True,
+                                  copy_stream=self._copy_stream)
+        self._enqueued += 1
         s.done.record(self._copy_stream)
 
     def close(self) -> None:

@@ -536,10 +536,26 @@ def run_b200(args):
                 w2, f2 = fe2._outputs(p2, 0)
                 res[tag] = time_loop(lambda: fe2.run_plan(p2, buffers=b2, wav=w2, feat=f2, upload=False), reps=3)
                 n_fx_rows = 0 if p2.fx is None else len(p2.fx)
+                # the same batches end to end (host note lists -> pinned host log-mel) through the pipeline
+                pipe2 = HostPipeline(fe2, workers=args.e2e_workers, n_sets=args.e2e_sets, seed=5, chunk_batches=args.chunk_batches)
+                g2 = [batches[i:i + group] for i in range(0, nb, group)]
+                for rep in range(2):
+                    torch.cuda.synchronize(dev)
+                    t0 = time.perf_counter()
+                    infl = []
+                    for r2 in pipe2.run(g2):
+                        infl.append(r2)
+                        if len(infl) > 2:
+                            infl.pop(0).wait().release()
+                    for r2 in infl:
+                        r2.wait().release()
+                    res["e2e_" + tag] = 1e3 * (time.perf_counter() - t0)
+                pipe2.close()
             fx_side = {"what": f"render + log-mel of {nb} batches with use_fx_prob = 0.3 (reverb / compressor / limiter kernels, "
                                "csrc/fx.cu) against the same batches without FX",
                        "ms_fx_off": res["off"], "ms_fx_on": res["on"], "segments_with_fx": n_fx_rows,
-                       "segments": nb * BATCH}
+                       "segments": nb * BATCH, "e2e_ms_fx_off": res["e2e_off"], "e2e_ms_fx_on": res["e2e_on"],
+                       "e2e": "the same batches through HostPipeline (host planning, H2D, kernels, log-mel D2H)"}
         except Exception as exc:
             fx_side = {"error": repr(exc)}
         try:

@@ -155,3 +155,29 @@ def test_fx_oracle_basic_properties():
     assert np.abs(loud).max() < np.abs(4 * x).max()
     lim = fx_oracle.limiter(8 * x, 24000, -1.0)
     assert np.abs(lim).max() <= 1.0
+
+
+def test_fx_normals_fifteen_at_a_time_are_the_single_draws():
+    """fill_fx_normals draws a batch's compressor / limiter parameters with randn(k <= 15) per call; the reference draws
+    them with one randn(1) per parameter (utils/utils.py:266-269).  Same values bit for bit, same generator state."""
+    import torch
+    from adt_str_b200.planner import FX_COMPRESSOR, FX_DTYPE, FX_LIMITER, fill_fx_normals, normal_draw
+    rng = np.random.default_rng(0)
+    fx = np.zeros(400, FX_DTYPE)
+    fx["flags"] = rng.integers(0, 8, len(fx))
+    got = fill_fx_normals(fx.copy(), torch.Generator().manual_seed(7))
+    g = torch.Generator().manual_seed(7)
+    want = fx.copy()
+    for r in range(len(want)):
+        f = int(want["flags"][r])
+        if f & FX_COMPRESSOR:
+            want["comp_threshold_db"][r] = -normal_draw(0.15, 0.5, 10, 0, g)
+            want["comp_ratio"][r] = normal_draw(0.15, 0.5, 10, 1.0, g)
+            want["comp_attack_ms"][r] = normal_draw(0.05, 0.1, 1000, 0, g)
+            want["comp_release_ms"][r] = normal_draw(0.15, 0.2, 1000, 0, g)
+        if f & FX_LIMITER:
+            want["lim_threshold_db"][r] = -normal_draw(0.2, 0.4, 3, 0, g)
+    assert got.tobytes() == want.tobytes()
+    g2 = torch.Generator().manual_seed(7)
+    fill_fx_normals(fx.copy(), g2)
+    assert torch.equal(torch.randn(3, generator=g), torch.randn(3, generator=g2))     # both generators stand at the same draw
