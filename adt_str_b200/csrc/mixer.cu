@@ -29,7 +29,7 @@
 namespace adtfe {
 
 constexpr int kPeakWarps = 8;        // warps per CTA of the peak pass: one (segment, instrument) group per warp
-constexpr int kPeakNotes = 8;        // notes of one group bounded together (they share every block scan)
+constexpr int kPeakNotes = ADTFE_PEAK_NOTES;   // notes of one group bounded together (they share every block scan)
 constexpr int kBlock = ADTFE_PEAK_BLOCK;   // samples per block of the bank's block maxima
 
 __device__ __forceinline__ float warp_max(float v) {

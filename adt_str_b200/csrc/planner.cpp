@@ -307,9 +307,14 @@ extern "C" int adtfe_planner_plan(adtfe_planner* P, const float* notes, const in
         it.a_off = P->offsets[head.main_id]; it.b_off = P->offsets[head.sub_id];
         it.la = P->lengths[head.main_id]; it.lb = P->lengths[head.sub_id];
         it.mix_len = P->mix_len[e0];
-        it.first_event = e0; it.n_events = P->group_ptr[g + 1] - e0;
-        it.chunk = 0;   // one item per group: the peak pass bounds and scans the blocks of the mixed one-shot itself
-        P->peak_work.push_back(it);
+        it.chunk = 0;
+        // one item (= one warp of the peak pass) per ADTFE_PEAK_NOTES notes of the group: a long-form render has a few
+        // groups of hundreds of notes each, which one warp per group would walk one after the other
+        for (int32_t e = e0; e < P->group_ptr[g + 1]; e += ADTFE_PEAK_NOTES) {
+            it.first_event = e;
+            it.n_events = std::min<int32_t>(ADTFE_PEAK_NOTES, P->group_ptr[g + 1] - e);
+            P->peak_work.push_back(it);
+        }
     }
     out_counts[0] = (int64_t)P->events.size();
     out_counts[1] = (int64_t)P->group_ptr.size() - 1;

@@ -411,19 +411,27 @@ def assemble(plans: Sequence[SegmentPlan], bank: OneShotBank, ld_wav: int | None
     return plan
 
 
+PEAK_NOTES = 8  # notes of a group per peak work item (ADTFE_PEAK_NOTES): one warp of the peak pass each
+
+
 def peak_work_items(events: np.ndarray, mix_len: np.ndarray, group_ptr: np.ndarray, bank: OneShotBank) -> np.ndarray:
-    """One record per group (the notes of one instrument in one segment), bank lookups resolved; ``chunk`` stays 0."""
+    """One record per PEAK_NOTES notes of a group (the notes of one instrument in one segment), bank lookups resolved;
+    ``chunk`` stays 0."""
     n_groups = len(group_ptr) - 1
     if n_groups <= 0:
         return np.zeros(0, PEAK_ITEM_DTYPE)
-    out = np.zeros(n_groups, PEAK_ITEM_DTYPE)
-    e0 = group_ptr[:-1].astype(np.int64)
-    main, sub = events["main_id"][e0], events["sub_id"][e0]
+    size = np.diff(group_ptr).astype(np.int64)
+    parts = np.maximum(1, -(-size // PEAK_NOTES))                       # items per group
+    group = np.repeat(np.arange(n_groups, dtype=np.int64), parts)
+    k = np.arange(len(group), dtype=np.int64) - np.repeat(np.cumsum(parts) - parts, parts)   # item index inside its group
+    out = np.zeros(len(group), PEAK_ITEM_DTYPE)
+    head = group_ptr[:-1].astype(np.int64)[group]
+    main, sub = events["main_id"][head], events["sub_id"][head]
     out["a_off"], out["b_off"] = bank.offsets[main], bank.offsets[sub]
     out["la"], out["lb"] = bank.lengths[main], bank.lengths[sub]
-    out["mix_len"] = mix_len[e0]
-    out["first_event"] = e0
-    out["n_events"] = np.diff(group_ptr)
+    out["mix_len"] = mix_len[head]
+    out["first_event"] = head + PEAK_NOTES * k
+    out["n_events"] = np.minimum(PEAK_NOTES, size[group] - PEAK_NOTES * k)
     return out
 
 

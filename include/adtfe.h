@@ -46,6 +46,7 @@ extern "C" {
 #define ADTFE_VERSION 5
 #define ADTFE_TILE 2048      /* output samples owned by one mixer CTA */
 #define ADTFE_PEAK_BLOCK 256 /* samples per block of the bank's block maxima (peak pass: branch and bound) */
+#define ADTFE_PEAK_NOTES 8   /* notes the peak pass bounds together: planners cut a group into items of that many */
 
 typedef enum adtfe_status {
     ADTFE_OK = 0,
@@ -81,8 +82,9 @@ typedef struct adtfe_segment {
 #define ADTFE_SEG_RAW 2
 
 /* One work item of the peak pass (40 bytes): the mixed one-shot shared by the notes first_event ..
- * first_event+n_events-1 (one instrument of one segment).  One item per group, chunk = 0 (ABI <= 4 split a group
- * into per-span items chunk = 0, 1, ...: items with chunk != 0 are ignored).  Offsets and lengths are the bank's,
+ * first_event+n_events-1 (notes of one instrument of one segment: they share the two one-shots).  Any number of
+ * notes per item is handled; the planners cut a group into items of ADTFE_PEAK_NOTES notes (one warp each).  chunk = 0
+ * (ABI <= 4 split a group into per-span items chunk = 0, 1, ...: items with chunk != 0 are ignored).  Offsets and lengths are the bank's,
  * resolved on the host so the kernel starts its loads after a single record fetch; events[first_event].main_id /
  * sub_id name the two one-shots (block maxima lookup). */
 typedef struct adtfe_peak_item {
