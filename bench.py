@@ -539,7 +539,7 @@ def run_b200(args):
                 # the same batches end to end (host note lists -> pinned host log-mel) through the pipeline
                 pipe2 = HostPipeline(fe2, workers=args.e2e_workers, n_sets=args.e2e_sets, seed=5, chunk_batches=args.chunk_batches)
                 g2 = [batches[i:i + group] for i in range(0, nb, group)]
-                for rep in range(2):
+                for rep in range(4):   # the shortest of three runs behind a warm-up (20 ms of wall clock each)
                     torch.cuda.synchronize(dev)
                     t0 = time.perf_counter()
                     infl = []
@@ -549,7 +549,8 @@ def run_b200(args):
                             infl.pop(0).wait().release()
                     for r2 in infl:
                         r2.wait().release()
-                    res["e2e_" + tag] = 1e3 * (time.perf_counter() - t0)
+                    if rep:
+                        res["e2e_" + tag] = min(res.get("e2e_" + tag, 1e30), 1e3 * (time.perf_counter() - t0))
                 pipe2.close()
             fx_side = {"what": f"render + log-mel of {nb} batches with use_fx_prob = 0.3 (reverb / compressor / limiter kernels, "
                                "csrc/fx.cu) against the same batches without FX",
