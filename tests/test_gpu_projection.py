@@ -41,6 +41,35 @@ def test_projection_matches_autocast_linear(rows, n_out, bias):
     assert frac_equal > 0.98, frac_equal                                   # and bit-equal almost everywhere
 
 
+@pytest.mark.parametrize("rows,n_out,bias", [(128 * 700 + 5, 768, True), (1, 768, True), (128 * 40, 512, True),
+                                            (128 * 9 + 127, 256, False), (300, 32, True), (128 * 3, 416, True),
+                                            (128 * 300, 96, True)])
+def test_both_schedules_give_the_same_bits(rows, n_out, bias):
+    """Column split (two CTAs per SM) and streaming (one warp-specialised CTA per SM, accumulator ring) are two launch
+    schedules of the same arithmetic: K = 128 is accumulated by the same eight tcgen05.mma per output element, so the
+    results must be bit-identical, for every part / chunk width and on the ragged last tile."""
+    from adt_str_b200 import ProjectToMel, _lib
+    torch.manual_seed(rows * 3 + n_out)
+    dev = torch.device("cuda", 0)
+    lin = torch.nn.Linear(128, n_out, bias=bias).to(dev)
+    proj = ProjectToMel.from_linear(lin).eval()
+    x = torch.rand(rows, 128, device=dev) * 2 - 0.5
+    outs = []
+    with torch.no_grad():
+        native = proj._handle(dev)
+        for schedule in (1, 2, 0):
+            _lib.check(native.lib.adtfe_linear_force_schedule(native.handle, schedule))
+            outs.append(proj(x).clone())
+        with torch.autocast("cuda", torch.bfloat16):
+            want = lin(x)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
+    assert torch.equal(outs[0].view(torch.int16), outs[2].view(torch.int16))
+    exact = _exact(x, lin.weight, lin.bias)
+    assert bool(((outs[1].double() - exact).abs() <= exact.abs() * 2.0 ** -8 + 1e-6).all())
+    assert float((outs[1] == want).float().mean()) > 0.98
+
+
 def test_projection_shapes_training_and_errors():
     from adt_str_b200 import ProjectToMel, _lib
     dev = torch.device("cuda", 0)
