@@ -21,7 +21,7 @@ EXPORTS = [
     "adtfe_trace_begin", "adtfe_trace_dump",
     "adtfe_planner_create", "adtfe_planner_destroy", "adtfe_planner_plan", "adtfe_planner_export", "adtfe_planner_pack_batches",
     "adtfe_planner_set_fx", "adtfe_planner_export_fx",
-    "adtfe_linear_create", "adtfe_linear_destroy", "adtfe_linear_forward", "adtfe_linear_force_schedule",
+    "adtfe_linear_create", "adtfe_linear_destroy", "adtfe_linear_forward",
 ]
 
 
@@ -86,7 +86,6 @@ def _declare(lib) -> None:
     lib.adtfe_linear_create.argtypes = [i32, i32, vp, vp, C.c_int, C.POINTER(vp)]
     lib.adtfe_linear_destroy.argtypes = [vp]
     lib.adtfe_linear_forward.argtypes = [vp, vp, i64, vp, vp]
-    lib.adtfe_linear_force_schedule.argtypes = [vp, i32]
 
 
 def load():

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define ADTFE_VERSION 6
+#define ADTFE_VERSION 5
 #define ADTFE_TILE 2048      /* output samples owned by one mixer CTA */
 #define ADTFE_PEAK_BLOCK 256 /* samples per block of the bank's block maxima (peak pass: branch and bound) */
 #define ADTFE_PEAK_NOTES 8   /* notes the peak pass bounds together: planners cut a group into items of that many */
@@ -265,11 +265,6 @@ int adtfe_linear_destroy(adtfe_linear* linear);
  * out_bf16_dev: (n_rows, n_out) bfloat16. */
 int adtfe_linear_forward(const adtfe_linear* linear, const float* x_dev, int64_t n_rows, void* out_bf16_dev,
                          void* stream);
-/* Two launch schedules compute the same bits: 1 = column split (two CTAs per SM, 192 columns each: the lowest latency
- * for one training batch, which is how model.py:249 is called), 2 = streaming (one warp-specialised CTA per SM, 384
- * columns each: the highest throughput over many batches).  0 (default) picks by the row count.  Per handle, for
- * cross-checks and measurements. */
-int adtfe_linear_force_schedule(adtfe_linear* linear, int32_t schedule);
 
 /* ---- diagnostics ----------------------------------------------------------------------- */
 /* Launch trace: after adtfe_trace_begin every kernel launched by adtfe_render / adtfe_render_logmel is bracketed

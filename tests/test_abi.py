@@ -40,7 +40,7 @@ def test_struct_sizes_match_numpy_views():
 
 
 def test_version_and_argument_errors_without_a_device(lib):
-    assert lib.adtfe_version() == 6
+    assert lib.adtfe_version() == 5
     assert lib.adtfe_render_workspace_bytes(10, 2, 30, 70) >= 10 * 48 + 2 * 30 * 4 + 70 * 32
     assert lib.adtfe_render_workspace_bytes(-1, 2, 30, 70) == 0
     shape = _lib.Plan(None, None, None, None, None, 100, 4, 31, 9, 63488)

@@ -41,33 +41,51 @@ def test_projection_matches_autocast_linear(rows, n_out, bias):
     assert frac_equal > 0.98, frac_equal                                   # and bit-equal almost everywhere
 
 
-@pytest.mark.parametrize("rows,n_out,bias", [(128 * 700 + 5, 768, True), (1, 768, True), (128 * 40, 512, True),
-                                            (128 * 9 + 127, 256, False), (300, 32, True), (128 * 3, 416, True),
-                                            (128 * 300, 96, True)])
-def test_both_schedules_give_the_same_bits(rows, n_out, bias):
-    """Column split (two CTAs per SM) and streaming (one warp-specialised CTA per SM, accumulator ring) are two launch
-    schedules of the same arithmetic: K = 128 is accumulated by the same eight tcgen05.mma per output element, so the
-    results must be bit-identical, for every part / chunk width and on the ragged last tile."""
-    from adt_str_b200 import ProjectToMel, _lib
+@pytest.mark.parametrize("rows,n_out,bias", [(128 * 700 + 5, 768, True), (128 * 40, 512, True), (128 * 9 + 127, 256, False),
+                                            (300, 32, True), (128 * 3, 416, True), (128 * 300, 96, True),
+                                            (128 * 151 + 33, 672, True)])
+def test_every_part_and_chunk_width(rows, n_out, bias):
+    """The column parts (<= 384 columns per CTA), the 128-column accumulator chunks and the drain's two store paths (a
+    TMA tensor store for a warp's 64 columns, a staged store for a lone 32-column unit) over output widths that mix them
+    (416 -> 224 + 192 -> chunks 128 + 96 / 128 + 64; 96 -> one chunk of three units; 32 -> half the drain warps idle),
+    over many tiles per CTA (the accumulator ring and the A buffers wrap) and a ragged last tile (the TMA clips it).
+    Input values outside [0, 1] and of both signs."""
+    from adt_str_b200 import ProjectToMel
     torch.manual_seed(rows * 3 + n_out)
     dev = torch.device("cuda", 0)
     lin = torch.nn.Linear(128, n_out, bias=bias).to(dev)
     proj = ProjectToMel.from_linear(lin).eval()
-    x = torch.rand(rows, 128, device=dev) * 2 - 0.5
-    outs = []
+    x = torch.rand(rows, 128, device=dev) * 4 - 2
     with torch.no_grad():
-        native = proj._handle(dev)
-        for schedule in (1, 2, 0):
-            _lib.check(native.lib.adtfe_linear_force_schedule(native.handle, schedule))
-            outs.append(proj(x).clone())
+        got = proj(x)
+        again = proj(x)
         with torch.autocast("cuda", torch.bfloat16):
             want = lin(x)
     torch.cuda.synchronize()
-    assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
-    assert torch.equal(outs[0].view(torch.int16), outs[2].view(torch.int16))
+    assert torch.equal(got.view(torch.int16), again.view(torch.int16))      # deterministic
     exact = _exact(x, lin.weight, lin.bias)
-    assert bool(((outs[1].double() - exact).abs() <= exact.abs() * 2.0 ** -8 + 1e-6).all())
-    assert float((outs[1] == want).float().mean()) > 0.98
+    assert bool(((got.double() - exact).abs() <= exact.abs() * 2.0 ** -8 + 1e-6).all())
+    assert float((got == want).float().mean()) > 0.98
+
+
+def test_projection_writes_nothing_beyond_its_rows():
+    """Rows beyond n_rows of the last tile are clipped by the tensor map (and by the staged store's row test): the
+    memory behind the output stays untouched."""
+    from adt_str_b200 import ProjectToMel, _lib
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    for n_out in (768, 416):
+        proj = ProjectToMel(128, n_out).to(dev).eval()
+        rows = 128 * 2 + 37
+        buf = torch.full((rows + 200, n_out), 5.0, dtype=torch.bfloat16, device=dev)
+        x = torch.rand(rows, 128, device=dev)
+        native = proj._handle(dev)
+        _lib.check(native.lib.adtfe_linear_forward(native.handle, x.data_ptr(), rows, buf.data_ptr(),
+                                                   torch.cuda.current_stream(dev).cuda_stream), "adtfe_linear_forward")
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            assert torch.equal(buf[:rows], proj(x))
+        assert bool((buf[rows:] == 5.0).all())
 
 
 def test_projection_shapes_training_and_errors():

@@ -16,15 +16,12 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import torch  # noqa: E402
 
 
-def measure(dev, rows=256 * 64 * 246, n_out=768, reps=5, schedule=0):
-    from adt_str_b200 import ProjectToMel, _lib
+def measure(dev, rows=256 * 64 * 246, n_out=768, reps=5):
+    from adt_str_b200 import ProjectToMel
     torch.manual_seed(0)
     lin = torch.nn.Linear(128, n_out).to(dev)
     proj = ProjectToMel.from_linear(lin).eval()
     x = torch.rand(rows, 128, device=dev)
-    if schedule:
-        native = proj._handle(dev)
-        _lib.check(native.lib.adtfe_linear_force_schedule(native.handle, schedule))
 
     def timed(fn):
         for _ in range(2):
@@ -65,14 +62,12 @@ def measure(dev, rows=256 * 64 * 246, n_out=768, reps=5, schedule=0):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--rows", type=int, default=256 * 64 * 246)
-    ap.add_argument("--schedule", type=int, default=0, help="0 = by row count, 1 = column split, 2 = streaming")
-    ap.add_argument("--sweep", action="store_true", help="both schedules over a ladder of row counts")
+    ap.add_argument("--sweep", action="store_true", help="a ladder of row counts: 1 .. 256 training batches")
     args = ap.parse_args()
     if args.sweep:
         for rows in (15744, 2 * 15744, 4 * 15744, 8 * 15744, 16 * 15744, 64 * 15744, 256 * 15744):
-            r = {s: measure(torch.device("cuda", 0), rows, schedule=s) for s in (1, 2)}
-            print(json.dumps({"rows": rows, "column_split_ms": r[1]["ms"], "streaming_ms": r[2]["ms"],
-                              "library_ms": r[1]["library_ms"], "bit_equal": [r[1]["bit_equal_fraction_vs_library"],
-                                                                             r[2]["bit_equal_fraction_vs_library"]]}))
+            r = measure(torch.device("cuda", 0), rows)
+            print(json.dumps({k: r[k] for k in ("rows", "ms", "library_ms", "speedup_vs_autocast_linear", "frac_of_hbm_peak",
+                                                "bit_equal_fraction_vs_library")}))
     else:
-        print(json.dumps(measure(torch.device("cuda", 0), args.rows, schedule=args.schedule)))
+        print(json.dumps(measure(torch.device("cuda", 0), args.rows)))
