@@ -539,7 +539,7 @@ def run_b200(args):
                 # the same batches end to end (host note lists -> pinned host log-mel) through the pipeline
                 pipe2 = HostPipeline(fe2, workers=args.e2e_workers, n_sets=args.e2e_sets, seed=5, chunk_batches=args.chunk_batches)
                 g2 = [batches[i:i + group] for i in range(0, nb, group)]
-                for rep in range(4):   # the shortest of three runs behind a warm-up (20 ms of wall clock each)
+                for rep in range(7):   # the shortest of six runs behind a warm-up (20 ms of wall clock each)
                     torch.cuda.synchronize(dev)
                     t0 = time.perf_counter()
                     infl = []
