@@ -563,6 +563,20 @@ __global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_seg
     const int tid = threadIdx.x;
     const int row_id = blockIdx.x / tiles_per_seg, lo = (blockIdx.x - row_id * tiles_per_seg) * ADTFE_TILE;
     const int seg = fx_rows ? fx_rows[row_id].seg : seg0 + row_id;
+    float* row = wav + (int64_t)seg * ld_wav + lo;  // ld_wav is a multiple of 4 and the base is 16-byte aligned
+    float4* row4 = reinterpret_cast<float4*>(row);
+    // The tile's samples are requested FIRST, whatever the row turns out to be: the segment record and the tile maxima
+    // are a chain of two dependent loads, and a CTA that waits for them before it asks for its 8 KB has nothing in
+    // flight for half of its life.  (Reads within the row's pitch are always inside the matrix.)
+    constexpr int kPer = ADTFE_TILE / 4 / kNormThreads;
+    static_assert(kPer * kNormThreads * 4 == ADTFE_TILE, "normalise_kernel: threads per tile");
+    const int n4_row = (int)min((int64_t)ADTFE_TILE, ld_wav - lo) >> 2;
+    float4 v[kPer];
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int i = tid + k * kNormThreads;
+        v[k] = i < n4_row ? row4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (!fx_rows && seg_fx[seg]) return;
     const adtfe_segment sg = segments[seg];
     if ((sg.flags & 1) == 0 || lo >= sg.len) return;   // 0: empty row; ADTFE_SEG_RAW: the caller wants the raw mix
@@ -573,23 +587,21 @@ __global__ void __launch_bounds__(kNormThreads) normalise_kernel(const adtfe_seg
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) peak = nan_max(peak, __shfl_xor_sync(0xffffffffu, peak, o));
     const float vol = sg.max_volume;
-    float* row = wav + (int64_t)seg * ld_wav + lo;  // ld_wav is a multiple of 4 and the base is 16-byte aligned
     const int n = min(ADTFE_TILE, sg.len - lo);
-    float4* row4 = reinterpret_cast<float4*>(row);
     const int n4 = n >> 2;
     // v / peak * vol with the division by an invariant done the way the hardware sequence does it: q = v*r,
     // one residual correction (correctly rounded for normal operands, i.e. everything a mix can hold), r = 1/peak
     // rounded to nearest once per thread.  peak = 0 (all-zero mix) or NaN still gives NaN everywhere.
     const float r = __frcp_rn(peak);
-    auto norm = [&](float v) {
-        const float q = __fmul_rn(v, r);
-        const float rem = __fmaf_rn(-q, peak, v);
+    auto norm = [&](float x) {
+        const float q = __fmul_rn(x, r);
+        const float rem = __fmaf_rn(-q, peak, x);
         return __fmul_rn(__fmaf_rn(rem, r, q), vol);
     };
-    for (int i = tid; i < n4; i += kNormThreads) {
-        float4 v = row4[i];
-        v.x = norm(v.x); v.y = norm(v.y); v.z = norm(v.z); v.w = norm(v.w);
-        row4[i] = v;
+#pragma unroll
+    for (int k = 0; k < kPer; ++k) {
+        const int i = tid + k * kNormThreads;
+        if (i < n4) row4[i] = make_float4(norm(v[k].x), norm(v[k].y), norm(v[k].z), norm(v[k].w));
     }
     for (int i = 4 * n4 + tid; i < n; i += kNormThreads) row[i] = norm(row[i]);
 }
