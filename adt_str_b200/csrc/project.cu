@@ -360,6 +360,11 @@ extern "C" int adtfe_linear_destroy(adtfe_linear* lin) {
     return ADTFE_OK;
 }
 
+// 1 KB of slack to align the staging rows | weight part | staging | two A buffers | mbarriers + TMEM address | bias pairs
+static size_t smem_bytes_of(int widest_part) {
+    return 1024 + (size_t)widest_part * 256 + 8 * kStageBytes + 2 * kATileBytes + (kBars + 1) * 8 + (size_t)widest_part * 2 + 32;
+}
+
 extern "C" int adtfe_linear_create(int32_t n_in, int32_t n_out, const float* weight_host, const float* bias_host,
                                    int device, adtfe_linear** out) {
     ADTFE_REQUIRE(out && weight_host, ADTFE_ERR_BAD_ARG, "adtfe_linear_create: null pointer");
@@ -390,14 +395,14 @@ extern "C" int adtfe_linear_create(int32_t n_in, int32_t n_out, const float* wei
     adtfe_linear* lin = new adtfe_linear();
     lin->device = device; lin->sm_count = device_sm_count(device); lin->n_in = n_in; lin->n_out = n_out;
     lin->n_parts = n_parts;
-    // 1 KB of slack to align the staging rows | weight part | staging | two A buffers | mbarriers + TMEM address | bias pairs
-    lin->smem_bytes = 1024 + (size_t)part_cols(n_out, 0) * 256 + 8 * kStageBytes + 2 * kATileBytes + (kBars + 1) * 8 +
-                      (size_t)part_cols(n_out, 0) * 2 + 32;
+    lin->smem_bytes = smem_bytes_of(part_cols(n_out, 0));
     if (cudaMalloc(&lin->w_image, image.size() * 2) != cudaSuccess ||
         cudaMemcpy(lin->w_image, image.data(), image.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMalloc((void**)&lin->bias, (size_t)n_out * 4) != cudaSuccess ||
         cudaMemcpy(lin->bias, bias.data(), (size_t)n_out * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lin->smem_bytes) != cudaSuccess) {
+        // the attribute belongs to the function, not to the handle: the widest part any handle can have (a later,
+        // narrower handle must not lower it under an earlier one's launch size)
+        cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes_of(kPartCols)) != cudaSuccess) {
         set_error("adtfe_linear_create: device setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         adtfe_linear_destroy(lin);
         return ADTFE_ERR_CUDA;

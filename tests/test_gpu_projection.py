@@ -116,6 +116,32 @@ def test_projection_shapes_training_and_errors():
         ProjectToMel(128, 768)(torch.rand(2, 128))
 
 
+@pytest.mark.timeout(120)
+def test_projections_on_concurrent_streams_share_the_tensor_memory():
+    """Every CTA of the kernel allocates all 512 columns of its SM's tensor memory.  Two launches on two streams, and a
+    library bf16 GEMM (tcgen05 too) on a third, must neither deadlock on tcgen05.alloc nor disturb each other's
+    accumulators: the results equal the ones computed alone."""
+    from adt_str_b200 import ProjectToMel
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(11)
+    p1, p2 = ProjectToMel(128, 768).to(dev).eval(), ProjectToMel(128, 512).to(dev).eval()
+    x1, x2 = torch.rand(128 * 600 + 3, 128, device=dev), torch.rand(128 * 450, 128, device=dev)
+    a, b = torch.randn(4096, 4096, device=dev, dtype=torch.bfloat16), torch.randn(4096, 4096, device=dev, dtype=torch.bfloat16)
+    with torch.no_grad():
+        want1, want2, want3 = p1(x1).clone(), p2(x2).clone(), (a @ b).clone()
+        torch.cuda.synchronize()
+        s1, s2, s3 = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        for _ in range(5):
+            with torch.cuda.stream(s1):
+                got1 = p1(x1)
+            with torch.cuda.stream(s3):
+                got3 = a @ b
+            with torch.cuda.stream(s2):
+                got2 = p2(x2)
+        torch.cuda.synchronize()
+    assert torch.equal(got1, want1) and torch.equal(got2, want2) and torch.equal(got3, want3)
+
+
 def test_projection_of_the_logmel_output():
     """The log-mel matrix adtfe_logmel writes feeds the projection directly (rows = B * T, 128 floats)."""
     from adt_str_b200 import ComputeMelSpectrogram, ProjectToMel
