@@ -11,6 +11,8 @@ SMALL="python bench.py --steps 2 --warmup 1 --batches-per-step 8 --bank-size 200
 # launch list of the whole small run (library comparator included: its cuFFT / cuBLAS / elementwise kernels are the
 # reference's GPU pipeline for the log-mel), then the same with DRAM bytes for the library kernels only
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv $SMALL > /dev/null 2>&1
+# the launch list at the bench's own size (shares to compare with the bench line's)
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_full_$TAG.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-long-form --no-traffic --no-library-baseline --e2e-steps 1 > /dev/null 2>&1
 for k in ${KERNELS:-logmel6_kernel mix_kernel peak_kernel normalise_kernel slice_kernel}; do
   ncu --set full --clock-control none --import-source on -k regex:$k -s 4 -c 1 -f -o gpurun_out/prof_${k}_$TAG $SMALL > /dev/null 2>&1
 done

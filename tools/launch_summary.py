@@ -32,7 +32,10 @@ def main(path):
             rd[k] += v * scale_b.get(u, 1.0)
         elif m.startswith("dram__bytes_write"):
             wr[k] += v * scale_b.get(u, 1.0)
-    ours = {k: v for k, v in t.items() if "adtfe::" in k}
+    mine = ("logmel6_kernel", "logmel_kernel", "mix_kernel", "normalise_kernel", "peak_kernel", "slice_kernel", "blockmax_kernel",
+            "fx_reverb_kernel", "fx_dynamics_kernel", "fx_mark_kernel", "project_kernel", "resample_kernel", "downmix_kernel")
+    # ncu prints the names with or without the namespace, depending on its demangler
+    ours = {k: v for k, v in t.items() if "adtfe::" in k or any(m in k for m in mine)}
     lib = {k: v for k, v in t.items() if k not in ours}
     tot_o = sum(ours.values()) or 1.0
     print(f"# {path}: per-launch times are cold-cache and serialised (compare shares, not absolutes)")
