@@ -323,7 +323,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_kernel(const LogmelArgs p,
     a1 = __ffma2_rn(make_float2(W1.z, W1.w), bc2(Q3), a1);                                 \
     if (G.y >= 0) { /* warp-uniform: the interval ends here */                             \
         const float2 a_ = __fadd2_rn(a0, a1);                                              \
-        s_s[G.y * kSPitch + lane] = up_prev + a_.y; /* falling edge completes the filter below */ \
+        /* falling edge completes the filter below; a warp's first flush belongs to nobody (row kDummyRow): */ \
+        /* not stored, or the warps would race on that row */                                  \
+        if (G.y != kDummyRow) s_s[G.y * kSPitch + lane] = up_prev + a_.y;                    \
         up_prev = a_.x;                             /* rising edge waits for the next interval */ \
         a0 = make_float2(0.0f, 0.0f);                                                      \
         a1 = make_float2(0.0f, 0.0f);                                                      \

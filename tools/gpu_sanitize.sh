@@ -6,7 +6,7 @@
 #   usage: tools/gpu_sanitize.sh [tool ...]      (default: memcheck racecheck synccheck)
 mkdir -p gpurun_out
 TOOLS=${@:-memcheck racecheck synccheck}
-TESTS="tests/test_gpu_parity.py::test_dense_polyphony_deterministic_and_correct tests/test_gpu_parity.py::test_batches_in_one_plan_equal_batch_by_batch tests/test_gpu_parity.py::test_peak_pass_on_banks_that_defeat_its_pruning tests/test_gpu_fx.py"
+TESTS="tests/test_gpu_parity.py::test_dense_polyphony_deterministic_and_correct tests/test_gpu_parity.py::test_batches_in_one_plan_equal_batch_by_batch tests/test_gpu_parity.py::test_peak_pass_on_banks_that_defeat_its_pruning tests/test_gpu_parity.py::test_mel_fast_and_generic_filterbank_paths tests/test_gpu_fx.py tests/test_gpu_projection.py tests/test_gpu_handles.py"
 for tool in $TOOLS; do
   timeout 900 compute-sanitizer --tool $tool --print-limit 30 --error-exitcode 0 \
       python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/sanitizer_${tool}_smoke.txt 2>&1
