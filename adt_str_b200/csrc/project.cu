@@ -7,8 +7,8 @@
 // It is the one dense contraction next to the path: (rows, 128) x (128, 768).  With K = 128 the
 // GEMM is bound by HBM, not by the tensor cores - 512 B read and 1536 B written per row against 197 kflop - so the
 // kernel is built around the bytes: the cast of the log-mel is fused in (the library path runs a separate cast kernel,
-// another 768 B per row), the whole weight matrix stays in shared memory for the life of a CTA, and the 768-wide
-// output row leaves through the epilogue once.
+// another 768 B per row), a CTA's part of the weight matrix stays in shared memory for its whole life, and every
+// output element leaves once, through a TMA store.
 //
 // ONE persistent CTA of 16 warps per SM; the phases of a tile of 128 rows belong to different warps and are handed
 // over through mbarriers, so that fetching, converting, multiplying, draining and storing all run at once:
